@@ -1,0 +1,104 @@
+"""ctypes binding of libgtb200.so (C-ABI declared in include/gtb200.h).
+
+There is no fallback: if the shared library is missing or no CUDA device is
+usable every entry point raises.  The library is built in-tree by
+`__graft_entry__.build()` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgtb200.so")
+
+
+class GtbRange(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("end", C.c_uint64)]
+
+
+class GtbStats(C.Structure):
+    _fields_ = [
+        ("totallength", C.c_uint64), ("specialcharacters", C.c_uint64),
+        ("nonspecials", C.c_uint64), ("sa_offset", C.c_uint64),
+        ("longest", C.c_uint64), ("numoflargelcpvalues", C.c_uint64),
+        ("maxbranchdepth", C.c_uint64), ("lcptabsum", C.c_double),
+        ("prefixlength", C.c_uint32), ("numofchars", C.c_uint32),
+        ("unresolved_after_first_sort", C.c_uint64),
+        ("doubling_rounds", C.c_uint32), ("radix_passes", C.c_uint32),
+        ("radix_pairs_moved", C.c_uint64), ("kernel_launches", C.c_uint32),
+        ("ms_total", C.c_float), ("ms_upload", C.c_float), ("ms_count", C.c_float),
+        ("ms_hist", C.c_float), ("ms_radix", C.c_float), ("ms_analyze", C.c_float),
+        ("ms_doubling", C.c_float), ("ms_lcp", C.c_float), ("ms_tail", C.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/gtb200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_U64 = C.c_uint64
+SYMBOLS = {
+    "gtb_abi_version": (C.c_int, []),
+    "gtb_device_count": (C.c_int, []),
+    "gtb_esa_new": (_P, [C.c_int, C.c_char_p, C.c_size_t]),
+    "gtb_esa_delete": (None, [_P]),
+    "gtb_esa_error": (C.c_char_p, [_P]),
+    "gtb_esa_set_input_2bit": (C.c_int, [_P, _P, _U64, _U64, _P, _U64]),
+    "gtb_esa_set_input_bytes": (C.c_int, [_P, _P, _U64, C.c_uint]),
+    "gtb_esa_set_code_range": (C.c_int, [_P, _U64, _U64, _U64, C.c_int]),
+    "gtb_esa_run": (C.c_int, [_P, C.c_uint, C.c_uint]),
+    "gtb_esa_count": (C.c_int, [_P, C.c_uint]),
+    "gtb_esa_get_stats": (C.c_int, [_P, C.POINTER(GtbStats)]),
+    "gtb_esa_boundary_keys": (C.c_int, [_P, C.POINTER(_U64), C.POINTER(_U64)]),
+    "gtb_esa_fix_seam": (C.c_int, [_P, _U64]),
+    "gtb_esa_num_entries": (_U64, [_P]),
+    "gtb_esa_num_llv": (_U64, [_P]),
+    "gtb_esa_copy_suftab_u64": (C.c_int, [_P, _P, _U64, _U64]),
+    "gtb_esa_copy_suftab_u32": (C.c_int, [_P, _P, _U64, _U64]),
+    "gtb_esa_copy_lcptab": (C.c_int, [_P, _P, _U64, _U64]),
+    "gtb_esa_copy_llv": (C.c_int, [_P, _P]),
+    "gtb_esa_copy_bcktab": (C.c_int, [_P, _P, _P, _P]),
+    "gtb_bck_sizes": (None, [C.c_uint, C.c_uint, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "gtb_esa_dev_suftab": (_P, [_P]),
+    "gtb_esa_dev_lcptab": (_P, [_P]),
+    "gtb_esa_dev_leftborder": (_P, [_P]),
+    "gtb_esa_build_2bit": (C.c_int, [C.c_int, _P, _U64, _U64, _P, _U64, C.c_uint, _P, _P, _P, _U64,
+                                     C.POINTER(_U64), _P, _P, _P, C.POINTER(GtbStats), C.c_char_p, C.c_size_t]),
+    "gtb_esa_build_bytes": (C.c_int, [C.c_int, _P, _U64, C.c_uint, C.c_uint, _P, _P, _P, _U64,
+                                      C.POINTER(_U64), _P, _P, _P, C.POINTER(GtbStats), C.c_char_p, C.c_size_t]),
+    "gtb_radixsort_pairs_u64_u32": (C.c_int, [C.c_int, _P, _P, _U64, C.c_uint, C.c_uint, C.c_char_p, C.c_size_t]),
+}
+
+GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK = 1, 2, 4
+
+_lib = None
+
+
+class GtbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libgtb200.so; raises GtbError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GtbError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). genometools_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    """raw address of a C-contiguous numpy array (or None)"""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data

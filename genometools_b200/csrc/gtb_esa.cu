@@ -1,0 +1,905 @@
+// gtb_esa.cu -- libgtb200.so: host orchestration + C-ABI (include/gtb200.h).
+//
+// Pipeline of gtb_esa_run (replaces gt_Sfxiterator_new/next + the GtOutlcpinfo side
+// channel, /root/reference/src/match/sfx-suffixer.c:1363-2204,
+// /root/reference/src/match/sfx-lcpvalues.c):
+//   0  special mask in HBM (from the special ranges / from the byte symbols)
+//   K1 code histogram (+ special k-mers)            -> leftborder counts, countspecialcodes,
+//   K2 exclusive scan                                   distpfxidx  (.bck)
+//   K3+K4 fused key generation + onesweep LSD radix sort of (key64, pos32)
+//   A  group analysis: lcp of resolved neighbours, compaction of ties, inverse SA
+//   K5 prefix doubling rounds on the ties (same radix engine)
+//   K6 exact lcp of deep pairs, .llv list, stats
+//   K7 special tail
+#include <stdarg.h>
+#include <stdlib.h>
+#include <new>
+
+#include "../../include/gtb200.h"
+#include "gtb_common.cuh"
+#include "gtb_radix.cuh"
+#include "gtb_esa_kernels.cuh"
+
+namespace gtb {
+
+void ErrBuf::set(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof msg, fmt, ap);
+  va_end(ap);
+}
+
+// a device buffer that only grows (re-runs on one handle do not reallocate)
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, ErrBuf &err)
+  {
+    if (bytes <= cap) return 0;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + (bytes >> 6) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      err.set("cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+      p = nullptr; return -1;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+static u64 ipow_u64(u64 b, unsigned e) { u64 r = 1; while (e--) r *= b; return r; }
+
+} // namespace gtb
+
+using namespace gtb;
+
+struct gtb_esa {
+  ErrBuf err;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  // input
+  bool have_input = false, dna = true;
+  u64 n = 0, S = 0;
+  unsigned K = 4;
+  DevBuf words, bytes, spmask, ranges;
+  u64 nmaskwords = 0;
+  // code range (shard)
+  bool full_range = true;
+  u64 mincode = 0, maxcode = 0;
+  int emit_tail = 1;
+  // bucket table
+  unsigned pl = 0;
+  bool counted = false;
+  u64 ncodes = 0, nspecialcodes = 0, ndist = 0;
+  DevBuf leftborder, csc, dist, distoff;
+  // sort state
+  DevBuf kbuf[2], vbuf[2], lcp8, isa, tile_a, tile_b, scantmp, dstats, misc;
+  DevBuf uidx0, ugrp0, uidx[2], ugrp[2], upos[2], dkeys, kd[2], vd[2], ulcp, llvflags, llv;
+  RadixWork rw;
+  int res = 0;              // which vbuf holds the suffix table
+  u64 N = 0;                // sorted (non-special) suffixes of this shard
+  u64 sa_offset = 0;        // global SA index of the shard's first entry
+  u64 entries = 0;          // N (+ S + 1 with tail)
+  u64 nllv = 0;
+  u64 first_key = 0, last_key = 0;
+  bool ran = false;
+  gtb_stats stats;
+};
+
+namespace {
+
+struct PhaseTimer {
+  gtb_esa *h;
+  cudaEvent_t a, b;
+  float *acc;
+  PhaseTimer(gtb_esa *h_, float *acc_) : h(h_), acc(acc_)
+  {
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, h->st);
+  }
+  void stop()
+  {
+    cudaEventRecord(b, h->st);
+    cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    *acc += ms;
+  }
+  ~PhaseTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+inline unsigned grid_for(u64 items, unsigned block, unsigned maxblocks = 148u * 16u)
+{
+  u64 g = div_up(items, block);
+  if (g < 1) g = 1;
+  return (unsigned) (g < maxblocks ? g : maxblocks);
+}
+
+int bitlen(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b < 1 ? 1 : b; }
+
+// exclusive scan of a u32 array in place (popc_mode: scan popcounts, out may differ)
+int device_scan_u32(gtb_esa *h, const u32 *in, u32 *out, u64 count, int popc_mode_tiles_only,
+                    u32 **tileoff_out, u64 *total_out)
+{
+  ErrBuf &err = h->err;
+  const u64 tiles = div_up(count, SC_TILE);
+  if (tiles == 0) { if (total_out) *total_out = 0; return 0; }
+  GTB_TRY(h->scantmp.ensure(sizeof(u32) * tiles + 64, err));
+  GTB_TRY(h->misc.ensure(256, err));
+  u32 *tilesum = h->scantmp.as<u32>();
+  u64 *d_total = h->misc.as<u64>();
+  k_scan_tilesums<<<(unsigned) tiles, SC_NT, 0, h->st>>>(in, count, tilesum, popc_mode_tiles_only);
+  GTB_LAUNCH_CHECK();
+  k_scan_single<<<1, 1024, 0, h->st>>>(tilesum, tiles, d_total);
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches += 2;
+  if (!popc_mode_tiles_only) {
+    k_scan_apply<<<(unsigned) tiles, SC_NT, 0, h->st>>>(in, out, count, tilesum);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  if (tileoff_out) *tileoff_out = tilesum;
+  if (total_out) {
+    GTB_CUDA(cudaMemcpyAsync(total_out, d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+    GTB_CUDA(cudaStreamSynchronize(h->st));
+  }
+  return 0;
+}
+
+template <bool DNA>
+TextSrc<DNA> make_src(gtb_esa *h, u64 klo, u64 khi)
+{
+  TextSrc<DNA> s;
+  s.words = h->words.as<u64>();
+  s.bytes = h->bytes.as<u8>();
+  s.spmask = h->spmask.as<u32>();
+  s.klo = klo; s.khi = khi;
+  return s;
+}
+
+// key range of the code interval [mincode, maxcode]
+void code_range_to_keys(const gtb_esa *h, u64 *klo, u64 *khi)
+{
+  if (h->full_range || h->pl == 0) { *klo = 0; *khi = ~0ull; return; }
+  if (h->dna) {
+    const unsigned sh = 64 - 2 * h->pl;
+    *klo = h->mincode << sh;
+    *khi = (h->maxcode << sh) | ((sh < 64 ? (1ull << sh) : 0ull) - 1ull);
+  } else {
+    const KeyFmt f = byte_fmt();
+    u64 lo = 0, hi = 0, a = h->mincode, b = h->maxcode;
+    u64 dl[16], dh[16];
+    for (int k = (int) h->pl - 1; k >= 0; k--) { dl[k] = a % h->K; a /= h->K; dh[k] = b % h->K; b /= h->K; }
+    for (unsigned k = 0; k < h->pl; k++) {
+      // the largest symbol of a code may stand for the filler (31) of a special k-mer
+      lo = (lo << f.b) | dl[k];
+      hi = (hi << f.b) | (dh[k] == h->K - 1 ? 31ull : dh[k]);
+    }
+    const unsigned sh = 64 - f.b * h->pl;
+    *klo = lo << sh;
+    *khi = (hi << sh) | ((1ull << sh) - 1ull);
+    // a min code ending in K-1 symbols must not exclude nothing below it: fine, dl kept as is
+  }
+}
+
+int build_mask(gtb_esa *h, const gtb_range *specials, u64 nranges)
+{
+  ErrBuf &err = h->err;
+  h->nmaskwords = (h->n >> 5) + 4;
+  GTB_TRY(h->spmask.ensure(sizeof(u32) * h->nmaskwords, err));
+  GTB_CUDA(cudaMemsetAsync(h->spmask.p, 0, sizeof(u32) * h->nmaskwords, h->st));
+  k_mask_tail<<<grid_for(h->nmaskwords - (h->n >> 5), 256, 64), 256, 0, h->st>>>(
+      h->spmask.as<u32>(), h->n, h->nmaskwords);
+  GTB_LAUNCH_CHECK();
+  if (h->dna) {
+    if (nranges > 0) {
+      GTB_TRY(h->ranges.ensure(sizeof(u64) * 2 * nranges, err));
+      GTB_CUDA(cudaMemcpyAsync(h->ranges.p, specials, sizeof(u64) * 2 * nranges,
+                               cudaMemcpyHostToDevice, h->st));
+      k_mask_ranges<<<grid_for(nranges * 32, 256), 256, 0, h->st>>>(
+          h->spmask.as<u32>(), h->ranges.as<u64>(), nranges);
+      GTB_LAUNCH_CHECK();
+    }
+  } else if (h->n > 0) {
+    k_mask_from_bytes<<<grid_for((h->n + 31) >> 5, 256), 256, 0, h->st>>>(
+        h->spmask.as<u32>(), h->bytes.as<u8>(), h->n);
+    GTB_LAUNCH_CHECK();
+  }
+  // S = popcount of the mask over positions < n
+  const u64 nw = (h->n + 31) >> 5;
+  u64 total = 0;
+  if (nw > 0) {
+    GTB_TRY(device_scan_u32(h, h->spmask.as<u32>(), nullptr, nw, 1, nullptr, &total));
+    if (h->n & 31u) total -= 32 - (h->n & 31u);
+  }
+  h->S = total;
+  return 0;
+}
+
+int count_codes(gtb_esa *h, unsigned pl)
+{
+  ErrBuf &err = h->err;
+  if (h->counted && h->pl == pl) return 0;
+  h->pl = pl;
+  h->ncodes = ipow_u64(h->K, pl);
+  h->nspecialcodes = ipow_u64(h->K, pl - 1);
+  h->ndist = 0;
+  u64 distoff[32] = {0};
+  for (unsigned i = 1; i + 2 <= pl; i++) { distoff[i] = h->ndist; h->ndist += ipow_u64(h->K, i); }
+  GTB_TRY(h->leftborder.ensure(sizeof(u32) * (h->ncodes + 2), err));
+  GTB_TRY(h->csc.ensure(sizeof(u32) * (h->nspecialcodes + 1), err));
+  GTB_TRY(h->dist.ensure(sizeof(u32) * (h->ndist + 1), err));
+  GTB_TRY(h->distoff.ensure(sizeof(u64) * 32, err));
+  GTB_CUDA(cudaMemsetAsync(h->leftborder.p, 0, sizeof(u32) * (h->ncodes + 2), h->st));
+  GTB_CUDA(cudaMemsetAsync(h->csc.p, 0, sizeof(u32) * (h->nspecialcodes + 1), h->st));
+  GTB_CUDA(cudaMemsetAsync(h->dist.p, 0, sizeof(u32) * (h->ndist + 1), h->st));
+  GTB_CUDA(cudaMemcpyAsync(h->distoff.p, distoff, sizeof distoff, cudaMemcpyHostToDevice, h->st));
+  if (h->n > 0) {
+    const unsigned grid = grid_for(h->n, 256, 148u * 8u);
+    if (h->dna)
+      k_count_codes<true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K,
+          h->leftborder.as<u32>(), h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
+    else
+      k_count_codes<false><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K,
+          h->leftborder.as<u32>(), h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  // counts -> bucket starts; entry ncodes becomes the number of non-special suffixes
+  GTB_TRY(device_scan_u32(h, h->leftborder.as<u32>(), h->leftborder.as<u32>(), h->ncodes + 1, 0,
+                          nullptr, nullptr));
+  h->counted = true;
+  return 0;
+}
+
+template <bool DNA>
+int run_pipeline(gtb_esa *h, unsigned flags)
+{
+  ErrBuf &err = h->err;
+  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  const bool want_lcp = (flags & GTB_WANT_LCP) != 0;
+  gtb_stats &S = h->stats;
+  cudaStream_t st = h->st;
+
+  // ---- K1/K2 bucket table ----
+  {
+    PhaseTimer t(h, &S.ms_count);
+    if (h->pl > 0 && ((flags & GTB_WANT_BCK) || !h->full_range)) GTB_TRY(count_codes(h, h->pl));
+    t.stop();
+  }
+  u64 klo, khi;
+  code_range_to_keys(h, &klo, &khi);
+  u64 Ncap = h->n - h->S;
+  h->sa_offset = 0;
+  if (!h->full_range) {
+    u32 lb[2];
+    GTB_CUDA(cudaMemcpyAsync(&lb[0], h->leftborder.as<u32>() + h->mincode, sizeof(u32),
+                             cudaMemcpyDeviceToHost, st));
+    GTB_CUDA(cudaMemcpyAsync(&lb[1], h->leftborder.as<u32>() + h->maxcode + 1, sizeof(u32),
+                             cudaMemcpyDeviceToHost, st));
+    GTB_CUDA(cudaStreamSynchronize(st));
+    h->sa_offset = lb[0];
+    Ncap = lb[1] - lb[0];
+  }
+  const u64 tailcnt = h->emit_tail ? h->S + 1 : 0;
+  const u64 cap_entries = Ncap + tailcnt;
+
+  // ---- buffers ----
+  for (int i = 0; i < 2; i++) {
+    GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * (Ncap + 1), err));
+    GTB_TRY(h->vbuf[i].ensure(sizeof(u32) * (cap_entries + 1), err));
+  }
+  GTB_TRY(h->lcp8.ensure(cap_entries + 16, err));
+  GTB_TRY(h->dstats.ensure(sizeof(DevStats), err));
+  {
+    DevStats z; memset(&z, 0, sizeof z); z.longest = ~0ull;
+    GTB_CUDA(cudaMemcpyAsync(h->dstats.p, &z, sizeof z, cudaMemcpyHostToDevice, st));
+  }
+  DevStats *dstats = h->dstats.as<DevStats>();
+
+  // ---- K3+K4: fused key generation + LSD radix sort over all key bits ----
+  TextSrc<DNA> src = make_src<DNA>(h, klo, khi);
+  u64 *kb[2] = {h->kbuf[0].as<u64>(), h->kbuf[1].as<u64>()};
+  u32 *vb[2] = {h->vbuf[0].as<u32>(), h->vbuf[1].as<u32>()};
+  PassPlan plan; plan.npass = 0;
+  plan_add_bits(plan, 0, 64);
+  u64 N = 0;
+  h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0; h->rw.ms_hist = 0; h->rw.ms_radix = 0;
+  GTB_TRY(radix_sort(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err));
+  if (N > Ncap) { err.set("internal: sorted %llu suffixes, expected at most %llu",
+                          (unsigned long long) N, (unsigned long long) Ncap); return -1; }
+  h->N = N;
+  h->entries = N + tailcnt;
+  u64 *keys = kb[h->res];
+  u32 *sa = vb[h->res];
+  u8 *lcp8 = h->lcp8.as<u8>();
+  GTB_CUDA(cudaMemsetAsync(lcp8, 0, h->entries + 16, st));
+  h->first_key = h->last_key = 0;
+  if (N > 0) {
+    GTB_CUDA(cudaMemcpyAsync(&h->first_key, keys, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    GTB_CUDA(cudaMemcpyAsync(&h->last_key, keys + N - 1, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  }
+
+  // ---- A: analysis ----
+  u64 M0 = 0;
+  const u64 atiles = div_up(N, AN_TILE);
+  {
+    PhaseTimer t(h, &S.ms_analyze);
+    if (N > 0) {
+      GTB_TRY(h->tile_a.ensure(sizeof(u32) * (atiles + 1), err));
+      GTB_TRY(h->tile_b.ensure(sizeof(u32) * (atiles + 1), err));
+      GTB_TRY(h->misc.ensure(256, err));
+      k_analyze_keys<<<(unsigned) atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, lcp8,
+          h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull);
+      GTB_LAUNCH_CHECK();
+      k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), atiles,
+                                               h->misc.as<u64>());
+      GTB_LAUNCH_CHECK();
+      k_find_longest<DNA><<<1, 1, 0, st>>>(src, keys, N, h->sa_offset, dstats);
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches += 3;
+      GTB_CUDA(cudaMemcpyAsync(&M0, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
+      GTB_CUDA(cudaStreamSynchronize(st));
+    }
+    t.stop();
+  }
+  S.unresolved_after_first_sort = M0;
+  S.doubling_rounds = 0;
+  h->nllv = 0;
+
+  // ---- K7 special tail (also gives the ranks of special positions) ----
+  const bool need_isa = M0 > 0;
+  if (need_isa) {
+    GTB_TRY(h->isa.ensure(sizeof(u32) * (h->n + 2), err));
+    k_set_u32<<<1, 1, 0, st>>>(h->isa.as<u32>() + h->n, (u32) h->n);
+    GTB_LAUNCH_CHECK();
+    S.kernel_launches++;
+  }
+  {
+    PhaseTimer t(h, &S.ms_tail);
+    const u64 nw = (h->n + 31) >> 5;
+    if ((h->emit_tail || need_isa) && h->S > 0 && nw > 0) {
+      u32 *tileoff = nullptr;
+      GTB_TRY(device_scan_u32(h, h->spmask.as<u32>(), nullptr, nw, 1, &tileoff, nullptr));
+      // without emit_tail the positions are written to a scratch area (only ranks needed)
+      u32 *tail_dst = sa + N;
+      if (!h->emit_tail) {
+        GTB_TRY(h->ulcp.ensure(sizeof(u32) * (h->S + 1), err));
+        tail_dst = h->ulcp.as<u32>();
+      }
+      k_emit_special_tail<<<(unsigned) div_up(nw, SC_TILE), SC_NT, 0, st>>>(
+          h->spmask.as<u32>(), nw, h->n, tileoff, tail_dst, need_isa ? h->isa.as<u32>() : nullptr,
+          h->n - h->S, h->emit_tail ? &dstats->longest : (unsigned long long *) h->misc.as<u64>() + 8);
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches++;
+    }
+    if (h->emit_tail) {
+      k_set_u32<<<1, 1, 0, st>>>(sa + N + h->S, (u32) h->n);
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches++;
+    }
+    t.stop();
+  }
+
+  // ---- K5 prefix doubling on the ties ----
+  if (M0 > 0) {
+    PhaseTimer t(h, &S.ms_doubling);
+    GTB_TRY(h->uidx0.ensure(sizeof(u32) * M0, err));
+    GTB_TRY(h->ugrp0.ensure(sizeof(u32) * M0, err));
+    for (int i = 0; i < 2; i++) {
+      GTB_TRY(h->uidx[i].ensure(sizeof(u32) * M0, err));
+      GTB_TRY(h->ugrp[i].ensure(sizeof(u32) * M0, err));
+      GTB_TRY(h->upos[i].ensure(sizeof(u32) * M0, err));
+      GTB_TRY(h->kd[i].ensure(sizeof(u64) * M0, err));
+      GTB_TRY(h->vd[i].ensure(sizeof(u32) * M0, err));
+    }
+    GTB_TRY(h->dkeys.ensure(sizeof(u64) * M0, err));
+    k_compact_keys<<<(unsigned) atiles, AN_NT, 0, st>>>(keys, sa, N, f, h->tile_a.as<u32>(),
+        h->tile_b.as<u32>(), h->uidx[0].as<u32>(), h->upos[0].as<u32>(), h->ugrp[0].as<u32>(),
+        h->isa.as<u32>(), h->sa_offset);
+    GTB_LAUNCH_CHECK();
+    S.kernel_launches++;
+    GTB_CUDA(cudaMemcpyAsync(h->uidx0.p, h->uidx[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
+    GTB_CUDA(cudaMemcpyAsync(h->ugrp0.p, h->ugrp[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
+
+    u64 M = M0;
+    int cur = 0;
+    const int bits_lo = bitlen(h->n), bits_hi = bitlen(N > 0 ? N - 1 : 0);
+    for (unsigned round = 0; M > 0; round++) {
+      if (round > 40) { err.set("internal: prefix doubling did not converge"); return -1; }
+      const u64 hlen = (u64) f.m << round;
+      k_build_dkeys<<<grid_for(M, 256), 256, 0, st>>>(h->upos[cur].as<u32>(), h->ugrp[cur].as<u32>(),
+          h->isa.as<u32>(), M, hlen, h->dkeys.as<u64>());
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches++;
+      PassPlan dp; dp.npass = 0;
+      plan_add_bits(dp, 0, bits_lo);
+      plan_add_bits(dp, 32, 32 + bits_hi);
+      PairSrc ps{h->dkeys.as<u64>(), h->upos[cur].as<u32>()};
+      u64 *kk[2] = {h->kd[0].as<u64>(), h->kd[1].as<u64>()};
+      u32 *vv[2] = {h->vd[0].as<u32>(), h->vd[1].as<u32>()};
+      int r2 = 0; u64 nout = 0;
+      GTB_TRY(radix_sort(h->rw, st, ps, M, kk, vv, dp, &r2, &nout, err));
+      if (nout != M) { err.set("internal: doubling sort lost elements"); return -1; }
+      const u64 dt = div_up(M, AN_TILE);
+      GTB_TRY(h->tile_a.ensure(sizeof(u32) * (dt + 1), err));
+      GTB_TRY(h->tile_b.ensure(sizeof(u32) * (dt + 1), err));
+      k_analyze_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], M, h->tile_a.as<u32>(), h->tile_b.as<u32>());
+      GTB_LAUNCH_CHECK();
+      k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), dt, h->misc.as<u64>());
+      GTB_LAUNCH_CHECK();
+      k_apply_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M,
+          h->tile_a.as<u32>(), h->tile_b.as<u32>(), sa, h->isa.as<u32>(), lcp8, (u8) round, h->sa_offset,
+          h->uidx[cur ^ 1].as<u32>(), h->upos[cur ^ 1].as<u32>(), h->ugrp[cur ^ 1].as<u32>(), dstats);
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches += 3;
+      u64 Mnext = 0;
+      GTB_CUDA(cudaMemcpyAsync(&Mnext, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
+      GTB_CUDA(cudaStreamSynchronize(st));
+      M = Mnext;
+      cur ^= 1;
+      S.doubling_rounds = round + 1;
+    }
+    t.stop();
+  }
+
+  // ---- K6 exact lcp of deep pairs + .llv ----
+  if (M0 > 0 && want_lcp) {
+    PhaseTimer t(h, &S.ms_lcp);
+    GTB_TRY(h->ulcp.ensure(sizeof(u32) * (M0 > h->S + 1 ? M0 : h->S + 1), err));
+    k_deep_lcp<DNA><<<grid_for(M0, 128), 128, 0, st>>>(h->uidx0.as<u32>(), h->ugrp0.as<u32>(), M0, sa,
+        h->words.as<u64>(), h->bytes.as<u8>(), h->spmask.as<u32>(), h->n, (unsigned) f.m, lcp8,
+        h->ulcp.as<u32>(), dstats);
+    GTB_LAUNCH_CHECK();
+    S.kernel_launches++;
+    DevStats hs;
+    GTB_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    GTB_CUDA(cudaStreamSynchronize(st));
+    if (hs.numlarge > 0) {
+      GTB_TRY(h->llvflags.ensure(sizeof(u32) * M0, err));
+      GTB_TRY(h->llv.ensure(sizeof(u64) * 2 * hs.numlarge, err));
+      k_llv_flags<<<grid_for(M0, 256), 256, 0, st>>>(h->ulcp.as<u32>(), M0, h->llvflags.as<u32>());
+      GTB_LAUNCH_CHECK();
+      u64 tot = 0;
+      GTB_TRY(device_scan_u32(h, h->llvflags.as<u32>(), h->llvflags.as<u32>(), M0, 0, nullptr, &tot));
+      if (tot != hs.numlarge) { err.set("internal: llv count mismatch"); return -1; }
+      k_llv_emit<<<grid_for(M0, 256), 256, 0, st>>>(h->ulcp.as<u32>(), h->uidx0.as<u32>(), M0,
+          h->llvflags.as<u32>(), h->sa_offset, h->llv.as<u64>());
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches += 2;
+      h->nllv = hs.numlarge;
+    }
+    t.stop();
+  }
+
+  // ---- stats ----
+  DevStats hs;
+  GTB_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
+  GTB_CUDA(cudaStreamSynchronize(st));
+  S.totallength = h->n; S.specialcharacters = h->S; S.nonspecials = N;
+  S.sa_offset = h->sa_offset;
+  S.longest = hs.longest;
+  S.numoflargelcpvalues = hs.numlarge;
+  S.maxbranchdepth = hs.maxlcp;
+  S.lcptabsum = (double) hs.lcpsum;
+  S.prefixlength = h->pl; S.numofchars = h->K;
+  S.radix_passes = h->rw.passes; S.radix_pairs_moved = h->rw.pairs_moved;
+  S.kernel_launches += h->rw.launches;
+  S.ms_hist = h->rw.ms_hist; S.ms_radix = h->rw.ms_radix;
+  return 0;
+}
+
+} // namespace
+
+// =============================== C-ABI =================================================
+extern "C" {
+
+int gtb_abi_version(void) { return GTB200_ABI_VERSION; }
+
+int gtb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void gtb_bck_sizes(unsigned K, unsigned pl, uint64_t *nall, uint64_t *nspecial, uint64_t *ndist)
+{
+  u64 d = 0;
+  for (unsigned i = 1; i + 2 <= pl; i++) d += ipow_u64(K, i);
+  if (nall) *nall = pl ? ipow_u64(K, pl) : 0;
+  if (nspecial) *nspecial = pl ? ipow_u64(K, pl - 1) : 0;
+  if (ndist) *ndist = d;
+}
+
+gtb_esa *gtb_esa_new(int device, char *errbuf, size_t errlen)
+{
+  auto fail = [&](const char *what, cudaError_t e) -> gtb_esa * {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "%s: %s", what, cudaGetErrorString(e));
+    return nullptr;
+  };
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    if (errbuf && errlen)
+      snprintf(errbuf, errlen, "libgtb200: no CUDA device available (%s); there is no CPU fallback",
+               e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "libgtb200: device %d out of range (%d devices)", device, ndev);
+    return nullptr;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  gtb_esa *h = new (std::nothrow) gtb_esa();
+  if (!h) { if (errbuf && errlen) snprintf(errbuf, errlen, "out of host memory"); return nullptr; }
+  h->device = device;
+  memset(&h->stats, 0, sizeof h->stats);
+  if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete h; return fail("cudaStreamCreate", e);
+  }
+  if (radix_work_init(h->rw, h->err) != 0) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "%s", h->err.msg);
+    cudaStreamDestroy(h->st); delete h; return nullptr;
+  }
+  return h;
+}
+
+void gtb_esa_delete(gtb_esa *h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->leftborder, &h->csc, &h->dist,
+                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->isa,
+                   &h->tile_a, &h->tile_b, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
+                   &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
+                   &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv};
+  for (DevBuf *b : all) b->release();
+  radix_work_free(h->rw);
+  cudaStreamDestroy(h->st);
+  delete h;
+}
+
+const char *gtb_esa_error(const gtb_esa *h) { return h ? h->err.msg : "null handle"; }
+
+int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nwords,
+                           uint64_t n, const gtb_range *specials, uint64_t nranges)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (n + 1 >= 0xffffffffull) { err.set("totallength %llu needs 64-bit suffix tables: not supported by this build (u32 positions)", (unsigned long long) n); return -1; }
+  if (nwords < (n + 31) / 32) { err.set("twobitencoding too short: %llu words for %llu bases", (unsigned long long) nwords, (unsigned long long) n); return -1; }
+  PhaseTimer t(h, &h->stats.ms_upload);
+  h->dna = true; h->K = 4; h->n = n; h->counted = false; h->ran = false;
+  const u64 need = (n >> 5) + 4;
+  GTB_TRY(h->words.ensure(sizeof(u64) * need, err));
+  GTB_CUDA(cudaMemsetAsync(h->words.p, 0, sizeof(u64) * need, h->st));
+  const u64 ncopy = nwords < need ? nwords : need;
+  if (ncopy) GTB_CUDA(cudaMemcpyAsync(h->words.p, twobitenc, sizeof(u64) * ncopy, cudaMemcpyHostToDevice, h->st));
+  for (u64 r = 0; r < nranges; r++) {
+    if (specials[r].start >= specials[r].end || specials[r].end > n ||
+        (r > 0 && specials[r].start < specials[r - 1].end)) {
+      err.set("special range %llu [%llu,%llu) is empty, unordered or beyond the text", (unsigned long long) r,
+              (unsigned long long) specials[r].start, (unsigned long long) specials[r].end);
+      return -1;
+    }
+  }
+  GTB_TRY(build_mask(h, specials, nranges));
+  t.stop();
+  h->have_input = true;
+  return 0;
+}
+
+int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols, uint64_t n, unsigned K)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (n + 1 >= 0xffffffffull) { err.set("totallength %llu needs 64-bit suffix tables: not supported by this build", (unsigned long long) n); return -1; }
+  if (K < 1 || K > 31) { err.set("numofchars %u not supported by the byte path (1..31)", K); return -1; }
+  PhaseTimer t(h, &h->stats.ms_upload);
+  h->dna = false; h->K = K; h->n = n; h->counted = false; h->ran = false;
+  const u64 need = ((n + 31) / 32) * 32 + 64;
+  GTB_TRY(h->bytes.ensure(need, err));
+  GTB_CUDA(cudaMemsetAsync(h->bytes.p, 0xff, need, h->st));
+  if (n) GTB_CUDA(cudaMemcpyAsync(h->bytes.p, symbols, n, cudaMemcpyHostToDevice, h->st));
+  GTB_TRY(build_mask(h, nullptr, 0));
+  t.stop();
+  h->have_input = true;
+  return 0;
+}
+
+int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint64_t sa_offset,
+                           int emit_special_tail)
+{
+  if (!h) return -1;
+  (void) sa_offset;   // derived from the bucket table; kept in the signature for callers that know it
+  if (mincode > maxcode) { h->err.set("empty code range"); return -1; }
+  h->full_range = false; h->mincode = mincode; h->maxcode = maxcode;
+  h->emit_tail = emit_special_tail ? 1 : 0;
+  return 0;
+}
+
+int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input) { err.set("gtb_esa_run: no input set"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  const unsigned maxpl = h->dna ? 15u : 7u;     // gt_maxbasepower, initbasepower.c:23
+  if (prefixlength > maxpl || (!h->dna && ipow_u64(h->K, prefixlength) > 0xffffffffull)) {
+    err.set("prefix length %u is too large for alphabet size %u", prefixlength, h->K); return -1;
+  }
+  if (prefixlength == 0 && ((flags & GTB_WANT_BCK) || !h->full_range)) {
+    err.set("prefixlength 0 cannot be combined with a bucket table or a code range"); return -1;
+  }
+  if (!h->full_range && h->maxcode >= ipow_u64(h->K, prefixlength)) {
+    err.set("code range beyond numofchars^prefixlength"); return -1;
+  }
+  const float up = h->stats.ms_upload;
+  memset(&h->stats, 0, sizeof h->stats);
+  h->stats.ms_upload = up;
+  if (h->pl != prefixlength) h->counted = false;
+  h->pl = prefixlength;
+  cudaEvent_t e0, e1;
+  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
+  GTB_CUDA(cudaEventRecord(e0, h->st));
+  int rc = h->dna ? run_pipeline<true>(h, flags) : run_pipeline<false>(h, flags);
+  cudaEventRecord(e1, h->st);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&h->stats.ms_total, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc == 0) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err.set("CUDA error after run: %s", cudaGetErrorString(e)); rc = -1; }
+  }
+  h->ran = rc == 0;
+  return rc;
+}
+
+int gtb_esa_count(gtb_esa *h, unsigned prefixlength)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input) { err.set("gtb_esa_count: no input set"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
+  if (h->pl != prefixlength) h->counted = false;
+  GTB_TRY(count_codes(h, prefixlength));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_get_stats(const gtb_esa *h, gtb_stats *st)
+{
+  if (!h || !st) return -1;
+  *st = h->stats;
+  return 0;
+}
+
+uint64_t gtb_esa_num_entries(const gtb_esa *h) { return h && h->ran ? h->entries : 0; }
+uint64_t gtb_esa_num_llv(const gtb_esa *h) { return h && h->ran ? h->nllv : 0; }
+
+int gtb_esa_boundary_keys(const gtb_esa *h, uint64_t *first_key, uint64_t *last_key)
+{
+  if (!h || !h->ran) return -1;
+  if (first_key) *first_key = h->first_key;
+  if (last_key) *last_key = h->last_key;
+  return 0;
+}
+
+// lcp between the last suffix of the previous shard and the first of this one
+// (computelocallcpvalue of two codes, sfx-lcpvalues.c:91-111: shards meet at bucket
+// borders so the filled keys decide); patches lcptab[0] and the stats.
+int gtb_esa_fix_seam(gtb_esa *h, uint64_t prev_last_key)
+{
+  if (!h || !h->ran) return -1;
+  ErrBuf &err = h->err;
+  if (h->N == 0) return 0;
+  GTB_CUDA(cudaSetDevice(h->device));
+  const KeyFmt f = h->dna ? dna_fmt() : byte_fmt();
+  const u64 tmask = (1ull << f.tb) - 1ull;
+  const u64 x = (prev_last_key ^ h->first_key) & ~tmask;
+  u32 l = x ? (u32) (__builtin_clzll(x) / f.b) : (u32) f.m;
+  const u32 ua = f.m - (u32) (prev_last_key & tmask), ub = f.m - (u32) (h->first_key & tmask);
+  l = l < ua ? l : ua; l = l < ub ? l : ub;
+  u8 v = (u8) l;
+  GTB_CUDA(cudaMemcpyAsync(h->lcp8.p, &v, 1, cudaMemcpyHostToDevice, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  if (ub >= h->pl) h->stats.lcptabsum += l;
+  if (l > h->stats.maxbranchdepth) h->stats.maxbranchdepth = l;
+  return 0;
+}
+
+static int check_range(gtb_esa *h, uint64_t first, uint64_t count)
+{
+  if (!h) return -1;
+  if (!h->ran) { h->err.set("no results: gtb_esa_run has not succeeded"); return -1; }
+  if (first > h->entries || count > h->entries - first) { h->err.set("copy range out of bounds"); return -1; }
+  return 0;
+}
+
+int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t count)
+{
+  GTB_TRY(check_range(h, first, count));
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (count) GTB_CUDA(cudaMemcpyAsync(dst, h->vbuf[h->res].as<u32>() + first, sizeof(u32) * count,
+                                      cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t count)
+{
+  GTB_TRY(check_range(h, first, count));
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  // widen on the device into a staging buffer (the dead key buffers), copy in chunks
+  const u64 chunk = 1ull << 25;                 // 32 Mi entries = 256 MiB per chunk
+  u64 *stage[2];
+  for (int i = 0; i < 2; i++) {
+    GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * (chunk < count ? chunk : count), err));
+    stage[i] = h->kbuf[i].as<u64>();
+  }
+  cudaEvent_t done[2];
+  for (int i = 0; i < 2; i++) GTB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  int b = 0;
+  for (u64 off = 0; off < count; off += chunk, b ^= 1) {
+    const u64 c = count - off < chunk ? count - off : chunk;
+    GTB_CUDA(cudaEventSynchronize(done[b]));
+    k_widen_u32_u64<<<grid_for(c, 256), 256, 0, h->st>>>(h->vbuf[h->res].as<u32>() + first + off, stage[b], c);
+    GTB_LAUNCH_CHECK();
+    GTB_CUDA(cudaMemcpyAsync(dst + off, stage[b], sizeof(u64) * c, cudaMemcpyDeviceToHost, h->st));
+    GTB_CUDA(cudaEventRecord(done[b], h->st));
+  }
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  for (int i = 0; i < 2; i++) cudaEventDestroy(done[i]);
+  return 0;
+}
+
+int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count)
+{
+  GTB_TRY(check_range(h, first, count));
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (count) GTB_CUDA(cudaMemcpyAsync(dst, h->lcp8.as<u8>() + first, count, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_copy_llv(gtb_esa *h, uint64_t *dst)
+{
+  if (!h || !h->ran) return -1;
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (h->nllv) GTB_CUDA(cudaMemcpyAsync(dst, h->llv.p, sizeof(u64) * 2 * h->nllv, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_copy_bcktab(gtb_esa *h, uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->counted) { err.set("no bucket table: run with GTB_WANT_BCK or call gtb_esa_count first"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (leftborder) GTB_CUDA(cudaMemcpyAsync(leftborder, h->leftborder.p, sizeof(u32) * (h->ncodes + 1), cudaMemcpyDeviceToHost, h->st));
+  if (countspecialcodes) GTB_CUDA(cudaMemcpyAsync(countspecialcodes, h->csc.p, sizeof(u32) * h->nspecialcodes, cudaMemcpyDeviceToHost, h->st));
+  if (distpfxidx && h->ndist) GTB_CUDA(cudaMemcpyAsync(distpfxidx, h->dist.p, sizeof(u32) * h->ndist, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+const uint32_t *gtb_esa_dev_suftab(const gtb_esa *h) { return h && h->ran ? h->vbuf[h->res].as<u32>() : nullptr; }
+const uint8_t *gtb_esa_dev_lcptab(const gtb_esa *h) { return h && h->ran ? h->lcp8.as<u8>() : nullptr; }
+const uint32_t *gtb_esa_dev_leftborder(const gtb_esa *h) { return h && h->counted ? h->leftborder.as<u32>() : nullptr; }
+
+static int one_shot(gtb_esa *h, unsigned pl, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
+                    uint64_t llv_capacity, uint64_t *nllv, uint32_t *leftborder, uint32_t *csc,
+                    uint32_t *dist, gtb_stats *stats)
+{
+  unsigned flags = 0;
+  if (suftab) flags |= GTB_WANT_SUF;
+  if (lcptab || llv) flags |= GTB_WANT_LCP;
+  if (leftborder || csc || dist) flags |= GTB_WANT_BCK;
+  GTB_TRY(gtb_esa_run(h, pl, flags));
+  const u64 e = gtb_esa_num_entries(h);
+  if (suftab) GTB_TRY(gtb_esa_copy_suftab_u64(h, suftab, 0, e));
+  if (lcptab) GTB_TRY(gtb_esa_copy_lcptab(h, lcptab, 0, e));
+  if (nllv) *nllv = h->nllv;
+  if (llv) {
+    if (h->nllv > llv_capacity) { h->err.set("llv buffer too small: %llu entries needed", (unsigned long long) h->nllv); return -1; }
+    GTB_TRY(gtb_esa_copy_llv(h, llv));
+  }
+  if (flags & GTB_WANT_BCK) GTB_TRY(gtb_esa_copy_bcktab(h, leftborder, csc, dist));
+  if (stats) *stats = h->stats;
+  return 0;
+}
+
+int gtb_esa_build_2bit(int device, const uint64_t *twobitenc, uint64_t nwords, uint64_t n,
+                       const gtb_range *specials, uint64_t nranges, unsigned pl,
+                       uint64_t *suftab, uint8_t *lcptab, uint64_t *llv, uint64_t llv_capacity,
+                       uint64_t *nllv, uint32_t *leftborder, uint32_t *csc, uint32_t *dist,
+                       gtb_stats *stats, char *errbuf, size_t errlen)
+{
+  gtb_esa *h = gtb_esa_new(device, errbuf, errlen);
+  if (!h) return -1;
+  int rc = gtb_esa_set_input_2bit(h, twobitenc, nwords, n, specials, nranges);
+  if (rc == 0) rc = one_shot(h, pl, suftab, lcptab, llv, llv_capacity, nllv, leftborder, csc, dist, stats);
+  if (rc != 0 && errbuf && errlen) snprintf(errbuf, errlen, "%s", h->err.msg);
+  gtb_esa_delete(h);
+  return rc;
+}
+
+int gtb_esa_build_bytes(int device, const uint8_t *symbols, uint64_t n, unsigned K, unsigned pl,
+                        uint64_t *suftab, uint8_t *lcptab, uint64_t *llv, uint64_t llv_capacity,
+                        uint64_t *nllv, uint32_t *leftborder, uint32_t *csc, uint32_t *dist,
+                        gtb_stats *stats, char *errbuf, size_t errlen)
+{
+  gtb_esa *h = gtb_esa_new(device, errbuf, errlen);
+  if (!h) return -1;
+  int rc = gtb_esa_set_input_bytes(h, symbols, n, K);
+  if (rc == 0) rc = one_shot(h, pl, suftab, lcptab, llv, llv_capacity, nllv, leftborder, csc, dist, stats);
+  if (rc != 0 && errbuf && errlen) snprintf(errbuf, errlen, "%s", h->err.msg);
+  gtb_esa_delete(h);
+  return rc;
+}
+
+int gtb_radixsort_pairs_u64_u32(int device, uint64_t *keys, uint32_t *values, uint64_t count,
+                                unsigned begin_bit, unsigned end_bit, char *errbuf, size_t errlen)
+{
+  ErrBuf err;
+  auto body = [&]() -> int {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      err.set("libgtb200: no CUDA device available; there is no CPU fallback"); return -1;
+    }
+    if (begin_bit >= end_bit || end_bit > 64) { err.set("bad bit range"); return -1; }
+    GTB_CUDA(cudaSetDevice(device));
+    if (count == 0) return 0;
+    cudaStream_t st;
+    GTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    RadixWork rw;
+    GTB_TRY(radix_work_init(rw, err));
+    DevBuf k[2], v[2], kin, vin;
+    int rc = 0;
+    for (int i = 0; i < 2 && rc == 0; i++) { rc |= k[i].ensure(sizeof(u64) * count, err); rc |= v[i].ensure(sizeof(u32) * count, err); }
+    if (rc == 0) { rc |= kin.ensure(sizeof(u64) * count, err); rc |= vin.ensure(sizeof(u32) * count, err); }
+    if (rc == 0) {
+      if (cudaMemcpyAsync(kin.p, keys, sizeof(u64) * count, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync(vin.p, values, sizeof(u32) * count, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        err.set("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1;
+      }
+    }
+    if (rc == 0) {
+      PassPlan plan; plan.npass = 0;
+      plan_add_bits(plan, (int) begin_bit, (int) end_bit);
+      PairSrc ps{kin.as<u64>(), vin.as<u32>()};    // the first pass reads the staged input
+      u64 *kk[2] = {k[0].as<u64>(), k[1].as<u64>()};
+      u32 *vv[2] = {v[0].as<u32>(), v[1].as<u32>()};
+      int res = 0; u64 nout = 0;
+      rc = radix_sort(rw, st, ps, count, kk, vv, plan, &res, &nout, err);
+      if (rc == 0) {
+        if (cudaMemcpyAsync(keys, kk[res], sizeof(u64) * count, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(values, vv[res], sizeof(u32) * count, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { err.set("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+      }
+    }
+    kin.release(); vin.release();
+    for (int i = 0; i < 2; i++) { k[i].release(); v[i].release(); }
+    radix_work_free(rw);
+    cudaStreamDestroy(st);
+    return rc;
+  };
+  int rc = body();
+  if (rc != 0 && errbuf && errlen) snprintf(errbuf, errlen, "%s", err.msg);
+  return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,650 @@
+// gtb_esa_kernels.cuh -- device code of the enhanced-suffix-array pipeline.
+//
+// Key layout ("filled key"):
+//   bits [63 : 64-m*b]  the first m symbols of the suffix, b bits each, MSB first;
+//                       symbols at and after the first special are replaced by the
+//                       all-ones filler (for DNA that is T, the filler GenomeTools
+//                       uses for its special k-mers, sfx-mapped4.gen:180-228)
+//   bits [tb-1 : 0]     m - u, where u = number of regular symbols before the first
+//                       special (capped at m);  0 for a "full" suffix
+//   DNA: m = 29, b = 2, tb = 6      protein/bytes: m = 12, b = 5, tb = 4
+// Sorting these keys with a stable sort from text order reproduces rule R
+// (/root/reference/src/core/encseq.c:6449-6528,7371-7460)
+// for every pair except full suffixes with identical keys, which are refined by
+// prefix doubling.
+#pragma once
+#include "gtb_common.cuh"
+
+namespace gtb {
+
+struct KeyFmt {
+  int m;        // symbols per key
+  int b;        // bits per symbol
+  int tb;       // tail bits
+};
+__host__ __device__ constexpr KeyFmt dna_fmt()  { return KeyFmt{29, 2, 6}; }
+__host__ __device__ constexpr KeyFmt byte_fmt() { return KeyFmt{12, 5, 4}; }
+
+// window of 32 mask bits starting at bit `pos`
+__device__ __forceinline__ u32 mask_window(const u32 *__restrict__ spmask, u64 pos)
+{
+  const u64 w = pos >> 5;
+  return __funnelshift_r(spmask[w], spmask[w + 1], (u32) (pos & 31u));
+}
+
+// 32 bases (64 bits, MSB first) starting at base `pos`
+__device__ __forceinline__ u64 dna_window(const u64 *__restrict__ words, u64 pos)
+{
+  const u64 w = pos >> 5;
+  const unsigned sh = (unsigned) (pos & 31u) * 2u;
+  const u64 w0 = words[w], w1 = words[w + 1];
+  return sh ? (w0 << sh) | (w1 >> (64u - sh)) : w0;
+}
+
+template <bool DNA>
+struct TextSrc {
+  const u64 *words;      // DNA: packed 2-bit words (padded by >= 2 words)
+  const u8  *bytes;      // bytes path: symbols (padded by >= 16 bytes of 255)
+  const u32 *spmask;     // bit i set <=> position i is special; bits >= n all set
+  u64 klo, khi;          // inclusive key range of this shard
+
+  __device__ __forceinline__ bool make_key(u64 pos, u64 &key) const
+  {
+    const u32 win = mask_window(spmask, pos);
+    if (win & 1u) return false;                         // special position
+    if (DNA) {
+      constexpr KeyFmt f = dna_fmt();
+      const unsigned z = win ? (unsigned) __ffs(win) - 1u : 32u;
+      const unsigned u = z < (unsigned) f.m ? z : (unsigned) f.m;
+      u64 sym = dna_window(words, pos) >> f.tb;         // 29 symbols in the low 58 bits
+      if (u < (unsigned) f.m) sym |= (1ull << (2u * (f.m - u))) - 1ull;
+      key = (sym << f.tb) | (u64) (f.m - u);
+    } else {
+      constexpr KeyFmt f = byte_fmt();
+      const unsigned z = win ? (unsigned) __ffs(win) - 1u : 32u;
+      const unsigned u = z < (unsigned) f.m ? z : (unsigned) f.m;
+      u64 sym = 0;
+#pragma unroll
+      for (int k = 0; k < f.m; k++) {
+        const u64 s = (unsigned) k < u ? (u64) bytes[pos + k] : 31ull;
+        sym = (sym << f.b) | s;
+      }
+      key = (sym << f.tb) | (u64) (f.m - u);
+    }
+    return key >= klo && key <= khi;
+  }
+  __device__ __forceinline__ bool load(u64 pos, u64 &k, u32 &v) const
+  { v = (u32) pos; return make_key(pos, k); }
+  __device__ __forceinline__ bool load_key(u64 pos, u64 &k) const
+  { return make_key(pos, k); }
+};
+
+// ---- special mask ------------------------------------------------------------------
+// bits >= n are set (the end of the text acts as a special, sfx-enumcodes.c:141-154)
+__global__ void k_mask_tail(u32 *spmask, u64 n, u64 nmaskwords)
+{
+  const u64 first = n >> 5;
+  for (u64 w = first + blockIdx.x * (u64) blockDim.x + threadIdx.x; w < nmaskwords;
+       w += (u64) gridDim.x * blockDim.x) {
+    if (w == first) atomicOr(&spmask[w], ~0u << (n & 31u));
+    else spmask[w] = ~0u;
+  }
+}
+
+// one warp per special range (ranges from gt_specialrangeiterator, encseq.h:127)
+__global__ void k_mask_ranges(u32 *spmask, const u64 *__restrict__ ranges, u64 nranges)
+{
+  const u64 warps = ((u64) gridDim.x * blockDim.x) >> 5;
+  const u64 wid = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = lane_id();
+  for (u64 r = wid; r < nranges; r += warps) {
+    const u64 s = ranges[2 * r], e = ranges[2 * r + 1];
+    if (e <= s) continue;
+    const u64 w0 = s >> 5, w1 = (e - 1) >> 5;
+    for (u64 w = w0 + lane; w <= w1; w += 32) {
+      u32 bits = ~0u;
+      if (w == w0) bits &= ~0u << (s & 31u);
+      if (w == w1) bits &= ~0u >> (31u - ((e - 1) & 31u));
+      atomicOr(&spmask[w], bits);
+    }
+  }
+}
+
+// bytes path: one thread builds one mask word from 32 symbols
+__global__ void k_mask_from_bytes(u32 *spmask, const u8 *__restrict__ bytes, u64 n)
+{
+  const u64 nw = (n + 31) >> 5;
+  for (u64 w = blockIdx.x * (u64) blockDim.x + threadIdx.x; w < nw;
+       w += (u64) gridDim.x * blockDim.x) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(bytes + w * 32);
+    const uint4 a = p[0], c = p[1];
+    const u32 v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    u32 bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const u32 by = (v[i] >> (8 * j)) & 0xffu;
+        if (by >= 254u) bits |= 1u << (4 * i + j);
+      }
+    }
+    const u64 lastpos = w * 32 + 31;
+    if (lastpos >= n) bits &= (n & 31u) ? ~(~0u << (n & 31u)) : 0u;   // positions >= n handled by k_mask_tail
+    if (w * 32 >= n) bits = 0;
+    if (bits) atomicOr(&spmask[w], bits);
+  }
+}
+
+// ---- generic exclusive scan of a u32 array (three launches) ---------------------------
+constexpr int SC_NT = 256, SC_IPT = 8, SC_TILE = SC_NT * SC_IPT;
+
+__global__ void __launch_bounds__(SC_NT)
+k_scan_tilesums(const u32 *__restrict__ in, u64 count, u32 *__restrict__ tilesum, int popc_mode)
+{
+  __shared__ u32 scratch[SC_NT / 32 + 1];
+  const u64 base = (u64) blockIdx.x * SC_TILE + (u64) threadIdx.x * SC_IPT;
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++)
+    if (base + k < count) s += popc_mode ? (u32) __popc(in[base + k]) : in[base + k];
+  u32 total;
+  block_exclusive_sum<SC_NT, u32>(s, scratch, &total);
+  if (threadIdx.x == 0) tilesum[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of `cnt` values; total -> *total_out (u64)
+__global__ void __launch_bounds__(1024)
+k_scan_single(u32 *vals, u64 cnt, u64 *total_out)
+{
+  __shared__ u32 scratch[1024 / 32 + 1];
+  __shared__ u32 carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  u64 grand = 0;
+  for (u64 base = 0; base < cnt; base += 1024) {
+    const u64 i = base + threadIdx.x;
+    const u32 v = i < cnt ? vals[i] : 0u;
+    u32 total;
+    const u32 ex = block_exclusive_sum<1024, u32>(v, scratch, &total);
+    const u32 carry = carry_s;
+    if (i < cnt) vals[i] = ex + carry;
+    grand += total;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = grand;
+}
+
+__global__ void __launch_bounds__(SC_NT)
+k_scan_apply(const u32 *in, u32 *out, u64 count,
+             const u32 *__restrict__ tileoff)
+{
+  __shared__ u32 scratch[SC_NT / 32 + 1];
+  const u64 base = (u64) blockIdx.x * SC_TILE + (u64) threadIdx.x * SC_IPT;
+  u32 v[SC_IPT], s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) { v[k] = base + k < count ? in[base + k] : 0u; s += v[k]; }
+  u32 total;
+  u32 ex = block_exclusive_sum<SC_NT, u32>(s, scratch, &total) + tileoff[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) { if (base + k < count) out[base + k] = ex; ex += v[k]; }
+}
+
+// ---- special tail: positions of specials ascending (sfx-suffixgetset.c:586-690) -------
+// tileoff: exclusive scan of the per-tile popcounts of the mask (over positions < n)
+__global__ void __launch_bounds__(SC_NT)
+k_emit_special_tail(const u32 *__restrict__ spmask, u64 nmaskwords_n, u64 n,
+                    const u32 *__restrict__ tileoff, u32 *__restrict__ sa_tail,
+                    u32 *__restrict__ isa, u64 rank_base, unsigned long long *longest)
+{
+  __shared__ u32 scratch[SC_NT / 32 + 1];
+  const u64 base = (u64) blockIdx.x * SC_TILE + (u64) threadIdx.x * SC_IPT;
+  u32 w[SC_IPT], s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) {
+    u32 x = base + k < nmaskwords_n ? spmask[base + k] : 0u;
+    const u64 p0 = (base + k) * 32;
+    if (p0 + 32 > n) x = p0 >= n ? 0u : (x & ~(~0u << (n - p0)));   // only positions < n
+    w[k] = x; s += __popc(x);
+  }
+  u32 total;
+  u32 ex = block_exclusive_sum<SC_NT, u32>(s, scratch, &total) + tileoff[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) {
+    u32 x = w[k];
+    while (x) {
+      const unsigned bit = __ffs(x) - 1u;
+      x &= x - 1u;
+      const u64 pos = (base + k) * 32 + bit;
+      sa_tail[ex] = (u32) pos;
+      if (isa) isa[pos] = (u32) (rank_base + ex);
+      if (pos == 0) *longest = rank_base + ex;
+      ex++;
+    }
+  }
+}
+
+// ---- bucket table (K1): code histogram incl. special k-mers ----------------------------
+// leftborder counts every suffix with u >= 1 under its filled pl-code
+// (sfx-suffixer.c:1070-1102); countspecialcodes / distpfxidx as bcktab.c:876-901.
+template <bool DNA>
+__global__ void __launch_bounds__(256)
+k_count_codes(TextSrc<DNA> src, u64 n, unsigned pl, unsigned K,
+              u32 *__restrict__ cnt, u32 *__restrict__ csc, u32 *__restrict__ dist,
+              const u64 *__restrict__ distoff /* [pl] offsets of level u (u>=1) */)
+{
+  constexpr KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  for (u64 pos = blockIdx.x * (u64) blockDim.x + threadIdx.x; ; pos += (u64) gridDim.x * blockDim.x) {
+    const bool inb = pos < n;
+    u64 key = 0;
+    bool ok = false;
+    if (inb) ok = src.make_key(pos, key);
+    u64 code = 0;
+    unsigned u = 0;
+    if (ok) {
+      u = (unsigned) f.m - (unsigned) (key & ((1u << f.tb) - 1u));
+      if (DNA) {
+        code = key >> (64 - 2 * pl);
+      } else {
+        for (unsigned k = 0; k < pl; k++) {
+          u64 s = (key >> (64 - f.b * (k + 1))) & 31u;
+          if (s >= K) s = K - 1;                   // filler -> largest symbol
+          code = code * K + s;
+        }
+      }
+    }
+    // warp-aggregated increment (poly-A buckets would otherwise serialise in L2)
+    const unsigned active = __ballot_sync(FULL_MASK, ok);
+    if (ok) {
+      const unsigned peers = __match_any_sync(active, code);
+      if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&cnt[code], (u32) __popc(peers));
+      if (u < pl) {
+        atomicAdd(&csc[code / K], 1u);
+        if (u + 1 < pl) {
+          u64 lead = 0;
+          if (DNA) lead = code >> (2 * (pl - u));
+          else { u64 d = 1; for (unsigned k = u; k < pl; k++) d *= K; lead = code / d; }
+          atomicAdd(&dist[distoff[u] + lead], 1u);
+        }
+      }
+    }
+    if (!__any_sync(FULL_MASK, inb)) break;
+  }
+}
+
+// ---- analysis of a sorted (key, pos) array ------------------------------------------------
+struct DevStats {
+  unsigned long long lcpsum;        // over suffixes with u >= pl
+  unsigned long long numlarge;
+  unsigned long long longest;
+  unsigned int maxlcp;
+  unsigned int pad;
+};
+
+constexpr int AN_NT = 256, AN_IPT = 8, AN_TILE = AN_NT * AN_IPT;
+
+__device__ __forceinline__ u32 key_lcp(u64 ka, u64 kb, KeyFmt f)
+{
+  const u64 tmask = (1ull << f.tb) - 1ull;
+  const u64 x = (ka ^ kb) & ~tmask;
+  u32 l = x ? (u32) (__clzll((long long) x) / f.b) : (u32) f.m;
+  const u32 ua = (u32) f.m - (u32) (ka & tmask), ub = (u32) f.m - (u32) (kb & tmask);
+  l = l < ua ? l : ua;
+  return l < ub ? l : ub;
+}
+
+// is j the head of a group (== not tied with its predecessor by a full key)?
+__device__ __forceinline__ bool key_head(u64 kprev, u64 kcur, u64 tmask)
+{
+  return kprev != kcur || (kcur & tmask) != 0;
+}
+
+// pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head
+__global__ void __launch_bounds__(AN_NT)
+k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl,
+               u8 *__restrict__ lcp8, u32 *__restrict__ tile_unres,
+               u32 *__restrict__ tile_lasthead, DevStats *stats, int seam_prev_valid,
+               u64 seam_prev_key)
+{
+  __shared__ u32 scratch[AN_NT / 32 + 1];
+  __shared__ u32 s_max[AN_NT / 32];
+  const u64 tmask = (1ull << f.tb) - 1ull;
+  const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
+  u64 k[AN_IPT + 2];
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 2; i++) {
+    const u64 j = base + i;           // k[i] = keys[j-1]
+    k[i] = (j >= 1 && j - 1 < N) ? keys[j - 1] : 0;
+  }
+  u32 unres = 0, lasthead = 0, mx = 0;
+  unsigned long long sum = 0;
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 j = base + i;
+    if (j >= N) break;
+    const bool head = j == 0 || key_head(k[i], k[i + 1], tmask);
+    const bool nexthead = j + 1 >= N || key_head(k[i + 1], k[i + 2], tmask);
+    if (head) {
+      lasthead = (u32) j + 1u;
+      u32 l = 0;
+      if (j > 0) l = key_lcp(k[i], k[i + 1], f);
+      else if (seam_prev_valid) l = key_lcp(seam_prev_key, k[i + 1], f);
+      lcp8[j] = (u8) l;
+      const u32 u = (u32) f.m - (u32) (k[i + 1] & tmask);
+      if (u >= pl) sum += l;
+      mx = l > mx ? l : mx;
+    } else {
+      lcp8[j] = 0;                    // pending: becomes the doubling level, then the value
+    }
+    if (!head || !nexthead) unres++;
+  }
+  u32 total;
+  block_exclusive_sum<AN_NT, u32>(unres, scratch, &total);
+  const u32 lh = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
+  if (threadIdx.x == AN_NT - 1) { tile_unres[blockIdx.x] = total; tile_lasthead[blockIdx.x] = lh; }
+  // stats
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(FULL_MASK, sum, d);
+    const u32 o = __shfl_xor_sync(FULL_MASK, mx, d);
+    mx = o > mx ? o : mx;
+  }
+  if (lane_id() == 0) {
+    if (sum) atomicAdd(&stats->lcpsum, sum);
+    s_max[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 m2 = 0;
+    for (int w = 0; w < AN_NT / 32; w++) m2 = s_max[w] > m2 ? s_max[w] : m2;
+    if (m2) atomicMax(&stats->maxlcp, m2);
+  }
+}
+
+// single block: exclusive sum of tile_unres (in place) and exclusive running max of
+// tile_lasthead (in place: becomes "last head before this tile", +1 encoded)
+__global__ void __launch_bounds__(1024)
+k_scan_tiles_sum_max(u32 *tile_unres, u32 *tile_lasthead, u64 ntiles, u64 *total_out)
+{
+  __shared__ u32 scratch[1024 / 32 + 1];
+  __shared__ u32 carry_sum, carry_max;
+  if (threadIdx.x == 0) { carry_sum = 0; carry_max = 0; }
+  __syncthreads();
+  u64 grand = 0;
+  for (u64 base = 0; base < ntiles; base += 1024) {
+    const u64 i = base + threadIdx.x;
+    const u32 v = i < ntiles ? tile_unres[i] : 0u;
+    const u32 h = i < ntiles ? tile_lasthead[i] : 0u;
+    u32 total;
+    const u32 ex = block_exclusive_sum<1024, u32>(v, scratch, &total);
+    const u32 incl = block_inclusive_max<1024, u32>(h, scratch);
+    // exclusive max = inclusive max of the previous element
+    u32 prev = __shfl_up_sync(FULL_MASK, incl, 1);
+    __shared__ u32 s_wlast[32];
+    if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (lane_id() == 0) prev = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
+    const u32 cs = carry_sum, cm = carry_max;
+    if (i < ntiles) {
+      tile_unres[i] = ex + cs;
+      tile_lasthead[i] = prev > cm ? prev : cm;
+    }
+    grand += total;
+    __syncthreads();
+    if (threadIdx.x == 1023) { carry_sum = cs + total; carry_max = incl > cm ? incl : cm; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = grand;
+}
+
+// pass 2: compact the unresolved elements and fill the inverse suffix array
+__global__ void __launch_bounds__(AN_NT)
+k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N, KeyFmt f,
+               const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
+               u32 *__restrict__ uidx, u32 *__restrict__ upos, u32 *__restrict__ ugrp,
+               u32 *__restrict__ isa, u64 sa_offset)
+{
+  __shared__ u32 scratch[AN_NT / 32 + 1];
+  const u64 tmask = (1ull << f.tb) - 1ull;
+  const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
+  u64 k[AN_IPT + 2];
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 2; i++) {
+    const u64 j = base + i;
+    k[i] = (j >= 1 && j - 1 < N) ? keys[j - 1] : 0;
+  }
+  bool head[AN_IPT + 1];
+  u32 unres = 0, lasthead = 0;
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 1; i++) {
+    const u64 j = base + i;
+    head[i] = j == 0 || j >= N || key_head(k[i], k[i + 1], tmask);
+  }
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 j = base + i;
+    if (j >= N) break;
+    if (head[i]) lasthead = (u32) j + 1u;
+    if (!head[i] || !head[i + 1]) unres++;
+  }
+  u32 total;
+  u32 off = block_exclusive_sum<AN_NT, u32>(unres, scratch, &total) + tile_off[blockIdx.x];
+  // head index carried into this thread = max over previous threads / tiles
+  u32 incl = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
+  u32 carry = __shfl_up_sync(FULL_MASK, incl, 1);
+  __shared__ u32 s_wlast[AN_NT / 32];
+  if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (lane_id() == 0) carry = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
+  const u32 hb = tile_headbefore[blockIdx.x];
+  carry = carry > hb ? carry : hb;          // "+1" encoded index of the current group head
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 j = base + i;
+    if (j >= N) break;
+    if (head[i]) carry = (u32) j + 1u;
+    const u32 g = carry - 1u;
+    const u32 p = pos[j];
+    isa[p] = (u32) (sa_offset + g);
+    if (!head[i] || !head[i + 1]) { uidx[off] = (u32) j; upos[off] = p; ugrp[off] = g; off++; }
+  }
+}
+
+// ---- prefix doubling ---------------------------------------------------------------------
+// key = (group head index, rank of the suffix h positions further)
+__global__ void k_build_dkeys(const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
+                              const u32 *__restrict__ isa, u64 M, u64 h, u64 *__restrict__ dkeys)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
+    dkeys[c] = ((u64) ugrp[c] << 32) | (u64) isa[(u64) upos[c] + h];
+}
+
+__global__ void __launch_bounds__(AN_NT)
+k_analyze_dkeys(const u64 *__restrict__ dkeys, u64 M, u32 *__restrict__ tile_unres,
+                u32 *__restrict__ tile_lasthead)
+{
+  __shared__ u32 scratch[AN_NT / 32 + 1];
+  const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
+  u64 k[AN_IPT + 2];
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 2; i++) {
+    const u64 c = base + i;
+    k[i] = (c >= 1 && c - 1 < M) ? dkeys[c - 1] : 0;
+  }
+  u32 unres = 0, lasthead = 0;
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 c = base + i;
+    if (c >= M) break;
+    const bool head = c == 0 || k[i] != k[i + 1];
+    const bool nexthead = c + 1 >= M || k[i + 1] != k[i + 2];
+    if (head) lasthead = (u32) c + 1u;
+    if (!head || !nexthead) unres++;
+  }
+  u32 total;
+  block_exclusive_sum<AN_NT, u32>(unres, scratch, &total);
+  const u32 lh = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
+  if (threadIdx.x == AN_NT - 1) { tile_unres[blockIdx.x] = total; tile_lasthead[blockIdx.x] = lh; }
+}
+
+// write the refined order back, update ranks, record the doubling level of new group
+// heads (a lower bound of their lcp), compact what is still tied
+__global__ void __launch_bounds__(AN_NT)
+k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sorted upos */,
+              const u32 *__restrict__ uidx, u64 M,
+              const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
+              u32 *__restrict__ sa, u32 *__restrict__ isa, u8 *__restrict__ lcp8, u8 level,
+              u64 sa_offset, u32 *__restrict__ nidx, u32 *__restrict__ npos,
+              u32 *__restrict__ ngrp, DevStats *stats)
+{
+  __shared__ u32 scratch[AN_NT / 32 + 1];
+  const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
+  u64 k[AN_IPT + 2];
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 2; i++) {
+    const u64 c = base + i;
+    k[i] = (c >= 1 && c - 1 < M) ? dkeys[c - 1] : 0;
+  }
+  bool head[AN_IPT + 1];
+  u32 unres = 0, lasthead = 0;
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 1; i++) {
+    const u64 c = base + i;
+    head[i] = c == 0 || c >= M || k[i] != k[i + 1];
+  }
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 c = base + i;
+    if (c >= M) break;
+    if (head[i]) lasthead = (u32) c + 1u;
+    if (!head[i] || !head[i + 1]) unres++;
+  }
+  u32 total;
+  u32 off = block_exclusive_sum<AN_NT, u32>(unres, scratch, &total) + tile_off[blockIdx.x];
+  u32 incl = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
+  u32 carry = __shfl_up_sync(FULL_MASK, incl, 1);
+  __shared__ u32 s_wlast[AN_NT / 32];
+  if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (lane_id() == 0) carry = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
+  const u32 hb = tile_headbefore[blockIdx.x];
+  carry = carry > hb ? carry : hb;
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 c = base + i;
+    if (c >= M) break;
+    if (head[i]) carry = (u32) c + 1u;
+    const u32 hc = carry - 1u;                 // compacted index of the group head
+    const u32 g = uidx[hc];                    // its SA slot = new rank of the group
+    const u32 j = uidx[c];
+    const u32 p = spos[c];
+    sa[j] = p;
+    isa[p] = (u32) (sa_offset + g);
+    if (p == 0) stats->longest = sa_offset + j;
+    const u32 oldgrp = (u32) (k[i + 1] >> 32);
+    if (head[i] && oldgrp != j) lcp8[j] = level;   // split off in this round
+    if (!head[i] || !head[i + 1]) { nidx[off] = j; npos[off] = p; ngrp[off] = g; off++; }
+  }
+}
+
+// ---- exact lcp of the deep pairs (Kasai-style comparison from a proven lower bound) ----
+template <bool DNA>
+__global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict__ ugrp0, u64 M0,
+                           const u32 *__restrict__ sa, const u64 *__restrict__ words,
+                           const u8 *__restrict__ bytes, const u32 *__restrict__ spmask,
+                           u64 n, unsigned m, u8 *__restrict__ lcp8, u32 *__restrict__ ulcp,
+                           DevStats *stats)
+{
+  u32 mx = 0;
+  unsigned long long sum = 0, large = 0;
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 j = uidx0[c];
+    u32 l = 0xffffffffu;                       // marker: not a deep entry
+    if (ugrp0[c] != j) {
+      const u64 a = sa[j - 1], b = sa[j];
+      u64 off = (u64) m << lcp8[j];            // proven common prefix
+      if (DNA) {
+        for (;;) {
+          const u32 wa = mask_window(spmask, a + off), wb = mask_window(spmask, b + off);
+          const u32 wab = wa | wb;
+          const unsigned lim = wab ? (unsigned) __ffs(wab) - 1u : 32u;
+          const u64 x = dna_window(words, a + off) ^ dna_window(words, b + off);
+          const unsigned common = x ? (unsigned) (__clzll((long long) x) >> 1) : 32u;
+          if (common < lim) { off += common; break; }
+          if (lim < 32u) { off += lim; break; }
+          off += 32;
+        }
+      } else {
+        for (;;) {
+          const u8 ca = bytes[a + off], cb = bytes[b + off];
+          if (ca >= 254u || cb >= 254u || ca != cb) break;
+          off++;
+        }
+      }
+      l = (u32) off;
+      lcp8[j] = (u8) (l < 255u ? l : 255u);
+      mx = l > mx ? l : mx;
+      sum += l;
+      if (l >= 255u) large++;
+    }
+    ulcp[c] = l;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(FULL_MASK, sum, d);
+    large += __shfl_xor_sync(FULL_MASK, large, d);
+    const u32 o = __shfl_xor_sync(FULL_MASK, mx, d);
+    mx = o > mx ? o : mx;
+  }
+  if (lane_id() == 0) {
+    if (sum) atomicAdd(&stats->lcpsum, sum);
+    if (large) atomicAdd(&stats->numlarge, large);
+    if (mx) atomicMax(&stats->maxlcp, mx);
+  }
+}
+
+// .llv exception list (lcpoverflow.h:25-29): flags, then scan (generic), then emit
+__global__ void k_llv_flags(const u32 *__restrict__ ulcp, u64 M0, u32 *__restrict__ flags)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 l = ulcp[c];
+    flags[c] = (l != 0xffffffffu && l >= 255u) ? 1u : 0u;
+  }
+}
+__global__ void k_llv_emit(const u32 *__restrict__ ulcp, const u32 *__restrict__ uidx0, u64 M0,
+                           const u32 *__restrict__ offs, u64 sa_offset, u64 *__restrict__ llv)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 l = ulcp[c];
+    if (l != 0xffffffffu && l >= 255u) {
+      llv[2 * (u64) offs[c]] = sa_offset + uidx0[c];
+      llv[2 * (u64) offs[c] + 1] = l;
+    }
+  }
+}
+
+// position of suffix 0 in a sorted key array (first element with key >= key0; suffix 0
+// has the smallest position so it leads any stable tie)
+template <bool DNA>
+__global__ void k_find_longest(TextSrc<DNA> src, const u64 *__restrict__ keys, u64 N,
+                               u64 sa_offset, DevStats *stats)
+{
+  u64 key0;
+  if (!src.make_key(0, key0)) return;
+  u64 lo = 0, hi = N;
+  while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (keys[mid] < key0) lo = mid + 1; else hi = mid; }
+  if (lo < N && keys[lo] == key0) stats->longest = sa_offset + lo;
+}
+
+__global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+
+__global__ void k_set_u32(u32 *p, u32 v) { *p = v; }
+
+// leftborder: after the scan entry c holds the start of bucket c; entry C = number of
+// non-special suffixes (bcktab.c:1274-1304 keeps the same convention on file)
+} // namespace gtb

@@ -1,0 +1,194 @@
+/*
+  gtb200.h -- C-ABI of libgtb200.so, the B200-native enhanced-suffix-array
+  constructor that replaces the sort core behind `gt suffixerator`.
+
+  The reference (GenomeTools 1.5.11) has no FFI for this path; the seam is the
+  Sfxiterator interface (src/match/sfx-suffixer.h:33-72) as driven by
+  suffixeratorwithoutput() (src/match/sfx-run.c:212-317).  Every entry point
+  below names the reference interface it stands in for.  Plain pointers and
+  sizes only; no CUDA or torch types cross this boundary.
+
+  Input conventions
+  -----------------
+  * 2-bit path: `twobitenc` is exactly what gt_encseq_twobitencoding_export()
+    (src/core/encseq.c:6687) returns: uint64 words, 32 bases per word, base i in
+    word i/32 at bits 62-2*(i%32) (src/core/intbits.h:78-83); positions that
+    hold a wildcard/separator contain an arbitrary filler base.  `specials` are
+    the maximal special runs as half-open ranges in ascending order, i.e. the
+    sequence gt_specialrangeiterator_next() (src/core/encseq.h:127-133) yields
+    in forward direction.
+  * byte path (protein and every other non-2-bit alphabet): one byte per
+    position as gt_encseq_extract_encoded() (src/core/encseq.h) delivers it:
+    0..numofchars-1 regular, 254 = WILDCARD, 255 = SEPARATOR
+    (src/core/chardef.h).
+
+  Result conventions (identical to the reference's files)
+  ---------------------------------------------------------------------------
+  * suftab: n+1 entries: sorted suffixes starting at a regular symbol, then the
+    special positions ascending, then n.            (.suf, uint64 each)
+  * lcptab: n+1 bytes min(lcp,255); entries >= 255 additionally listed as
+    {uint64 index; uint64 lcp} pairs in ascending index order (.lcp / .llv).
+  * bucket table: leftborder[K^pl+1], countspecialcodes[K^(pl-1)],
+    distpfxidx[sum_{i=1}^{pl-2} K^i], uint32 each (.bck; the caller pads every
+    table to 8 bytes as gt_mapspec_write does, src/core/mapspec.c:350-365).
+
+  All functions return 0 on success and -1 on error with a message in the
+  handle (gtb_esa_error) or in errbuf.  There is no CPU fallback: if no CUDA
+  device is usable every call fails.
+*/
+#ifndef GTB200_H
+#define GTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTB200_ABI_VERSION 1
+
+typedef struct gtb_esa gtb_esa;              /* stands in for Sfxiterator   */
+
+typedef struct { uint64_t start, end; } gtb_range;
+
+/* what gt_Sfxiterator_longest, gt_Outlcpinfo_numoflargelcpvalues /
+   _maxbranchdepth / _lcptabsum (sfx-run.c:300,676-680) report */
+typedef struct {
+  uint64_t totallength;          /* n                                           */
+  uint64_t specialcharacters;    /* S                                           */
+  uint64_t nonspecials;          /* suffixes sorted by this handle (shard)      */
+  uint64_t sa_offset;            /* global SA index of the shard's first entry  */
+  uint64_t longest;              /* SA index of suffix 0 (UINT64_MAX: not in shard) */
+  uint64_t numoflargelcpvalues;  /* #{lcp >= 255}                               */
+  uint64_t maxbranchdepth;       /* max lcp                                     */
+  double   lcptabsum;            /* sum lcp over suffixes with >= pl regular
+                                    leading symbols (averagelcp = sum/(n+1))    */
+  uint32_t prefixlength;
+  uint32_t numofchars;
+  uint64_t unresolved_after_first_sort; /* elements that needed prefix doubling */
+  uint32_t doubling_rounds;
+  uint32_t radix_passes;         /* onesweep launches in the last run           */
+  uint64_t radix_pairs_moved;    /* sum over passes of elements moved           */
+  uint32_t kernel_launches;      /* all kernels launched by the last run        */
+  /* device times of the last run in milliseconds (CUDA events on the handle's
+     stream) */
+  float ms_total, ms_upload, ms_count, ms_hist, ms_radix, ms_analyze,
+        ms_doubling, ms_lcp, ms_tail;
+} gtb_stats;
+
+/* flags for gtb_esa_run (mirror the -suf -lcp -bck switches, index_options.c) */
+#define GTB_WANT_SUF 1u
+#define GTB_WANT_LCP 2u
+#define GTB_WANT_BCK 4u
+
+int  gtb_abi_version(void);
+int  gtb_device_count(void);
+
+/* gt_Sfxiterator_new_withadditionalvalues (sfx-suffixer.c:1363): create the
+   sorter object on CUDA device `device`. NULL on error (message in errbuf). */
+gtb_esa *gtb_esa_new(int device, char *errbuf, size_t errlen);
+/* gt_Sfxiterator_delete (sfx-suffixer.c:537-598) */
+void gtb_esa_delete(gtb_esa *h);
+const char *gtb_esa_error(const gtb_esa *h);
+
+/* replicate the packed sequence to HBM (north_star: "keeps GtEncseq as the
+   2-bit packed input, replicates it to HBM").  Host buffers; copies are done
+   inside the call.  nwords = number of uint64 words readable at twobitenc
+   (>= ceil(n/32)). */
+int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nwords,
+                           uint64_t totallength, const gtb_range *specials,
+                           uint64_t nspecialranges);
+int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols,
+                            uint64_t totallength, unsigned numofchars);
+
+/* restrict the handle to the bucket codes [mincode, maxcode] (inclusive), the
+   role of one part of gt_suftabparts_new (sfx-partssuf.c:172-347, filter at
+   sfx-suffixer.c:375-376). sa_offset = leftborder[mincode] of the global
+   table. The handle that owns the last code also emits the special tail.
+   Default: all codes. */
+int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode,
+                           uint64_t sa_offset, int emit_special_tail);
+
+/* gt_Sfxiterator_next over all parts + the GtOutlcpinfo side channel
+   (sfx-lcpvalues.c:591-795): count codes, sort, prefix-double, lcp. Results
+   stay in HBM until copied. */
+int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags);
+
+/* only the counting phase (updateleftborder_getencseqkmers_twobitencoding,
+   sfx-suffixer.c:1132-1138 + gt_bcktab_leftborderpartialsums): fills the bucket
+   table so that the caller can derive balanced code ranges
+   (gt_suftabparts_new) before sorting. */
+int gtb_esa_count(gtb_esa *h, unsigned prefixlength);
+
+int gtb_esa_get_stats(const gtb_esa *h, gtb_stats *st);
+
+/* filled keys of the first / last sorted suffix of this handle's code range, and
+   the seam fix-up: lcp between the previous range's last suffix and this
+   range's first one (computelocallcpvalue, sfx-lcpvalues.c:91-111); patches
+   lcptab[0] and the stats of this handle. */
+int gtb_esa_boundary_keys(const gtb_esa *h, uint64_t *first_key, uint64_t *last_key);
+int gtb_esa_fix_seam(gtb_esa *h, uint64_t prev_last_key);
+
+/* number of suftab / lcptab entries this handle produced (shard part incl.
+   its share of the special tail) */
+uint64_t gtb_esa_num_entries(const gtb_esa *h);
+uint64_t gtb_esa_num_llv(const gtb_esa *h);
+
+/* gt_suffixsortspace_to_file (sfx-suffixgetset.c:462-477): copy suftab entries
+   [first, first+count) of this handle to host memory, widened to the file's
+   uint64, or as the device-native uint32. */
+int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t count);
+int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t count);
+/* outlcpvalues (sfx-lcpvalues.c:371-433) */
+int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count);
+/* Largelcpvalue pairs (lcpoverflow.h:25-29): dst holds 2*gtb_esa_num_llv()
+   uint64 {index, value}; index is global (sa_offset added). */
+int gtb_esa_copy_llv(gtb_esa *h, uint64_t *dst);
+/* gt_Sfxiterator_bcktab2file (sfx-suffixer.c:2206): the three tables of the
+   whole text (not only the shard); any pointer may be NULL. Sizes from
+   gtb_bck_sizes. */
+int gtb_esa_copy_bcktab(gtb_esa *h, uint32_t *leftborder,
+                        uint32_t *countspecialcodes, uint32_t *distpfxidx);
+void gtb_bck_sizes(unsigned numofchars, unsigned prefixlength,
+                   uint64_t *numofallcodes, uint64_t *numofspecialcodes,
+                   uint64_t *numofdistpfxidx);
+
+/* device pointers of the results, for callers that exchange shards with NCCL
+   (the pointers stay owned by the handle) */
+const uint32_t *gtb_esa_dev_suftab(const gtb_esa *h);
+const uint8_t  *gtb_esa_dev_lcptab(const gtb_esa *h);
+const uint32_t *gtb_esa_dev_leftborder(const gtb_esa *h);
+
+/* One-shot convenience with host buffers: what suffixeratorwithoutput()
+   (sfx-run.c:212-317) gets from the iterator. Output pointers may be NULL.
+   llv must hold 2*llv_capacity uint64; *nllv receives the count (error if it
+   exceeds the capacity). */
+int gtb_esa_build_2bit(int device, const uint64_t *twobitenc, uint64_t nwords,
+                       uint64_t totallength, const gtb_range *specials,
+                       uint64_t nspecialranges, unsigned prefixlength,
+                       uint64_t *suftab, uint8_t *lcptab,
+                       uint64_t *llv, uint64_t llv_capacity, uint64_t *nllv,
+                       uint32_t *leftborder, uint32_t *countspecialcodes,
+                       uint32_t *distpfxidx, gtb_stats *stats,
+                       char *errbuf, size_t errlen);
+int gtb_esa_build_bytes(int device, const uint8_t *symbols, uint64_t totallength,
+                        unsigned numofchars, unsigned prefixlength,
+                        uint64_t *suftab, uint8_t *lcptab,
+                        uint64_t *llv, uint64_t llv_capacity, uint64_t *nllv,
+                        uint32_t *leftborder, uint32_t *countspecialcodes,
+                        uint32_t *distpfxidx, gtb_stats *stats,
+                        char *errbuf, size_t errlen);
+
+/* stand-alone access to the hand-written onesweep LSD radix sort (the engine of
+   every sorting step; also the replacement for gt_radixsort_inplace_ulong /
+   _GtUwordPair, src/core/radix_sort.h:91,107 -- SURVEY section 8f).  Host
+   buffers, sorted in place by the bits [begin_bit, end_bit) of the key. */
+int gtb_radixsort_pairs_u64_u32(int device, uint64_t *keys, uint32_t *values,
+                                uint64_t count, unsigned begin_bit,
+                                unsigned end_bit, char *errbuf, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,188 @@
+"""GPU: the CUDA path, called through the C-ABI (ctypes -> libgtb200.so), against
+  * the outputs of the unmodified reference (tests/golden/reference_vectors.npz),
+  * the pinned oracle on seeded inputs,
+  * size-independent properties at larger sizes.
+Bit-exact: integer/byte work only, no tolerance anywhere."""
+import ctypes
+import hashlib
+import numpy as np
+import pytest
+
+import esa_oracle as eo
+import synth
+from conftest import golden_cases
+from genometools_b200 import _lib, encode_symbols
+from genometools_b200.suffixerator import Suffixerator, build_esa
+
+pytestmark = pytest.mark.gpu
+
+
+def first_diff(a, b):
+    a = np.frombuffer(a, dtype=np.uint8); b = np.frombuffer(b, dtype=np.uint8)
+    if a.shape != b.shape:
+        return f"length {a.shape[0]} vs {b.shape[0]}"
+    d = np.flatnonzero(a != b)
+    return "equal" if d.size == 0 else f"{d.size} bytes differ, first at byte {d[0]}"
+
+
+def check_against_oracle(sym, K, pl, res, what=""):
+    o = eo.esa(sym, K, pl)
+    im = eo.file_images(o)
+    got = {"suf": res.suf_bytes(), "lcp": res.lcp_bytes(), "llv": res.llv_bytes(), "bck": res.bck_bytes()}
+    for ext in ("bck", "suf", "lcp", "llv"):
+        assert got[ext] == im[ext], f"{what} .{ext}: {first_diff(got[ext], im[ext])}"
+    assert res.longest == o["longest"], what
+    assert res.maxbranchdepth == o["maxbranchdepth"], what
+    assert res.numoflargelcpvalues == o["numoflargelcpvalues"], what
+    assert res.lcptabsum == o["lcptabsum"], what
+
+
+@pytest.mark.parametrize("case", golden_cases(small_only=True))
+def test_cuda_matches_reference_outputs(golden, case):
+    m = golden.meta(case)
+    sym = golden.symbols(case)
+    enc = encode_symbols(sym, m["numofchars"], m["numofsequences"])
+    rng = np.random.default_rng(len(case))
+    filler = rng.integers(0, 4, size=max(1, int((sym >= 254).sum())), dtype=np.uint8)   # arbitrary filler bases
+    res = build_esa(enc, m["prefixlength"], filler=filler if enc.is_dna else None)
+    got = {"suf": res.suf_bytes(), "lcp": res.lcp_bytes(), "llv": res.llv_bytes(), "bck": res.bck_bytes()}
+    ref = {"suf": golden.get(case, "suf").astype("<u8").tobytes(), "lcp": bytes(golden.get(case, "lcp")),
+           "llv": golden.get(case, "llv").astype("<u8").tobytes(), "bck": bytes(golden.get(case, "bck"))}
+    for ext in ("bck", "suf", "lcp", "llv"):
+        assert got[ext] == ref[ext], f".{ext}: {first_diff(got[ext], ref[ext])}"
+        assert hashlib.md5(got[ext]).hexdigest() == str(golden.get(case, "md5_" + ext))
+    prj, text = golden.prj(case)
+    info = {k: int(prj[k]) for k in ("specialcharacters", "specialranges", "realspecialranges",
+                                     "lengthofspecialprefix", "lengthofspecialsuffix", "wildcards",
+                                     "wildcardranges", "realwildcardranges", "lengthofwildcardprefix",
+                                     "lengthofwildcardsuffix")}   # encseq-derived lines: GtEncseq's job
+    assert res.prj_text(info, m["numofsequences"]) == text
+
+
+def test_cuda_big_golden_md5(golden):
+    case = "synth/rand_dna_2M"
+    m = golden.meta(case)
+    sym = golden.symbols(case)
+    res = build_esa(encode_symbols(sym, 4), m["prefixlength"])
+    for ext, b in (("suf", res.suf_bytes()), ("lcp", res.lcp_bytes()), ("llv", res.llv_bytes()), ("bck", res.bck_bytes())):
+        assert hashlib.md5(b).hexdigest() == str(golden.get(case, "md5_" + ext)), ext
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cuda_matches_oracle_random_dna(seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 30000))
+    sym = synth.random_dna(n, seed, p_n=[0.0, 0.001, 0.05, 0.3, 0.0, 0.9][seed])
+    pl = int(rng.integers(1, 7))
+    res = build_esa(encode_symbols(sym, 4), pl)
+    check_against_oracle(sym, 4, pl, res, f"seed {seed} n {n} pl {pl}")
+
+
+@pytest.mark.parametrize("name", ["reads", "repeats", "lowcomplex", "protein", "protein_dup", "tiny_alphabet"])
+def test_cuda_matches_oracle_shapes(name):
+    if name == "reads":
+        sym, K, pl = synth.reads(3000, 150, 5, 0.001), 4, 6
+    elif name == "repeats":
+        sym, K, pl = synth.repeats_dna(300_000, 9, unit=6000, copies=20, exact_len=20000, exact_copies=4), 4, 7
+    elif name == "lowcomplex":
+        sym, K, pl = synth.low_complexity_dna(100_000, 2), 4, 4
+    elif name == "protein":
+        sym, K, pl = synth.protein(200_000, 3), 20, 3
+    elif name == "protein_dup":
+        sym, K, pl = np.concatenate([synth.protein(30_000, 4), [255], synth.protein(30_000, 4)]).astype(np.uint8), 20, 2
+    else:
+        sym, K, pl = (np.random.default_rng(1).integers(0, 3, 50_000).astype(np.uint8)), 3, 4
+    res = build_esa(encode_symbols(sym, K), pl)
+    check_against_oracle(sym, K, pl, res, name)
+
+
+@pytest.mark.parametrize("sym", [[], [254], [255, 254, 255], [0], [3, 3, 3, 3], [0, 254, 0], [2] * 70,
+                                 [0, 1] * 40 + [254] + [0, 1] * 40])
+def test_cuda_edge_cases(sym):
+    s = np.array(sym, dtype=np.uint8)
+    res = build_esa(encode_symbols(s, 4), 1)
+    check_against_oracle(s, 4, 1, res, str(sym[:8]))
+
+
+@pytest.mark.parametrize("parts", [2, 3, 7])
+def test_parts_do_not_change_the_output(parts):
+    # sfx-partssuf.c: the output is independent of -parts (reference test :64-68)
+    sym = synth.random_dna(200_000, 77, p_n=0.001)
+    enc = encode_symbols(sym, 4)
+    one = build_esa(enc, 6)
+    many = build_esa(enc, 6, parts=parts)
+    assert len(many.stats) == parts
+    assert one.suf_bytes() == many.suf_bytes()
+    assert one.lcp_bytes() == many.lcp_bytes()
+    assert one.bck_bytes() == many.bck_bytes()
+    assert (one.longest, one.maxbranchdepth, one.lcptabsum) == (many.longest, many.maxbranchdepth, many.lcptabsum)
+    check_against_oracle(sym, 4, 6, many, f"parts {parts}")
+
+
+def test_handle_is_reusable_and_deterministic():
+    sym = synth.random_dna(150_000, 5, p_n=0.01)
+    enc = encode_symbols(sym, 4)
+    with Suffixerator(0) as s:
+        s.set_sequence(enc)
+        a = s.run(6)
+        b = s.run(6)
+        c = s.run(3)
+    assert a.suf_bytes() == b.suf_bytes() == c.suf_bytes()
+    assert a.lcp_bytes() == b.lcp_bytes() == c.lcp_bytes()
+    assert a.bck_bytes() == b.bck_bytes() != c.bck_bytes()
+
+
+@pytest.mark.parametrize("n,bits", [(1, (0, 64)), (4096, (0, 64)), (4097, (0, 64)), (1_000_003, (0, 64)),
+                                    (300_000, (8, 40)), (200_000, (0, 5))])
+def test_onesweep_radix_sort_pairs(n, bits):
+    """the stand-alone entry of the sort engine: stable LSD sort on a bit range"""
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n, dtype=np.uint64)
+    if n > 1000:
+        keys[::7] = keys[3]                        # many duplicates -> stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = keys.copy(), vals.copy()
+    buf = ctypes.create_string_buffer(256)
+    rc = lib.gtb_radixsort_pairs_u64_u32(0, k.ctypes.data, v.ctypes.data, n, bits[0], bits[1], buf, 256)
+    assert rc == 0, buf.value
+    mask = np.uint64(((1 << (bits[1] - bits[0])) - 1) << bits[0])
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(v, vals[order])
+    assert np.array_equal(k, keys[order])
+
+
+def test_large_input_properties():
+    """beyond oracle size: permutation, sortedness of sampled neighbours, lcp consistency"""
+    n = 20_000_000
+    sym = synth.random_dna(n, 123, p_n=0.0005)
+    enc = encode_symbols(sym, 4)
+    res = build_esa(enc, 10)
+    suf = res.suftab
+    assert suf.shape[0] == n + 1 and suf[-1] == n
+    seen = np.zeros(n + 1, dtype=np.uint8); seen[suf] = 1
+    assert seen.all()                                              # permutation of 0..n
+    S = int((sym >= 254).sum())
+    assert np.array_equal(suf[n - S:n], np.flatnonzero(sym >= 254).astype(np.uint64))   # special tail
+    assert not res.lcptab[n - S:].any()
+    run = np.zeros(n + 1, dtype=np.int64)                          # regular run lengths
+    idx = np.flatnonzero(sym >= 254)
+    nxt = np.full(n + 1, n, dtype=np.int64)
+    nxt[idx] = idx
+    nxt = np.minimum.accumulate(nxt[::-1])[::-1]
+    run = nxt - np.arange(n + 1)
+    rng = np.random.default_rng(0)
+    for j in rng.integers(1, n - S, size=3000):
+        a, b = int(suf[j - 1]), int(suf[j])
+        lim = int(min(run[a], run[b]))
+        l = 0
+        while l < lim and sym[a + l] == sym[b + l]:
+            l += 1
+        assert min(l, 255) == int(res.lcptab[j]), j
+        if l < lim:
+            assert sym[a + l] < sym[b + l], j                      # order
+        else:
+            assert run[a] > run[b] or (run[a] == run[b] and a < b), j
+    lb = res.leftborder
+    assert lb[0] == 0 and lb[-1] == n - S and np.all(np.diff(lb.astype(np.int64)) >= 0)
+    assert res.stats[0]["kernel_launches"] > 0
