@@ -482,6 +482,7 @@ int run_pipeline(gtb_esa *h, unsigned flags)
   S.totallength = h->n; S.specialcharacters = h->S; S.nonspecials = N;
   S.sa_offset = h->sa_offset;
   S.longest = hs.longest;
+  if (h->n == 0 && h->emit_tail) S.longest = 0;   // the empty text: suffix 0 is the final entry n
   S.numoflargelcpvalues = hs.numlarge;
   S.maxbranchdepth = hs.maxlcp;
   S.lcptabsum = (double) hs.lcpsum;
