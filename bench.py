@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- enhanced-suffix-array construction (`gt suffixerator -suf -lcp -bck`)
+on B200: Msuffixes/s for the BASELINE.json workload, the roofline of the dominant
+kernel (the onesweep radix pass) and the reference CPU path beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--scale f]
+  python bench.py --impl reference ...      # the unmodified reference on host cores
+
+A step = one complete pass of the hot path over the workload: bucket counting,
+fused key generation + 8 radix passes, group analysis, prefix doubling, lcp, special
+tail -- results left in HBM (`value`), or through the host-buffer C-ABI including the
+H2D copy of the packed sequence and the D2H copy of .suf/.lcp/.llv/.bck (`e2e`).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Msuffixes/s, suffixerator -suf -lcp"
+UNIT = "Msuffixes/s"
+FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("GTB_BENCH_WORKLOAD", "c4"))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("GTB_BENCH_SCALE", "1.0")))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="bases/residues of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"} if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else \
+                {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def reference_sample(workload_name, nsample):
+    """a bounded sample of the same workload (same generator, smaller n)"""
+    from genometools_b200 import synthetic as sy
+    full = {"c2": 100_000_000, "c3": 10_000_000 * 151, "c4": 3_100_000_000, "c5": 500_000_000}[workload_name]
+    w = sy.make_workload(workload_name, nsample / full)
+    return w
+
+
+def write_fasta(w, path):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import synth
+    synth.to_fasta(w.to_symbols(), path, "dna" if w.is_dna else "protein")
+
+
+def time_reference(w, workdir, runs=1):
+    """`gt suffixerator -suf -lcp -bck -pl` of the unmodified reference (oracle/_ref/gtref) --
+    single thread: with -j N the reference does not compute lcp values."""
+    gtref = os.path.join(ROOT, "oracle", "_ref", "gtref")
+    if not os.path.exists(gtref):
+        return None
+    fa = os.path.join(workdir, "sample.fa")
+    write_fasta(w, fa)
+    times = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        subprocess.check_call([gtref, "suffixerator", "-dna" if w.is_dna else "-protein", "-suf", "-lcp", "-bck",
+                               "-pl", "-indexname", os.path.join(workdir, "ref"), "-db", fa],
+                              stdout=subprocess.DEVNULL)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def time_oracle_port(w):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import esa_oracle as eo
+    from genometools_b200.suffixerator import recommendedprefixlength
+    sym = w.to_symbols()
+    t0 = time.perf_counter()
+    eo.esa(sym, w.numofchars, recommendedprefixlength(w.numofchars, w.totallength))
+    return [time.perf_counter() - t0]
+
+
+def cpu_baseline(args, wl_name):
+    w = reference_sample(wl_name, args.cpu_sample)
+    tmp = tempfile.mkdtemp(prefix="gtb_ref_")
+    try:
+        times = time_reference(w, tmp)
+        kind = "reference"
+        if times is None:
+            times = time_oracle_port(w)
+            kind = "port"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    t = min(times)
+    return {"value": (w.totallength + 1) / t / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+            "seconds": t,
+            "sample": f"{w.name} generator at n={w.totallength} ({w.description}); "
+                      + ("oracle/_ref/gtref suffixerator -suf -lcp -bck -pl, 1 thread (lcp is wrong with -j N)"
+                         if kind == "reference" else "oracle/esa_oracle.c restatement")}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    wl = args.workload
+    w = reference_sample(wl, args.cpu_sample)
+    tmp = tempfile.mkdtemp(prefix="gtb_ref_")
+    try:
+        fa = os.path.join(tmp, "sample.fa")
+        gtref = os.path.join(ROOT, "oracle", "_ref", "gtref")
+        kind = "reference" if os.path.exists(gtref) else "port"
+        times = []
+        for it in range(args.warmup + args.steps):
+            if kind == "reference":
+                t = time_reference(w, tmp)[0]
+            else:
+                t = time_oracle_port(w)[0]
+            if it >= args.warmup:
+                times.append(t)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    tot = sum(times)
+    val = (w.totallength + 1) * len(times) / tot / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": wl, "sample_totallength": w.totallength, "description": w.description,
+                       "command": "suffixerator -suf -lcp -bck -pl (1 thread: the reference computes no lcp "
+                                  "values with -j N)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": f"{w.name} generator at n={w.totallength}, every step"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ the B200 arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    import torch
+    from genometools_b200 import _lib, synthetic as sy
+    from genometools_b200._lib import GtbStats, GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, ptr
+    from genometools_b200.suffixerator import recommendedprefixlength
+    from genometools_b200.sharding import suftab_parts
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = _lib.load()
+    w = sy.make_workload(args.workload, args.scale)
+    n = w.totallength
+    pl = recommendedprefixlength(w.numofchars, n)
+    buf = C.create_string_buffer(512)
+    h = lib.gtb_esa_new(local_rank, buf, 512)
+    if not h:
+        raise SystemExit("gtb_esa_new: " + buf.value.decode())
+
+    def ck(rc):
+        if rc != 0:
+            raise SystemExit("libgtb200: " + lib.gtb_esa_error(h).decode())
+
+    def upload():
+        if w.is_dna:
+            ck(lib.gtb_esa_set_input_2bit(h, ptr(w.words), w.words.shape[0], n,
+                                          ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
+        else:
+            ck(lib.gtb_esa_set_input_bytes(h, ptr(w.symbols), n, w.numofchars))
+
+    upload()
+    flags = GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK
+    # weak scaling: the sequence is replicated, the bucket codes are sharded over the ranks
+    shard = None
+    if world > 1:
+        ck(lib.gtb_esa_count(h, pl))
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a), C.byref(b), C.byref(c))
+        lb = np.empty(a.value + 1, dtype=np.uint32)
+        ck(lib.gtb_esa_copy_bcktab(h, ptr(lb), None, None))
+        parts = suftab_parts(lb, world)
+        if len(parts) != world:
+            raise SystemExit("could not cut the bucket table into one part per rank")
+        shard = parts[rank]
+        ck(lib.gtb_esa_set_code_range(h, shard[0], shard[1], shard[2], 1 if rank == world - 1 else 0))
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = GtbStats()
+
+    def step():
+        ck(lib.gtb_esa_run(h, pl, flags))
+        ck(lib.gtb_esa_get_stats(h, C.byref(st)))
+        return st.as_dict()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync_all()
+    t0 = time.perf_counter()
+    dev_ms, radix_ms, hist_ms, launches, radix_passes, pairs = 0.0, 0.0, 0.0, 0, 0, 0
+    last = None
+    for _ in range(args.steps):
+        last = step()
+        dev_ms += last["ms_total"]; radix_ms += last["ms_radix"]; hist_ms += last["ms_hist"]
+        launches += last["kernel_launches"]; radix_passes += last["radix_passes"]; pairs += last["radix_pairs_moved"]
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.result()
+    # device time of the K steps, max over ranks
+    tm = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = tm.tolist()
+    total_units = (n + 1) * args.steps          # all ranks together sort every suffix once per step
+    value = total_units / (dev_ms_max / 1e3) / 1e6
+
+    # ---- roofline of the dominant kernel (rs_onesweep_kernel), measured live (ms_radix =
+    # CUDA events around the pass launches on the library's stream) ----
+    N = last["nonspecials"]
+    # every pass moves 24 B per pair (12 read + 12 written) except the first pass of a step, which
+    # reads the 2-bit text (n/4) and the special mask (n/8) instead of 12 B per pair
+    alg_bytes = 24.0 * pairs - args.steps * 12.0 * N + args.steps * 0.375 * n
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (radix_ms / 1e3) / 1e9 if radix_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel (one 8-bit LSD pass over (key64,pos32) pairs)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": (alg_bytes / radix_passes) if radix_passes else None,
+                "launches_timed": radix_passes, "ms_per_launch": radix_ms / radix_passes if radix_passes else None,
+                "share_of_step": radix_ms / dev_ms if dev_ms else None}
+
+    # ---- end to end through the host-buffer API: H2D of the packed sequence, all kernels,
+    # D2H of suftab (uint64), lcptab, llv, bucket table ----
+    e2e = None
+    if args.e2e_steps > 0:
+        ent_max = n + 1
+        suf = torch.empty(ent_max, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        lcp = torch.empty(ent_max, dtype=torch.uint8, pin_memory=True).numpy()
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a), C.byref(b), C.byref(c))
+        lbh = np.empty(a.value + 1, dtype=np.uint32); csch = np.empty(b.value, dtype=np.uint32)
+        disth = np.empty(max(c.value, 1), dtype=np.uint32)
+        if w.is_dna:
+            pw = torch.empty(w.words.shape[0], dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+            pw[:] = w.words
+            words_pinned = pw
+        else:
+            ps = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
+            ps[:] = w.symbols
+        d2h = 0
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            if w.is_dna:
+                ck(lib.gtb_esa_set_input_2bit(h, ptr(words_pinned), words_pinned.shape[0], n,
+                                              ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
+            else:
+                ck(lib.gtb_esa_set_input_bytes(h, ptr(ps), n, w.numofchars))
+            ck(lib.gtb_esa_run(h, pl, flags))
+            e = lib.gtb_esa_num_entries(h)
+            ck(lib.gtb_esa_copy_suftab_u64(h, ptr(suf), 0, e))
+            ck(lib.gtb_esa_copy_lcptab(h, ptr(lcp), 0, e))
+            k = lib.gtb_esa_num_llv(h)
+            llv = np.empty((max(k, 1), 2), dtype=np.uint64)
+            if k:
+                ck(lib.gtb_esa_copy_llv(h, ptr(llv)))
+            ck(lib.gtb_esa_copy_bcktab(h, ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
+            d2h = 8 * e + e + 16 * k + 4 * (a.value + 1 + b.value + c.value)
+        sync_all()
+        ewall = time.perf_counter() - t0
+        te = torch.tensor([ewall], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": (n + 1) * args.e2e_steps / te.item() / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": w.input_bytes(), "d2h_bytes_per_step": int(d2h),
+               "steps": args.e2e_steps, "ms_per_step": te.item() / args.e2e_steps * 1e3,
+               "note": "pinned host buffers; suftab widened to the file's uint64 on the device"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(args, args.workload)
+        except Exception as ex:      # the baseline is reported, never fatal
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(ex)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w.description, "totallength": n,
+                   "specialcharacters": int(last["specialcharacters"]), "prefixlength": pl,
+                   "numofchars": w.numofchars, "outputs": "-suf -lcp -bck (results resident in HBM)",
+                   "l2": "inputs_exceed_l2 (no flush needed)", "sharding": f"{world} bucket-code ranges"
+                   if world > 1 else "single range", "scale": args.scale},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "wall_ms_per_step": wall_ms_max / args.steps,
+        "breakdown_ms_last_step": {k: last[k] for k in ("ms_count", "ms_hist", "ms_radix", "ms_analyze",
+                                                         "ms_doubling", "ms_lcp", "ms_tail")},
+        "last_step": {k: int(last[k]) for k in ("unresolved_after_first_sort", "doubling_rounds", "radix_passes",
+                                                 "maxbranchdepth", "numoflargelcpvalues", "longest")},
+    }
+    print(json.dumps(line))
+    lib.gtb_esa_delete(h)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

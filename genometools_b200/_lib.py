@@ -69,7 +69,7 @@ SYMBOLS = {
     "gtb_radixsort_pairs_u64_u32": (C.c_int, [C.c_int, _P, _P, _U64, C.c_uint, C.c_uint, C.c_char_p, C.c_size_t]),
 }
 
-GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK = 1, 2, 4
+GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS = 1, 2, 4, 8
 
 _lib = None
 

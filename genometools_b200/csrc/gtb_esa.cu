@@ -645,7 +645,7 @@ int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags)
   const float up = h->stats.ms_upload;
   memset(&h->stats, 0, sizeof h->stats);
   h->stats.ms_upload = up;
-  if (h->pl != prefixlength) h->counted = false;
+  if (h->pl != prefixlength || !(flags & GTB_REUSE_COUNTS)) h->counted = false;
   h->pl = prefixlength;
   cudaEvent_t e0, e1;
   GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));

@@ -23,7 +23,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from ._lib import GtbError, GtbStats, ptr, GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK
+from ._lib import GtbError, GtbStats, ptr, GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS
 from .encseq import EncodedSequence, encode_fasta
 from .sharding import suftab_parts
 
@@ -300,7 +300,7 @@ class Suffixerator:
             if part is not None:
                 mincode, maxcode, off, _w = part
                 self._ck(self.lib.gtb_esa_set_code_range(self.h, mincode, maxcode, off, 1 if pi == len(plist) - 1 else 0))
-            self._ck(self.lib.gtb_esa_run(self.h, prefixlength, flags))
+            self._ck(self.lib.gtb_esa_run(self.h, prefixlength, flags | (GTB_REUSE_COUNTS if part is not None else 0)))
             if part is not None and prev_last_key is not None and want_lcp:
                 self._ck(self.lib.gtb_esa_fix_seam(self.h, prev_last_key))
             st = self.stats()

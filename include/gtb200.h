@@ -81,6 +81,9 @@ typedef struct {
 #define GTB_WANT_SUF 1u
 #define GTB_WANT_LCP 2u
 #define GTB_WANT_BCK 4u
+/* reuse the bucket table a preceding gtb_esa_count / gtb_esa_run on the same input
+   and prefix length left in HBM (the -parts loop); without it every run recounts */
+#define GTB_REUSE_COUNTS 8u
 
 int  gtb_abi_version(void);
 int  gtb_device_count(void);
