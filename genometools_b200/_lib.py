@@ -45,9 +45,19 @@ SYMBOLS = {
     "gtb_esa_error": (C.c_char_p, [_P]),
     "gtb_esa_set_input_2bit": (C.c_int, [_P, _P, _U64, _U64, _P, _U64]),
     "gtb_esa_set_input_bytes": (C.c_int, [_P, _P, _U64, C.c_uint]),
+    "gtb_esa_share_input": (C.c_int, [_P, _P]),
     "gtb_esa_set_code_range": (C.c_int, [_P, _U64, _U64, _U64, C.c_int]),
     "gtb_esa_run": (C.c_int, [_P, C.c_uint, C.c_uint]),
     "gtb_esa_count": (C.c_int, [_P, C.c_uint]),
+    "gtb_esa_sort_begin": (C.c_int, [_P, C.c_uint, C.c_uint]),
+    "gtb_esa_unresolved": (_U64, [_P]),
+    "gtb_esa_ensure_ranks": (C.c_int, [_P]),
+    "gtb_esa_round_local": (C.c_int, [_P]),
+    "gtb_esa_round_prepare": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _U64, _P]),
+    "gtb_esa_rank_lookup": (C.c_int, [_P, _P, _U64, _P]),
+    "gtb_esa_round_finish": (C.c_int, [_P, _P]),
+    "gtb_esa_sort_end": (C.c_int, [_P]),
+    "gtb_code_first_key": (_U64, [C.c_uint, C.c_uint, _U64]),
     "gtb_esa_get_stats": (C.c_int, [_P, C.POINTER(GtbStats)]),
     "gtb_esa_boundary_keys": (C.c_int, [_P, C.POINTER(_U64), C.POINTER(_U64)]),
     "gtb_esa_fix_seam": (C.c_int, [_P, _U64]),

@@ -34,10 +34,12 @@ void ErrBuf::set(const char *fmt, ...)
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  bool borrowed = false;     // memory owned by another handle (gtb_esa_share_input)
   int ensure(size_t bytes, ErrBuf &err)
   {
-    if (bytes <= cap) return 0;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    if (bytes <= cap && !borrowed) return 0;
+    if (p && !borrowed) cudaFree(p);
+    p = nullptr; cap = 0; borrowed = false;
     size_t want = bytes + (bytes >> 6) + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
@@ -47,7 +49,8 @@ struct DevBuf {
     cap = want;
     return 0;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
+  void borrow(const DevBuf &o) { release(); p = o.p; cap = o.cap; borrowed = o.p != nullptr; }
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -87,6 +90,12 @@ struct gtb_esa {
   u64 nllv = 0;
   u64 first_key = 0, last_key = 0;
   bool ran = false;
+  // staged execution (multi-range prefix doubling)
+  unsigned flags = 0, round = 0;
+  u64 M0 = 0, M = 0, atiles = 0, pending_send = 0;
+  int cur = 0, bits_lo = 1, bits_hi = 1;
+  bool isa_built = false, in_progress = false;
+  DevBuf ranks, owner, sendidx, rcounts;
   gtb_stats stats;
 };
 
@@ -255,14 +264,19 @@ int count_codes(gtb_esa *h, unsigned pl)
   return 0;
 }
 
+template <bool DNA> int ensure_isa(gtb_esa *h, bool compact);
+
+// ---- stage 1: bucket table, first-level sort, analysis, special tail, compaction of ties ----
 template <bool DNA>
-int run_pipeline(gtb_esa *h, unsigned flags)
+int stage_begin(gtb_esa *h, unsigned flags)
 {
   ErrBuf &err = h->err;
   const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
-  const bool want_lcp = (flags & GTB_WANT_LCP) != 0;
   gtb_stats &S = h->stats;
   cudaStream_t st = h->st;
+  h->flags = flags;
+  h->isa_built = false;
+  h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0;
 
   // ---- K1/K2 bucket table ----
   {
@@ -294,6 +308,7 @@ int run_pipeline(gtb_esa *h, unsigned flags)
   }
   GTB_TRY(h->lcp8.ensure(cap_entries + 16, err));
   GTB_TRY(h->dstats.ensure(sizeof(DevStats), err));
+  GTB_TRY(h->misc.ensure(256, err));
   {
     DevStats z; memset(&z, 0, sizeof z); z.longest = ~0ull;
     GTB_CUDA(cudaMemcpyAsync(h->dstats.p, &z, sizeof z, cudaMemcpyHostToDevice, st));
@@ -325,17 +340,16 @@ int run_pipeline(gtb_esa *h, unsigned flags)
 
   // ---- A: analysis ----
   u64 M0 = 0;
-  const u64 atiles = div_up(N, AN_TILE);
+  h->atiles = div_up(N, AN_TILE);
   {
     PhaseTimer t(h, &S.ms_analyze);
     if (N > 0) {
-      GTB_TRY(h->tile_a.ensure(sizeof(u32) * (atiles + 1), err));
-      GTB_TRY(h->tile_b.ensure(sizeof(u32) * (atiles + 1), err));
-      GTB_TRY(h->misc.ensure(256, err));
-      k_analyze_keys<<<(unsigned) atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, lcp8,
+      GTB_TRY(h->tile_a.ensure(sizeof(u32) * (h->atiles + 1), err));
+      GTB_TRY(h->tile_b.ensure(sizeof(u32) * (h->atiles + 1), err));
+      k_analyze_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, lcp8,
           h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull);
       GTB_LAUNCH_CHECK();
-      k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), atiles,
+      k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,
                                                h->misc.as<u64>());
       GTB_LAUNCH_CHECK();
       k_find_longest<DNA><<<1, 1, 0, st>>>(src, keys, N, h->sa_offset, dstats);
@@ -348,31 +362,17 @@ int run_pipeline(gtb_esa *h, unsigned flags)
   }
   S.unresolved_after_first_sort = M0;
   S.doubling_rounds = 0;
-  h->nllv = 0;
+  h->M0 = h->M = M0;
 
-  // ---- K7 special tail (also gives the ranks of special positions) ----
-  const bool need_isa = M0 > 0;
-  if (need_isa) {
-    GTB_TRY(h->isa.ensure(sizeof(u32) * (h->n + 2), err));
-    k_set_u32<<<1, 1, 0, st>>>(h->isa.as<u32>() + h->n, (u32) h->n);
-    GTB_LAUNCH_CHECK();
-    S.kernel_launches++;
-  }
+  // ---- K7 special tail ----
   {
     PhaseTimer t(h, &S.ms_tail);
     const u64 nw = (h->n + 31) >> 5;
-    if ((h->emit_tail || need_isa) && h->S > 0 && nw > 0) {
+    if (h->emit_tail && h->S > 0 && nw > 0) {
       u32 *tileoff = nullptr;
       GTB_TRY(device_scan_u32(h, h->spmask.as<u32>(), nullptr, nw, 1, &tileoff, nullptr));
-      // without emit_tail the positions are written to a scratch area (only ranks needed)
-      u32 *tail_dst = sa + N;
-      if (!h->emit_tail) {
-        GTB_TRY(h->ulcp.ensure(sizeof(u32) * (h->S + 1), err));
-        tail_dst = h->ulcp.as<u32>();
-      }
       k_emit_special_tail<<<(unsigned) div_up(nw, SC_TILE), SC_NT, 0, st>>>(
-          h->spmask.as<u32>(), nw, h->n, tileoff, tail_dst, need_isa ? h->isa.as<u32>() : nullptr,
-          h->n - h->S, h->emit_tail ? &dstats->longest : (unsigned long long *) h->misc.as<u64>() + 8);
+          h->spmask.as<u32>(), nw, h->n, tileoff, sa + N, nullptr, h->n - h->S, &dstats->longest);
       GTB_LAUNCH_CHECK();
       S.kernel_launches++;
     }
@@ -384,7 +384,7 @@ int run_pipeline(gtb_esa *h, unsigned flags)
     t.stop();
   }
 
-  // ---- K5 prefix doubling on the ties ----
+  // ---- ties: compaction + ranks (inverse suffix array) ----
   if (M0 > 0) {
     PhaseTimer t(h, &S.ms_doubling);
     GTB_TRY(h->uidx0.ensure(sizeof(u32) * M0, err));
@@ -397,57 +397,198 @@ int run_pipeline(gtb_esa *h, unsigned flags)
       GTB_TRY(h->vd[i].ensure(sizeof(u32) * M0, err));
     }
     GTB_TRY(h->dkeys.ensure(sizeof(u64) * M0, err));
-    k_compact_keys<<<(unsigned) atiles, AN_NT, 0, st>>>(keys, sa, N, f, h->tile_a.as<u32>(),
-        h->tile_b.as<u32>(), h->uidx[0].as<u32>(), h->upos[0].as<u32>(), h->ugrp[0].as<u32>(),
-        h->isa.as<u32>(), h->sa_offset);
-    GTB_LAUNCH_CHECK();
-    S.kernel_launches++;
+    GTB_TRY(ensure_isa<DNA>(h, true));
     GTB_CUDA(cudaMemcpyAsync(h->uidx0.p, h->uidx[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
     GTB_CUDA(cudaMemcpyAsync(h->ugrp0.p, h->ugrp[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
-
-    u64 M = M0;
-    int cur = 0;
-    const int bits_lo = bitlen(h->n), bits_hi = bitlen(N > 0 ? N - 1 : 0);
-    for (unsigned round = 0; M > 0; round++) {
-      if (round > 40) { err.set("internal: prefix doubling did not converge"); return -1; }
-      const u64 hlen = (u64) f.m << round;
-      k_build_dkeys<<<grid_for(M, 256), 256, 0, st>>>(h->upos[cur].as<u32>(), h->ugrp[cur].as<u32>(),
-          h->isa.as<u32>(), M, hlen, h->dkeys.as<u64>());
-      GTB_LAUNCH_CHECK();
-      S.kernel_launches++;
-      PassPlan dp; dp.npass = 0;
-      plan_add_bits(dp, 0, bits_lo);
-      plan_add_bits(dp, 32, 32 + bits_hi);
-      PairSrc ps{h->dkeys.as<u64>(), h->upos[cur].as<u32>()};
-      u64 *kk[2] = {h->kd[0].as<u64>(), h->kd[1].as<u64>()};
-      u32 *vv[2] = {h->vd[0].as<u32>(), h->vd[1].as<u32>()};
-      int r2 = 0; u64 nout = 0;
-      GTB_TRY(radix_sort(h->rw, st, ps, M, kk, vv, dp, &r2, &nout, err));
-      if (nout != M) { err.set("internal: doubling sort lost elements"); return -1; }
-      const u64 dt = div_up(M, AN_TILE);
-      GTB_TRY(h->tile_a.ensure(sizeof(u32) * (dt + 1), err));
-      GTB_TRY(h->tile_b.ensure(sizeof(u32) * (dt + 1), err));
-      k_analyze_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], M, h->tile_a.as<u32>(), h->tile_b.as<u32>());
-      GTB_LAUNCH_CHECK();
-      k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), dt, h->misc.as<u64>());
-      GTB_LAUNCH_CHECK();
-      k_apply_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M,
-          h->tile_a.as<u32>(), h->tile_b.as<u32>(), sa, h->isa.as<u32>(), lcp8, (u8) round, h->sa_offset,
-          h->uidx[cur ^ 1].as<u32>(), h->upos[cur ^ 1].as<u32>(), h->ugrp[cur ^ 1].as<u32>(), dstats);
-      GTB_LAUNCH_CHECK();
-      S.kernel_launches += 3;
-      u64 Mnext = 0;
-      GTB_CUDA(cudaMemcpyAsync(&Mnext, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
-      GTB_CUDA(cudaStreamSynchronize(st));
-      M = Mnext;
-      cur ^= 1;
-      S.doubling_rounds = round + 1;
-    }
     t.stop();
   }
+  h->bits_lo = bitlen(h->n);
+  h->bits_hi = bitlen(N > 0 ? N - 1 : 0);
+  h->in_progress = true;
+  return 0;
+}
 
-  // ---- K6 exact lcp of deep pairs + .llv ----
-  if (M0 > 0 && want_lcp) {
+// ranks of this range's suffixes (+ of all special positions); with `compact` also the list of ties
+template <bool DNA>
+int ensure_isa(gtb_esa *h, bool compact)
+{
+  ErrBuf &err = h->err;
+  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  cudaStream_t st = h->st;
+  if (h->isa_built && !compact) return 0;
+  u64 *keys = h->kbuf[h->res].as<u64>();
+  u32 *sa = h->vbuf[h->res].as<u32>();
+  GTB_TRY(h->isa.ensure(sizeof(u32) * (h->n + 2), err));
+  k_set_u32<<<1, 1, 0, st>>>(h->isa.as<u32>() + h->n, (u32) h->n);
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches++;
+  const u64 nw = (h->n + 31) >> 5;
+  if (h->S > 0 && nw > 0) {
+    u32 *tileoff = nullptr;
+    GTB_TRY(device_scan_u32(h, h->spmask.as<u32>(), nullptr, nw, 1, &tileoff, nullptr));
+    GTB_TRY(h->ulcp.ensure(sizeof(u32) * (h->S + 1), err));       // positions go to scratch
+    k_emit_special_tail<<<(unsigned) div_up(nw, SC_TILE), SC_NT, 0, st>>>(
+        h->spmask.as<u32>(), nw, h->n, tileoff, h->ulcp.as<u32>(), h->isa.as<u32>(), h->n - h->S,
+        (unsigned long long *) h->misc.as<u64>() + 8);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  if (h->N > 0) {
+    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, sa, h->N, f, h->tile_a.as<u32>(),
+        h->tile_b.as<u32>(), compact ? h->uidx[0].as<u32>() : nullptr,
+        compact ? h->upos[0].as<u32>() : nullptr, compact ? h->ugrp[0].as<u32>() : nullptr,
+        h->isa.as<u32>(), h->sa_offset);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  h->isa_built = true;
+  return 0;
+}
+
+// sort the ties by (group, rank of the suffix h further), write back, re-compact
+template <bool DNA>
+int round_sort_apply(gtb_esa *h)
+{
+  ErrBuf &err = h->err;
+  cudaStream_t st = h->st;
+  gtb_stats &S = h->stats;
+  const u64 M = h->M;
+  const int cur = h->cur;
+  PassPlan dp; dp.npass = 0;
+  plan_add_bits(dp, 0, h->bits_lo);
+  plan_add_bits(dp, 32, 32 + h->bits_hi);
+  PairSrc ps{h->dkeys.as<u64>(), h->upos[cur].as<u32>()};
+  u64 *kk[2] = {h->kd[0].as<u64>(), h->kd[1].as<u64>()};
+  u32 *vv[2] = {h->vd[0].as<u32>(), h->vd[1].as<u32>()};
+  int r2 = 0; u64 nout = 0;
+  GTB_TRY(radix_sort(h->rw, st, ps, M, kk, vv, dp, &r2, &nout, err));
+  if (nout != M) { err.set("internal: doubling sort lost elements"); return -1; }
+  const u64 dt = div_up(M, AN_TILE);
+  GTB_TRY(h->tile_a.ensure(sizeof(u32) * (dt + 1), err));
+  GTB_TRY(h->tile_b.ensure(sizeof(u32) * (dt + 1), err));
+  k_analyze_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], M, h->tile_a.as<u32>(), h->tile_b.as<u32>());
+  GTB_LAUNCH_CHECK();
+  k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), dt, h->misc.as<u64>());
+  GTB_LAUNCH_CHECK();
+  k_apply_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M,
+      h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->vbuf[h->res].as<u32>(), h->isa.as<u32>(),
+      h->lcp8.as<u8>(), (u8) h->round, h->sa_offset,
+      h->uidx[cur ^ 1].as<u32>(), h->upos[cur ^ 1].as<u32>(), h->ugrp[cur ^ 1].as<u32>(),
+      h->dstats.as<DevStats>());
+  GTB_LAUNCH_CHECK();
+  S.kernel_launches += 3;
+  u64 Mnext = 0;
+  GTB_CUDA(cudaMemcpyAsync(&Mnext, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  GTB_CUDA(cudaStreamSynchronize(st));
+  h->M = Mnext;
+  h->cur ^= 1;
+  h->round++;
+  S.doubling_rounds = h->round;
+  return 0;
+}
+
+template <bool DNA>
+int round_local(gtb_esa *h)
+{
+  ErrBuf &err = h->err;
+  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  if (h->M == 0) { h->round++; return 0; }
+  if (h->round > 40) { err.set("internal: prefix doubling did not converge"); return -1; }
+  PhaseTimer t(h, &h->stats.ms_doubling);
+  const u64 hlen = (u64) f.m << h->round;
+  k_build_dkeys<<<grid_for(h->M, 256), 256, 0, h->st>>>(h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(),
+      h->isa.as<u32>(), h->M, hlen, h->dkeys.as<u64>());
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches++;
+  GTB_TRY(round_sort_apply<DNA>(h));
+  t.stop();
+  return 0;
+}
+
+// multi-range round, part 1: ranks this range can read itself; positions to ask the other ranges
+template <bool DNA>
+int round_prepare(gtb_esa *h, const u64 *first_keys, int nranges, int mine, u32 *dev_send,
+                  u64 capacity, u64 *counts_out)
+{
+  ErrBuf &err = h->err;
+  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  cudaStream_t st = h->st;
+  for (int i = 0; i < nranges; i++) counts_out[i] = 0;
+  h->pending_send = 0;
+  if (h->M == 0) return 0;
+  if (nranges < 1 || nranges > MAX_RANGES || mine < 0 || mine >= nranges) { err.set("bad range table"); return -1; }
+  if (h->round > 40) { err.set("internal: prefix doubling did not converge"); return -1; }
+  PhaseTimer t(h, &h->stats.ms_doubling);
+  const u64 M = h->M;
+  GTB_TRY(h->ranks.ensure(sizeof(u32) * M, err));
+  GTB_TRY(h->owner.ensure(M, err));
+  GTB_TRY(h->sendidx.ensure(sizeof(u32) * M, err));
+  GTB_TRY(h->rcounts.ensure(sizeof(unsigned int) * 3 * MAX_RANGES, err));
+  GTB_CUDA(cudaMemsetAsync(h->rcounts.p, 0, sizeof(unsigned int) * 3 * MAX_RANGES, st));
+  RangeBounds rb; rb.n = nranges; rb.mine = mine;
+  for (int i = 0; i < nranges; i++) rb.first_key[i] = first_keys[i];
+  rb.first_key[0] = 0;
+  const u64 hlen = (u64) f.m << h->round;
+  unsigned int *cnt = h->rcounts.as<unsigned int>();
+  k_round_classify<DNA><<<grid_for(M, 256), 256, 0, st>>>(make_src<DNA>(h, 0, ~0ull), h->upos[h->cur].as<u32>(),
+      M, hlen, rb, h->isa.as<u32>(), h->ranks.as<u32>(), h->owner.as<u8>(), cnt);
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches++;
+  unsigned int hc[MAX_RANGES], off[MAX_RANGES];
+  GTB_CUDA(cudaMemcpyAsync(hc, cnt, sizeof(unsigned int) * nranges, cudaMemcpyDeviceToHost, st));
+  GTB_CUDA(cudaStreamSynchronize(st));
+  u64 total = 0;
+  for (int i = 0; i < nranges; i++) { off[i] = (unsigned int) total; total += hc[i]; counts_out[i] = hc[i]; }
+  if (total > capacity) { err.set("send buffer too small: %llu positions", (unsigned long long) total); return -1; }
+  if (total > 0) {
+    GTB_CUDA(cudaMemcpyAsync(cnt + MAX_RANGES, off, sizeof(unsigned int) * nranges, cudaMemcpyHostToDevice, st));
+    k_round_fill<<<grid_for(M, 256), 256, 0, st>>>(h->upos[h->cur].as<u32>(), h->owner.as<u8>(), M, hlen,
+        cnt + MAX_RANGES, cnt + 2 * MAX_RANGES, dev_send, h->sendidx.as<u32>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  GTB_CUDA(cudaStreamSynchronize(st));
+  h->pending_send = total;
+  t.stop();
+  return 0;
+}
+
+// multi-range round, part 2: the answers arrived (same order as the send buffer)
+template <bool DNA>
+int round_finish(gtb_esa *h, const u32 *dev_answers)
+{
+  ErrBuf &err = h->err;
+  if (h->M == 0) { h->round++; return 0; }
+  PhaseTimer t(h, &h->stats.ms_doubling);
+  if (h->pending_send > 0) {
+    k_round_scatter<<<grid_for(h->pending_send, 256), 256, 0, h->st>>>(dev_answers, h->sendidx.as<u32>(),
+        h->pending_send, h->ranks.as<u32>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  k_build_dkeys_ranks<<<grid_for(h->M, 256), 256, 0, h->st>>>(h->ugrp[h->cur].as<u32>(), h->ranks.as<u32>(),
+      h->M, h->dkeys.as<u64>());
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches++;
+  GTB_TRY(round_sort_apply<DNA>(h));
+  t.stop();
+  return 0;
+}
+
+// ---- last stage: exact lcp of the deep pairs, .llv list, stats ----
+template <bool DNA>
+int stage_end(gtb_esa *h)
+{
+  ErrBuf &err = h->err;
+  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  gtb_stats &S = h->stats;
+  cudaStream_t st = h->st;
+  const u64 M0 = h->M0, N = h->N;
+  DevStats *dstats = h->dstats.as<DevStats>();
+  u32 *sa = h->vbuf[h->res].as<u32>();
+  u8 *lcp8 = h->lcp8.as<u8>();
+  if (h->M != 0) { err.set("prefix doubling not finished: %llu suffixes still tied", (unsigned long long) h->M); return -1; }
+  if (M0 > 0 && (h->flags & GTB_WANT_LCP)) {
     PhaseTimer t(h, &S.ms_lcp);
     GTB_TRY(h->ulcp.ensure(sizeof(u32) * (M0 > h->S + 1 ? M0 : h->S + 1), err));
     k_deep_lcp<DNA><<<grid_for(M0, 128), 128, 0, st>>>(h->uidx0.as<u32>(), h->ugrp0.as<u32>(), M0, sa,
@@ -474,8 +615,6 @@ int run_pipeline(gtb_esa *h, unsigned flags)
     }
     t.stop();
   }
-
-  // ---- stats ----
   DevStats hs;
   GTB_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
   GTB_CUDA(cudaStreamSynchronize(st));
@@ -490,10 +629,57 @@ int run_pipeline(gtb_esa *h, unsigned flags)
   S.radix_passes = h->rw.passes; S.radix_pairs_moved = h->rw.pairs_moved;
   S.kernel_launches += h->rw.launches;
   S.ms_hist = h->rw.ms_hist; S.ms_radix = h->rw.ms_radix;
+  h->in_progress = false;
   return 0;
 }
 
 } // namespace
+
+static int check_run_args(gtb_esa *h, unsigned prefixlength, unsigned flags)
+{
+  ErrBuf &err = h->err;
+  if (!h->have_input) { err.set("no input set"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  const unsigned maxpl = h->dna ? 15u : 7u;     // gt_maxbasepower, initbasepower.c:23
+  if (prefixlength > maxpl || (!h->dna && ipow_u64(h->K, prefixlength) > 0xffffffffull)) {
+    err.set("prefix length %u is too large for alphabet size %u", prefixlength, h->K); return -1;
+  }
+  if (prefixlength == 0 && ((flags & GTB_WANT_BCK) || !h->full_range)) {
+    err.set("prefixlength 0 cannot be combined with a bucket table or a code range"); return -1;
+  }
+  if (!h->full_range && h->maxcode >= ipow_u64(h->K, prefixlength)) {
+    err.set("code range beyond numofchars^prefixlength"); return -1;
+  }
+  const float up = h->stats.ms_upload;
+  memset(&h->stats, 0, sizeof h->stats);
+  h->stats.ms_upload = up;
+  if (h->pl != prefixlength || !(flags & GTB_REUSE_COUNTS)) h->counted = false;
+  h->pl = prefixlength;
+  h->ran = false;
+  return 0;
+}
+
+// wraps one stage: device time of the stage is added to ms_total
+template <typename F>
+static int timed_stage(gtb_esa *h, F body)
+{
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  cudaEvent_t e0, e1;
+  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
+  GTB_CUDA(cudaEventRecord(e0, h->st));
+  int rc = body();
+  cudaEventRecord(e1, h->st);
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  h->stats.ms_total += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc == 0) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err.set("CUDA error: %s", cudaGetErrorString(e)); rc = -1; }
+  }
+  return rc;
+}
 
 // =============================== C-ABI =================================================
 extern "C" {
@@ -558,7 +744,8 @@ void gtb_esa_delete(gtb_esa *h)
                    &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->isa,
                    &h->tile_a, &h->tile_b, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
-                   &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv};
+                   &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
+                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts};
   for (DevBuf *b : all) b->release();
   radix_work_free(h->rw);
   cudaStreamDestroy(h->st);
@@ -615,6 +802,17 @@ int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols, uint64_t n, unsi
   return 0;
 }
 
+int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src)
+{
+  if (!h || !src) return -1;
+  if (!src->have_input) { h->err.set("gtb_esa_share_input: source has no input"); return -1; }
+  if (h->device != src->device) { h->err.set("gtb_esa_share_input: handles live on different devices"); return -1; }
+  h->dna = src->dna; h->K = src->K; h->n = src->n; h->S = src->S; h->nmaskwords = src->nmaskwords;
+  h->words.borrow(src->words); h->bytes.borrow(src->bytes); h->spmask.borrow(src->spmask);
+  h->counted = false; h->ran = false; h->have_input = true;
+  return 0;
+}
+
 int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint64_t sa_offset,
                            int emit_special_tail)
 {
@@ -629,38 +827,91 @@ int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint6
 int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags)
 {
   if (!h) return -1;
-  ErrBuf &err = h->err;
-  if (!h->have_input) { err.set("gtb_esa_run: no input set"); return -1; }
-  GTB_CUDA(cudaSetDevice(h->device));
-  const unsigned maxpl = h->dna ? 15u : 7u;     // gt_maxbasepower, initbasepower.c:23
-  if (prefixlength > maxpl || (!h->dna && ipow_u64(h->K, prefixlength) > 0xffffffffull)) {
-    err.set("prefix length %u is too large for alphabet size %u", prefixlength, h->K); return -1;
-  }
-  if (prefixlength == 0 && ((flags & GTB_WANT_BCK) || !h->full_range)) {
-    err.set("prefixlength 0 cannot be combined with a bucket table or a code range"); return -1;
-  }
-  if (!h->full_range && h->maxcode >= ipow_u64(h->K, prefixlength)) {
-    err.set("code range beyond numofchars^prefixlength"); return -1;
-  }
-  const float up = h->stats.ms_upload;
-  memset(&h->stats, 0, sizeof h->stats);
-  h->stats.ms_upload = up;
-  if (h->pl != prefixlength || !(flags & GTB_REUSE_COUNTS)) h->counted = false;
-  h->pl = prefixlength;
-  cudaEvent_t e0, e1;
-  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
-  GTB_CUDA(cudaEventRecord(e0, h->st));
-  int rc = h->dna ? run_pipeline<true>(h, flags) : run_pipeline<false>(h, flags);
-  cudaEventRecord(e1, h->st);
-  cudaEventSynchronize(e1);
-  cudaEventElapsedTime(&h->stats.ms_total, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (rc == 0) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { err.set("CUDA error after run: %s", cudaGetErrorString(e)); rc = -1; }
-  }
+  GTB_TRY(check_run_args(h, prefixlength, flags));
+  int rc = timed_stage(h, [&]() -> int {
+    GTB_TRY(h->dna ? stage_begin<true>(h, flags) : stage_begin<false>(h, flags));
+    while (h->M > 0) GTB_TRY(h->dna ? round_local<true>(h) : round_local<false>(h));
+    return h->dna ? stage_end<true>(h) : stage_end<false>(h);
+  });
   h->ran = rc == 0;
   return rc;
+}
+
+int gtb_esa_sort_begin(gtb_esa *h, unsigned prefixlength, unsigned flags)
+{
+  if (!h) return -1;
+  GTB_TRY(check_run_args(h, prefixlength, flags));
+  return timed_stage(h, [&]() -> int { return h->dna ? stage_begin<true>(h, flags) : stage_begin<false>(h, flags); });
+}
+
+uint64_t gtb_esa_unresolved(const gtb_esa *h) { return h ? h->M : 0; }
+
+int gtb_esa_ensure_ranks(gtb_esa *h)
+{
+  if (!h) return -1;
+  if (!h->in_progress) { h->err.set("gtb_esa_ensure_ranks outside gtb_esa_sort_begin/_end"); return -1; }
+  return timed_stage(h, [&]() -> int { return h->dna ? ensure_isa<true>(h, false) : ensure_isa<false>(h, false); });
+}
+
+int gtb_esa_round_local(gtb_esa *h)
+{
+  if (!h) return -1;
+  if (!h->in_progress) { h->err.set("gtb_esa_round_local outside gtb_esa_sort_begin/_end"); return -1; }
+  return timed_stage(h, [&]() -> int { return h->dna ? round_local<true>(h) : round_local<false>(h); });
+}
+
+int gtb_esa_round_prepare(gtb_esa *h, const uint64_t *range_first_keys, int nranges, int my_range,
+                          uint32_t *dev_send_positions, uint64_t send_capacity, uint64_t *counts_out)
+{
+  if (!h) return -1;
+  if (!h->in_progress) { h->err.set("gtb_esa_round_prepare outside gtb_esa_sort_begin/_end"); return -1; }
+  return timed_stage(h, [&]() -> int {
+    return h->dna ? round_prepare<true>(h, range_first_keys, nranges, my_range, dev_send_positions, send_capacity, counts_out)
+                  : round_prepare<false>(h, range_first_keys, nranges, my_range, dev_send_positions, send_capacity, counts_out);
+  });
+}
+
+int gtb_esa_rank_lookup(gtb_esa *h, const uint32_t *dev_positions, uint64_t count, uint32_t *dev_ranks)
+{
+  if (!h) return -1;
+  if (!h->in_progress || !h->isa_built) { h->err.set("gtb_esa_rank_lookup: ranks not built (gtb_esa_ensure_ranks)"); return -1; }
+  return timed_stage(h, [&]() -> int {
+    ErrBuf &err = h->err;
+    if (count == 0) return 0;
+    k_rank_lookup<<<grid_for(count, 256), 256, 0, h->st>>>(h->isa.as<u32>(), dev_positions, count, dev_ranks);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+    GTB_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+  });
+}
+
+int gtb_esa_round_finish(gtb_esa *h, const uint32_t *dev_answers)
+{
+  if (!h) return -1;
+  if (!h->in_progress) { h->err.set("gtb_esa_round_finish outside gtb_esa_sort_begin/_end"); return -1; }
+  return timed_stage(h, [&]() -> int { return h->dna ? round_finish<true>(h, dev_answers) : round_finish<false>(h, dev_answers); });
+}
+
+int gtb_esa_sort_end(gtb_esa *h)
+{
+  if (!h) return -1;
+  if (!h->in_progress) { h->err.set("gtb_esa_sort_end without gtb_esa_sort_begin"); return -1; }
+  int rc = timed_stage(h, [&]() -> int { return h->dna ? stage_end<true>(h) : stage_end<false>(h); });
+  h->ran = rc == 0;
+  return rc;
+}
+
+// the smallest filled key of bucket `code`: the first key of a code range
+uint64_t gtb_code_first_key(unsigned numofchars, unsigned prefixlength, uint64_t code)
+{
+  if (prefixlength == 0) return 0;
+  if (numofchars == 4) return code << (64 - 2 * prefixlength);
+  const KeyFmt f = byte_fmt();
+  u64 d[16], k = 0;
+  for (int i = (int) prefixlength - 1; i >= 0; i--) { d[i] = code % numofchars; code /= numofchars; }
+  for (unsigned i = 0; i < prefixlength; i++) k = (k << f.b) | d[i];
+  return k << (64 - f.b * prefixlength);
 }
 
 int gtb_esa_count(gtb_esa *h, unsigned prefixlength)

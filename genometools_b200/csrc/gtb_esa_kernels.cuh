@@ -446,8 +446,8 @@ k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N,
     if (head[i]) carry = (u32) j + 1u;
     const u32 g = carry - 1u;
     const u32 p = pos[j];
-    isa[p] = (u32) (sa_offset + g);
-    if (!head[i] || !head[i + 1]) { uidx[off] = (u32) j; upos[off] = p; ugrp[off] = g; off++; }
+    if (isa) isa[p] = (u32) (sa_offset + g);
+    if (uidx && (!head[i] || !head[i + 1])) { uidx[off] = (u32) j; upos[off] = p; ugrp[off] = g; off++; }
   }
 }
 
@@ -547,6 +547,77 @@ k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sor
     if (!head[i] || !head[i + 1]) { nidx[off] = j; npos[off] = p; ngrp[off] = g; off++; }
   }
 }
+
+// ---- prefix doubling across code ranges (multi-GPU / -parts): rank exchange -------------------
+// Each range owns the ranks of its own suffixes (its slice of the inverse suffix array).  In a
+// doubling round the rank of position q = p + h is needed; the owner of q is the range whose
+// code interval contains the filled key of q.  Ranks of special positions and of q in the own
+// range are read directly, the others are routed to their owner.
+constexpr int MAX_RANGES = 64;
+struct RangeBounds { u64 first_key[MAX_RANGES]; int n; int mine; };
+constexpr u32 OWNER_LOCAL = 0xffu;
+
+template <bool DNA>
+__global__ void k_round_classify(TextSrc<DNA> src, const u32 *__restrict__ upos, u64 M, u64 h,
+                                 RangeBounds rb, const u32 *__restrict__ isa, u32 *__restrict__ ranks,
+                                 u8 *__restrict__ owner, unsigned int *__restrict__ counts)
+{
+  __shared__ unsigned int s_cnt[MAX_RANGES];
+  for (int i = threadIdx.x; i < MAX_RANGES; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x) {
+    const u64 q = (u64) upos[c] + h;
+    u64 key;
+    u32 o = OWNER_LOCAL;
+    if (src.make_key(q, key)) {               // regular position: find its range
+      int lo = 0, hi = rb.n - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rb.first_key[mid] <= key) lo = mid; else hi = mid - 1; }
+      if (lo != rb.mine) o = (u32) lo;
+    }
+    owner[c] = (u8) o;
+    if (o == OWNER_LOCAL) ranks[c] = isa[q];
+    else atomicAdd(&s_cnt[o], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < rb.n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&counts[i], s_cnt[i]);
+}
+
+// fill the send buffer: segment of range o starts at offs[o]
+__global__ void k_round_fill(const u32 *__restrict__ upos, const u8 *__restrict__ owner, u64 M, u64 h,
+                             const unsigned int *__restrict__ offs, unsigned int *__restrict__ fill,
+                             u32 *__restrict__ sendq, u32 *__restrict__ sendidx)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x) {
+    const u32 o = owner[c];
+    if (o == OWNER_LOCAL) continue;
+    const u32 slot = offs[o] + atomicAdd(&fill[o], 1u);
+    sendq[slot] = (u32) ((u64) upos[c] + h);
+    sendidx[slot] = (u32) c;
+  }
+}
+
+__global__ void k_rank_lookup(const u32 *__restrict__ isa, const u32 *__restrict__ q, u64 cnt,
+                              u32 *__restrict__ out)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < cnt; i += (u64) gridDim.x * blockDim.x)
+    out[i] = isa[q[i]];
+}
+
+__global__ void k_round_scatter(const u32 *__restrict__ answers, const u32 *__restrict__ sendidx, u64 cnt,
+                                u32 *__restrict__ ranks)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < cnt; i += (u64) gridDim.x * blockDim.x)
+    ranks[sendidx[i]] = answers[i];
+}
+
+__global__ void k_build_dkeys_ranks(const u32 *__restrict__ ugrp, const u32 *__restrict__ ranks, u64 M,
+                                    u64 *__restrict__ dkeys)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
+    dkeys[c] = ((u64) ugrp[c] << 32) | (u64) ranks[c];
+}
+
+// the filled key of the smallest suffix of bucket `code` (all further symbols smallest, full)
 
 // ---- exact lcp of the deep pairs (Kasai-style comparison from a proven lower bound) ----
 template <bool DNA>

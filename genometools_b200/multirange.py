@@ -1,0 +1,209 @@
+"""Prefix doubling across bucket-code ranges: the lock-step protocol that lets several
+ranges (one per GPU, or several on one GPU for -parts) sort their buckets independently
+and still refine ties by rank.
+
+A range owns the ranks (inverse suffix array entries) of its own suffixes.  In doubling
+round r (h = m * 2^r) a tied suffix p needs rank(p + h); positions owned by another range
+are sent to the owner, looked up there, and the ranks are sent back:
+
+    all-to-all(positions)  ->  rank lookup on the owner  ->  all-to-all(ranks)
+
+The only other exchanges are a max-reduction of the number of tied suffixes (loop
+condition) and the boundary keys for the seam lcp.  The reference has no counterpart:
+its sorters compare text (src/core/encseq.c:6719) inside one address space; the
+partitioning itself mirrors gt_suftabparts_new (src/match/sfx-partssuf.c:172-347).
+
+`RangeWorker` is the interface; GpuRangeWorker binds it to libgtb200.so.  The
+orchestration is backend-agnostic (torch.distributed with NCCL on GPUs; the tests drive
+it with gloo and a CPU stand-in worker).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import GtbError, GtbStats, ptr
+
+
+class RangeWorker:
+    """what the lock-step driver needs from one code range"""
+
+    def sort_begin(self): raise NotImplementedError
+    def unresolved(self): raise NotImplementedError
+    def ensure_ranks(self): raise NotImplementedError
+    def round_prepare(self, first_keys, my_range): raise NotImplementedError   # -> (positions tensor, counts list)
+    def rank_lookup(self, positions): raise NotImplementedError                # -> ranks tensor
+    def round_finish(self, answers): raise NotImplementedError
+    def sort_end(self): raise NotImplementedError
+    def boundary_keys(self): raise NotImplementedError                         # -> (nonempty, first, last)
+    def fix_seam(self, prev_last_key): raise NotImplementedError
+
+
+class GpuRangeWorker(RangeWorker):
+    """one code range on one CUDA device, driven through the staged C-ABI"""
+
+    def __init__(self, handle, prefixlength, flags, device):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.h = handle
+        self.pl = prefixlength
+        self.flags = flags
+        self.device = torch.device("cuda", device)
+        self.send = None
+        self.sent = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GtbError(self.lib.gtb_esa_error(self.h).decode())
+
+    def sort_begin(self):
+        self._ck(self.lib.gtb_esa_sort_begin(self.h, self.pl, self.flags))
+
+    def unresolved(self):
+        return int(self.lib.gtb_esa_unresolved(self.h))
+
+    def ensure_ranks(self):
+        self._ck(self.lib.gtb_esa_ensure_ranks(self.h))
+
+    def round_prepare(self, first_keys, my_range):
+        torch = self.torch
+        M = self.unresolved()
+        if self.send is None or self.send.numel() < max(M, 1):
+            self.send = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)
+        fk = np.ascontiguousarray(first_keys, dtype=np.uint64)
+        counts = np.zeros(fk.shape[0], dtype=np.uint64)
+        self._ck(self.lib.gtb_esa_round_prepare(self.h, ptr(fk), fk.shape[0], my_range, self.send.data_ptr(),
+                                                self.send.numel(), ptr(counts)))
+        self.sent = int(counts.sum())
+        return self.send[: self.sent], [int(c) for c in counts]
+
+    def rank_lookup(self, positions):
+        torch = self.torch
+        out = torch.empty(max(positions.numel(), 1), dtype=torch.int32, device=self.device)[: positions.numel()]
+        if positions.numel():
+            assert positions.is_contiguous()
+            self._ck(self.lib.gtb_esa_rank_lookup(self.h, positions.data_ptr(), positions.numel(), out.data_ptr()))
+        return out
+
+    def round_finish(self, answers):
+        assert answers.numel() == self.sent
+        if answers.numel():
+            assert answers.is_contiguous()
+        self._ck(self.lib.gtb_esa_round_finish(self.h, answers.data_ptr() if answers.numel() else None))
+
+    def sort_end(self):
+        self._ck(self.lib.gtb_esa_sort_end(self.h))
+
+    def stats(self):
+        st = GtbStats()
+        self._ck(self.lib.gtb_esa_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def boundary_keys(self):
+        fk, lk = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.gtb_esa_boundary_keys(self.h, C.byref(fk), C.byref(lk)))
+        return self.stats()["nonspecials"] > 0, fk.value, lk.value
+
+    def fix_seam(self, prev_last_key):
+        self._ck(self.lib.gtb_esa_fix_seam(self.h, prev_last_key))
+
+
+def range_first_keys(numofchars, prefixlength, parts):
+    lib = _lib.load()
+    return np.array([lib.gtb_code_first_key(numofchars, prefixlength, p[0]) for p in parts], dtype=np.uint64)
+
+
+# ---------------------------------------------------------------- all ranges in one process
+def run_ranges_local(workers, first_keys, want_lcp=True):
+    """lock-step over ranges that live in this process (same GPU): positions and ranks
+    are read in place, nothing is copied"""
+    R = len(workers)
+    for w in workers:
+        w.sort_begin()
+    if any(w.unresolved() > 0 for w in workers):
+        for w in workers:
+            w.ensure_ranks()
+        rounds = 0
+        while any(w.unresolved() > 0 for w in workers):
+            prepared = [w.round_prepare(first_keys, r) for r, w in enumerate(workers)]
+            answers = []
+            for r, (send, counts) in enumerate(prepared):
+                parts, off = [], 0
+                for o in range(R):
+                    if counts[o]:
+                        parts.append(workers[o].rank_lookup(send[off: off + counts[o]].contiguous()))
+                        off += counts[o]
+                if parts:
+                    ans = parts[0] if len(parts) == 1 else parts[0].new_empty(off)
+                    if len(parts) > 1:
+                        o2 = 0
+                        for ptn in parts:
+                            ans[o2: o2 + ptn.numel()] = ptn
+                            o2 += ptn.numel()
+                else:
+                    ans = send[:0]
+                answers.append(ans)
+            for w, ans in zip(workers, answers):
+                w.round_finish(ans)
+            rounds += 1
+            if rounds > 64:
+                raise GtbError("prefix doubling across ranges did not converge")
+    for w in workers:
+        w.sort_end()
+    if want_lcp:
+        prev = None
+        for w in workers:
+            nonempty, first, last = w.boundary_keys()
+            if nonempty:
+                if prev is not None:
+                    w.fix_seam(prev)
+                prev = last
+
+
+# ---------------------------------------------------------------- one range per process
+def run_range_distributed(worker, first_keys, dist, device, want_lcp=True):
+    """lock-step over torch.distributed (NCCL on GPUs, gloo in the CPU tests): rank r of
+    the process group runs code range r"""
+    import torch
+    world, me = dist.get_world_size(), dist.get_rank()
+
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
+    worker.sort_begin()
+    rounds = 0
+    if allmax(worker.unresolved()) > 0:
+        worker.ensure_ranks()
+        dist.barrier()                                  # every range can answer from here on
+        while allmax(worker.unresolved()) > 0:
+            send, counts = worker.round_prepare(first_keys, me)
+            sc = torch.tensor(counts, dtype=torch.int64, device=device)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc)
+            rcl = [int(x) for x in rc.tolist()]
+            recv_q = torch.empty(sum(rcl), dtype=send.dtype, device=device)
+            dist.all_to_all_single(recv_q, send.contiguous(), output_split_sizes=rcl, input_split_sizes=counts)
+            recv_a = worker.rank_lookup(recv_q)
+            back = torch.empty(sum(counts), dtype=send.dtype, device=device)
+            dist.all_to_all_single(back, recv_a.contiguous(), output_split_sizes=counts, input_split_sizes=rcl)
+            worker.round_finish(back)
+            rounds += 1
+            if rounds > 64:
+                raise GtbError("prefix doubling across ranges did not converge")
+    worker.sort_end()
+    if want_lcp:
+        nonempty, first, last = worker.boundary_keys()
+        mine = torch.tensor([1 if nonempty else 0, first & 0x7fffffffffffffff, first >> 63,
+                             last & 0x7fffffffffffffff, last >> 63], dtype=torch.int64, device=device)
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        prev = None
+        for r in range(me):
+            ne, _f, _fh, l, lh = [int(x) for x in allk[r].tolist()]
+            if ne:
+                prev = l | (lh << 63)
+        if nonempty and prev is not None:
+            worker.fix_seam(prev)
+    return rounds

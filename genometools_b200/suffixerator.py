@@ -228,6 +228,7 @@ class Suffixerator:
     def __init__(self, device=0):
         self.lib = _lib.load()
         buf = C.create_string_buffer(512)
+        self.device = device
         self.h = self.lib.gtb_esa_new(device, buf, 512)
         if not self.h:
             raise GtbError(buf.value.decode() or "gtb_esa_new failed")
@@ -282,59 +283,99 @@ class Suffixerator:
         return lb, csc, dist
 
     # ---- the sort ----
+    def _collect(self, h, res_lists, want_suf, want_lcp):
+        suf_parts, lcp_parts, llv_parts = res_lists
+        e = self.lib.gtb_esa_num_entries(h)
+        if want_suf:
+            a = np.empty(e, dtype=np.uint64)
+            self._ckh(h, self.lib.gtb_esa_copy_suftab_u64(h, ptr(a), 0, e))
+            suf_parts.append(a)
+        if want_lcp:
+            a = np.empty(e, dtype=np.uint8)
+            self._ckh(h, self.lib.gtb_esa_copy_lcptab(h, ptr(a), 0, e))
+            lcp_parts.append(a)
+            k = self.lib.gtb_esa_num_llv(h)
+            a = np.empty((k, 2), dtype=np.uint64)
+            if k:
+                self._ckh(h, self.lib.gtb_esa_copy_llv(h, ptr(a)))
+            llv_parts.append(a)
+
+    def _ckh(self, h, rc):
+        if rc != 0:
+            raise GtbError(self.lib.gtb_esa_error(h).decode())
+
+    def _stats_of(self, h):
+        st = GtbStats()
+        self._ckh(h, self.lib.gtb_esa_get_stats(h, C.byref(st)))
+        return st.as_dict()
+
     def run(self, prefixlength, want_suf=True, want_lcp=True, want_bck=True, parts=1, copy=True):
+        """gt_Sfxiterator_next over all parts.  parts > 1 (option -parts) cuts the bucket
+        codes into ranges (gt_suftabparts_new) that are sorted as independent problems --
+        the same code path that puts one range on each GPU -- and concatenated."""
         enc = self.enc
         n = enc.totallength
         flags = (GTB_WANT_SUF if want_suf else 0) | (GTB_WANT_LCP if want_lcp else 0) | \
-                (GTB_WANT_BCK if (want_bck or parts > 1) else 0)
+                (GTB_WANT_BCK if want_bck else 0)
         res = EsaResult(n, enc.numofchars, prefixlength)
+        plist = []
         if parts > 1 and prefixlength >= 1:
             lb, _, _ = self.bucket_table(prefixlength)
             plist = suftab_parts(lb, parts)
+        lists = ([], [], [])
+        if len(plist) <= 1:
+            self._ck(self.lib.gtb_esa_run(self.h, prefixlength, flags))
+            handles = [self.h]
+            extra = []
         else:
-            plist = [None]
-        suf_parts, lcp_parts, llv_parts = [], [], []
-        prev_last_key = None
-        lcpsum, maxbd, nlarge, longest = 0.0, 0, 0, None
-        for pi, part in enumerate(plist):
-            if part is not None:
-                mincode, maxcode, off, _w = part
-                self._ck(self.lib.gtb_esa_set_code_range(self.h, mincode, maxcode, off, 1 if pi == len(plist) - 1 else 0))
-            self._ck(self.lib.gtb_esa_run(self.h, prefixlength, flags | (GTB_REUSE_COUNTS if part is not None else 0)))
-            if part is not None and prev_last_key is not None and want_lcp:
-                self._ck(self.lib.gtb_esa_fix_seam(self.h, prev_last_key))
-            st = self.stats()
-            res.stats.append(st)
-            if st["nonspecials"] > 0:
-                fk, lk = C.c_uint64(), C.c_uint64()
-                self._ck(self.lib.gtb_esa_boundary_keys(self.h, C.byref(fk), C.byref(lk)))
-                prev_last_key = lk.value
-            lcpsum += st["lcptabsum"]; maxbd = max(maxbd, st["maxbranchdepth"]); nlarge += st["numoflargelcpvalues"]
-            if st["longest"] != 0xFFFFFFFFFFFFFFFF:
-                longest = st["longest"]
-            if copy:
-                e = self.lib.gtb_esa_num_entries(self.h)
-                if want_suf:
-                    a = np.empty(e, dtype=np.uint64)
-                    self._ck(self.lib.gtb_esa_copy_suftab_u64(self.h, ptr(a), 0, e))
-                    suf_parts.append(a)
-                if want_lcp:
-                    a = np.empty(e, dtype=np.uint8)
-                    self._ck(self.lib.gtb_esa_copy_lcptab(self.h, ptr(a), 0, e))
-                    lcp_parts.append(a)
-                    k = self.lib.gtb_esa_num_llv(self.h)
-                    a = np.empty((k, 2), dtype=np.uint64)
-                    if k:
-                        self._ck(self.lib.gtb_esa_copy_llv(self.h, ptr(a)))
-                    llv_parts.append(a)
+            from .multirange import GpuRangeWorker, run_ranges_local, range_first_keys
+            buf = C.create_string_buffer(512)
+            extra, workers = [], []
+            try:
+                for pi, (mincode, maxcode, off, _w) in enumerate(plist):
+                    h = self.lib.gtb_esa_new(self.device, buf, 512)
+                    if not h:
+                        raise GtbError(buf.value.decode())
+                    extra.append(h)
+                    self._ckh(h, self.lib.gtb_esa_share_input(h, self.h))
+                    self._ckh(h, self.lib.gtb_esa_set_code_range(h, mincode, maxcode, off,
+                                                                 1 if pi == len(plist) - 1 else 0))
+                    workers.append(GpuRangeWorker(h, prefixlength, flags | GTB_WANT_BCK, self.device))
+                run_ranges_local(workers, range_first_keys(enc.numofchars, prefixlength, plist), want_lcp)
+            except Exception:
+                for h in extra:
+                    self.lib.gtb_esa_delete(h)
+                raise
+            handles = extra
+        try:
+            lcpsum, maxbd, nlarge, longest = 0.0, 0, 0, None
+            for h in handles:
+                st = self._stats_of(h)
+                res.stats.append(st)
+                lcpsum += st["lcptabsum"]; maxbd = max(maxbd, st["maxbranchdepth"])
+                nlarge += st["numoflargelcpvalues"]
+                if st["longest"] != 0xFFFFFFFFFFFFFFFF:
+                    longest = st["longest"]
+                if copy:
+                    self._collect(h, lists, want_suf, want_lcp)
+            if want_bck and prefixlength >= 1:
+                hb = handles[0]
+                a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+                self.lib.gtb_bck_sizes(enc.numofchars, prefixlength, C.byref(a), C.byref(b), C.byref(c))
+                lb = np.empty(a.value + 1, dtype=np.uint32); csc = np.empty(b.value, dtype=np.uint32)
+                dist = np.empty(c.value, dtype=np.uint32)
+                self._ckh(hb, self.lib.gtb_esa_copy_bcktab(hb, ptr(lb), ptr(csc), ptr(dist) if c.value else None))
+                res.leftborder, res.countspecialcodes, res.distpfxidx = lb, csc, dist
+        finally:
+            for h in extra:
+                self.lib.gtb_esa_delete(h)
+        suf_parts, lcp_parts, llv_parts = lists
         if copy:
             if want_suf:
                 res.suftab = np.concatenate(suf_parts) if len(suf_parts) > 1 else suf_parts[0]
             if want_lcp:
                 res.lcptab = np.concatenate(lcp_parts) if len(lcp_parts) > 1 else lcp_parts[0]
                 res.llvtab = np.concatenate(llv_parts) if len(llv_parts) > 1 else llv_parts[0]
-        if want_bck and prefixlength >= 1:
-            res.leftborder, res.countspecialcodes, res.distpfxidx = self._copy_bck(prefixlength)
         res.longest = longest
         res.lcptabsum, res.maxbranchdepth, res.numoflargelcpvalues = lcpsum, maxbd, nlarge
         return res

@@ -105,6 +105,10 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
 int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols,
                             uint64_t totallength, unsigned numofchars);
 
+/* let `h` use the sequence `src` already holds in HBM (same device; `src` must outlive
+   the use): several code ranges processed on one GPU share one copy of the input */
+int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src);
+
 /* restrict the handle to the bucket codes [mincode, maxcode] (inclusive), the
    role of one part of gt_suftabparts_new (sfx-partssuf.c:172-347, filter at
    sfx-suffixer.c:375-376). sa_offset = leftborder[mincode] of the global
@@ -117,6 +121,39 @@ int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode,
    (sfx-lcpvalues.c:591-795): count codes, sort, prefix-double, lcp. Results
    stay in HBM until copied. */
 int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags);
+
+/* ---- staged execution: prefix doubling across code ranges (multi-GPU, -parts) ----
+   A tie group lies inside one bucket, hence inside one code range, but a doubling
+   round needs the rank of the suffix h positions further, which another range may
+   own.  gtb_esa_run = sort_begin; while (unresolved) round_local; sort_end.
+   With several ranges the caller runs the rounds in lock step on all handles and
+   moves the requested positions / returned ranks between them (NCCL all-to-all,
+   or device copies when the handles share a GPU):
+
+     sort_begin on every range; if any range has unresolved suffixes:
+       ensure_ranks on every range
+       repeat until no range has unresolved suffixes:
+         round_prepare  -> positions whose rank another range owns, grouped by range
+         (exchange positions)   rank_lookup on the owner   (exchange ranks back)
+         round_finish
+     sort_end on every range
+
+   The reference needs nothing of the kind because every CPU sorter compares text
+   (gt_encseq_compare_viatwobitencoding, src/core/encseq.c:6719). */
+int gtb_esa_sort_begin(gtb_esa *h, unsigned prefixlength, unsigned flags);
+uint64_t gtb_esa_unresolved(const gtb_esa *h);
+int gtb_esa_ensure_ranks(gtb_esa *h);
+int gtb_esa_round_local(gtb_esa *h);
+/* range_first_keys[r] = gtb_code_first_key(mincode of range r); counts_out[r] (host)
+   receives how many positions of dev_send_positions (device, uint32) belong to range r;
+   they are stored grouped by range in ascending range order. */
+int gtb_esa_round_prepare(gtb_esa *h, const uint64_t *range_first_keys, int nranges, int my_range,
+                          uint32_t *dev_send_positions, uint64_t send_capacity, uint64_t *counts_out);
+int gtb_esa_rank_lookup(gtb_esa *h, const uint32_t *dev_positions, uint64_t count, uint32_t *dev_ranks);
+/* dev_answers[i] = rank of dev_send_positions[i] */
+int gtb_esa_round_finish(gtb_esa *h, const uint32_t *dev_answers);
+int gtb_esa_sort_end(gtb_esa *h);
+uint64_t gtb_code_first_key(unsigned numofchars, unsigned prefixlength, uint64_t code);
 
 /* only the counting phase (updateleftborder_getencseqkmers_twobitencoding,
    sfx-suffixer.c:1132-1138 + gt_bcktab_leftborderpartialsums): fills the bucket

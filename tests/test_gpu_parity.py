@@ -112,11 +112,32 @@ def test_parts_do_not_change_the_output(parts):
     one = build_esa(enc, 6)
     many = build_esa(enc, 6, parts=parts)
     assert len(many.stats) == parts
+    assert many.numoflargelcpvalues == one.numoflargelcpvalues
     assert one.suf_bytes() == many.suf_bytes()
     assert one.lcp_bytes() == many.lcp_bytes()
     assert one.bck_bytes() == many.bck_bytes()
     assert (one.longest, one.maxbranchdepth, one.lcptabsum) == (many.longest, many.maxbranchdepth, many.lcptabsum)
     check_against_oracle(sym, 4, 6, many, f"parts {parts}")
+
+
+@pytest.mark.parametrize("name,parts", [("repeats", 2), ("repeats", 5), ("lowcomplex", 3), ("reads_dup", 4),
+                                        ("protein_dup", 3)])
+def test_parts_with_ties_across_ranges(name, parts):
+    """ties whose doubling partner lives in another code range: the rank exchange between
+    ranges (the multi-GPU protocol, here with all ranges on one device)"""
+    if name == "repeats":
+        sym, K, pl = synth.repeats_dna(200_000, 19, unit=5000, copies=12, exact_len=9000, exact_copies=4), 4, 5
+    elif name == "lowcomplex":
+        sym, K, pl = synth.low_complexity_dna(60_000, 8), 4, 3
+    elif name == "reads_dup":
+        r = synth.reads(500, 120, 3, 0.002)
+        sym, K, pl = np.concatenate([r, [255], r, [255], r[:30000]]).astype(np.uint8), 4, 4
+    else:
+        sym, K, pl = np.concatenate([synth.protein(20_000, 6), [255], synth.protein(20_000, 6)]).astype(np.uint8), 20, 2
+    res = build_esa(encode_symbols(sym, K), pl, parts=parts)
+    assert len(res.stats) > 1
+    assert sum(st["unresolved_after_first_sort"] for st in res.stats) > 0
+    check_against_oracle(sym, K, pl, res, f"{name} parts {parts}")
 
 
 def test_handle_is_reusable_and_deterministic():
