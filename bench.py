@@ -257,26 +257,41 @@ def main():
         torch.cuda.synchronize()
 
     st = GtbStats()
+    worker, first_keys = None, None
+    if world > 1:
+        from genometools_b200.multirange import GpuRangeWorker, run_range_distributed, range_first_keys
+        worker = GpuRangeWorker(h, pl, flags, local_rank)
+        first_keys = range_first_keys(w.numofchars, pl, parts)
+    dev = torch.device("cuda", local_rank)
 
     def step():
-        ck(lib.gtb_esa_run(h, pl, flags))
+        if world > 1:
+            run_range_distributed(worker, first_keys, dist, dev)
+        else:
+            ck(lib.gtb_esa_run(h, pl, flags))
         ck(lib.gtb_esa_get_stats(h, C.byref(st)))
         return st.as_dict()
+
+    lib_stream = torch.cuda.ExternalStream(lib.gtb_esa_stream(h), device=dev)
 
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(lib_stream)                      # CUDA events on the stream the kernels are launched on
     t0 = time.perf_counter()
-    dev_ms, radix_ms, hist_ms, launches, radix_passes, pairs = 0.0, 0.0, 0.0, 0, 0, 0
+    radix_ms, hist_ms, launches, radix_passes, pairs = 0.0, 0.0, 0, 0, 0
     last = None
     for _ in range(args.steps):
         last = step()
-        dev_ms += last["ms_total"]; radix_ms += last["ms_radix"]; hist_ms += last["ms_hist"]
+        radix_ms += last["ms_radix"]; hist_ms += last["ms_hist"]
         launches += last["kernel_launches"]; radix_passes += last["radix_passes"]; pairs += last["radix_pairs_moved"]
+    ev1.record(lib_stream)
     sync_all()
     wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.result()
     # device time of the K steps, max over ranks
     tm = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
@@ -316,7 +331,7 @@ def main():
     # D2H of suftab (uint64), lcptab, llv, bucket table ----
     e2e = None
     if args.e2e_steps > 0:
-        ent_max = n + 1
+        ent_max = int(lib.gtb_esa_num_entries(h)) + 16      # this rank's share of suftab/lcptab
         suf = torch.empty(ent_max, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
         lcp = torch.empty(ent_max, dtype=torch.uint8, pin_memory=True).numpy()
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -339,7 +354,10 @@ def main():
                                               ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
             else:
                 ck(lib.gtb_esa_set_input_bytes(h, ptr(ps), n, w.numofchars))
-            ck(lib.gtb_esa_run(h, pl, flags))
+            if world > 1:
+                run_range_distributed(worker, first_keys, dist, dev)
+            else:
+                ck(lib.gtb_esa_run(h, pl, flags))
             e = lib.gtb_esa_num_entries(h)
             ck(lib.gtb_esa_copy_suftab_u64(h, ptr(suf), 0, e))
             ck(lib.gtb_esa_copy_lcptab(h, ptr(lcp), 0, e))
@@ -359,6 +377,23 @@ def main():
                "steps": args.e2e_steps, "ms_per_step": te.item() / args.e2e_steps * 1e3,
                "note": "pinned host buffers; suftab widened to the file's uint64 on the device"}
 
+    # cheap global check: the shards together are a permutation of 0..n (sum of entries)
+    class _DevArr:
+        def __init__(self, p, count, typestr):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (p, False), "version": 2}
+    ent = lib.gtb_esa_num_entries(h)
+    sa_t = torch.as_tensor(_DevArr(lib.gtb_esa_dev_suftab(h), ent, "<u4"), device=dev) if ent else None
+    ssum = int(sa_t.to(torch.int64).sum().item()) if ent else 0
+    chk = torch.tensor([ssum, ent, last["nonspecials"], int(last["lcptabsum"]), last["numoflargelcpvalues"]],
+                       dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(chk)
+    mx = torch.tensor([last["maxbranchdepth"], last["doubling_rounds"]], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    checks = {"suftab_is_permutation_sum": int(chk[0].item()) == n * (n + 1) // 2 and int(chk[1].item()) == n + 1,
+              "lcptabsum": int(chk[3].item()), "largelcpvalues": int(chk[4].item()),
+              "maxbranchdepth": int(mx[0].item()), "doubling_rounds": int(mx[1].item())}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -383,6 +418,7 @@ def main():
         "wall_ms_per_step": wall_ms_max / args.steps,
         "breakdown_ms_last_step": {k: last[k] for k in ("ms_count", "ms_hist", "ms_radix", "ms_analyze",
                                                          "ms_doubling", "ms_lcp", "ms_tail")},
+        "checks": checks,
         "last_step": {k: int(last[k]) for k in ("unresolved_after_first_sort", "doubling_rounds", "radix_passes",
                                                  "maxbranchdepth", "numoflargelcpvalues", "longest")},
     }

@@ -1048,6 +1048,8 @@ int gtb_esa_copy_bcktab(gtb_esa *h, uint32_t *leftborder, uint32_t *countspecial
   return 0;
 }
 
+void *gtb_esa_stream(const gtb_esa *h) { return h ? (void *) h->st : nullptr; }
+
 const uint32_t *gtb_esa_dev_suftab(const gtb_esa *h) { return h && h->ran ? h->vbuf[h->res].as<u32>() : nullptr; }
 const uint8_t *gtb_esa_dev_lcptab(const gtb_esa *h) { return h && h->ran ? h->lcp8.as<u8>() : nullptr; }
 const uint32_t *gtb_esa_dev_leftborder(const gtb_esa *h) { return h && h->counted ? h->leftborder.as<u32>() : nullptr; }

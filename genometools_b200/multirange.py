@@ -167,6 +167,12 @@ def run_range_distributed(worker, first_keys, dist, device, want_lcp=True):
     import torch
     world, me = dist.get_world_size(), dist.get_rank()
 
+    def wait():
+        # collectives run on torch's stream, the library on its own: the received data must have
+        # landed before the next library kernel reads it
+        if device.type == "cuda":
+            torch.cuda.current_stream(device).synchronize()
+
     def allmax(v):
         t = torch.tensor([v], dtype=torch.int64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -185,9 +191,11 @@ def run_range_distributed(worker, first_keys, dist, device, want_lcp=True):
             rcl = [int(x) for x in rc.tolist()]
             recv_q = torch.empty(sum(rcl), dtype=send.dtype, device=device)
             dist.all_to_all_single(recv_q, send.contiguous(), output_split_sizes=rcl, input_split_sizes=counts)
+            wait()
             recv_a = worker.rank_lookup(recv_q)
             back = torch.empty(sum(counts), dtype=send.dtype, device=device)
             dist.all_to_all_single(back, recv_a.contiguous(), output_split_sizes=counts, input_split_sizes=rcl)
+            wait()
             worker.round_finish(back)
             rounds += 1
             if rounds > 64:

@@ -194,6 +194,10 @@ void gtb_bck_sizes(unsigned numofchars, unsigned prefixlength,
                    uint64_t *numofallcodes, uint64_t *numofspecialcodes,
                    uint64_t *numofdistpfxidx);
 
+/* the CUDA stream (cudaStream_t) all work of this handle is launched on, so that a caller
+   can record its own timing events on it */
+void *gtb_esa_stream(const gtb_esa *h);
+
 /* device pointers of the results, for callers that exchange shards with NCCL
    (the pointers stay owned by the handle) */
 const uint32_t *gtb_esa_dev_suftab(const gtb_esa *h);
