@@ -1,0 +1,249 @@
+/*
+  host/gt_suffixerator_b200.c -- the drop-in `gt suffixerator` for GenomeTools 1.5.11.
+
+  This object defines   int gt_suffixerator(int argc, const char **argv, GtError *err)
+  and is linked into `gt` IN PLACE OF obj/src/tools/gt_suffixerator.o (the toolbox
+  binds the tool by symbol, src/gtt.c:188).  Everything around the sort core stays the
+  reference's own code, called through its public functions:
+
+    * option parsing / -help:  gt_suffixeratoroptions        (src/match/sfx-opt.c:225)
+    * FASTA -> GtEncseq:       gt_encseq_encoder_encode, gt_encseq_loader_load
+                               (as src/match/sfx-run.c:496-531 does)
+    * prefix length policy:    gt_recommendedprefixlength, gt_whatisthemaximalprefixlength,
+                               gt_checkprefixlength          (src/match/sfx-apfxlen.c)
+    * project file:            gt_outprjfile                 (src/match/sfx-outprj.c:84)
+
+  What it replaces is suffixeratorwithoutput() (src/match/sfx-run.c:212-317), i.e. the
+  Sfxiterator + GtOutlcpinfo pair: the packed sequence is exported from the GtEncseq
+  (gt_encseq_twobitencoding_export + gt_specialrangeiterator_*, or
+  gt_encseq_extract_encoded for non-2-bit alphabets), handed to libgtb200.so through the
+  C-ABI of include/gtb200.h, and the tables that come back are written in the reference's
+  file formats (.suf .lcp .llv .bck).  Written from scratch; no reference code is copied.
+
+  Options outside the accelerated path fail loudly (no silent CPU fallback).
+  Build: see host/Makefile (needs the reference tree for headers and libgenometools.a).
+*/
+#include <limits.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "core/encseq.h"
+#include "core/error_api.h"
+#include "core/fa.h"
+#include "core/logger.h"
+#include "core/ma_api.h"
+#include "core/range_api.h"
+#include "core/readmode.h"
+#include "core/str_api.h"
+#include "core/xansi_api.h"
+#include "match/bcktab.h"
+#include "match/sfx-apfxlen.h"
+#include "match/sfx-opt.h"
+#include "match/sfx-outprj.h"
+#include "match/sfx-strategy.h"
+#include "gtb200.h"
+
+static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
+{
+  Sfxstrategy st = gt_index_options_sfxstrategy_value(so->idxopts);
+  const char *what = NULL;
+
+  if (so->inputindex != NULL && gt_str_length(so->inputindex) > 0) what = "-ii";
+  else if (gt_index_options_readmode_value(so->idxopts) != GT_READMODE_FORWARD) what = "-dir";
+  else if (gt_index_options_outbwttab_value(so->idxopts)) what = "-bwt";
+  else if (gt_index_options_outkystab_value(so->idxopts)) what = "-kys";
+  else if (gt_index_options_lcpdist_value(so->idxopts)) what = "-lcpdist";
+  else if (gt_index_options_maximumspace_value(so->idxopts) > 0) what = "-memlimit";
+  else if (so->genomediff) what = "-genomediff";
+  else if (st.differencecover > 0) what = "-dc";
+  else if (st.spmopt_minlength > 0) what = "-spmopt";
+  else if (st.userdefinedsortmaxdepth > 0) what = "-sortmaxdepth";
+  else if (st.suftabuint) what = "-suftabuint";
+  else if (st.compressedoutput) what = "-compressedoutput";
+  else if (st.onlybucketinsertion) what = "-onlybucketinsertion";
+  if (what != NULL) {
+    gt_error_set(err, "option %s is not supported by the B200 suffixerator path "
+                      "(no silent fallback); use the CPU build of gt for it", what);
+    return -1;
+  }
+  return 0;
+}
+
+static int b200_write(const char *indexname, const char *suffix, const void *data,
+                      size_t size, size_t nmemb, size_t pad_to, GtError *err)
+{
+  static const char zeros[8] = {0};
+  FILE *fp = gt_fa_fopen_with_suffix(indexname, suffix, "wb", err);
+  if (fp == NULL) return -1;
+  if (nmemb > 0) gt_xfwrite(data, size, nmemb, fp);
+  if (pad_to > 0 && (size * nmemb) % pad_to != 0)
+    gt_xfwrite(zeros, 1, pad_to - (size * nmemb) % pad_to, fp);
+  gt_fa_xfclose(fp);
+  return 0;
+}
+
+static int b200_append_table(FILE *fp, const uint32_t *tab, uint64_t n)
+{
+  static const char zeros[8] = {0};
+  if (n > 0) gt_xfwrite(tab, sizeof *tab, (size_t) n, fp);
+  if ((n * sizeof *tab) % 8 != 0)               /* gt_mapspec_write pads to 8 bytes,   */
+    gt_xfwrite(zeros, 1, 8 - (n * sizeof *tab) % 8, fp);  /* src/core/mapspec.c:350-365 */
+  return 0;
+}
+
+int gt_suffixerator(int argc, const char **argv, GtError *err)
+{
+  Suffixeratoroptions so;
+  GtEncseq *encseq = NULL;
+  GtLogger *logger = NULL;
+  int retval, had_err = 0;
+
+  gt_error_check(err);
+  retval = gt_suffixeratoroptions(&so, true, argc, argv, err);
+  if (retval != 0) {                     /* > 0: -help/-version were served */
+    gt_sfxoptions_delete(&so);
+    return retval < 0 ? -1 : 0;
+  }
+  logger = gt_logger_new(so.beverbose, GT_LOGGER_DEFLT_PREFIX, stdout);
+  had_err = b200_unsupported(&so, err);
+
+  if (!had_err) {                        /* encode + load, exactly the reference's calls */
+    GtEncseqEncoder *ee = gt_encseq_encoder_new_from_options(so.encopts, err);
+    if (ee == NULL) had_err = -1;
+    if (!had_err) {
+      gt_encseq_encoder_set_logger(ee, logger);
+      if (gt_encseq_encoder_encode(ee, so.db, gt_str_get(so.indexname), err) != 0)
+        had_err = -1;
+    }
+    gt_encseq_encoder_delete(ee);
+    if (!had_err) {
+      GtEncseqLoader *el = gt_encseq_loader_new_from_options(so.loadopts, err);
+      gt_encseq_loader_disable_autosupport(el);
+      gt_encseq_loader_do_not_require_des_tab(el);
+      gt_encseq_loader_do_not_require_sds_tab(el);
+      gt_encseq_loader_do_not_require_ssp_tab(el);
+      encseq = gt_encseq_loader_load(el, gt_str_get(so.indexname), err);
+      gt_encseq_loader_delete(el);
+      if (encseq == NULL) had_err = -1;
+    }
+  }
+
+  if (!had_err) {
+    const bool want_suf = gt_index_options_outsuftab_value(so.idxopts),
+               want_lcp = gt_index_options_outlcptab_value(so.idxopts),
+               want_bck = gt_index_options_outbcktab_value(so.idxopts);
+    const GtUword n = gt_encseq_total_length(encseq);
+    const unsigned int numofchars = gt_encseq_alphabetnumofchars(encseq);
+    unsigned int prefixlength = gt_index_options_prefixlength_value(so.idxopts);
+    uint64_t *suftab = NULL, *llv = NULL, nllv = 0, nall = 0, nspec = 0, ndist = 0;
+    uint8_t *lcptab = NULL;
+    uint32_t *leftborder = NULL, *csc = NULL, *dist = NULL;
+    gtb_stats stats;
+    char msg[512];
+
+    memset(&stats, 0, sizeof stats);
+    if (want_suf || want_lcp || want_bck) {
+      /* detpfxlen, src/match/sfx-run.c:319-367 */
+      unsigned int rec = gt_recommendedprefixlength(numofchars, n,
+                                                    GT_RECOMMENDED_MULTIPLIER_DEFAULT, true);
+      if (prefixlength == GT_PREFIXLENGTH_AUTOMATIC) {
+        prefixlength = rec;
+        gt_logger_log(logger, "automatically determined prefixlength=%u", prefixlength);
+      } else {
+        unsigned int maxpl = gt_whatisthemaximalprefixlength(numofchars, n, 0, true);
+        if (gt_checkprefixlength(maxpl, prefixlength, err) != 0) had_err = -1;
+      }
+    }
+    if (!had_err && (uint64_t) n + 1 >= (uint64_t) UINT32_MAX) {
+      gt_error_set(err, "sequences of total length >= 2^32-2 are not supported by the B200 "
+                        "suffixerator path");
+      had_err = -1;
+    }
+    if (!had_err && (want_suf || want_lcp || want_bck)) {
+      int rc;
+      if (want_suf) suftab = gt_malloc(sizeof *suftab * (n + 1));
+      if (want_lcp) {
+        lcptab = gt_malloc(sizeof *lcptab * (n + 1));
+        llv = gt_malloc(sizeof *llv * 2 * (n + 1));    /* worst case; mostly untouched pages */
+      }
+      if (want_bck) {
+        gtb_bck_sizes(numofchars, prefixlength, &nall, &nspec, &ndist);
+        leftborder = gt_malloc(sizeof *leftborder * (nall + 1));
+        csc = gt_malloc(sizeof *csc * (nspec + 1));
+        dist = gt_malloc(sizeof *dist * (ndist + 1));
+      }
+      if (gt_encseq_has_twobitencoding(encseq)) {
+        /* the 2-bit words and the special ranges as the reference's own sorter reads them */
+        const GtTwobitencoding *tbe = gt_encseq_twobitencoding_export(encseq);
+        GtUword nranges = 0, fill = 0;
+        gtb_range *ranges = NULL;
+        if (gt_encseq_has_specialranges(encseq)) {
+          GtSpecialrangeiterator *sri = gt_specialrangeiterator_new(encseq, true);
+          GtRange range;
+          GtUword alloc = gt_encseq_realspecialranges(encseq) + 16;
+          ranges = gt_malloc(sizeof *ranges * alloc);
+          while (gt_specialrangeiterator_next(sri, &range)) {
+            /* the iterator may split one run into several pieces: merge them */
+            if (fill > 0 && ranges[fill-1].end == (uint64_t) range.start) {
+              ranges[fill-1].end = range.end;
+            } else {
+              if (fill == alloc) { alloc *= 2; ranges = gt_realloc(ranges, sizeof *ranges * alloc); }
+              ranges[fill].start = range.start; ranges[fill].end = range.end; fill++;
+            }
+          }
+          gt_specialrangeiterator_delete(sri);
+          nranges = fill;
+        }
+        rc = gtb_esa_build_2bit(0, (const uint64_t *) tbe, gt_unitsoftwobitencoding(n), n,
+                                ranges, nranges, prefixlength, suftab, lcptab, llv, n + 1, &nllv,
+                                leftborder, csc, dist, &stats, msg, sizeof msg);
+        gt_free(ranges);
+      } else {
+        GtUchar *symbols = gt_malloc(n + 1);
+        if (n > 0) gt_encseq_extract_encoded(encseq, symbols, 0, n - 1);
+        rc = gtb_esa_build_bytes(0, symbols, n, numofchars, prefixlength, suftab, lcptab, llv,
+                                 n + 1, &nllv, leftborder, csc, dist, &stats, msg, sizeof msg);
+        gt_free(symbols);
+      }
+      if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
+    }
+    /* the reference's files */
+    if (!had_err && want_suf)
+      had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, err);
+    if (!had_err && want_lcp) {
+      had_err = b200_write(gt_str_get(so.indexname), ".lcp", lcptab, 1, n + 1, 0, err);
+      if (!had_err)
+        had_err = b200_write(gt_str_get(so.indexname), ".llv", llv, sizeof *llv, 2 * nllv, 0, err);
+    }
+    if (!had_err && want_bck) {
+      FILE *fp = gt_fa_fopen_with_suffix(gt_str_get(so.indexname), ".bck", "wb", err);
+      if (fp == NULL) had_err = -1;
+      else {
+        b200_append_table(fp, leftborder, nall + 1);
+        b200_append_table(fp, csc, nspec);
+        b200_append_table(fp, dist, ndist);
+        gt_fa_xfclose(fp);
+      }
+    }
+    if (!had_err) {
+      Definedunsignedlong longest;
+      longest.defined = want_suf || want_lcp || want_bck;
+      longest.valueunsignedlong = (GtUword) stats.longest;
+      if (gt_outprjfile(gt_str_get(so.indexname), GT_READMODE_FORWARD, encseq,
+                        (want_suf || want_lcp || want_bck) ? n + 1 : 0, prefixlength,
+                        want_lcp ? (GtUword) stats.numoflargelcpvalues : 0,
+                        want_lcp ? stats.lcptabsum / (double) (n + 1) : 0.0,
+                        want_lcp ? (GtUword) stats.maxbranchdepth : 0,
+                        &longest, err) != 0)
+        had_err = -1;
+    }
+    gt_logger_log(logger, "B200 device time %.3f ms, %u kernel launches, %u radix passes",
+                  stats.ms_total, stats.kernel_launches, stats.radix_passes);
+    gt_free(suftab); gt_free(lcptab); gt_free(llv);
+    gt_free(leftborder); gt_free(csc); gt_free(dist);
+  }
+  gt_encseq_delete(encseq);
+  gt_logger_delete(logger);
+  gt_sfxoptions_delete(&so);
+  return had_err ? -1 : 0;
+}

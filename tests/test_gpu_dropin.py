@@ -1,0 +1,69 @@
+"""GPU: the C host drop-in (host/gt_suffixerator_b200.c linked with the reference's own
+option parser, encoder and project-file writer -> host/_build/gt_b200) against the
+unmodified reference binary (oracle/_ref/gtref) on the same FASTA files: all five index
+files must be byte-identical, and the option set outside the path must fail loudly."""
+import os
+import subprocess
+import numpy as np
+import pytest
+
+import synth
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+GT_B200 = os.path.join(ROOT, "host", "_build", "gt_b200")
+GTREF = os.path.join(ROOT, "oracle", "_ref", "gtref")
+need_bins = pytest.mark.skipif(not (os.path.exists(GT_B200) and os.path.exists(GTREF)),
+                               reason="host/_build/gt_b200 or oracle/_ref/gtref not built")
+
+
+def run_both(tmp_path, fasta, alphabet, extra=()):
+    out = {}
+    for name, exe in (("b200", GT_B200), ("ref", GTREF)):
+        idx = str(tmp_path / name)
+        subprocess.check_call([exe, "suffixerator", "-" + alphabet, "-suf", "-lcp", "-bck", "-pl", *extra,
+                               "-indexname", idx, "-db", *fasta], stdout=subprocess.DEVNULL)
+        out[name] = {ext: open(idx + "." + ext, "rb").read() for ext in ("suf", "lcp", "llv", "bck", "prj", "esq")}
+    return out
+
+
+@need_bins
+@pytest.mark.parametrize("case", ["repeats", "reads", "protein", "two_files"])
+def test_dropin_files_identical_to_reference(tmp_path, case):
+    if case == "repeats":
+        sym, alpha = synth.repeats_dna(400_000, 31, unit=8000, copies=10, exact_len=30000, exact_copies=3), "dna"
+    elif case == "reads":
+        sym, alpha = synth.reads(4000, 100, 8, 0.002), "dna"
+    elif case == "protein":
+        sym, alpha = synth.protein(150_000, 21), "protein"
+    else:
+        sym, alpha = synth.random_dna(100_000, 9, 0.001), "dna"
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(sym, fa, alpha)
+    files = [fa]
+    if case == "two_files":
+        fb = str(tmp_path / "in2.fa")
+        synth.to_fasta(synth.reads(300, 90, 4), fb, alpha)
+        files.append(fb)
+    out = run_both(tmp_path, files, alpha)
+    for ext in ("esq", "bck", "suf", "lcp", "llv", "prj"):
+        assert out["b200"][ext] == out["ref"][ext], ext
+
+
+@need_bins
+def test_dropin_explicit_prefixlength_and_errors(tmp_path):
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(synth.random_dna(50_000, 3, 0.01), fa, "dna")
+    out = run_both(tmp_path, [fa], "dna", extra=("4",))
+    for ext in ("bck", "suf", "lcp", "llv", "prj"):
+        assert out["b200"][ext] == out["ref"][ext], ext
+    for bad in (["-dir", "rev"], ["-dc", "32"], ["-bwt"]):
+        r = subprocess.run([GT_B200, "suffixerator", "-dna", "-suf", *bad, "-indexname", str(tmp_path / "x"), "-db", fa],
+                           capture_output=True, text=True)
+        assert r.returncode != 0 and "not supported by the B200" in r.stderr
+    r = subprocess.run([GT_B200, "suffixerator", "-dna", "-suf", "-pl", "9", "-indexname", str(tmp_path / "x"), "-db", fa],
+                       capture_output=True, text=True)
+    r2 = subprocess.run([GTREF, "suffixerator", "-dna", "-suf", "-pl", "9", "-indexname", str(tmp_path / "y"), "-db", fa],
+                        capture_output=True, text=True)
+    assert r.returncode != 0 and r2.returncode != 0
+    assert r.stderr.split("error:")[1] == r2.stderr.split("error:")[1]      # same message as the reference
