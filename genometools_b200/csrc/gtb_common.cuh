@@ -69,6 +69,20 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p)
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// Weak load that does not allocate in L1 (SASS LDG.E.NA): served by L2, the point of
+// coherence.  Enough for words that are self-validating (written by one 64-bit store,
+// tag and payload together).  Unlike ld.relaxed.gpu / ld.global.cg (both LDG.STRONG.GPU
+// on sm_100a, which complete one at a time per thread) many of these can be in flight.
+__device__ __forceinline__ u64 ld_na_u64(const u64 *p)
+{
+  u64 v;
+  asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_weak_u64(u64 *p, u64 v)
+{
+  asm volatile("st.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v)
 {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");

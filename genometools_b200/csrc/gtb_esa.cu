@@ -80,7 +80,7 @@ struct gtb_esa {
   u64 ncodes = 0, nspecialcodes = 0, ndist = 0;
   DevBuf leftborder, csc, dist, distoff;
   // sort state
-  DevBuf kbuf[2], vbuf[2], lcp8, isa, tile_a, tile_b, scantmp, dstats, misc;
+  DevBuf kbuf[2], vbuf[2], lcp8, isa, tile_a, tile_b, tile_c, tile_d, scantmp, dstats, misc;
   DevBuf uidx0, ugrp0, uidx[2], ugrp[2], upos[2], dkeys, kd[2], vd[2], ulcp, llvflags, llv;
   RadixWork rw;
   int res = 0;              // which vbuf holds the suffix table
@@ -95,6 +95,11 @@ struct gtb_esa {
   u64 M0 = 0, M = 0, atiles = 0, pending_send = 0;
   int cur = 0, bits_lo = 1, bits_hi = 1;
   bool isa_built = false, in_progress = false;
+  KeyFmt fmt = byte_fmt();  // key format of this run (DNA: chosen from the text length)
+  int opt_key_symbols = 0;  // test knobs (environment GTB200_KEY_SYMBOLS = 17|21|25|29,
+  int opt_text_rounds = -1; // GTB200_TEXT_ROUNDS = 0..8): override the automatic choices
+  unsigned text_left = 0;   // text-driven rounds still allowed before ranks are built
+  u64 depth[64];            // depth[r] = common prefix of the groups entering round r
   DevBuf ranks, owner, sendidx, rcounts;
   gtb_stats stats;
 };
@@ -166,6 +171,7 @@ TextSrc<DNA> make_src(gtb_esa *h, u64 klo, u64 khi)
   s.bytes = h->bytes.as<u8>();
   s.spmask = h->spmask.as<u32>();
   s.klo = klo; s.khi = khi;
+  s.f = h->fmt;
   return s;
 }
 
@@ -228,7 +234,10 @@ int build_mask(gtb_esa *h, const gtb_range *specials, u64 nranges)
   return 0;
 }
 
-int count_codes(gtb_esa *h, unsigned pl)
+// all = true: the three tables by counting (one atomic per suffix), then the scan.
+// all = false: only countspecialcodes / distpfxidx; leftborder is zeroed and then filled
+// from the sorted keys by k_analyze_keys.
+int count_codes(gtb_esa *h, unsigned pl, bool all)
 {
   ErrBuf &err = h->err;
   if (h->counted && h->pl == pl) return 0;
@@ -246,42 +255,61 @@ int count_codes(gtb_esa *h, unsigned pl)
   GTB_CUDA(cudaMemsetAsync(h->csc.p, 0, sizeof(u32) * (h->nspecialcodes + 1), h->st));
   GTB_CUDA(cudaMemsetAsync(h->dist.p, 0, sizeof(u32) * (h->ndist + 1), h->st));
   GTB_CUDA(cudaMemcpyAsync(h->distoff.p, distoff, sizeof distoff, cudaMemcpyHostToDevice, h->st));
-  if (h->n > 0) {
+  if (h->n > 0) {     // (even without wildcards: the last pl-1 suffixes meet the end of the text)
     const unsigned grid = grid_for(h->n, 256, 148u * 8u);
-    if (h->dna)
-      k_count_codes<true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K,
-          h->leftborder.as<u32>(), h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
+    u32 *lb = h->leftborder.as<u32>(), *cs = h->csc.as<u32>(), *di = h->dist.as<u32>();
+    const u64 *dof = h->distoff.as<u64>();
+    if (h->dna && all)
+      k_count_codes<true, true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
+    else if (h->dna)
+      k_count_codes<true, false><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
+    else if (all)
+      k_count_codes<false, true><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
     else
-      k_count_codes<false><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K,
-          h->leftborder.as<u32>(), h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
+      k_count_codes<false, false><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
   }
-  // counts -> bucket starts; entry ncodes becomes the number of non-special suffixes
-  GTB_TRY(device_scan_u32(h, h->leftborder.as<u32>(), h->leftborder.as<u32>(), h->ncodes + 1, 0,
-                          nullptr, nullptr));
-  h->counted = true;
+  if (all) {
+    // counts -> bucket starts; entry ncodes becomes the number of non-special suffixes
+    GTB_TRY(device_scan_u32(h, h->leftborder.as<u32>(), h->leftborder.as<u32>(), h->ncodes + 1, 0,
+                            nullptr, nullptr));
+    h->counted = true;
+  }
   return 0;
 }
 
-template <bool DNA> int ensure_isa(gtb_esa *h, bool compact);
+template <bool DNA> int compact_ties(gtb_esa *h, bool with_ranks);
+template <bool DNA> int build_ranks(gtb_esa *h);
+template <bool DNA> int round_local(gtb_esa *h);
 
 // ---- stage 1: bucket table, first-level sort, analysis, special tail, compaction of ties ----
 template <bool DNA>
 int stage_begin(gtb_esa *h, unsigned flags)
 {
   ErrBuf &err = h->err;
-  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
   gtb_stats &S = h->stats;
   cudaStream_t st = h->st;
   h->flags = flags;
   h->isa_built = false;
-  h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0;
+  h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0; h->text_left = 0;
+  h->fmt = DNA ? dna_fmt_for(h->n, h->pl) : byte_fmt();
+  if (DNA && h->opt_key_symbols >= (int) h->pl && h->opt_key_symbols >= 1 && h->opt_key_symbols <= 29)
+    h->fmt = make_fmt(h->opt_key_symbols, 2, h->opt_key_symbols > 15 ? (h->opt_key_symbols == 29 ? 6 : 5) : 4);
+  const KeyFmt f = h->fmt;
+  h->depth[0] = (u64) f.m;
 
   // ---- K1/K2 bucket table ----
+  // a single range takes the bucket starts from its sorted keys (k_analyze_keys) unless
+  // the table is much larger than the text; code ranges need them before the sort
+  const bool want_table = h->pl > 0 && ((flags & GTB_WANT_BCK) || !h->full_range);
+  bool lb_from_keys = false;
   {
     PhaseTimer t(h, &S.ms_count);
-    if (h->pl > 0 && ((flags & GTB_WANT_BCK) || !h->full_range)) GTB_TRY(count_codes(h, h->pl));
+    if (want_table && !h->counted) {
+      lb_from_keys = h->full_range && ipow_u64(h->K, h->pl) <= 4 * (h->n - h->S) + 1024;
+      GTB_TRY(count_codes(h, h->pl, !lb_from_keys));
+    }
     t.stop();
   }
   u64 klo, khi;
@@ -315,12 +343,12 @@ int stage_begin(gtb_esa *h, unsigned flags)
   }
   DevStats *dstats = h->dstats.as<DevStats>();
 
-  // ---- K3+K4: fused key generation + LSD radix sort over all key bits ----
+  // ---- K3+K4: fused key generation + LSD radix sort over the significant key bytes ----
   TextSrc<DNA> src = make_src<DNA>(h, klo, khi);
   u64 *kb[2] = {h->kbuf[0].as<u64>(), h->kbuf[1].as<u64>()};
   u32 *vb[2] = {h->vbuf[0].as<u32>(), h->vbuf[1].as<u32>()};
-  PassPlan plan; plan.npass = 0;
-  plan_add_bits(plan, 0, 64);
+  PassPlan plan; plan.npass = 0; plan.padded = true;
+  plan_add_bits(plan, f.lowbit() & ~7, 64);
   u64 N = 0;
   h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0; h->rw.ms_hist = 0; h->rw.ms_radix = 0;
   GTB_TRY(radix_sort(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err));
@@ -338,7 +366,7 @@ int stage_begin(gtb_esa *h, unsigned flags)
     GTB_CUDA(cudaMemcpyAsync(&h->last_key, keys + N - 1, sizeof(u64), cudaMemcpyDeviceToHost, st));
   }
 
-  // ---- A: analysis ----
+  // ---- A: analysis (+ bucket starts) ----
   u64 M0 = 0;
   h->atiles = div_up(N, AN_TILE);
   {
@@ -346,8 +374,12 @@ int stage_begin(gtb_esa *h, unsigned flags)
     if (N > 0) {
       GTB_TRY(h->tile_a.ensure(sizeof(u32) * (h->atiles + 1), err));
       GTB_TRY(h->tile_b.ensure(sizeof(u32) * (h->atiles + 1), err));
-      k_analyze_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, lcp8,
-          h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull);
+      if (lb_from_keys)
+        k_analyze_keys<DNA, true><<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
+            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes);
+      else
+        k_analyze_keys<DNA, false><<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
+            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0);
       GTB_LAUNCH_CHECK();
       k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,
                                                h->misc.as<u64>());
@@ -358,6 +390,7 @@ int stage_begin(gtb_esa *h, unsigned flags)
       GTB_CUDA(cudaMemcpyAsync(&M0, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
       GTB_CUDA(cudaStreamSynchronize(st));
     }
+    if (lb_from_keys) h->counted = true;       // (N = 0: the zeroed table is already right)
     t.stop();
   }
   S.unresolved_after_first_sort = M0;
@@ -384,7 +417,8 @@ int stage_begin(gtb_esa *h, unsigned flags)
     t.stop();
   }
 
-  // ---- ties: compaction + ranks (inverse suffix array) ----
+  // ---- ties: compaction; a small tie set of a single range is first refined by the text
+  // itself (no inverse suffix array needed), ranks are built when that does not finish ----
   if (M0 > 0) {
     PhaseTimer t(h, &S.ms_doubling);
     GTB_TRY(h->uidx0.ensure(sizeof(u32) * M0, err));
@@ -397,7 +431,10 @@ int stage_begin(gtb_esa *h, unsigned flags)
       GTB_TRY(h->vd[i].ensure(sizeof(u32) * M0, err));
     }
     GTB_TRY(h->dkeys.ensure(sizeof(u64) * M0, err));
-    GTB_TRY(ensure_isa<DNA>(h, true));
+    bool text_first = h->full_range && (M0 <= 65536 || M0 * 128 <= h->n);
+    h->text_left = text_first ? 2 : 0;
+    if (h->full_range && h->opt_text_rounds >= 0) { h->text_left = (unsigned) h->opt_text_rounds; text_first = h->text_left > 0; }
+    GTB_TRY(compact_ties<DNA>(h, !text_first));
     GTB_CUDA(cudaMemcpyAsync(h->uidx0.p, h->uidx[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
     GTB_CUDA(cudaMemcpyAsync(h->ugrp0.p, h->ugrp[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
     t.stop();
@@ -405,19 +442,16 @@ int stage_begin(gtb_esa *h, unsigned flags)
   h->bits_lo = bitlen(h->n);
   h->bits_hi = bitlen(N > 0 ? N - 1 : 0);
   h->in_progress = true;
+  // the text-driven rounds are local to the range: run them here
+  while (h->M > 0 && h->text_left > 0) GTB_TRY(round_local<DNA>(h));
   return 0;
 }
 
-// ranks of this range's suffixes (+ of all special positions); with `compact` also the list of ties
-template <bool DNA>
-int ensure_isa(gtb_esa *h, bool compact)
+// ranks of the special positions (they follow the sorted suffixes of all ranges)
+int special_ranks(gtb_esa *h)
 {
   ErrBuf &err = h->err;
-  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
   cudaStream_t st = h->st;
-  if (h->isa_built && !compact) return 0;
-  u64 *keys = h->kbuf[h->res].as<u64>();
-  u32 *sa = h->vbuf[h->res].as<u32>();
   GTB_TRY(h->isa.ensure(sizeof(u32) * (h->n + 2), err));
   k_set_u32<<<1, 1, 0, st>>>(h->isa.as<u32>() + h->n, (u32) h->n);
   GTB_LAUNCH_CHECK();
@@ -433,45 +467,93 @@ int ensure_isa(gtb_esa *h, bool compact)
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
   }
+  return 0;
+}
+
+// list of the tied suffixes (SA index, position, group head); with_ranks: the inverse
+// suffix array of this range in the same pass over the sorted keys
+template <bool DNA>
+int compact_ties(gtb_esa *h, bool with_ranks)
+{
+  ErrBuf &err = h->err;
+  cudaStream_t st = h->st;
+  if (with_ranks) GTB_TRY(special_ranks(h));
   if (h->N > 0) {
-    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, sa, h->N, f, h->tile_a.as<u32>(),
-        h->tile_b.as<u32>(), compact ? h->uidx[0].as<u32>() : nullptr,
-        compact ? h->upos[0].as<u32>() : nullptr, compact ? h->ugrp[0].as<u32>() : nullptr,
+    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(h->kbuf[h->res].as<u64>(), h->vbuf[h->res].as<u32>(),
+        h->N, h->fmt, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->uidx[0].as<u32>(), h->upos[0].as<u32>(),
+        h->ugrp[0].as<u32>(), with_ranks ? h->isa.as<u32>() : nullptr, h->sa_offset);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  if (with_ranks) h->isa_built = true;
+  return 0;
+}
+
+// inverse suffix array of this range (+ of all special positions) in its current state of
+// refinement: group heads from the first-level keys, then the corrections of the
+// text-driven rounds
+template <bool DNA>
+int build_ranks(gtb_esa *h)
+{
+  ErrBuf &err = h->err;
+  cudaStream_t st = h->st;
+  if (h->isa_built) return 0;
+  GTB_TRY(special_ranks(h));
+  if (h->N > 0) {
+    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(h->kbuf[h->res].as<u64>(), h->vbuf[h->res].as<u32>(),
+        h->N, h->fmt, h->tile_a.as<u32>(), h->tile_b.as<u32>(), nullptr, nullptr, nullptr,
         h->isa.as<u32>(), h->sa_offset);
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
+  }
+  if (h->round > 0 && h->M0 > 0) {
+    k_isa_fix_resolved<<<grid_for(h->M0, 256), 256, 0, st>>>(h->uidx0.as<u32>(), h->M0,
+        h->vbuf[h->res].as<u32>(), h->isa.as<u32>(), h->sa_offset);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+    if (h->M > 0) {
+      k_isa_fix_tied<<<grid_for(h->M, 256), 256, 0, st>>>(h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(),
+          h->M, h->isa.as<u32>(), h->sa_offset);
+      GTB_LAUNCH_CHECK();
+      h->stats.kernel_launches++;
+    }
   }
   h->isa_built = true;
   return 0;
 }
 
-// sort the ties by (group, rank of the suffix h further), write back, re-compact
+// sort the ties by the keys in h->dkeys (group head : 32, refinement key : 32), write the
+// order back, re-compact.  tm: bits that mark a key as resolved (text-driven rounds);
+// keybits: significant bits of the refinement key
 template <bool DNA>
-int round_sort_apply(gtb_esa *h)
+int round_sort_apply(gtb_esa *h, u64 tm, int keybits, bool text_round)
 {
   ErrBuf &err = h->err;
   cudaStream_t st = h->st;
   gtb_stats &S = h->stats;
   const u64 M = h->M;
   const int cur = h->cur;
-  PassPlan dp; dp.npass = 0;
-  plan_add_bits(dp, 0, h->bits_lo);
+  if (h->round >= 62) { err.set("internal: refinement did not converge"); return -1; }
+  PassPlan dp; dp.npass = 0; dp.padded = true;
+  if (text_round) plan_add_bits(dp, 32 - ((keybits + 7) & ~7), 32);   // the key is top-aligned in its half
+  else plan_add_bits(dp, 0, keybits);
   plan_add_bits(dp, 32, 32 + h->bits_hi);
   PairSrc ps{h->dkeys.as<u64>(), h->upos[cur].as<u32>()};
   u64 *kk[2] = {h->kd[0].as<u64>(), h->kd[1].as<u64>()};
   u32 *vv[2] = {h->vd[0].as<u32>(), h->vd[1].as<u32>()};
   int r2 = 0; u64 nout = 0;
   GTB_TRY(radix_sort(h->rw, st, ps, M, kk, vv, dp, &r2, &nout, err));
-  if (nout != M) { err.set("internal: doubling sort lost elements"); return -1; }
+  if (nout != M) { err.set("internal: refinement sort lost elements"); return -1; }
   const u64 dt = div_up(M, AN_TILE);
-  GTB_TRY(h->tile_a.ensure(sizeof(u32) * (dt + 1), err));
-  GTB_TRY(h->tile_b.ensure(sizeof(u32) * (dt + 1), err));
-  k_analyze_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], M, h->tile_a.as<u32>(), h->tile_b.as<u32>());
+  GTB_TRY(h->tile_c.ensure(sizeof(u32) * (dt + 1), err));
+  GTB_TRY(h->tile_d.ensure(sizeof(u32) * (dt + 1), err));
+  k_analyze_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], M, tm, h->tile_c.as<u32>(), h->tile_d.as<u32>());
   GTB_LAUNCH_CHECK();
-  k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), dt, h->misc.as<u64>());
+  k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_c.as<u32>(), h->tile_d.as<u32>(), dt, h->misc.as<u64>());
   GTB_LAUNCH_CHECK();
-  k_apply_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M,
-      h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->vbuf[h->res].as<u32>(), h->isa.as<u32>(),
+  k_apply_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M, tm,
+      h->tile_c.as<u32>(), h->tile_d.as<u32>(), h->vbuf[h->res].as<u32>(),
+      h->isa_built ? h->isa.as<u32>() : nullptr,
       h->lcp8.as<u8>(), (u8) h->round, h->sa_offset,
       h->uidx[cur ^ 1].as<u32>(), h->upos[cur ^ 1].as<u32>(), h->ugrp[cur ^ 1].as<u32>(),
       h->dstats.as<DevStats>());
@@ -487,20 +569,34 @@ int round_sort_apply(gtb_esa *h)
   return 0;
 }
 
+// one local refinement round: by the next symbols of the text while text rounds are
+// allowed, else by the ranks of the suffixes depth[round] further (prefix doubling)
 template <bool DNA>
 int round_local(gtb_esa *h)
 {
   ErrBuf &err = h->err;
-  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
-  if (h->M == 0) { h->round++; return 0; }
-  if (h->round > 40) { err.set("internal: prefix doubling did not converge"); return -1; }
+  if (h->M == 0) { h->depth[h->round + 1] = h->depth[h->round]; h->round++; return 0; }
+  if (h->round >= 62) { err.set("internal: refinement did not converge"); return -1; }
   PhaseTimer t(h, &h->stats.ms_doubling);
-  const u64 hlen = (u64) f.m << h->round;
-  k_build_dkeys<<<grid_for(h->M, 256), 256, 0, h->st>>>(h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(),
-      h->isa.as<u32>(), h->M, hlen, h->dkeys.as<u64>());
-  GTB_LAUNCH_CHECK();
-  h->stats.kernel_launches++;
-  GTB_TRY(round_sort_apply<DNA>(h));
+  const u64 hlen = h->depth[h->round];
+  if (h->text_left > 0) {
+    const KeyFmt g = DNA ? dna_tfmt() : byte_tfmt();
+    k_build_tkeys<DNA><<<grid_for(h->M, 256), 256, 0, h->st>>>(make_src<DNA>(h, 0, ~0ull), g,
+        h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(), h->M, hlen, h->dkeys.as<u64>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+    h->depth[h->round + 1] = hlen + (u64) g.m;
+    h->text_left--;
+    GTB_TRY(round_sort_apply<DNA>(h, g.tailmask() >> 32, g.m * g.b + g.tb, true));
+  } else {
+    GTB_TRY(build_ranks<DNA>(h));
+    k_build_dkeys<<<grid_for(h->M, 256), 256, 0, h->st>>>(h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(),
+        h->isa.as<u32>(), h->M, hlen, h->dkeys.as<u64>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+    h->depth[h->round + 1] = 2 * hlen;
+    GTB_TRY(round_sort_apply<DNA>(h, 0ull, h->bits_lo, false));
+  }
   t.stop();
   return 0;
 }
@@ -511,15 +607,15 @@ int round_prepare(gtb_esa *h, const u64 *first_keys, int nranges, int mine, u32 
                   u64 capacity, u64 *counts_out)
 {
   ErrBuf &err = h->err;
-  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
   cudaStream_t st = h->st;
   for (int i = 0; i < nranges; i++) counts_out[i] = 0;
   h->pending_send = 0;
   if (h->M == 0) return 0;
   if (nranges < 1 || nranges > MAX_RANGES || mine < 0 || mine >= nranges) { err.set("bad range table"); return -1; }
-  if (h->round > 40) { err.set("internal: prefix doubling did not converge"); return -1; }
+  if (h->round >= 62) { err.set("internal: prefix doubling did not converge"); return -1; }
   PhaseTimer t(h, &h->stats.ms_doubling);
   const u64 M = h->M;
+  GTB_TRY(build_ranks<DNA>(h));
   GTB_TRY(h->ranks.ensure(sizeof(u32) * M, err));
   GTB_TRY(h->owner.ensure(M, err));
   GTB_TRY(h->sendidx.ensure(sizeof(u32) * M, err));
@@ -528,7 +624,7 @@ int round_prepare(gtb_esa *h, const u64 *first_keys, int nranges, int mine, u32 
   RangeBounds rb; rb.n = nranges; rb.mine = mine;
   for (int i = 0; i < nranges; i++) rb.first_key[i] = first_keys[i];
   rb.first_key[0] = 0;
-  const u64 hlen = (u64) f.m << h->round;
+  const u64 hlen = h->depth[h->round];
   unsigned int *cnt = h->rcounts.as<unsigned int>();
   k_round_classify<DNA><<<grid_for(M, 256), 256, 0, st>>>(make_src<DNA>(h, 0, ~0ull), h->upos[h->cur].as<u32>(),
       M, hlen, rb, h->isa.as<u32>(), h->ranks.as<u32>(), h->owner.as<u8>(), cnt);
@@ -558,7 +654,7 @@ template <bool DNA>
 int round_finish(gtb_esa *h, const u32 *dev_answers)
 {
   ErrBuf &err = h->err;
-  if (h->M == 0) { h->round++; return 0; }
+  if (h->M == 0) { h->depth[h->round + 1] = 2 * h->depth[h->round]; h->round++; return 0; }
   PhaseTimer t(h, &h->stats.ms_doubling);
   if (h->pending_send > 0) {
     k_round_scatter<<<grid_for(h->pending_send, 256), 256, 0, h->st>>>(dev_answers, h->sendidx.as<u32>(),
@@ -570,7 +666,8 @@ int round_finish(gtb_esa *h, const u32 *dev_answers)
       h->M, h->dkeys.as<u64>());
   GTB_LAUNCH_CHECK();
   h->stats.kernel_launches++;
-  GTB_TRY(round_sort_apply<DNA>(h));
+  h->depth[h->round + 1] = 2 * h->depth[h->round];
+  GTB_TRY(round_sort_apply<DNA>(h, 0ull, h->bits_lo, false));
   t.stop();
   return 0;
 }
@@ -580,7 +677,6 @@ template <bool DNA>
 int stage_end(gtb_esa *h)
 {
   ErrBuf &err = h->err;
-  const KeyFmt f = DNA ? dna_fmt() : byte_fmt();
   gtb_stats &S = h->stats;
   cudaStream_t st = h->st;
   const u64 M0 = h->M0, N = h->N;
@@ -591,8 +687,10 @@ int stage_end(gtb_esa *h)
   if (M0 > 0 && (h->flags & GTB_WANT_LCP)) {
     PhaseTimer t(h, &S.ms_lcp);
     GTB_TRY(h->ulcp.ensure(sizeof(u32) * (M0 > h->S + 1 ? M0 : h->S + 1), err));
+    DepthTab dt;
+    for (int i = 0; i < 64; i++) dt.d[i] = i <= (int) h->round ? h->depth[i] : 0;
     k_deep_lcp<DNA><<<grid_for(M0, 128), 128, 0, st>>>(h->uidx0.as<u32>(), h->ugrp0.as<u32>(), M0, sa,
-        h->words.as<u64>(), h->bytes.as<u8>(), h->spmask.as<u32>(), h->n, (unsigned) f.m, lcp8,
+        h->words.as<u64>(), h->bytes.as<u8>(), h->spmask.as<u32>(), h->n, dt, lcp8,
         h->ulcp.as<u32>(), dstats);
     GTB_LAUNCH_CHECK();
     S.kernel_launches++;
@@ -724,6 +822,8 @@ gtb_esa *gtb_esa_new(int device, char *errbuf, size_t errlen)
   gtb_esa *h = new (std::nothrow) gtb_esa();
   if (!h) { if (errbuf && errlen) snprintf(errbuf, errlen, "out of host memory"); return nullptr; }
   h->device = device;
+  if (const char *e = getenv("GTB200_KEY_SYMBOLS")) h->opt_key_symbols = atoi(e);
+  if (const char *e = getenv("GTB200_TEXT_ROUNDS")) h->opt_text_rounds = atoi(e) > 8 ? 8 : atoi(e);
   memset(&h->stats, 0, sizeof h->stats);
   if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h; return fail("cudaStreamCreate", e);
@@ -742,7 +842,7 @@ void gtb_esa_delete(gtb_esa *h)
   cudaStreamSynchronize(h->st);
   DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->leftborder, &h->csc, &h->dist,
                    &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->isa,
-                   &h->tile_a, &h->tile_b, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
+                   &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
                    &h->ranks, &h->owner, &h->sendidx, &h->rcounts};
@@ -850,7 +950,7 @@ int gtb_esa_ensure_ranks(gtb_esa *h)
 {
   if (!h) return -1;
   if (!h->in_progress) { h->err.set("gtb_esa_ensure_ranks outside gtb_esa_sort_begin/_end"); return -1; }
-  return timed_stage(h, [&]() -> int { return h->dna ? ensure_isa<true>(h, false) : ensure_isa<false>(h, false); });
+  return timed_stage(h, [&]() -> int { return h->dna ? build_ranks<true>(h) : build_ranks<false>(h); });
 }
 
 int gtb_esa_round_local(gtb_esa *h)
@@ -922,7 +1022,8 @@ int gtb_esa_count(gtb_esa *h, unsigned prefixlength)
   GTB_CUDA(cudaSetDevice(h->device));
   if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
   if (h->pl != prefixlength) h->counted = false;
-  GTB_TRY(count_codes(h, prefixlength));
+  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt();
+  GTB_TRY(count_codes(h, prefixlength, true));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;
 }
@@ -954,11 +1055,10 @@ int gtb_esa_fix_seam(gtb_esa *h, uint64_t prev_last_key)
   ErrBuf &err = h->err;
   if (h->N == 0) return 0;
   GTB_CUDA(cudaSetDevice(h->device));
-  const KeyFmt f = h->dna ? dna_fmt() : byte_fmt();
-  const u64 tmask = (1ull << f.tb) - 1ull;
-  const u64 x = (prev_last_key ^ h->first_key) & ~tmask;
+  const KeyFmt f = h->fmt;
+  const u64 x = (prev_last_key ^ h->first_key) & f.symmask();
   u32 l = x ? (u32) (__builtin_clzll(x) / f.b) : (u32) f.m;
-  const u32 ua = f.m - (u32) (prev_last_key & tmask), ub = f.m - (u32) (h->first_key & tmask);
+  const u32 ua = f.m - f.tail(prev_last_key), ub = f.m - f.tail(h->first_key);
   l = l < ua ? l : ua; l = l < ub ? l : ub;
   u8 v = (u8) l;
   GTB_CUDA(cudaMemcpyAsync(h->lcp8.p, &v, 1, cudaMemcpyHostToDevice, h->st));

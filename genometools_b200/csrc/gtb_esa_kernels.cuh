@@ -1,17 +1,20 @@
 // gtb_esa_kernels.cuh -- device code of the enhanced-suffix-array pipeline.
 //
-// Key layout ("filled key"):
-//   bits [63 : 64-m*b]  the first m symbols of the suffix, b bits each, MSB first;
-//                       symbols at and after the first special are replaced by the
-//                       all-ones filler (for DNA that is T, the filler GenomeTools
-//                       uses for its special k-mers, sfx-mapped4.gen:180-228)
-//   bits [tb-1 : 0]     m - u, where u = number of regular symbols before the first
-//                       special (capped at m);  0 for a "full" suffix
-//   DNA: m = 29, b = 2, tb = 6      protein/bytes: m = 12, b = 5, tb = 4
+// Key layout ("filled key"), top-aligned in 64 bits:
+//   bits [63 : 64-m*b]      the first m symbols of the suffix, b bits each, MSB first;
+//                           symbols at and after the first special are replaced by the
+//                           all-ones filler (for DNA that is T, the filler GenomeTools
+//                           uses for its special k-mers, sfx-mapped4.gen:180-228)
+//   bits [sh+tb-1 : sh]     m - u, where u = number of regular symbols before the first
+//                           special (capped at m);  0 for a "full" suffix.  sh = 64-m*b-tb
+//   bits [sh-1 : 0]         zero
+//   DNA: b = 2, m = 17 / 21 / 25 (tb = 5) or 29 (tb = 6), chosen from the text length so
+//   that chance ties stay rare -- 39 / 47 / 55 / 64 significant bits = 5 / 6 / 7 / 8 radix
+//   passes;  protein/bytes: m = 12, b = 5, tb = 4
 // Sorting these keys with a stable sort from text order reproduces rule R
 // (/root/reference/src/core/encseq.c:6449-6528,7371-7460)
 // for every pair except full suffixes with identical keys, which are refined by
-// prefix doubling.
+// text-driven rounds (the next symbols) or prefix doubling (ranks).
 #pragma once
 #include "gtb_common.cuh"
 
@@ -21,9 +24,31 @@ struct KeyFmt {
   int m;        // symbols per key
   int b;        // bits per symbol
   int tb;       // tail bits
+  int sh;       // position of the tail field
+  __host__ __device__ u64 tailmask() const { return ((1ull << tb) - 1ull) << sh; }
+  __host__ __device__ u64 symmask() const { return ~0ull << (64 - m * b); }
+  __host__ __device__ unsigned tail(u64 key) const { return (unsigned) (key >> sh) & ((1u << tb) - 1u); }
+  __host__ __device__ int lowbit() const { return sh; }
 };
-__host__ __device__ constexpr KeyFmt dna_fmt()  { return KeyFmt{29, 2, 6}; }
-__host__ __device__ constexpr KeyFmt byte_fmt() { return KeyFmt{12, 5, 4}; }
+__host__ __device__ inline KeyFmt make_fmt(int m, int b, int tb) { return KeyFmt{m, b, tb, 64 - m * b - tb}; }
+__host__ __device__ inline KeyFmt byte_fmt() { return make_fmt(12, 5, 4); }
+// DNA key length for a text of n symbols: the smallest m in {17, 21, 25, 29} (not below
+// the prefix length) for which the expected share of chance ties n / 4^m is below 1 %
+static inline KeyFmt dna_fmt_for(u64 n, unsigned pl)
+{
+  const int cand[4] = {17, 21, 25, 29};
+  for (int i = 0; i < 4; i++) {
+    const int m = cand[i];
+    if ((unsigned) m < pl) continue;
+    const double ties = (double) n / (double) (1ull << (2 * m));
+    if (ties <= 0.01 || m == 29) return make_fmt(m, 2, m == 29 ? 6 : 5);
+  }
+  return make_fmt(29, 2, 6);
+}
+// key of the text-driven refinement rounds: 13 symbols + 4 tail bits (DNA), 5 symbols +
+// 3 tail bits (bytes), top-aligned in 32 bits
+__host__ __device__ inline KeyFmt dna_tfmt()  { return make_fmt(13, 2, 4); }
+__host__ __device__ inline KeyFmt byte_tfmt() { return make_fmt(5, 5, 3); }
 
 // window of 32 mask bits starting at bit `pos`
 __device__ __forceinline__ u32 mask_window(const u32 *__restrict__ spmask, u64 pos)
@@ -43,40 +68,42 @@ __device__ __forceinline__ u64 dna_window(const u64 *__restrict__ words, u64 pos
 
 template <bool DNA>
 struct TextSrc {
+  static constexpr bool ALWAYS_VALID = false;
   const u64 *words;      // DNA: packed 2-bit words (padded by >= 2 words)
   const u8  *bytes;      // bytes path: symbols (padded by >= 16 bytes of 255)
   const u32 *spmask;     // bit i set <=> position i is special; bits >= n all set
   u64 klo, khi;          // inclusive key range of this shard
+  KeyFmt f;
 
-  __device__ __forceinline__ bool make_key(u64 pos, u64 &key) const
+  // filled key of position pos in format g (any m <= 29 for DNA, m*b + tb <= 64)
+  __device__ __forceinline__ bool make_key_fmt(u64 pos, u64 &key, const KeyFmt &g) const
   {
     const u32 win = mask_window(spmask, pos);
     if (win & 1u) return false;                         // special position
+    const unsigned z = win ? (unsigned) __ffs(win) - 1u : 32u;
+    const unsigned u = z < (unsigned) g.m ? z : (unsigned) g.m;
+    u64 sym;
     if (DNA) {
-      constexpr KeyFmt f = dna_fmt();
-      const unsigned z = win ? (unsigned) __ffs(win) - 1u : 32u;
-      const unsigned u = z < (unsigned) f.m ? z : (unsigned) f.m;
-      u64 sym = dna_window(words, pos) >> f.tb;         // 29 symbols in the low 58 bits
-      if (u < (unsigned) f.m) sym |= (1ull << (2u * (f.m - u))) - 1ull;
-      key = (sym << f.tb) | (u64) (f.m - u);
+      sym = dna_window(words, pos) >> (64 - 2 * g.m);   // m symbols in the low 2m bits
+      if (u < (unsigned) g.m) sym |= (1ull << (2u * (g.m - u))) - 1ull;
     } else {
-      constexpr KeyFmt f = byte_fmt();
-      const unsigned z = win ? (unsigned) __ffs(win) - 1u : 32u;
-      const unsigned u = z < (unsigned) f.m ? z : (unsigned) f.m;
-      u64 sym = 0;
-#pragma unroll
-      for (int k = 0; k < f.m; k++) {
-        const u64 s = (unsigned) k < u ? (u64) bytes[pos + k] : 31ull;
-        sym = (sym << f.b) | s;
+      sym = 0;
+      for (int k = 0; k < g.m; k++) {
+        const u64 c = (unsigned) k < u ? (u64) bytes[pos + k] : 31ull;
+        sym = (sym << g.b) | c;
       }
-      key = (sym << f.tb) | (u64) (f.m - u);
     }
+    key = (sym << (64 - g.m * g.b)) | ((u64) (g.m - u) << g.sh);
+    return true;
+  }
+  __device__ __forceinline__ bool make_key(u64 pos, u64 &key) const
+  {
+    if (!make_key_fmt(pos, key, f)) return false;
     return key >= klo && key <= khi;
   }
-  __device__ __forceinline__ bool load(u64 pos, u64 &k, u32 &v) const
-  { v = (u32) pos; return make_key(pos, k); }
   __device__ __forceinline__ bool load_key(u64 pos, u64 &k) const
   { return make_key(pos, k); }
+  __device__ __forceinline__ u32 load_val(u64 pos) const { return (u32) pos; }
 };
 
 // ---- special mask ------------------------------------------------------------------
@@ -228,45 +255,62 @@ k_emit_special_tail(const u32 *__restrict__ spmask, u64 nmaskwords_n, u64 n,
 // ---- bucket table (K1): code histogram incl. special k-mers ----------------------------
 // leftborder counts every suffix with u >= 1 under its filled pl-code
 // (sfx-suffixer.c:1070-1102); countspecialcodes / distpfxidx as bcktab.c:876-901.
+// bucket code of a filled key (top pl symbols; the filler counts as the largest symbol)
 template <bool DNA>
+__device__ __forceinline__ u64 key_code(u64 key, unsigned pl, unsigned K, const KeyFmt &f)
+{
+  if (DNA) return key >> (64 - 2 * pl);
+  u64 code = 0;
+  for (unsigned k = 0; k < pl; k++) {
+    u64 s = (key >> (64 - f.b * (k + 1))) & 31u;
+    if (s >= K) s = K - 1;
+    code = code * K + s;
+  }
+  return code;
+}
+
+// COUNT_ALL = false: only the two special-code tables (the bucket starts are then taken
+// from the sorted keys by k_analyze_keys -- no atomic per suffix)
+template <bool DNA, bool COUNT_ALL>
 __global__ void __launch_bounds__(256)
 k_count_codes(TextSrc<DNA> src, u64 n, unsigned pl, unsigned K,
               u32 *__restrict__ cnt, u32 *__restrict__ csc, u32 *__restrict__ dist,
               const u64 *__restrict__ distoff /* [pl] offsets of level u (u>=1) */)
 {
-  constexpr KeyFmt f = DNA ? dna_fmt() : byte_fmt();
+  const KeyFmt f = src.f;
   for (u64 pos = blockIdx.x * (u64) blockDim.x + threadIdx.x; ; pos += (u64) gridDim.x * blockDim.x) {
     const bool inb = pos < n;
     u64 key = 0;
     bool ok = false;
-    if (inb) ok = src.make_key(pos, key);
+    if (inb) {
+      if (COUNT_ALL) ok = src.make_key(pos, key);
+      else {
+        // only positions with a special among the next pl symbols matter
+        const u32 win = mask_window(src.spmask, pos);
+        if (!(win & 1u) && (win & ((1u << pl) - 1u))) ok = src.make_key(pos, key);
+      }
+    }
     u64 code = 0;
     unsigned u = 0;
     if (ok) {
-      u = (unsigned) f.m - (unsigned) (key & ((1u << f.tb) - 1u));
-      if (DNA) {
-        code = key >> (64 - 2 * pl);
-      } else {
-        for (unsigned k = 0; k < pl; k++) {
-          u64 s = (key >> (64 - f.b * (k + 1))) & 31u;
-          if (s >= K) s = K - 1;                   // filler -> largest symbol
-          code = code * K + s;
-        }
+      u = (unsigned) f.m - f.tail(key);
+      code = key_code<DNA>(key, pl, K, f);
+    }
+    if (COUNT_ALL) {
+      // warp-aggregated increment (poly-A buckets would otherwise serialise in L2)
+      const unsigned active = __ballot_sync(FULL_MASK, ok);
+      if (ok) {
+        const unsigned peers = __match_any_sync(active, code);
+        if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&cnt[code], (u32) __popc(peers));
       }
     }
-    // warp-aggregated increment (poly-A buckets would otherwise serialise in L2)
-    const unsigned active = __ballot_sync(FULL_MASK, ok);
-    if (ok) {
-      const unsigned peers = __match_any_sync(active, code);
-      if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&cnt[code], (u32) __popc(peers));
-      if (u < pl) {
-        atomicAdd(&csc[code / K], 1u);
-        if (u + 1 < pl) {
-          u64 lead = 0;
-          if (DNA) lead = code >> (2 * (pl - u));
-          else { u64 d = 1; for (unsigned k = u; k < pl; k++) d *= K; lead = code / d; }
-          atomicAdd(&dist[distoff[u] + lead], 1u);
-        }
+    if (ok && u < pl) {
+      atomicAdd(&csc[code / K], 1u);
+      if (u + 1 < pl) {
+        u64 lead = 0;
+        if (DNA) lead = code >> (2 * (pl - u));
+        else { u64 d = 1; for (unsigned k = u; k < pl; k++) d *= K; lead = code / d; }
+        atomicAdd(&dist[distoff[u] + lead], 1u);
       }
     }
     if (!__any_sync(FULL_MASK, inb)) break;
@@ -284,12 +328,11 @@ struct DevStats {
 
 constexpr int AN_NT = 256, AN_IPT = 8, AN_TILE = AN_NT * AN_IPT;
 
-__device__ __forceinline__ u32 key_lcp(u64 ka, u64 kb, KeyFmt f)
+__device__ __forceinline__ u32 key_lcp(u64 ka, u64 kb, const KeyFmt &f)
 {
-  const u64 tmask = (1ull << f.tb) - 1ull;
-  const u64 x = (ka ^ kb) & ~tmask;
+  const u64 x = (ka ^ kb) & f.symmask();
   u32 l = x ? (u32) (__clzll((long long) x) / f.b) : (u32) f.m;
-  const u32 ua = (u32) f.m - (u32) (ka & tmask), ub = (u32) f.m - (u32) (kb & tmask);
+  const u32 ua = (u32) f.m - f.tail(ka), ub = (u32) f.m - f.tail(kb);
   l = l < ua ? l : ua;
   return l < ub ? l : ub;
 }
@@ -300,16 +343,18 @@ __device__ __forceinline__ bool key_head(u64 kprev, u64 kcur, u64 tmask)
   return kprev != kcur || (kcur & tmask) != 0;
 }
 
-// pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head
+// pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head; with
+// FILL_LB also the bucket starts: leftborder[c] = index of the first key with code >= c
+template <bool DNA, bool FILL_LB>
 __global__ void __launch_bounds__(AN_NT)
-k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl,
+k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsigned K,
                u8 *__restrict__ lcp8, u32 *__restrict__ tile_unres,
                u32 *__restrict__ tile_lasthead, DevStats *stats, int seam_prev_valid,
-               u64 seam_prev_key)
+               u64 seam_prev_key, u32 *__restrict__ leftborder, u64 ncodes)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
   __shared__ u32 s_max[AN_NT / 32];
-  const u64 tmask = (1ull << f.tb) - 1ull;
+  const u64 tmask = f.tailmask();
   const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
   u64 k[AN_IPT + 2];
 #pragma unroll
@@ -331,11 +376,20 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl,
       if (j > 0) l = key_lcp(k[i], k[i + 1], f);
       else if (seam_prev_valid) l = key_lcp(seam_prev_key, k[i + 1], f);
       lcp8[j] = (u8) l;
-      const u32 u = (u32) f.m - (u32) (k[i + 1] & tmask);
+      const u32 u = (u32) f.m - f.tail(k[i + 1]);
       if (u >= pl) sum += l;
       mx = l > mx ? l : mx;
+      if (FILL_LB && (j == 0 || l < pl)) {
+        // a new bucket starts here: every code in (code of j-1, code of j] starts at j
+        const u64 c1 = key_code<DNA>(k[i + 1], pl, K, f);
+        u64 c0 = j == 0 ? 0 : key_code<DNA>(k[i], pl, K, f) + 1;
+        for (; c0 <= c1; c0++) leftborder[c0] = (u32) j;
+      }
     } else {
-      lcp8[j] = 0;                    // pending: becomes the doubling level, then the value
+      lcp8[j] = 0;                    // pending: becomes the refinement level, then the value
+    }
+    if (FILL_LB && j + 1 == N) {
+      for (u64 c0 = key_code<DNA>(k[i + 1], pl, K, f) + 1; c0 <= ncodes; c0++) leftborder[c0] = (u32) N;
     }
     if (!head || !nexthead) unres++;
   }
@@ -406,7 +460,7 @@ k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N,
                u32 *__restrict__ isa, u64 sa_offset)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
-  const u64 tmask = (1ull << f.tb) - 1ull;
+  const u64 tmask = f.tailmask();
   const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
   u64 k[AN_IPT + 2];
 #pragma unroll
@@ -460,8 +514,24 @@ __global__ void k_build_dkeys(const u32 *__restrict__ upos, const u32 *__restric
     dkeys[c] = ((u64) ugrp[c] << 32) | (u64) isa[(u64) upos[c] + h];
 }
 
+// text-driven round: key = (group head index, filled key of the next symbols in the
+// short format g, top 32 bits).  A continuation that starts at a special sorts last
+// (all filler, u = 0).  Keys whose tail field is non-zero met a special: resolved.
+template <bool DNA>
+__global__ void k_build_tkeys(TextSrc<DNA> src, KeyFmt g, const u32 *__restrict__ upos,
+                              const u32 *__restrict__ ugrp, u64 M, u64 h, u64 *__restrict__ dkeys)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x) {
+    u64 key;
+    if (!src.make_key_fmt((u64) upos[c] + h, key, g)) key = g.symmask() | ((u64) g.m << g.sh);
+    dkeys[c] = ((u64) ugrp[c] << 32) | (key >> 32);
+  }
+}
+
+// `tm`: bits of a sort key that, when set, mark it as resolved whatever its neighbours
+// are (the tail field of a text-driven key; 0 for rank keys)
 __global__ void __launch_bounds__(AN_NT)
-k_analyze_dkeys(const u64 *__restrict__ dkeys, u64 M, u32 *__restrict__ tile_unres,
+k_analyze_dkeys(const u64 *__restrict__ dkeys, u64 M, u64 tm, u32 *__restrict__ tile_unres,
                 u32 *__restrict__ tile_lasthead)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
@@ -477,8 +547,8 @@ k_analyze_dkeys(const u64 *__restrict__ dkeys, u64 M, u32 *__restrict__ tile_unr
   for (int i = 0; i < AN_IPT; i++) {
     const u64 c = base + i;
     if (c >= M) break;
-    const bool head = c == 0 || k[i] != k[i + 1];
-    const bool nexthead = c + 1 >= M || k[i + 1] != k[i + 2];
+    const bool head = c == 0 || key_head(k[i], k[i + 1], tm);
+    const bool nexthead = c + 1 >= M || key_head(k[i + 1], k[i + 2], tm);
     if (head) lasthead = (u32) c + 1u;
     if (!head || !nexthead) unres++;
   }
@@ -492,7 +562,7 @@ k_analyze_dkeys(const u64 *__restrict__ dkeys, u64 M, u32 *__restrict__ tile_unr
 // heads (a lower bound of their lcp), compact what is still tied
 __global__ void __launch_bounds__(AN_NT)
 k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sorted upos */,
-              const u32 *__restrict__ uidx, u64 M,
+              const u32 *__restrict__ uidx, u64 M, u64 tm,
               const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
               u32 *__restrict__ sa, u32 *__restrict__ isa, u8 *__restrict__ lcp8, u8 level,
               u64 sa_offset, u32 *__restrict__ nidx, u32 *__restrict__ npos,
@@ -511,7 +581,7 @@ k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sor
 #pragma unroll
   for (int i = 0; i < AN_IPT + 1; i++) {
     const u64 c = base + i;
-    head[i] = c == 0 || c >= M || k[i] != k[i + 1];
+    head[i] = c == 0 || c >= M || key_head(k[i], k[i + 1], tm);
   }
 #pragma unroll
   for (int i = 0; i < AN_IPT; i++) {
@@ -540,7 +610,7 @@ k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sor
     const u32 j = uidx[c];
     const u32 p = spos[c];
     sa[j] = p;
-    isa[p] = (u32) (sa_offset + g);
+    if (isa) isa[p] = (u32) (sa_offset + g);   // (no ranks are kept during text-driven rounds)
     if (p == 0) stats->longest = sa_offset + j;
     const u32 oldgrp = (u32) (k[i + 1] >> 32);
     if (head[i] && oldgrp != j) lcp8[j] = level;   // split off in this round
@@ -620,11 +690,14 @@ __global__ void k_build_dkeys_ranks(const u32 *__restrict__ ugrp, const u32 *__r
 // the filled key of the smallest suffix of bucket `code` (all further symbols smallest, full)
 
 // ---- exact lcp of the deep pairs (Kasai-style comparison from a proven lower bound) ----
+// depth[r] = common prefix proven for a pair that was separated in refinement round r
+struct DepthTab { u64 d[64]; };
+
 template <bool DNA>
 __global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict__ ugrp0, u64 M0,
                            const u32 *__restrict__ sa, const u64 *__restrict__ words,
                            const u8 *__restrict__ bytes, const u32 *__restrict__ spmask,
-                           u64 n, unsigned m, u8 *__restrict__ lcp8, u32 *__restrict__ ulcp,
+                           u64 n, DepthTab depth, u8 *__restrict__ lcp8, u32 *__restrict__ ulcp,
                            DevStats *stats)
 {
   u32 mx = 0;
@@ -634,7 +707,7 @@ __global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict_
     u32 l = 0xffffffffu;                       // marker: not a deep entry
     if (ugrp0[c] != j) {
       const u64 a = sa[j - 1], b = sa[j];
-      u64 off = (u64) m << lcp8[j];            // proven common prefix
+      u64 off = depth.d[lcp8[j] & 63u];        // proven common prefix
       if (DNA) {
         for (;;) {
           const u32 wa = mask_window(spmask, a + off), wb = mask_window(spmask, b + off);
@@ -706,6 +779,24 @@ __global__ void k_find_longest(TextSrc<DNA> src, const u64 *__restrict__ keys, u
   u64 lo = 0, hi = N;
   while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (keys[mid] < key0) lo = mid + 1; else hi = mid; }
   if (lo < N && keys[lo] == key0) stats->longest = sa_offset + lo;
+}
+
+// ranks of the suffixes that went through text-driven rounds (the inverse suffix array is
+// built from the first-level keys, which know nothing of those rounds): first every
+// initially tied suffix as if resolved, then the still tied ones with their group head
+__global__ void k_isa_fix_resolved(const u32 *__restrict__ uidx0, u64 M0, const u32 *__restrict__ sa,
+                                   u32 *__restrict__ isa, u64 sa_offset)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 j = uidx0[c];
+    isa[sa[j]] = (u32) (sa_offset + j);
+  }
+}
+__global__ void k_isa_fix_tied(const u32 *__restrict__ upos, const u32 *__restrict__ ugrp, u64 M,
+                               u32 *__restrict__ isa, u64 sa_offset)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
+    isa[upos[c]] = (u32) (sa_offset + ugrp[c]);
 }
 
 __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)

@@ -2,12 +2,21 @@
 // pairs on sm_100a.  No Thrust/CUB.
 //
 // One "pass" = one launch of rs_onesweep_kernel: every CTA takes a tile of
-// RS_TILE elements (ticket order), ranks them by one digit with warp-level
+// Cfg::TILE elements (ticket order), ranks them by one 8-bit digit with warp-level
 // match/ballot histograms, obtains the global offset of each of its digit bins
 // with a decoupled look-back over the per-tile status words, stages the tile in
 // shared memory in digit order and writes it out so that runs of equal digits
 // go to consecutive global addresses.  The digit histograms of ALL passes are
 // computed up front by one rs_hist_kernel launch (one read of the keys).
+//
+// Look-back: with ~450 tiles in flight on 148 SMs a tile usually has to walk over several
+// predecessors that have published their aggregate but not yet their inclusive prefix,
+// and every hop is an L2 round trip.  Each bin thread therefore fetches Cfg::LB
+// predecessor words at once with weak L1-bypassing loads (LDG.NA -- the strong
+// ld.relaxed.gpu form completes one at a time per thread on sm_100a) and consumes them in
+// order; only a word that is not ready yet is re-read with a strong load.
+// (Also measured with tools/rs_bench.cu and not kept: dedicated scanner CTAs that turn
+// aggregates into prefixes -- correct, but latency-bound at ~80 cycles per tile.)
 //
 // The first pass can read its keys from a "source" object instead of memory, so
 // the 2-bit text -> 64-bit key generation is fused into the first pass (the keys
@@ -22,12 +31,32 @@
 
 namespace gtb {
 
-constexpr int RS_NT    = 256;               // threads per CTA ( == number of bins )
-constexpr int RS_IPT   = 16;                // items per thread
-constexpr int RS_TILE  = RS_NT * RS_IPT;    // 4096 pairs per tile
-constexpr int RS_WARPS = RS_NT / 32;
 constexpr int RS_BINS  = 256;
 constexpr int RS_MAXPASS = 8;
+
+// Kernel shape.  NT threads x IPT pairs per tile; MINB = CTAs per SM the register
+// allocation is bounded for; VAL_EARLY: values are loaded together with the keys
+// (IPT more live registers) instead of just before they are staged; LB: predecessor
+// status words fetched at once by the look-back (0 = timing experiment without it).
+// (Measured on B200 with tools/rs_bench.cu: match.any.sync is slower than the ballot
+// loop for 8-bit digits, shared-memory atomics cost 2 cycles per active lane on the
+// LSU and lose against load + leader store -- neither is kept.)
+template <int NT_, int IPT_, int MINB_, bool VAL_EARLY_, int LB_ = 4>
+struct RsCfg {
+  static constexpr int NT = NT_, IPT = IPT_, MINB = MINB_, TILE = NT_ * IPT_, WARPS = NT_ / 32, LB = LB_;
+  static constexpr bool VAL_EARLY = VAL_EARLY_;
+  static_assert(NT_ >= RS_BINS && NT_ % 32 == 0, "one thread per bin needed");
+  static_assert(IPT_ * 32 < 4096, "warp-local ranks are kept in 12 bits");
+  static constexpr size_t SMEM = sizeof(u64) * TILE + sizeof(u32) * TILE +
+                                 sizeof(u32) * WARPS * RS_BINS + sizeof(u32) * (WARPS + 4);
+};
+
+// the shape the library uses (chosen with tools/rs_bench.cu on B200, see profiles/)
+#ifndef GTB_RS_DEFAULT_CFG
+#define GTB_RS_DEFAULT_CFG RsCfg<256, 16, 3, false>
+#endif
+typedef GTB_RS_DEFAULT_CFG RsDefault;
+constexpr int RS_TILE = RsDefault::TILE;      // granularity the status array is sized for
 
 // status word: [63:48] epoch  [47:46] flag  [45:0] value
 constexpr u64 RS_FLAG_AGG  = 1ull << 46;
@@ -38,9 +67,10 @@ struct PassPlan {
   int npass;
   int shift[RS_MAXPASS];
   int bits[RS_MAXPASS];
+  bool padded = false;    // keys are zero in the unused upper bits of every partial digit's byte
 };
 
-// plan 8-bit digits covering key bits [begin_bit, end_bit)
+// plan digits of at most 8 bits covering key bits [begin_bit, end_bit)
 static inline void plan_add_bits(PassPlan &p, int begin_bit, int end_bit)
 {
   for (int b = begin_bit; b < end_bit; b += 8) {
@@ -52,33 +82,31 @@ static inline void plan_add_bits(PassPlan &p, int begin_bit, int end_bit)
 
 // ---- key sources -------------------------------------------------------------
 struct PairSrc {                 // pairs already in memory
+  static constexpr bool ALWAYS_VALID = true;
   const u64 *keys;
   const u32 *vals;
-  __device__ __forceinline__ bool load(u64 idx, u64 &k, u32 &v) const
-  { k = keys[idx]; v = vals[idx]; return true; }
   __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
   { k = keys[idx]; return true; }
+  __device__ __forceinline__ u32 load_val(u64 idx) const { return vals[idx]; }
 };
 
-constexpr size_t RS_SMEM_BYTES =
-    sizeof(u64) * RS_TILE + sizeof(u32) * RS_TILE + sizeof(u32) * RS_WARPS * RS_BINS +
-    sizeof(u32) * RS_BINS + sizeof(u64) * RS_BINS + sizeof(u32) * (RS_WARPS + 2);
-
 // ---- histogram of all digits in one read ---------------------------------------
+constexpr int RH_NT = 256, RH_IPT = 16, RH_TILE = RH_NT * RH_IPT;
+
 template <class Src>
-__global__ void __launch_bounds__(RS_NT)
+__global__ void __launch_bounds__(RH_NT)
 rs_hist_kernel(Src src, u64 N, PassPlan plan, unsigned long long *__restrict__ ghist)
 {
   __shared__ u32 s_h[RS_MAXPASS * RS_BINS];
-  for (int i = threadIdx.x; i < RS_MAXPASS * RS_BINS; i += RS_NT) s_h[i] = 0;
+  for (int i = threadIdx.x; i < RS_MAXPASS * RS_BINS; i += RH_NT) s_h[i] = 0;
   __syncthreads();
-  const u64 ntiles = (N + RS_TILE - 1) / RS_TILE;
+  const u64 ntiles = (N + RH_TILE - 1) / RH_TILE;
   const unsigned lane = lane_id();
   for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const u64 base = tile * RS_TILE;
+    const u64 base = tile * RH_TILE;
 #pragma unroll 4
-    for (int k = 0; k < RS_IPT; k++) {
-      const u64 idx = base + (u64) k * RS_NT + threadIdx.x;
+    for (int k = 0; k < RH_IPT; k++) {
+      const u64 idx = base + (u64) k * RH_NT + threadIdx.x;
       u64 key = 0;
       bool ok = idx < N;
       if (ok) ok = src.load_key(idx, key);
@@ -96,7 +124,7 @@ rs_hist_kernel(Src src, u64 N, PassPlan plan, unsigned long long *__restrict__ g
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_NT)
+  for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RH_NT)
     if (s_h[i]) atomicAdd(&ghist[i], (unsigned long long) s_h[i]);
 }
 
@@ -111,122 +139,259 @@ rs_scan_kernel(const unsigned long long *__restrict__ ghist, u64 *__restrict__ g
   gbase[p * RS_BINS + threadIdx.x] = ex;
 }
 
-// ---- one onesweep pass ---------------------------------------------------------
-template <class Src>
-__global__ void __launch_bounds__(RS_NT)
-rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 N,
-                   int shift, unsigned dmask, const u64 *__restrict__ gbase,
-                   u64 *status, u32 epoch, u32 *ticket, u32 ticket_base)
+// lanes of the warp whose 8-bit digit equals mine: one ballot per bit; lanes with
+// valid == false match nobody
+template <bool CHECK_VALID>
+__device__ __forceinline__ unsigned warp_peers(unsigned d, bool valid)
 {
-  extern __shared__ __align__(16) unsigned char rs_smem[];
-  u64 *s_keys     = reinterpret_cast<u64 *>(rs_smem);
-  u64 *s_adj      = s_keys + RS_TILE;
-  u32 *s_vals     = reinterpret_cast<u32 *>(s_adj + RS_BINS);
-  u32 *s_whist    = s_vals + RS_TILE;                 // [RS_WARPS][RS_BINS]
-  u32 *s_binstart = s_whist + RS_WARPS * RS_BINS;
-  u32 *s_scan     = s_binstart + RS_BINS;             // RS_WARPS + 1
-  u32 *s_tile     = s_scan + RS_WARPS + 1;
+  unsigned peers;
+  if (CHECK_VALID) peers = __ballot_sync(FULL_MASK, valid);
+  else peers = FULL_MASK;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    unsigned m;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "@!p not.b32 %0, %0;\n\t}"
+        : "=r"(m) : "r"(d), "r"(1u << b));
+    peers &= m;
+  }
+  return CHECK_VALID ? (valid ? peers : 0u) : peers;
+}
+
+// digit extraction.  MODE 0 / 1: the digit is byte `bsel` of the low / high half of the
+// key (one PRMT); MODE 2: any (shift, mask)
+template <int MODE>
+__device__ __forceinline__ unsigned rs_digit(u64 key, unsigned bsel, unsigned dmask)
+{
+  if (MODE == 0) return __byte_perm((u32) key, 0u, bsel);
+  if (MODE == 1) return __byte_perm((u32) (key >> 32), 0u, bsel);
+  return (unsigned) (key >> bsel) & dmask;
+}
+
+// optional phase timing (tools/rs_bench.cu): cycles per phase summed over all tiles
+#ifdef GTB_RS_PROFILE
+__device__ unsigned long long g_rs_phase[8];
+#define RS_PHASE(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); \
+    atomicAdd(&g_rs_phase[i], (unsigned long long) (now_ - t_phase_)); t_phase_ = now_; } } while (0)
+#else
+#define RS_PHASE(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ bool rs_status_ready(u64 s, u32 epoch)
+{
+  return (s >> 48) == (u64) epoch && (s & (3ull << 46)) != 0;
+}
+
+// status words are self-validating (tag + payload in one 64-bit store).  Prefetches and
+// first polls use weak L1-bypassing loads, which pipeline; a poll that keeps failing
+// falls back to the strong form so that progress never depends on L1 behaviour.
+#ifdef GTB_RS_STRONG
+#define RS_LD(p) ld_relaxed_u64(p)
+#define RS_ST(p, v) st_relaxed_u64(p, v)
+#else
+#define RS_LD(p) ld_na_u64(p)
+#define RS_ST(p, v) st_weak_u64(p, v)
+#endif
+
+// ---- one onesweep pass ---------------------------------------------------------
+// FULL: the tile is complete and the source has no invalid items: no guards at all.
+template <class Src, class Cfg, int MODE, bool FULL>
+__device__ __forceinline__ void
+rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u32 count,
+        u64 tile, unsigned bsel, unsigned dmask, const u64 *__restrict__ gbase,
+        u64 *status, u32 epoch, unsigned char *rs_smem)
+{
+  constexpr int NT = Cfg::NT, IPT = Cfg::IPT, TILE = Cfg::TILE, WARPS = Cfg::WARPS;
+  u64 *s_keys = reinterpret_cast<u64 *>(rs_smem);
+  u32 *s_vals = reinterpret_cast<u32 *>(s_keys + TILE);
+  u32 *s_wh   = s_vals + TILE;                        // [WARPS][RS_BINS] warp histograms -> slots
+  u64 **s_pk  = reinterpret_cast<u64 **>(s_wh);       // [RS_BINS] per-bin output pointers, reuse
+  u32 **s_pv  = reinterpret_cast<u32 **>(s_pk + RS_BINS);   // s_wh after staging (needs WARPS >= 4)
+  u32 *s_scan = s_wh + WARPS * RS_BINS;               // WARPS + 2
+  static_assert(WARPS >= 4, "pointer tables reuse the warp histograms");
+#ifdef GTB_RS_PROFILE
+  long long t_phase_ = clock64();
+#endif
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  if (tid == 0) *s_tile = atomicAdd(ticket, 1u) - ticket_base;
-  for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_NT) s_whist[i] = 0;
-  __syncthreads();
-  const u64 tile = *s_tile;
-  const u64 base = tile * (u64) RS_TILE;
-  const u32 count = (N - base) < (u64) RS_TILE ? (u32) (N - base) : (u32) RS_TILE;
+  const u64 ep = (u64) epoch << 48;
+  const u32 wbase = warp * (32u * IPT) + lane;        // index of this thread's row-0 item
 
-  u64 key[RS_IPT];
-  u32 val[RS_IPT];
-  u32 rnk[RS_IPT];
-  unsigned okmask = 0;
+  u64 key[IPT];
+  u32 val[Cfg::VAL_EARLY ? IPT : 1];
+  u32 rk[IPT];                  // warp-local rank, later the staging slot
+  unsigned okmask = FULL ? ~0u : 0u;
 
   // warp-striped load: warp w owns [w*32*IPT, (w+1)*32*IPT), lane-contiguous rows
 #pragma unroll
-  for (int k = 0; k < RS_IPT; k++) {
-    const u32 idx = warp * (32u * RS_IPT) + (u32) k * 32u + lane;
-    bool ok = idx < count;
-    key[k] = 0; val[k] = 0;
-    if (ok) ok = src.load(base + idx, key[k], val[k]);
-    okmask |= (ok ? 1u : 0u) << k;
+  for (int k = 0; k < IPT; k++) {
+    const u32 idx = wbase + (u32) k * 32u;
+    if (FULL) {
+      src.load_key(base + idx, key[k]);
+      if (Cfg::VAL_EARLY) val[k] = src.load_val(base + idx);
+    } else {
+      bool ok = idx < count;
+      key[k] = 0;
+      if (ok) ok = src.load_key(base + idx, key[k]);
+      if (Cfg::VAL_EARLY) val[k] = idx < count ? src.load_val(base + idx) : 0u;
+      okmask |= (ok ? 1u : 0u) << k;
+    }
   }
 
-  // stable ranking inside the warp: rows in order, lanes in order
-  u32 *wh = s_whist + warp * RS_BINS;
+  // stable ranking inside the warp (rows in order, lanes in order): every lane reads the
+  // warp's bin counter, the first lane of each set of equal digits writes it back
+  // bumped by the size of the set
+  u32 *wh = s_wh + warp * RS_BINS;
   const unsigned lt = lanemask_lt();
 #pragma unroll
-  for (int k = 0; k < RS_IPT; k++) {
-    const bool ok = (okmask >> k) & 1u;
-    const unsigned d = (unsigned) (key[k] >> shift) & dmask;
-    const unsigned dd = ok ? d : 0x1ffu;
-    const unsigned peers = __match_any_sync(FULL_MASK, dd);
-    const int leader = __ffs(peers) - 1;
-    u32 old = 0;
-    if (ok && (int) lane == leader) {
-      old = wh[d];
-      wh[d] = old + __popc(peers);
-    }
-    old = __shfl_sync(FULL_MASK, old, leader);
-    rnk[k] = old + __popc(peers & lt);
+  for (int k = 0; k < IPT; k++) {
+    const bool ok = FULL || ((okmask >> k) & 1u);
+    const unsigned d = rs_digit<MODE>(key[k], bsel, dmask);
+    const unsigned peers = warp_peers<!FULL>(d, ok);
+    const unsigned lower = peers & lt;
+    const u32 old = wh[d];
     __syncwarp();
+    if (ok && lower == 0u) wh[d] = old + (u32) __popc(peers);
+    __syncwarp();
+    rk[k] = old + (u32) __popc(lower);
   }
   __syncthreads();
+  RS_PHASE(0);                  // load + ranking
 
-  // one thread per bin: warp offsets, tile-local bin starts, decoupled look-back
+  // one thread per bin: warp offsets, tile-local bin starts, publish the tile aggregate
+  u32 cnt = 0, excl = 0;
   {
-    u32 run = 0;
+    if (tid < RS_BINS) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) {
-      const u32 c = s_whist[w * RS_BINS + tid];
-      s_whist[w * RS_BINS + tid] = run;
-      run += c;
+      for (int w = 0; w < WARPS; w++) cnt += s_wh[w * RS_BINS + tid];
     }
-    const u32 cnt = run;
     u32 total;
-    const u32 excl = block_exclusive_sum<RS_NT, u32>(cnt, s_scan, &total);
-    s_binstart[tid] = excl;
-    if (tid == 0) s_scan[RS_WARPS + 0] = total;   // keep the tile total (slot reused)
-    const u64 ep = (u64) epoch << 48;
-    u64 *mine = status + tile * RS_BINS + tid;
-    u64 prefix = 0;
-    if (tile == 0) {
-      st_relaxed_u64(mine, ep | RS_FLAG_INCL | (u64) cnt);
-    } else {
-      st_relaxed_u64(mine, ep | RS_FLAG_AGG | (u64) cnt);
-      for (u64 t = tile; t-- > 0; ) {
-        const u64 *pp = status + t * RS_BINS + tid;
-        u64 s;
-        do {
-          s = ld_relaxed_u64(pp);
-        } while ((s >> 48) != (u64) epoch || (s & (3ull << 46)) == 0);
-        prefix += s & RS_VALUE_MASK;
-        if (s & RS_FLAG_INCL) break;
+    excl = block_exclusive_sum<NT, u32>(cnt, s_scan, &total);
+    if (!FULL && tid == 0) s_scan[WARPS + 1] = total;  // slot not used by the scan any more
+    if (tid < RS_BINS) {
+      u32 run = excl;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) {
+        const u32 c = s_wh[w * RS_BINS + tid];
+        s_wh[w * RS_BINS + tid] = run;
+        run += c;
       }
-      st_relaxed_u64(mine, ep | RS_FLAG_INCL | ((prefix + cnt) & RS_VALUE_MASK));
+      RS_ST(status + tile * RS_BINS + tid, ep | (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | (u64) cnt);
     }
-    s_adj[tid] = gbase[tid] + prefix - (u64) excl;
   }
   __syncthreads();
-  const u32 total = s_scan[RS_WARPS + 0];
+  RS_PHASE(1);                  // bin scan + publish
+  const u32 total = FULL ? (u32) TILE : s_scan[WARPS + 1];   // staged (= valid) items
 
   // stage the tile in digit order
 #pragma unroll
-  for (int k = 0; k < RS_IPT; k++) {
-    if ((okmask >> k) & 1u) {
-      const unsigned d = (unsigned) (key[k] >> shift) & dmask;
-      const u32 slot = s_binstart[d] + wh[d] + rnk[k];
-      s_keys[slot] = key[k];
-      s_vals[slot] = val[k];
+  for (int k = 0; k < IPT; k++) {
+    if (FULL || ((okmask >> k) & 1u)) {
+      const unsigned d = rs_digit<MODE>(key[k], bsel, dmask);
+      rk[k] += wh[d];
+      s_keys[rk[k]] = key[k];
     }
   }
-  __syncthreads();
-  // coalesced scatter: consecutive threads -> consecutive slots -> runs per bin
-  for (u32 i = tid; i < total; i += RS_NT) {
-    const u64 kk = s_keys[i];
-    const unsigned d = (unsigned) (kk >> shift) & dmask;
-    const u64 dst = s_adj[d] + i;
-    okeys[dst] = kk;
-    ovals[dst] = s_vals[i];
+  if (Cfg::VAL_EARLY) {
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+      if (FULL || ((okmask >> k) & 1u)) s_vals[rk[k]] = val[k];
+  } else {
+    u32 v[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const u32 idx = wbase + (u32) k * 32u;
+      v[k] = (FULL || ((okmask >> k) & 1u)) ? src.load_val(base + idx) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+      if (FULL || ((okmask >> k) & 1u)) s_vals[rk[k]] = v[k];
   }
+  __syncthreads();
+  RS_PHASE(2);                  // staging
+
+  // decoupled look-back, LB predecessors per round trip (the warp histograms are dead:
+  // the pointer tables reuse their memory)
+  if (tid < RS_BINS) {
+    u64 prefix = gbase[tid];
+    if (Cfg::LB > 0 && tile != 0) {              // (LB = 0: timing experiment, wrong output)
+      constexpr int LB = Cfg::LB > 0 ? Cfg::LB : 1;
+      u64 sum = 0;
+      u64 t = tile;                              // predecessors t-1, t-2, ... are still to visit
+      bool done = false;
+      while (!done) {
+        u64 s[LB];
+#pragma unroll
+        for (int i = 0; i < LB; i++)
+          s[i] = t > (u64) i ? RS_LD(status + (t - 1 - i) * RS_BINS + tid) : 0ull;
+#pragma unroll
+        for (int i = 0; i < LB; i++) {
+          if (!done) {
+            u64 v = s[i];
+#ifdef GTB_RS_PROFILE
+            if (tid == 0) atomicAdd(&g_rs_phase[5], 1ull);
+#endif
+            while (!rs_status_ready(v, epoch)) {
+              v = ld_relaxed_u64(status + (t - 1 - i) * RS_BINS + tid);
+#ifdef GTB_RS_PROFILE
+              if (tid == 0) atomicAdd(&g_rs_phase[6], 1ull);
+#endif
+            }
+            sum += v & RS_VALUE_MASK;
+            if (v & RS_FLAG_INCL) done = true;   // tile 0 is always inclusive: never walks past it
+          }
+        }
+        t -= LB;
+      }
+      RS_ST(status + tile * RS_BINS + tid, ep | RS_FLAG_INCL | ((sum + cnt) & RS_VALUE_MASK));
+      prefix += sum;
+    }
+    const u64 adj = prefix - (u64) excl;   // output index of slot 0 of this bin
+    s_pk[tid] = okeys + adj;
+    s_pv[tid] = ovals + adj;
+  }
+  __syncthreads();
+  RS_PHASE(3);                  // look-back
+
+  // coalesced scatter: consecutive threads -> consecutive slots -> runs per bin
+#pragma unroll
+  for (int k = 0; k < IPT; k++) {
+    const u32 i = tid + (u32) k * NT;
+    if (FULL || i < total) {
+      const u64 kk = s_keys[i];
+      const unsigned d = rs_digit<MODE>(kk, bsel, dmask);
+      s_pk[d][i] = kk;
+      s_pv[d][i] = s_vals[i];
+    }
+  }
+  RS_PHASE(4);                  // scatter (issue only: the stores drain asynchronously)
+}
+
+template <class Src, class Cfg, int MODE>
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
+rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 N,
+                   unsigned bsel, unsigned dmask, const u64 *__restrict__ gbase,
+                   u64 *status, u32 epoch, u32 *ticket, u32 ticket_base)
+{
+  constexpr int TILE = Cfg::TILE;
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  __shared__ u32 s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
+  {
+    u32 *s_wh = reinterpret_cast<u32 *>(rs_smem + (sizeof(u64) + sizeof(u32)) * TILE);
+    for (int i = threadIdx.x; i < Cfg::WARPS * RS_BINS; i += Cfg::NT) s_wh[i] = 0;
+  }
+  __syncthreads();
+  const u64 tile = s_ticket;
+  const u64 base = tile * (u64) TILE;
+  const u32 count = (N - base) < (u64) TILE ? (u32) (N - base) : (u32) TILE;
+  if (Src::ALWAYS_VALID && count == (u32) TILE)
+    rs_tile<Src, Cfg, MODE, true>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+  else
+    rs_tile<Src, Cfg, MODE, false>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
 }
 
 // ---- host-side driver ------------------------------------------------------------
@@ -266,9 +431,12 @@ static inline void radix_work_free(RadixWork &w)
   w = RadixWork();
 }
 
+// the status array is sized for the smallest tile any configuration uses (2048)
+constexpr int RS_MIN_TILE = 2048;
+
 static inline int radix_work_reserve(RadixWork &w, u64 nitems, ErrBuf &err)
 {
-  const u64 tiles = div_up(nitems, RS_TILE) + 1;
+  const u64 tiles = div_up(nitems, RS_MIN_TILE) + 1;
   if (tiles > w.status_tiles) {
     if (w.status) GTB_CUDA(cudaFree(w.status));
     w.status = nullptr; w.status_tiles = 0;
@@ -280,29 +448,48 @@ static inline int radix_work_reserve(RadixWork &w, u64 nitems, ErrBuf &err)
   return 0;
 }
 
-template <class Src>
-static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
-                          u64 *okeys, u32 *ovals, int shift, int bits, int passidx,
+template <class Src, class Cfg, int MODE>
+static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, u64 tiles,
+                          u64 *okeys, u32 *ovals, unsigned bsel, unsigned dmask, int passidx,
                           ErrBuf &err)
 {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    GTB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<Src>,
+    GTB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<Src, Cfg, MODE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int) RS_SMEM_BYTES));
+                                  (int) Cfg::SMEM));
     attr_set = true;
   }
-  const u64 tiles = div_up(nsrc, RS_TILE);
+  rs_onesweep_kernel<Src, Cfg, MODE><<<(unsigned) tiles, Cfg::NT, Cfg::SMEM, st>>>(
+      src, okeys, ovals, nsrc, bsel, dmask, w.gbase + passidx * RS_BINS,
+      w.status, w.epoch, w.ticket, w.ticket_base);
+  GTB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class Src, class Cfg>
+static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
+                          u64 *okeys, u32 *ovals, int shift, int bits, bool padded, int passidx,
+                          ErrBuf &err)
+{
+  static_assert(Cfg::TILE >= RS_MIN_TILE, "status array sizing");
+  const u64 tiles = div_up(nsrc, Cfg::TILE);
   if (tiles == 0) return 0;
   if (tiles > w.status_tiles) { err.set("radix: status array too small"); return -1; }
   if (++w.epoch >= 0xffffu) {           // epoch space exhausted: start over
     GTB_CUDA(cudaMemsetAsync(w.status, 0, sizeof(u64) * RS_BINS * w.status_tiles, st));
     w.epoch = 1;
   }
-  rs_onesweep_kernel<Src><<<(unsigned) tiles, RS_NT, RS_SMEM_BYTES, st>>>(
-      src, okeys, ovals, nsrc, shift, (1u << bits) - 1u, w.gbase + passidx * RS_BINS,
-      w.status, w.epoch, w.ticket, w.ticket_base);
-  GTB_LAUNCH_CHECK();
+  // a digit that is a whole byte of one key half (or a shorter one whose byte is zero
+  // padded) is extracted with one PRMT
+  const unsigned dmask = (1u << bits) - 1u;
+  if (shift % 8 == 0 && (bits == 8 || padded)) {
+    const unsigned bsel = 0x4440u + (unsigned) (shift % 32) / 8u;
+    if (shift < 32) GTB_TRY((rs_launch_mode<Src, Cfg, 0>(w, st, src, nsrc, tiles, okeys, ovals, bsel, dmask, passidx, err)));
+    else GTB_TRY((rs_launch_mode<Src, Cfg, 1>(w, st, src, nsrc, tiles, okeys, ovals, bsel, dmask, passidx, err)));
+  } else {
+    GTB_TRY((rs_launch_mode<Src, Cfg, 2>(w, st, src, nsrc, tiles, okeys, ovals, (unsigned) shift, dmask, passidx, err)));
+  }
   w.ticket_base += (u32) tiles;
   w.passes++; w.launches++;
   return 0;
@@ -313,7 +500,7 @@ static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
 // kbuf[*res]/vbuf[*res], *nout = number of valid pairs.  Passes whose digit is the
 // same for every key are skipped.  Synchronises the stream once (histogram
 // read-back).
-template <class Src>
+template <class Src, class Cfg = RsDefault>
 static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
                       u64 *kbuf[2], u32 *vbuf[2], const PassPlan &plan,
                       int *res, u64 *nout, ErrBuf &err)
@@ -325,9 +512,9 @@ static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
   GTB_CUDA(cudaEventRecord(w.ev[0], st));
   GTB_CUDA(cudaMemsetAsync(w.ghist, 0, sizeof(unsigned long long) * RS_MAXPASS * RS_BINS, st));
   {
-    u64 tiles = div_up(nsrc, RS_TILE);
+    u64 tiles = div_up(nsrc, RH_TILE);
     unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
-    rs_hist_kernel<Src><<<grid, RS_NT, 0, st>>>(src, nsrc, plan, w.ghist);
+    rs_hist_kernel<Src><<<grid, RH_NT, 0, st>>>(src, nsrc, plan, w.ghist);
     GTB_LAUNCH_CHECK();
     rs_scan_kernel<<<plan.npass, RS_BINS, 0, st>>>(w.ghist, w.gbase);
     GTB_LAUNCH_CHECK();
@@ -358,12 +545,12 @@ static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
   for (int p = 0; p < plan.npass; p++) {
     if (skip[p]) continue;
     if (cur < 0) {
-      GTB_TRY(rs_launch_pass(w, st, src, nsrc, kbuf[0], vbuf[0], plan.shift[p], plan.bits[p], p, err));
+      GTB_TRY((rs_launch_pass<Src, Cfg>(w, st, src, nsrc, kbuf[0], vbuf[0], plan.shift[p], plan.bits[p], plan.padded, p, err)));
       cur = 0;
     } else {
       PairSrc ps{kbuf[cur], vbuf[cur]};
-      GTB_TRY(rs_launch_pass(w, st, ps, total, kbuf[cur ^ 1], vbuf[cur ^ 1], plan.shift[p],
-                             plan.bits[p], p, err));
+      GTB_TRY((rs_launch_pass<PairSrc, Cfg>(w, st, ps, total, kbuf[cur ^ 1], vbuf[cur ^ 1], plan.shift[p],
+                                            plan.bits[p], plan.padded, p, err)));
       cur ^= 1;
     }
     w.pairs_moved += total;

@@ -207,3 +207,21 @@ def test_large_input_properties():
     lb = res.leftborder
     assert lb[0] == 0 and lb[-1] == n - S and np.all(np.diff(lb.astype(np.int64)) >= 0)
     assert res.stats[0]["kernel_launches"] > 0
+
+
+# every key length (5/6/7/8 radix passes) and every refinement path: text-driven rounds
+# only, text rounds followed by prefix doubling (ranks corrected after the text rounds),
+# prefix doubling only -- all must give the oracle's bytes
+@pytest.mark.parametrize("m,text_rounds", [(17, 0), (17, 1), (17, 8), (21, 2), (25, 0), (29, 2), (29, 0), (9, 1)])
+def test_cuda_key_lengths_and_refinement_paths(monkeypatch, m, text_rounds):
+    monkeypatch.setenv("GTB200_KEY_SYMBOLS", str(m))
+    monkeypatch.setenv("GTB200_TEXT_ROUNDS", str(text_rounds))
+    cases = [
+        ("repeats", synth.repeats_dna(40_000, 5, unit=1500, copies=5, exact_len=900, exact_copies=3), 5),
+        ("reads", synth.reads(300, 60, 7, p_n=0.01), 4),
+        ("polyA", np.concatenate([np.zeros(3000, np.uint8), synth.random_dna(2000, 3, p_n=0.01),
+                                  np.zeros(2500, np.uint8)]), 3),
+    ]
+    for name, sym, pl in cases:
+        res = build_esa(encode_symbols(sym, 4), pl)
+        check_against_oracle(sym, 4, pl, res, f"{name} m={m} text_rounds={text_rounds}")
