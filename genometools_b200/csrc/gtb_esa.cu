@@ -80,7 +80,7 @@ struct gtb_esa {
   u64 ncodes = 0, nspecialcodes = 0, ndist = 0;
   DevBuf leftborder, csc, dist, distoff;
   // sort state
-  DevBuf kbuf[2], vbuf[2], lcp8, isa, tile_a, tile_b, tile_c, tile_d, scantmp, dstats, misc;
+  DevBuf kbuf[2], vbuf[2], lcp8, tbits, tpre, trank, spre, tile_a, tile_b, tile_c, tile_d, scantmp, dstats, misc;
   DevBuf uidx0, ugrp0, uidx[2], ugrp[2], upos[2], dkeys, kd[2], vd[2], ulcp, llvflags, llv;
   RadixWork rw;
   int res = 0;              // which vbuf holds the suffix table
@@ -279,7 +279,7 @@ int count_codes(gtb_esa *h, unsigned pl, bool all)
   return 0;
 }
 
-template <bool DNA> int compact_ties(gtb_esa *h, bool with_ranks);
+template <bool DNA> int compact_ties(gtb_esa *h);
 template <bool DNA> int build_ranks(gtb_esa *h);
 template <bool DNA> int round_local(gtb_esa *h);
 
@@ -434,7 +434,8 @@ int stage_begin(gtb_esa *h, unsigned flags)
     bool text_first = h->full_range && (M0 <= 65536 || M0 * 128 <= h->n);
     h->text_left = text_first ? 2 : 0;
     if (h->full_range && h->opt_text_rounds >= 0) { h->text_left = (unsigned) h->opt_text_rounds; text_first = h->text_left > 0; }
-    GTB_TRY(compact_ties<DNA>(h, !text_first));
+    GTB_TRY(compact_ties<DNA>(h));
+    (void) text_first;
     GTB_CUDA(cudaMemcpyAsync(h->uidx0.p, h->uidx[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
     GTB_CUDA(cudaMemcpyAsync(h->ugrp0.p, h->ugrp[0].p, sizeof(u32) * M0, cudaMemcpyDeviceToDevice, st));
     t.stop();
@@ -447,73 +448,80 @@ int stage_begin(gtb_esa *h, unsigned flags)
   return 0;
 }
 
-// ranks of the special positions (they follow the sorted suffixes of all ranges)
-int special_ranks(gtb_esa *h)
+// list of the tied suffixes (SA index, position, group head)
+template <bool DNA>
+int compact_ties(gtb_esa *h)
 {
   ErrBuf &err = h->err;
-  cudaStream_t st = h->st;
-  GTB_TRY(h->isa.ensure(sizeof(u32) * (h->n + 2), err));
-  k_set_u32<<<1, 1, 0, st>>>(h->isa.as<u32>() + h->n, (u32) h->n);
+  if (h->N > 0) {
+    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, h->st>>>(h->kbuf[h->res].as<u64>(), h->vbuf[h->res].as<u32>(),
+        h->N, h->fmt, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->uidx[0].as<u32>(), h->upos[0].as<u32>(),
+        h->ugrp[0].as<u32>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+  }
+  return 0;
+}
+
+template <bool DNA>
+RankMap<DNA> make_rankmap(gtb_esa *h)
+{
+  RankMap<DNA> rm;
+  rm.src = make_src<DNA>(h, 0, ~0ull);
+  rm.keys = h->kbuf[h->res].as<u64>();
+  rm.sa = h->vbuf[h->res].as<u32>();
+  rm.N = h->N;
+  rm.tbits = h->tbits.as<u32>(); rm.tpre = h->tpre.as<u32>(); rm.trank = h->trank.as<u32>();
+  rm.spre = h->spre.as<u32>();
+  rm.n = h->n; rm.nonspecials = h->n - h->S; rm.sa_offset = h->sa_offset;
+  return rm;
+}
+
+// exclusive popcount prefix per word of a bitmap
+int popcount_prefix(gtb_esa *h, const u32 *bits, u32 *pre, u64 nwords)
+{
+  ErrBuf &err = h->err;
+  if (nwords == 0) return 0;
+  u32 *tileoff = nullptr;
+  GTB_TRY(device_scan_u32(h, bits, nullptr, nwords, 1, &tileoff, nullptr));
+  k_scan_apply_popc<<<(unsigned) div_up(nwords, SC_TILE), SC_NT, 0, h->st>>>(bits, pre, nwords, tileoff);
   GTB_LAUNCH_CHECK();
   h->stats.kernel_launches++;
-  const u64 nw = (h->n + 31) >> 5;
-  if (h->S > 0 && nw > 0) {
-    u32 *tileoff = nullptr;
-    GTB_TRY(device_scan_u32(h, h->spmask.as<u32>(), nullptr, nw, 1, &tileoff, nullptr));
-    GTB_TRY(h->ulcp.ensure(sizeof(u32) * (h->S + 1), err));       // positions go to scratch
-    k_emit_special_tail<<<(unsigned) div_up(nw, SC_TILE), SC_NT, 0, st>>>(
-        h->spmask.as<u32>(), nw, h->n, tileoff, h->ulcp.as<u32>(), h->isa.as<u32>(), h->n - h->S,
-        (unsigned long long *) h->misc.as<u64>() + 8);
-    GTB_LAUNCH_CHECK();
-    h->stats.kernel_launches++;
-  }
   return 0;
 }
 
-// list of the tied suffixes (SA index, position, group head); with_ranks: the inverse
-// suffix array of this range in the same pass over the sorted keys
-template <bool DNA>
-int compact_ties(gtb_esa *h, bool with_ranks)
-{
-  ErrBuf &err = h->err;
-  cudaStream_t st = h->st;
-  if (with_ranks) GTB_TRY(special_ranks(h));
-  if (h->N > 0) {
-    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(h->kbuf[h->res].as<u64>(), h->vbuf[h->res].as<u32>(),
-        h->N, h->fmt, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->uidx[0].as<u32>(), h->upos[0].as<u32>(),
-        h->ugrp[0].as<u32>(), with_ranks ? h->isa.as<u32>() : nullptr, h->sa_offset);
-    GTB_LAUNCH_CHECK();
-    h->stats.kernel_launches++;
-  }
-  if (with_ranks) h->isa_built = true;
-  return 0;
-}
-
-// inverse suffix array of this range (+ of all special positions) in its current state of
-// refinement: group heads from the first-level keys, then the corrections of the
-// text-driven rounds
+// the sparse rank map of this range in its current state of refinement (RankMap,
+// gtb_esa_kernels.cuh): no inverse suffix array is ever built
 template <bool DNA>
 int build_ranks(gtb_esa *h)
 {
   ErrBuf &err = h->err;
   cudaStream_t st = h->st;
   if (h->isa_built) return 0;
-  GTB_TRY(special_ranks(h));
-  if (h->N > 0) {
-    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, st>>>(h->kbuf[h->res].as<u64>(), h->vbuf[h->res].as<u32>(),
-        h->N, h->fmt, h->tile_a.as<u32>(), h->tile_b.as<u32>(), nullptr, nullptr, nullptr,
-        h->isa.as<u32>(), h->sa_offset);
-    GTB_LAUNCH_CHECK();
-    h->stats.kernel_launches++;
+  const u64 nw = (h->n >> 5) + 2;
+  if (h->S > 0) {
+    GTB_TRY(h->spre.ensure(sizeof(u32) * nw, err));
+    GTB_TRY(popcount_prefix(h, h->spmask.as<u32>(), h->spre.as<u32>(), nw));
   }
-  if (h->round > 0 && h->M0 > 0) {
-    k_isa_fix_resolved<<<grid_for(h->M0, 256), 256, 0, st>>>(h->uidx0.as<u32>(), h->M0,
-        h->vbuf[h->res].as<u32>(), h->isa.as<u32>(), h->sa_offset);
+  GTB_TRY(h->tbits.ensure(sizeof(u32) * nw, err));
+  GTB_CUDA(cudaMemsetAsync(h->tbits.p, 0, sizeof(u32) * nw, st));
+  if (h->M0 > 0) {
+    GTB_TRY(h->tpre.ensure(sizeof(u32) * nw, err));
+    GTB_TRY(h->trank.ensure(sizeof(u32) * h->M0, err));
+    k_tied_bits<<<grid_for(h->M0, 256), 256, 0, st>>>(h->uidx0.as<u32>(), h->M0, h->vbuf[h->res].as<u32>(),
+                                                       h->tbits.as<u32>());
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
+    GTB_TRY(popcount_prefix(h, h->tbits.as<u32>(), h->tpre.as<u32>(), nw));
+    RankMap<DNA> rm = make_rankmap<DNA>(h);
+    if (h->round > 0) {          // text-driven rounds have resolved some of the initial ties
+      k_trank_resolved<DNA><<<grid_for(h->M0, 256), 256, 0, st>>>(rm, h->uidx0.as<u32>(), h->M0);
+      GTB_LAUNCH_CHECK();
+      h->stats.kernel_launches++;
+    }
     if (h->M > 0) {
-      k_isa_fix_tied<<<grid_for(h->M, 256), 256, 0, st>>>(h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(),
-          h->M, h->isa.as<u32>(), h->sa_offset);
+      k_trank_tied<DNA><<<grid_for(h->M, 256), 256, 0, st>>>(rm, h->upos[h->cur].as<u32>(),
+                                                             h->ugrp[h->cur].as<u32>(), h->M);
       GTB_LAUNCH_CHECK();
       h->stats.kernel_launches++;
     }
@@ -551,9 +559,9 @@ int round_sort_apply(gtb_esa *h, u64 tm, int keybits, bool text_round)
   GTB_LAUNCH_CHECK();
   k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_c.as<u32>(), h->tile_d.as<u32>(), dt, h->misc.as<u64>());
   GTB_LAUNCH_CHECK();
-  k_apply_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M, tm,
+  k_apply_dkeys<DNA><<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M, tm,
       h->tile_c.as<u32>(), h->tile_d.as<u32>(), h->vbuf[h->res].as<u32>(),
-      h->isa_built ? h->isa.as<u32>() : nullptr,
+      make_rankmap<DNA>(h), h->isa_built ? 1 : 0,
       h->lcp8.as<u8>(), (u8) h->round, h->sa_offset,
       h->uidx[cur ^ 1].as<u32>(), h->upos[cur ^ 1].as<u32>(), h->ugrp[cur ^ 1].as<u32>(),
       h->dstats.as<DevStats>());
@@ -590,8 +598,8 @@ int round_local(gtb_esa *h)
     GTB_TRY(round_sort_apply<DNA>(h, g.tailmask() >> 32, g.m * g.b + g.tb, true));
   } else {
     GTB_TRY(build_ranks<DNA>(h));
-    k_build_dkeys<<<grid_for(h->M, 256), 256, 0, h->st>>>(h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(),
-        h->isa.as<u32>(), h->M, hlen, h->dkeys.as<u64>());
+    k_build_dkeys<DNA><<<grid_for(h->M, 256), 256, 0, h->st>>>(make_rankmap<DNA>(h), h->upos[h->cur].as<u32>(),
+        h->ugrp[h->cur].as<u32>(), h->M, hlen, h->dkeys.as<u64>());
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
     h->depth[h->round + 1] = 2 * hlen;
@@ -627,7 +635,7 @@ int round_prepare(gtb_esa *h, const u64 *first_keys, int nranges, int mine, u32 
   const u64 hlen = h->depth[h->round];
   unsigned int *cnt = h->rcounts.as<unsigned int>();
   k_round_classify<DNA><<<grid_for(M, 256), 256, 0, st>>>(make_src<DNA>(h, 0, ~0ull), h->upos[h->cur].as<u32>(),
-      M, hlen, rb, h->isa.as<u32>(), h->ranks.as<u32>(), h->owner.as<u8>(), cnt);
+      M, hlen, rb, make_rankmap<DNA>(h), h->ranks.as<u32>(), h->owner.as<u8>(), cnt);
   GTB_LAUNCH_CHECK();
   h->stats.kernel_launches++;
   unsigned int hc[MAX_RANGES], off[MAX_RANGES];
@@ -841,7 +849,7 @@ void gtb_esa_delete(gtb_esa *h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->leftborder, &h->csc, &h->dist,
-                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->isa,
+                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->tbits, &h->tpre, &h->trank, &h->spre,
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
@@ -978,7 +986,8 @@ int gtb_esa_rank_lookup(gtb_esa *h, const uint32_t *dev_positions, uint64_t coun
   return timed_stage(h, [&]() -> int {
     ErrBuf &err = h->err;
     if (count == 0) return 0;
-    k_rank_lookup<<<grid_for(count, 256), 256, 0, h->st>>>(h->isa.as<u32>(), dev_positions, count, dev_ranks);
+    if (h->dna) k_rank_lookup<true><<<grid_for(count, 256), 256, 0, h->st>>>(make_rankmap<true>(h), dev_positions, count, dev_ranks);
+    else k_rank_lookup<false><<<grid_for(count, 256), 256, 0, h->st>>>(make_rankmap<false>(h), dev_positions, count, dev_ranks);
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
     GTB_CUDA(cudaStreamSynchronize(h->st));

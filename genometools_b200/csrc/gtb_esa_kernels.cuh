@@ -106,6 +106,52 @@ struct TextSrc {
   __device__ __forceinline__ u32 load_val(u64 pos) const { return (u32) pos; }
 };
 
+// ---- ranks without an inverse suffix array -----------------------------------------------
+// Prefix doubling needs rank(q) = suffix-array index of q (of its group head while q is
+// tied) for the positions q = p + h of the tied suffixes p only -- about 1 % of a genome.
+// Instead of an n-sized inverse suffix array (one random 4-byte write per suffix) the
+// rank is derived on demand:
+//   q special      -> (n - S) + number of specials before q   (popcount prefix of the mask)
+//   q tied         -> trank[dense id of q]   (bitmap of the tied positions + popcount
+//                     prefix; trank holds the current group head, updated every round)
+//   q anything else-> binary search of (key(q), q) in the sorted first-level keys: its
+//                     key is unique, or shared only by suffixes that meet a special at
+//                     the same depth, which are stored in text order
+template <bool DNA>
+struct RankMap {
+  TextSrc<DNA> src;
+  const u64 *keys;           // first-level sorted keys of this range
+  const u32 *sa;             // its suffix table
+  u64 N;
+  const u32 *tbits, *tpre;   // bitmap of the initially tied positions, popcount prefix
+  u32 *trank;
+  const u32 *spre;           // popcount prefix of the special mask (null if no specials)
+  u64 n, nonspecials, sa_offset;
+
+  __device__ __forceinline__ bool tied(u64 p) const { return (tbits[p >> 5] >> (p & 31u)) & 1u; }
+  __device__ __forceinline__ u32 dense(u64 p) const
+  { return tpre[p >> 5] + (u32) __popc(tbits[p >> 5] & ((1u << (p & 31u)) - 1u)); }
+  __device__ __forceinline__ void set(u64 p, u32 r) const { trank[dense(p)] = r; }
+  __device__ u32 get(u64 q) const
+  {
+    if (q >= n) return (u32) n;
+    const u32 mw = src.spmask[q >> 5];
+    if ((mw >> (q & 31u)) & 1u)
+      return (u32) (nonspecials + spre[q >> 5] + (u32) __popc(mw & ((1u << (q & 31u)) - 1u)));
+    if (tied(q)) return trank[dense(q)];
+    u64 kq;
+    src.make_key_fmt(q, kq, src.f);
+    u64 lo = 0, hi = N;
+    while (lo < hi) {
+      const u64 mid = (lo + hi) >> 1;
+      const u64 km = keys[mid];
+      const bool less = km < kq || (km == kq && (u64) sa[mid] < q);
+      if (less) lo = mid + 1; else hi = mid;
+    }
+    return (u32) (sa_offset + lo);
+  }
+};
+
 // ---- special mask ------------------------------------------------------------------
 // bits >= n are set (the end of the text acts as a special, sfx-enumcodes.c:141-154)
 __global__ void k_mask_tail(u32 *spmask, u64 n, u64 nmaskwords)
@@ -212,6 +258,21 @@ k_scan_apply(const u32 *in, u32 *out, u64 count,
   u32 v[SC_IPT], s = 0;
 #pragma unroll
   for (int k = 0; k < SC_IPT; k++) { v[k] = base + k < count ? in[base + k] : 0u; s += v[k]; }
+  u32 total;
+  u32 ex = block_exclusive_sum<SC_NT, u32>(s, scratch, &total) + tileoff[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) { if (base + k < count) out[base + k] = ex; ex += v[k]; }
+}
+
+// out[w] = number of set bits in in[0..w) (exclusive popcount prefix per word)
+__global__ void __launch_bounds__(SC_NT)
+k_scan_apply_popc(const u32 *in, u32 *out, u64 count, const u32 *__restrict__ tileoff)
+{
+  __shared__ u32 scratch[SC_NT / 32 + 1];
+  const u64 base = (u64) blockIdx.x * SC_TILE + (u64) threadIdx.x * SC_IPT;
+  u32 v[SC_IPT], s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) { v[k] = base + k < count ? (u32) __popc(in[base + k]) : 0u; s += v[k]; }
   u32 total;
   u32 ex = block_exclusive_sum<SC_NT, u32>(s, scratch, &total) + tileoff[blockIdx.x];
 #pragma unroll
@@ -452,12 +513,11 @@ k_scan_tiles_sum_max(u32 *tile_unres, u32 *tile_lasthead, u64 ntiles, u64 *total
   if (threadIdx.x == 0 && total_out) *total_out = grand;
 }
 
-// pass 2: compact the unresolved elements and fill the inverse suffix array
+// pass 2: compact the unresolved elements (SA index, position, group head)
 __global__ void __launch_bounds__(AN_NT)
 k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N, KeyFmt f,
                const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
-               u32 *__restrict__ uidx, u32 *__restrict__ upos, u32 *__restrict__ ugrp,
-               u32 *__restrict__ isa, u64 sa_offset)
+               u32 *__restrict__ uidx, u32 *__restrict__ upos, u32 *__restrict__ ugrp)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
   const u64 tmask = f.tailmask();
@@ -499,19 +559,44 @@ k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N,
     if (j >= N) break;
     if (head[i]) carry = (u32) j + 1u;
     const u32 g = carry - 1u;
-    const u32 p = pos[j];
-    if (isa) isa[p] = (u32) (sa_offset + g);
-    if (uidx && (!head[i] || !head[i + 1])) { uidx[off] = (u32) j; upos[off] = p; ugrp[off] = g; off++; }
+    if (!head[i] || !head[i + 1]) { uidx[off] = (u32) j; upos[off] = pos[j]; ugrp[off] = g; off++; }
   }
 }
 
 // ---- prefix doubling ---------------------------------------------------------------------
 // key = (group head index, rank of the suffix h positions further)
-__global__ void k_build_dkeys(const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
-                              const u32 *__restrict__ isa, u64 M, u64 h, u64 *__restrict__ dkeys)
+template <bool DNA>
+__global__ void k_build_dkeys(RankMap<DNA> rm, const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
+                              u64 M, u64 h, u64 *__restrict__ dkeys)
 {
   for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
-    dkeys[c] = ((u64) ugrp[c] << 32) | (u64) isa[(u64) upos[c] + h];
+    dkeys[c] = ((u64) ugrp[c] << 32) | (u64) rm.get((u64) upos[c] + h);
+}
+
+// bitmap of the tied positions
+__global__ void k_tied_bits(const u32 *__restrict__ uidx0, u64 M0, const u32 *__restrict__ sa,
+                            u32 *__restrict__ tbits)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 p = sa[uidx0[c]];
+    atomicOr(&tbits[p >> 5], 1u << (p & 31u));
+  }
+}
+// ranks of the initially tied suffixes: first each as if resolved (its own index), then
+// the still tied ones with their group head
+template <bool DNA>
+__global__ void k_trank_resolved(RankMap<DNA> rm, const u32 *__restrict__ uidx0, u64 M0)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 j = uidx0[c];
+    rm.set(rm.sa[j], (u32) (rm.sa_offset + j));
+  }
+}
+template <bool DNA>
+__global__ void k_trank_tied(RankMap<DNA> rm, const u32 *__restrict__ upos, const u32 *__restrict__ ugrp, u64 M)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
+    rm.set(upos[c], (u32) (rm.sa_offset + ugrp[c]));
 }
 
 // text-driven round: key = (group head index, filled key of the next symbols in the
@@ -560,11 +645,12 @@ k_analyze_dkeys(const u64 *__restrict__ dkeys, u64 M, u64 tm, u32 *__restrict__ 
 
 // write the refined order back, update ranks, record the doubling level of new group
 // heads (a lower bound of their lcp), compact what is still tied
+template <bool DNA>
 __global__ void __launch_bounds__(AN_NT)
 k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sorted upos */,
               const u32 *__restrict__ uidx, u64 M, u64 tm,
               const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
-              u32 *__restrict__ sa, u32 *__restrict__ isa, u8 *__restrict__ lcp8, u8 level,
+              u32 *__restrict__ sa, RankMap<DNA> rm, int have_ranks, u8 *__restrict__ lcp8, u8 level,
               u64 sa_offset, u32 *__restrict__ nidx, u32 *__restrict__ npos,
               u32 *__restrict__ ngrp, DevStats *stats)
 {
@@ -610,7 +696,7 @@ k_apply_dkeys(const u64 *__restrict__ dkeys, const u32 *__restrict__ spos /* sor
     const u32 j = uidx[c];
     const u32 p = spos[c];
     sa[j] = p;
-    if (isa) isa[p] = (u32) (sa_offset + g);   // (no ranks are kept during text-driven rounds)
+    if (have_ranks) rm.set(p, (u32) (sa_offset + g));   // (no ranks are kept during text-driven rounds)
     if (p == 0) stats->longest = sa_offset + j;
     const u32 oldgrp = (u32) (k[i + 1] >> 32);
     if (head[i] && oldgrp != j) lcp8[j] = level;   // split off in this round
@@ -629,7 +715,7 @@ constexpr u32 OWNER_LOCAL = 0xffu;
 
 template <bool DNA>
 __global__ void k_round_classify(TextSrc<DNA> src, const u32 *__restrict__ upos, u64 M, u64 h,
-                                 RangeBounds rb, const u32 *__restrict__ isa, u32 *__restrict__ ranks,
+                                 RangeBounds rb, RankMap<DNA> rm, u32 *__restrict__ ranks,
                                  u8 *__restrict__ owner, unsigned int *__restrict__ counts)
 {
   __shared__ unsigned int s_cnt[MAX_RANGES];
@@ -645,7 +731,7 @@ __global__ void k_round_classify(TextSrc<DNA> src, const u32 *__restrict__ upos,
       if (lo != rb.mine) o = (u32) lo;
     }
     owner[c] = (u8) o;
-    if (o == OWNER_LOCAL) ranks[c] = isa[q];
+    if (o == OWNER_LOCAL) ranks[c] = rm.get(q);
     else atomicAdd(&s_cnt[o], 1u);
   }
   __syncthreads();
@@ -666,11 +752,11 @@ __global__ void k_round_fill(const u32 *__restrict__ upos, const u8 *__restrict_
   }
 }
 
-__global__ void k_rank_lookup(const u32 *__restrict__ isa, const u32 *__restrict__ q, u64 cnt,
-                              u32 *__restrict__ out)
+template <bool DNA>
+__global__ void k_rank_lookup(RankMap<DNA> rm, const u32 *__restrict__ q, u64 cnt, u32 *__restrict__ out)
 {
   for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < cnt; i += (u64) gridDim.x * blockDim.x)
-    out[i] = isa[q[i]];
+    out[i] = rm.get(q[i]);
 }
 
 __global__ void k_round_scatter(const u32 *__restrict__ answers, const u32 *__restrict__ sendidx, u64 cnt,
@@ -779,24 +865,6 @@ __global__ void k_find_longest(TextSrc<DNA> src, const u64 *__restrict__ keys, u
   u64 lo = 0, hi = N;
   while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (keys[mid] < key0) lo = mid + 1; else hi = mid; }
   if (lo < N && keys[lo] == key0) stats->longest = sa_offset + lo;
-}
-
-// ranks of the suffixes that went through text-driven rounds (the inverse suffix array is
-// built from the first-level keys, which know nothing of those rounds): first every
-// initially tied suffix as if resolved, then the still tied ones with their group head
-__global__ void k_isa_fix_resolved(const u32 *__restrict__ uidx0, u64 M0, const u32 *__restrict__ sa,
-                                   u32 *__restrict__ isa, u64 sa_offset)
-{
-  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
-    const u32 j = uidx0[c];
-    isa[sa[j]] = (u32) (sa_offset + j);
-  }
-}
-__global__ void k_isa_fix_tied(const u32 *__restrict__ upos, const u32 *__restrict__ ugrp, u64 M,
-                               u32 *__restrict__ isa, u64 sa_offset)
-{
-  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
-    isa[upos[c]] = (u32) (sa_offset + ugrp[c]);
 }
 
 __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)
