@@ -235,8 +235,8 @@ int build_mask(gtb_esa *h, const gtb_range *specials, u64 nranges)
 }
 
 // all = true: the three tables by counting (one atomic per suffix), then the scan.
-// all = false: only countspecialcodes / distpfxidx; leftborder is zeroed and then filled
-// from the sorted keys by k_analyze_keys.
+// all = false: the tables are only zeroed; k_analyze_keys fills all three from the sorted
+// keys.
 int count_codes(gtb_esa *h, unsigned pl, bool all)
 {
   ErrBuf &err = h->err;
@@ -255,18 +255,14 @@ int count_codes(gtb_esa *h, unsigned pl, bool all)
   GTB_CUDA(cudaMemsetAsync(h->csc.p, 0, sizeof(u32) * (h->nspecialcodes + 1), h->st));
   GTB_CUDA(cudaMemsetAsync(h->dist.p, 0, sizeof(u32) * (h->ndist + 1), h->st));
   GTB_CUDA(cudaMemcpyAsync(h->distoff.p, distoff, sizeof distoff, cudaMemcpyHostToDevice, h->st));
-  if (h->n > 0) {     // (even without wildcards: the last pl-1 suffixes meet the end of the text)
+  if (h->n > 0 && all) {
     const unsigned grid = grid_for(h->n, 256, 148u * 8u);
     u32 *lb = h->leftborder.as<u32>(), *cs = h->csc.as<u32>(), *di = h->dist.as<u32>();
     const u64 *dof = h->distoff.as<u64>();
-    if (h->dna && all)
+    if (h->dna)
       k_count_codes<true, true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
-    else if (h->dna)
-      k_count_codes<true, false><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
-    else if (all)
-      k_count_codes<false, true><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
     else
-      k_count_codes<false, false><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
+      k_count_codes<false, true><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
   }
@@ -293,7 +289,9 @@ int stage_begin(gtb_esa *h, unsigned flags)
   h->flags = flags;
   h->isa_built = false;
   h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0; h->text_left = 0;
-  h->fmt = DNA ? dna_fmt_for(h->n, h->pl) : byte_fmt();
+  h->fmt = DNA ? dna_fmt_for(h->n, h->pl) : byte_fmt_for(h->n, h->K, h->pl);
+  if (!DNA && (h->opt_key_symbols == 8 || h->opt_key_symbols == 10 || h->opt_key_symbols == 12) && h->opt_key_symbols >= (int) h->pl)
+    h->fmt = make_fmt(h->opt_key_symbols, 5, 4);
   if (DNA && h->opt_key_symbols >= (int) h->pl && h->opt_key_symbols >= 1 && h->opt_key_symbols <= 29)
     h->fmt = make_fmt(h->opt_key_symbols, 2, h->opt_key_symbols > 15 ? (h->opt_key_symbols == 29 ? 6 : 5) : 4);
   const KeyFmt f = h->fmt;
@@ -376,10 +374,11 @@ int stage_begin(gtb_esa *h, unsigned flags)
       GTB_TRY(h->tile_b.ensure(sizeof(u32) * (h->atiles + 1), err));
       if (lb_from_keys)
         k_analyze_keys<DNA, true><<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
-            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes);
+            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes,
+            h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
       else
         k_analyze_keys<DNA, false><<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
-            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0);
+            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0, nullptr, nullptr, nullptr);
       GTB_LAUNCH_CHECK();
       k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,
                                                h->misc.as<u64>());
@@ -1031,7 +1030,7 @@ int gtb_esa_count(gtb_esa *h, unsigned prefixlength)
   GTB_CUDA(cudaSetDevice(h->device));
   if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
   if (h->pl != prefixlength) h->counted = false;
-  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt();
+  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
   GTB_TRY(count_codes(h, prefixlength, true));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;

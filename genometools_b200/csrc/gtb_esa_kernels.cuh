@@ -32,6 +32,21 @@ struct KeyFmt {
 };
 __host__ __device__ inline KeyFmt make_fmt(int m, int b, int tb) { return KeyFmt{m, b, tb, 64 - m * b - tb}; }
 __host__ __device__ inline KeyFmt byte_fmt() { return make_fmt(12, 5, 4); }
+// byte path (5 bits per symbol): the smallest m in {8, 10, 12} (44 / 54 / 64 significant
+// bits = 6 / 7 / 8 radix passes) with an expected share of chance ties n / K^m below 0.1 %
+// (the margin covers skewed residue frequencies)
+static inline KeyFmt byte_fmt_for(u64 n, unsigned K, unsigned pl)
+{
+  const int cand[3] = {8, 10, 12};
+  for (int i = 0; i < 3; i++) {
+    const int m = cand[i];
+    if ((unsigned) m < pl) continue;
+    double km = 1.0;
+    for (int j = 0; j < m; j++) km *= (double) (K < 2 ? 2 : K);
+    if ((double) n / km <= 0.001 || m == 12) return make_fmt(m, 5, 4);
+  }
+  return make_fmt(12, 5, 4);
+}
 // DNA key length for a text of n symbols: the smallest m in {17, 21, 25, 29} (not below
 // the prefix length) for which the expected share of chance ties n / 4^m is below 1 %
 static inline KeyFmt dna_fmt_for(u64 n, unsigned pl)
@@ -405,26 +420,37 @@ __device__ __forceinline__ bool key_head(u64 kprev, u64 kcur, u64 tmask)
 }
 
 // pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head; with
-// FILL_LB also the bucket starts: leftborder[c] = index of the first key with code >= c
+// FILL_LB also the whole bucket table from the sorted keys: leftborder[c] = index of the
+// first key with code >= c; countspecialcodes / distpfxidx from the keys that met a special
+// within their first pl symbols (equal ones are adjacent: one atomic per run and thread)
 template <bool DNA, bool FILL_LB>
 __global__ void __launch_bounds__(AN_NT)
 k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsigned K,
                u8 *__restrict__ lcp8, u32 *__restrict__ tile_unres,
                u32 *__restrict__ tile_lasthead, DevStats *stats, int seam_prev_valid,
-               u64 seam_prev_key, u32 *__restrict__ leftborder, u64 ncodes)
+               u64 seam_prev_key, u32 *__restrict__ leftborder, u64 ncodes,
+               u32 *__restrict__ csc, u32 *__restrict__ dist, const u64 *__restrict__ distoff)
 {
+  static_assert(AN_IPT == 8, "one 8-byte lcp store per thread");
   __shared__ u32 scratch[AN_NT / 32 + 1];
   __shared__ u32 s_max[AN_NT / 32];
   const u64 tmask = f.tailmask();
   const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
-  u64 k[AN_IPT + 2];
+  u64 k[AN_IPT + 2];                   // k[i] = keys[base + i - 1]
+  k[0] = (base >= 1 && base - 1 < N) ? keys[base - 1] : 0;
+  if (base + AN_IPT <= N) {            // keys + base is 64-byte aligned
+    const ulonglong2 *v = reinterpret_cast<const ulonglong2 *>(keys + base);
 #pragma unroll
-  for (int i = 0; i < AN_IPT + 2; i++) {
-    const u64 j = base + i;           // k[i] = keys[j-1]
-    k[i] = (j >= 1 && j - 1 < N) ? keys[j - 1] : 0;
+    for (int i = 0; i < AN_IPT / 2; i++) { const ulonglong2 x = v[i]; k[1 + 2 * i] = x.x; k[2 + 2 * i] = x.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < AN_IPT; i++) k[1 + i] = base + i < N ? keys[base + i] : 0;
   }
+  k[AN_IPT + 1] = base + AN_IPT < N ? keys[base + AN_IPT] : 0;
   u32 unres = 0, lasthead = 0, mx = 0;
   unsigned long long sum = 0;
+  u64 lcpword = 0;
+  u32 run = 0;                         // length of the current run of equal special keys
 #pragma unroll
   for (int i = 0; i < AN_IPT; i++) {
     const u64 j = base + i;
@@ -436,7 +462,7 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
       u32 l = 0;
       if (j > 0) l = key_lcp(k[i], k[i + 1], f);
       else if (seam_prev_valid) l = key_lcp(seam_prev_key, k[i + 1], f);
-      lcp8[j] = (u8) l;
+      lcpword |= (u64) l << (8 * i);
       const u32 u = (u32) f.m - f.tail(k[i + 1]);
       if (u >= pl) sum += l;
       mx = l > mx ? l : mx;
@@ -446,13 +472,30 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
         u64 c0 = j == 0 ? 0 : key_code<DNA>(k[i], pl, K, f) + 1;
         for (; c0 <= c1; c0++) leftborder[c0] = (u32) j;
       }
-    } else {
-      lcp8[j] = 0;                    // pending: becomes the refinement level, then the value
-    }
+      if (FILL_LB && u < pl) {
+        run++;
+        if (i == AN_IPT - 1 || j + 1 >= N || k[i + 2] != k[i + 1]) {   // the run ends in this thread
+          const u64 code = key_code<DNA>(k[i + 1], pl, K, f);
+          atomicAdd(&csc[code / K], run);
+          if (u + 1 < pl) {
+            u64 lead = 0;
+            if (DNA) lead = code >> (2 * (pl - u));
+            else { u64 d = 1; for (unsigned q = u; q < pl; q++) d *= K; lead = code / d; }
+            atomicAdd(&dist[distoff[u] + lead], run);
+          }
+          run = 0;
+        }
+      }
+    }                                   // else: pending, lcp byte 0 = refinement level 0
     if (FILL_LB && j + 1 == N) {
       for (u64 c0 = key_code<DNA>(k[i + 1], pl, K, f) + 1; c0 <= ncodes; c0++) leftborder[c0] = (u32) N;
     }
     if (!head || !nexthead) unres++;
+  }
+  if (base + AN_IPT <= N) {
+    *reinterpret_cast<u64 *>(lcp8 + base) = lcpword;
+  } else {
+    for (int i = 0; i < AN_IPT && base + i < N; i++) lcp8[base + i] = (u8) (lcpword >> (8 * i));
   }
   u32 total;
   block_exclusive_sum<AN_NT, u32>(unres, scratch, &total);

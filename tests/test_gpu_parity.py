@@ -225,3 +225,14 @@ def test_cuda_key_lengths_and_refinement_paths(monkeypatch, m, text_rounds):
     for name, sym, pl in cases:
         res = build_esa(encode_symbols(sym, 4), pl)
         check_against_oracle(sym, 4, pl, res, f"{name} m={m} text_rounds={text_rounds}")
+
+
+@pytest.mark.parametrize("m,text_rounds", [(8, 0), (8, 2), (10, 1), (12, 2)])
+def test_cuda_protein_key_lengths(monkeypatch, m, text_rounds):
+    monkeypatch.setenv("GTB200_KEY_SYMBOLS", str(m))
+    monkeypatch.setenv("GTB200_TEXT_ROUNDS", str(text_rounds))
+    sym = synth.protein(6000, 21, reclen=90, p_x=0.003)
+    sym[1000:1400] = sym[3000:3400]            # a 400-residue repeat: lcp >= 255 -> .llv
+    for pl in (1, 2):
+        res = build_esa(encode_symbols(sym, 20), pl)
+        check_against_oracle(sym, 20, pl, res, f"protein m={m} text_rounds={text_rounds} pl={pl}")
