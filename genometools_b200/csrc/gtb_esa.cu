@@ -373,11 +373,11 @@ int stage_begin(gtb_esa *h, unsigned flags)
       GTB_TRY(h->tile_a.ensure(sizeof(u32) * (h->atiles + 1), err));
       GTB_TRY(h->tile_b.ensure(sizeof(u32) * (h->atiles + 1), err));
       if (lb_from_keys)
-        k_analyze_keys<DNA, true><<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
+        k_analyze_keys<DNA, true><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes,
             h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
       else
-        k_analyze_keys<DNA, false><<<(unsigned) h->atiles, AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
+        k_analyze_keys<DNA, false><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0, nullptr, nullptr, nullptr);
       GTB_LAUNCH_CHECK();
       k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,

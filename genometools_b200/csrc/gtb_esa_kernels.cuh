@@ -404,10 +404,33 @@ struct DevStats {
 
 constexpr int AN_NT = 256, AN_IPT = 8, AN_TILE = AN_NT * AN_IPT;
 
+// Every thread of a tile needs AN_IPT consecutive keys plus one on either side.  The
+// tile is read coalesced into shared memory (one padding word per 8 keys: the blocked
+// reads are then free of bank conflicts) and handed out: k[i] = keys[base + i - 1].
+constexpr int AN_SMEM_KEYS = AN_TILE + 2 + (AN_TILE + 2) / 8 + 1;
+__device__ __forceinline__ void load_keys_blocked(const u64 *__restrict__ keys, u64 N, u64 tile, u64 *s_k,
+                                                  u64 (&k)[AN_IPT + 2])
+{
+  const u64 tilebase = tile * AN_TILE;
+  __syncthreads();                                // (s_k may still be read for the previous tile)
+  for (int e = threadIdx.x; e < AN_TILE + 2; e += AN_NT) {
+    const u64 j = tilebase + e;                   // element e = keys[tilebase + e - 1]
+    s_k[e + (e >> 3)] = (j >= 1 && j - 1 < N) ? keys[j - 1] : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < AN_IPT + 2; i++) {
+    const int e = threadIdx.x * AN_IPT + i;
+    k[i] = s_k[e + (e >> 3)];
+  }
+}
+
+template <bool DNA>
 __device__ __forceinline__ u32 key_lcp(u64 ka, u64 kb, const KeyFmt &f)
 {
+  constexpr u32 B = DNA ? 2u : 5u;      // bits per symbol (a compile-time divisor)
   const u64 x = (ka ^ kb) & f.symmask();
-  u32 l = x ? (u32) (__clzll((long long) x) / f.b) : (u32) f.m;
+  u32 l = x ? (u32) __clzll((long long) x) / B : (u32) f.m;
   const u32 ua = (u32) f.m - f.tail(ka), ub = (u32) f.m - f.tail(kb);
   l = l < ua ? l : ua;
   return l < ub ? l : ub;
@@ -417,6 +440,63 @@ __device__ __forceinline__ u32 key_lcp(u64 ka, u64 kb, const KeyFmt &f)
 __device__ __forceinline__ bool key_head(u64 kprev, u64 kcur, u64 tmask)
 {
   return kprev != kcur || (kcur & tmask) != 0;
+}
+
+struct AnalyzeArgs {
+  u64 N; KeyFmt f; u64 tmask; unsigned pl, K; int seam_prev_valid; u64 seam_prev_key;
+  u32 *leftborder; u64 ncodes; u32 *csc; u32 *dist; const u64 *distoff;
+};
+
+// the AN_IPT elements of one thread; INNER: the tile lies strictly inside the array
+template <bool DNA, bool FILL_LB, bool INNER>
+__device__ __forceinline__ void
+analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &unres, u32 &lasthead,
+               u64 &lcpword, u32 &mx, unsigned long long &sum)
+{
+  const KeyFmt f = a.f;
+  const u64 N = a.N;
+  u32 run = 0;                         // length of the current run of equal special keys
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 j = base + i;
+    if (!INNER && j >= N) break;
+    const bool head = (!INNER && j == 0) || key_head(k[i], k[i + 1], a.tmask);
+    const bool nexthead = (!INNER && j + 1 >= N) || key_head(k[i + 1], k[i + 2], a.tmask);
+    if (head) {
+      lasthead = (u32) j + 1u;
+      u32 l = 0;
+      if (INNER || j > 0) l = key_lcp<DNA>(k[i], k[i + 1], f);
+      else if (a.seam_prev_valid) l = key_lcp<DNA>(a.seam_prev_key, k[i + 1], f);
+      lcpword |= (u64) l << (8 * i);
+      const u32 u = (u32) f.m - f.tail(k[i + 1]);
+      if (u >= a.pl) sum += l;
+      mx = l > mx ? l : mx;
+      if (FILL_LB && ((!INNER && j == 0) || l < a.pl)) {
+        // a new bucket starts here: every code in (code of j-1, code of j] starts at j
+        const u64 c1 = key_code<DNA>(k[i + 1], a.pl, a.K, f);
+        u64 c0 = (!INNER && j == 0) ? 0 : key_code<DNA>(k[i], a.pl, a.K, f) + 1;
+        for (; c0 <= c1; c0++) a.leftborder[c0] = (u32) j;
+      }
+      if (FILL_LB && u < a.pl) {
+        run++;
+        if (i == AN_IPT - 1 || (!INNER && j + 1 >= N) || k[i + 2] != k[i + 1]) {   // the run ends here
+          const u64 code = key_code<DNA>(k[i + 1], a.pl, a.K, f);
+          atomicAdd(&a.csc[code / a.K], run);
+          if (u + 1 < a.pl) {
+            u64 lead = 0;
+            if (DNA) lead = code >> (2 * (a.pl - u));
+            else { u64 d = 1; for (unsigned q = u; q < a.pl; q++) d *= a.K; lead = code / d; }
+            atomicAdd(&a.dist[a.distoff[u] + lead], run);
+          }
+          run = 0;
+        }
+      }
+    }                                   // else: pending, lcp byte 0 = refinement level 0
+    if (FILL_LB && !INNER && j + 1 == N) {
+      for (u64 c0 = key_code<DNA>(k[i + 1], a.pl, a.K, f) + 1; c0 <= a.ncodes; c0++) a.leftborder[c0] = (u32) N;
+    }
+    if (!head || !nexthead) unres++;
+  }
 }
 
 // pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head; with
@@ -434,73 +514,35 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
   static_assert(AN_IPT == 8, "one 8-byte lcp store per thread");
   __shared__ u32 scratch[AN_NT / 32 + 1];
   __shared__ u32 s_max[AN_NT / 32];
+  __shared__ unsigned long long s_sum[AN_NT / 32];
+  __shared__ u64 s_k[AN_SMEM_KEYS];
   const u64 tmask = f.tailmask();
-  const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
-  u64 k[AN_IPT + 2];                   // k[i] = keys[base + i - 1]
-  k[0] = (base >= 1 && base - 1 < N) ? keys[base - 1] : 0;
-  if (base + AN_IPT <= N) {            // keys + base is 64-byte aligned
-    const ulonglong2 *v = reinterpret_cast<const ulonglong2 *>(keys + base);
-#pragma unroll
-    for (int i = 0; i < AN_IPT / 2; i++) { const ulonglong2 x = v[i]; k[1 + 2 * i] = x.x; k[2 + 2 * i] = x.y; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < AN_IPT; i++) k[1 + i] = base + i < N ? keys[base + i] : 0;
-  }
-  k[AN_IPT + 1] = base + AN_IPT < N ? keys[base + AN_IPT] : 0;
-  u32 unres = 0, lasthead = 0, mx = 0;
+  const u64 ntiles = (N + AN_TILE - 1) / AN_TILE;
+  u32 mx = 0;
   unsigned long long sum = 0;
-  u64 lcpword = 0;
-  u32 run = 0;                         // length of the current run of equal special keys
-#pragma unroll
-  for (int i = 0; i < AN_IPT; i++) {
-    const u64 j = base + i;
-    if (j >= N) break;
-    const bool head = j == 0 || key_head(k[i], k[i + 1], tmask);
-    const bool nexthead = j + 1 >= N || key_head(k[i + 1], k[i + 2], tmask);
-    if (head) {
-      lasthead = (u32) j + 1u;
-      u32 l = 0;
-      if (j > 0) l = key_lcp(k[i], k[i + 1], f);
-      else if (seam_prev_valid) l = key_lcp(seam_prev_key, k[i + 1], f);
-      lcpword |= (u64) l << (8 * i);
-      const u32 u = (u32) f.m - f.tail(k[i + 1]);
-      if (u >= pl) sum += l;
-      mx = l > mx ? l : mx;
-      if (FILL_LB && (j == 0 || l < pl)) {
-        // a new bucket starts here: every code in (code of j-1, code of j] starts at j
-        const u64 c1 = key_code<DNA>(k[i + 1], pl, K, f);
-        u64 c0 = j == 0 ? 0 : key_code<DNA>(k[i], pl, K, f) + 1;
-        for (; c0 <= c1; c0++) leftborder[c0] = (u32) j;
-      }
-      if (FILL_LB && u < pl) {
-        run++;
-        if (i == AN_IPT - 1 || j + 1 >= N || k[i + 2] != k[i + 1]) {   // the run ends in this thread
-          const u64 code = key_code<DNA>(k[i + 1], pl, K, f);
-          atomicAdd(&csc[code / K], run);
-          if (u + 1 < pl) {
-            u64 lead = 0;
-            if (DNA) lead = code >> (2 * (pl - u));
-            else { u64 d = 1; for (unsigned q = u; q < pl; q++) d *= K; lead = code / d; }
-            atomicAdd(&dist[distoff[u] + lead], run);
-          }
-          run = 0;
-        }
-      }
-    }                                   // else: pending, lcp byte 0 = refinement level 0
-    if (FILL_LB && j + 1 == N) {
-      for (u64 c0 = key_code<DNA>(k[i + 1], pl, K, f) + 1; c0 <= ncodes; c0++) leftborder[c0] = (u32) N;
+  // a CTA walks over many tiles and keeps the statistics in registers: one atomic per CTA
+  // (one per warp and tile would serialise on the two addresses in L2)
+  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const u64 base = tile * AN_TILE + (u64) threadIdx.x * AN_IPT;
+    u64 k[AN_IPT + 2];                   // k[i] = keys[base + i - 1]
+    load_keys_blocked(keys, N, tile, s_k, k);
+    u32 unres = 0, lasthead = 0;
+    u64 lcpword = 0;
+    const AnalyzeArgs a{N, f, tmask, pl, K, seam_prev_valid, seam_prev_key, leftborder, ncodes, csc, dist, distoff};
+    if (tile > 0 && (tile + 1) * AN_TILE < N)      // inner tile: no bounds to check
+      analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum);
+    else
+      analyze_thread<DNA, FILL_LB, false>(k, base, a, unres, lasthead, lcpword, mx, sum);
+    if (base + AN_IPT <= N) {
+      *reinterpret_cast<u64 *>(lcp8 + base) = lcpword;
+    } else {
+      for (int i = 0; i < AN_IPT && base + i < N; i++) lcp8[base + i] = (u8) (lcpword >> (8 * i));
     }
-    if (!head || !nexthead) unres++;
+    u32 total;
+    block_exclusive_sum<AN_NT, u32>(unres, scratch, &total);
+    const u32 lh = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
+    if (threadIdx.x == AN_NT - 1) { tile_unres[tile] = total; tile_lasthead[tile] = lh; }
   }
-  if (base + AN_IPT <= N) {
-    *reinterpret_cast<u64 *>(lcp8 + base) = lcpword;
-  } else {
-    for (int i = 0; i < AN_IPT && base + i < N; i++) lcp8[base + i] = (u8) (lcpword >> (8 * i));
-  }
-  u32 total;
-  block_exclusive_sum<AN_NT, u32>(unres, scratch, &total);
-  const u32 lh = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
-  if (threadIdx.x == AN_NT - 1) { tile_unres[blockIdx.x] = total; tile_lasthead[blockIdx.x] = lh; }
   // stats
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -508,14 +550,13 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
     const u32 o = __shfl_xor_sync(FULL_MASK, mx, d);
     mx = o > mx ? o : mx;
   }
-  if (lane_id() == 0) {
-    if (sum) atomicAdd(&stats->lcpsum, sum);
-    s_max[threadIdx.x >> 5] = mx;
-  }
+  if (lane_id() == 0) { s_sum[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
     u32 m2 = 0;
-    for (int w = 0; w < AN_NT / 32; w++) m2 = s_max[w] > m2 ? s_max[w] : m2;
+    unsigned long long s2 = 0;
+    for (int w = 0; w < AN_NT / 32; w++) { m2 = s_max[w] > m2 ? s_max[w] : m2; s2 += s_sum[w]; }
+    if (s2) atomicAdd(&stats->lcpsum, s2);
     if (m2) atomicMax(&stats->maxlcp, m2);
   }
 }
@@ -563,14 +604,11 @@ k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N,
                u32 *__restrict__ uidx, u32 *__restrict__ upos, u32 *__restrict__ ugrp)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
+  __shared__ u64 s_k[AN_SMEM_KEYS];
   const u64 tmask = f.tailmask();
   const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
   u64 k[AN_IPT + 2];
-#pragma unroll
-  for (int i = 0; i < AN_IPT + 2; i++) {
-    const u64 j = base + i;
-    k[i] = (j >= 1 && j - 1 < N) ? keys[j - 1] : 0;
-  }
+  load_keys_blocked(keys, N, blockIdx.x, s_k, k);
   bool head[AN_IPT + 1];
   u32 unres = 0, lasthead = 0;
 #pragma unroll

@@ -93,7 +93,10 @@ struct PairSrc {                 // pairs already in memory
 // ---- histogram of all digits in one read ---------------------------------------
 constexpr int RH_NT = 256, RH_IPT = 16, RH_TILE = RH_NT * RH_IPT;
 
-template <class Src>
+// SKEWED: whole warps tend to fall into one bin (keys that arrive sorted by their high
+// digits, as in the refinement rounds): one atomic per warp then instead of 32 on one
+// shared-memory address
+template <class Src, bool SKEWED>
 __global__ void __launch_bounds__(RH_NT)
 rs_hist_kernel(Src src, u64 N, PassPlan plan, unsigned long long *__restrict__ ghist)
 {
@@ -110,16 +113,25 @@ rs_hist_kernel(Src src, u64 N, PassPlan plan, unsigned long long *__restrict__ g
       u64 key = 0;
       bool ok = idx < N;
       if (ok) ok = src.load_key(idx, key);
-      for (int p = 0; p < plan.npass; p++) {
-        const unsigned d = (unsigned) (key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
-        const unsigned dd = ok ? d : 0x1ffu;
-        int pred;
-        __match_all_sync(FULL_MASK, dd, &pred);
-        if (pred) {                       // whole warp in one bin: one atomic
-          if (lane == 0 && ok) atomicAdd(&s_h[p * RS_BINS + d], 32u);
-        } else if (ok) {
-          atomicAdd(&s_h[p * RS_BINS + d], 1u);
+      if (SKEWED) {
+#pragma unroll
+        for (int p = 0; p < RS_MAXPASS; p++) {    // (fully unrolled: the plan stays in registers)
+          if (p < plan.npass) {
+            const unsigned d = (unsigned) (key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+            int pred;
+            __match_all_sync(FULL_MASK, ok ? d : 0x1ffu, &pred);
+            if (pred) {                       // whole warp in one bin: one atomic
+              if (lane == 0 && ok) atomicAdd(&s_h[p * RS_BINS + d], 32u);
+            } else if (ok) {
+              atomicAdd(&s_h[p * RS_BINS + d], 1u);
+            }
+          }
         }
+      } else if (ok) {
+#pragma unroll
+        for (int p = 0; p < RS_MAXPASS; p++)
+          if (p < plan.npass)
+            atomicAdd(&s_h[p * RS_BINS + ((unsigned) (key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
       }
     }
   }
@@ -514,7 +526,7 @@ static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
   {
     u64 tiles = div_up(nsrc, RH_TILE);
     unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
-    rs_hist_kernel<Src><<<grid, RH_NT, 0, st>>>(src, nsrc, plan, w.ghist);
+    rs_hist_kernel<Src, Src::ALWAYS_VALID><<<grid, RH_NT, 0, st>>>(src, nsrc, plan, w.ghist);   // pairs in memory may be skewed
     GTB_LAUNCH_CHECK();
     rs_scan_kernel<<<plan.npass, RS_BINS, 0, st>>>(w.ghist, w.gbase);
     GTB_LAUNCH_CHECK();
