@@ -6,10 +6,13 @@ kernel (the onesweep radix pass) and the reference CPU path beside it.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--scale f]
   python bench.py --impl reference ...      # the unmodified reference on host cores
 
-A step = one complete pass of the hot path over the workload: bucket counting,
-fused key generation + 8 radix passes, group analysis, prefix doubling, lcp, special
+A step = one complete pass of the hot path over the workload: fused key generation +
+5-8 radix passes (key length chosen from the text length), group analysis + bucket table
+from the sorted keys, text-driven / prefix-doubling refinement of the ties, lcp, special
 tail -- results left in HBM (`value`), or through the host-buffer C-ABI including the
 H2D copy of the packed sequence and the D2H copy of .suf/.lcp/.llv/.bck (`e2e`).
+With N > 1 ranks (torchrun) the bucket codes are sharded: count allreduce (NCCL), the
+rank's own code range sorted, rank exchange (all-to-all) in the doubling rounds.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -42,7 +45,8 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("GTB_BENCH_SCALE", "1.0")))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="bases/residues of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=64_000_000,
+                    help="bases/residues of the CPU baseline sample (about 10-20 s of one host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -203,7 +207,7 @@ def main():
         return
     import torch
     from genometools_b200 import _lib, synthetic as sy
-    from genometools_b200._lib import GtbStats, GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, ptr
+    from genometools_b200._lib import GtbStats, GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS, ptr
     from genometools_b200.suffixerator import recommendedprefixlength
     from genometools_b200.sharding import suftab_parts
 
@@ -237,19 +241,10 @@ def main():
 
     upload()
     flags = GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK
-    # weak scaling: the sequence is replicated, the bucket codes are sharded over the ranks
-    shard = None
-    if world > 1:
-        ck(lib.gtb_esa_count(h, pl))
-        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a), C.byref(b), C.byref(c))
-        lb = np.empty(a.value + 1, dtype=np.uint32)
-        ck(lib.gtb_esa_copy_bcktab(h, ptr(lb), None, None))
-        parts = suftab_parts(lb, world)
-        if len(parts) != world:
-            raise SystemExit("could not cut the bucket table into one part per rank")
-        shard = parts[rank]
-        ck(lib.gtb_esa_set_code_range(h, shard[0], shard[1], shard[2], 1 if rank == world - 1 else 0))
+    # weak scaling: the sequence is replicated, the bucket codes are sharded over the ranks.
+    # Every step: count allreduce (each rank counts 1/world of the text), the same code ranges
+    # cut on every rank, then the lock-step sort of the rank's own range.
+    dev = torch.device("cuda", local_rank)
 
     def sync_all():
         if dist is not None:
@@ -257,16 +252,20 @@ def main():
         torch.cuda.synchronize()
 
     st = GtbStats()
-    worker, first_keys = None, None
+    worker = None
     if world > 1:
-        from genometools_b200.multirange import GpuRangeWorker, run_range_distributed, range_first_keys
-        worker = GpuRangeWorker(h, pl, flags, local_rank)
-        first_keys = range_first_keys(w.numofchars, pl, parts)
-    dev = torch.device("cuda", local_rank)
+        from genometools_b200.multirange import (GpuRangeWorker, run_range_distributed, range_first_keys,
+                                                 count_allreduce_and_split)
+        worker = GpuRangeWorker(h, pl, flags | GTB_REUSE_COUNTS, local_rank)
 
     def step():
         if world > 1:
-            run_range_distributed(worker, first_keys, dist, dev)
+            parts = count_allreduce_and_split(lib, h, w.numofchars, pl, n, dist, dev)
+            if len(parts) != world:
+                raise SystemExit("could not cut the bucket table into one part per rank")
+            mn, mx, off, _ = parts[rank]
+            ck(lib.gtb_esa_set_code_range(h, mn, mx, off, 1 if rank == world - 1 else 0))
+            run_range_distributed(worker, range_first_keys(w.numofchars, pl, parts), dist, dev)
         else:
             ck(lib.gtb_esa_run(h, pl, flags))
         ck(lib.gtb_esa_get_stats(h, C.byref(st)))
@@ -354,10 +353,7 @@ def main():
                                               ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
             else:
                 ck(lib.gtb_esa_set_input_bytes(h, ptr(ps), n, w.numofchars))
-            if world > 1:
-                run_range_distributed(worker, first_keys, dist, dev)
-            else:
-                ck(lib.gtb_esa_run(h, pl, flags))
+            step()
             e = lib.gtb_esa_num_entries(h)
             ck(lib.gtb_esa_copy_suftab_u64(h, ptr(suf), 0, e))
             ck(lib.gtb_esa_copy_lcptab(h, ptr(lcp), 0, e))

@@ -80,7 +80,7 @@ struct gtb_esa {
   u64 ncodes = 0, nspecialcodes = 0, ndist = 0;
   DevBuf leftborder, csc, dist, distoff;
   // sort state
-  DevBuf kbuf[2], vbuf[2], lcp8, tbits, tpre, trank, spre, tile_a, tile_b, tile_c, tile_d, scantmp, dstats, misc;
+  DevBuf kbuf[2], vbuf[2], lcp8, hbits, ubits, tbits, tpre, trank, spre, tile_a, tile_b, tile_c, tile_d, scantmp, dstats, misc;
   DevBuf uidx0, ugrp0, uidx[2], ugrp[2], upos[2], dkeys, kd[2], vd[2], ulcp, llvflags, llv;
   RadixWork rw;
   int res = 0;              // which vbuf holds the suffix table
@@ -99,6 +99,7 @@ struct gtb_esa {
   int opt_key_symbols = 0;  // test knobs (environment GTB200_KEY_SYMBOLS = 17|21|25|29,
   int opt_text_rounds = -1; // GTB200_TEXT_ROUNDS = 0..8): override the automatic choices
   unsigned text_left = 0;   // text-driven rounds still allowed before ranks are built
+  float ms_count_ext = 0;   // device time of gtb_esa_count_partial/_finish since the last run
   u64 depth[64];            // depth[r] = common prefix of the groups entering round r
   DevBuf ranks, owner, sendidx, rcounts;
   gtb_stats stats;
@@ -237,7 +238,7 @@ int build_mask(gtb_esa *h, const gtb_range *specials, u64 nranges)
 // all = true: the three tables by counting (one atomic per suffix), then the scan.
 // all = false: the tables are only zeroed; k_analyze_keys fills all three from the sorted
 // keys.
-int count_codes(gtb_esa *h, unsigned pl, bool all)
+int count_codes(gtb_esa *h, unsigned pl, bool all, u64 first = 0, u64 end = ~0ull, bool finish = true)
 {
   ErrBuf &err = h->err;
   if (h->counted && h->pl == pl) return 0;
@@ -255,18 +256,19 @@ int count_codes(gtb_esa *h, unsigned pl, bool all)
   GTB_CUDA(cudaMemsetAsync(h->csc.p, 0, sizeof(u32) * (h->nspecialcodes + 1), h->st));
   GTB_CUDA(cudaMemsetAsync(h->dist.p, 0, sizeof(u32) * (h->ndist + 1), h->st));
   GTB_CUDA(cudaMemcpyAsync(h->distoff.p, distoff, sizeof distoff, cudaMemcpyHostToDevice, h->st));
-  if (h->n > 0 && all) {
-    const unsigned grid = grid_for(h->n, 256, 148u * 8u);
+  if (end > h->n) end = h->n;
+  if (h->n > 0 && all && first < end) {
+    const unsigned grid = grid_for(end - first, 256, 148u * 8u);
     u32 *lb = h->leftborder.as<u32>(), *cs = h->csc.as<u32>(), *di = h->dist.as<u32>();
     const u64 *dof = h->distoff.as<u64>();
     if (h->dna)
-      k_count_codes<true, true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
+      k_count_codes<true, true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), first, end, pl, h->K, lb, cs, di, dof);
     else
-      k_count_codes<false, true><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), h->n, pl, h->K, lb, cs, di, dof);
+      k_count_codes<false, true><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), first, end, pl, h->K, lb, cs, di, dof);
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
   }
-  if (all) {
+  if (all && finish) {
     // counts -> bucket starts; entry ncodes becomes the number of non-special suffixes
     GTB_TRY(device_scan_u32(h, h->leftborder.as<u32>(), h->leftborder.as<u32>(), h->ncodes + 1, 0,
                             nullptr, nullptr));
@@ -372,13 +374,16 @@ int stage_begin(gtb_esa *h, unsigned flags)
     if (N > 0) {
       GTB_TRY(h->tile_a.ensure(sizeof(u32) * (h->atiles + 1), err));
       GTB_TRY(h->tile_b.ensure(sizeof(u32) * (h->atiles + 1), err));
+      GTB_TRY(h->hbits.ensure(N / 8 + 16, err));
+      GTB_TRY(h->ubits.ensure(N / 8 + 16, err));
       if (lb_from_keys)
         k_analyze_keys<DNA, true><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes,
-            h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>());
+            h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>(), h->hbits.as<u8>(), h->ubits.as<u8>());
       else
         k_analyze_keys<DNA, false><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
-            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0, nullptr, nullptr, nullptr);
+            h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0, nullptr, nullptr, nullptr,
+            h->hbits.as<u8>(), h->ubits.as<u8>());
       GTB_LAUNCH_CHECK();
       k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,
                                                h->misc.as<u64>());
@@ -453,9 +458,9 @@ int compact_ties(gtb_esa *h)
 {
   ErrBuf &err = h->err;
   if (h->N > 0) {
-    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, h->st>>>(h->kbuf[h->res].as<u64>(), h->vbuf[h->res].as<u32>(),
-        h->N, h->fmt, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->uidx[0].as<u32>(), h->upos[0].as<u32>(),
-        h->ugrp[0].as<u32>());
+    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, h->st>>>(h->hbits.as<u8>(), h->ubits.as<u8>(),
+        h->vbuf[h->res].as<u32>(), h->N, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->uidx[0].as<u32>(),
+        h->upos[0].as<u32>(), h->ugrp[0].as<u32>());
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
   }
@@ -472,6 +477,8 @@ RankMap<DNA> make_rankmap(gtb_esa *h)
   rm.N = h->N;
   rm.tbits = h->tbits.as<u32>(); rm.tpre = h->tpre.as<u32>(); rm.trank = h->trank.as<u32>();
   rm.spre = h->spre.as<u32>();
+  rm.leftborder = (h->counted && h->pl > 0) ? h->leftborder.as<u32>() : nullptr;
+  rm.pl = h->pl; rm.K = h->K;
   rm.n = h->n; rm.nonspecials = h->n - h->S; rm.sa_offset = h->sa_offset;
   return rm;
 }
@@ -758,6 +765,8 @@ static int check_run_args(gtb_esa *h, unsigned prefixlength, unsigned flags)
   const float up = h->stats.ms_upload;
   memset(&h->stats, 0, sizeof h->stats);
   h->stats.ms_upload = up;
+  if (flags & GTB_REUSE_COUNTS) { h->stats.ms_count = h->ms_count_ext; h->stats.ms_total = h->ms_count_ext; }
+  h->ms_count_ext = 0;
   if (h->pl != prefixlength || !(flags & GTB_REUSE_COUNTS)) h->counted = false;
   h->pl = prefixlength;
   h->ran = false;
@@ -848,7 +857,7 @@ void gtb_esa_delete(gtb_esa *h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->leftborder, &h->csc, &h->dist,
-                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->tbits, &h->tpre, &h->trank, &h->spre,
+                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->hbits, &h->ubits, &h->tbits, &h->tpre, &h->trank, &h->spre,
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
@@ -1033,6 +1042,76 @@ int gtb_esa_count(gtb_esa *h, unsigned prefixlength)
   h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
   GTB_TRY(count_codes(h, prefixlength, true));
   GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_count_partial(gtb_esa *h, unsigned prefixlength, uint64_t first_pos, uint64_t end_pos)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input) { err.set("gtb_esa_count_partial: no input set"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
+  h->counted = false;
+  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  cudaEvent_t e0, e1;
+  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
+  GTB_CUDA(cudaEventRecord(e0, h->st));
+  int rc = count_codes(h, prefixlength, true, first_pos, end_pos, false);
+  cudaEventRecord(e1, h->st);
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  h->ms_count_ext = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+
+int gtb_esa_count_finish(gtb_esa *h)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input || h->pl == 0 || h->ncodes == 0) { err.set("gtb_esa_count_finish without gtb_esa_count_partial"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  cudaEvent_t e0, e1;
+  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
+  GTB_CUDA(cudaEventRecord(e0, h->st));
+  int rc = device_scan_u32(h, h->leftborder.as<u32>(), h->leftborder.as<u32>(), h->ncodes + 1, 0, nullptr, nullptr);
+  cudaEventRecord(e1, h->st);
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  h->ms_count_ext += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc == 0) h->counted = true;
+  return rc;
+}
+
+int gtb_esa_dev_bcktab(const gtb_esa *h, uint32_t **leftborder, uint32_t **countspecialcodes, uint32_t **distpfxidx)
+{
+  if (!h || h->ncodes == 0) return -1;
+  if (leftborder) *leftborder = h->leftborder.as<u32>();
+  if (countspecialcodes) *countspecialcodes = h->csc.as<u32>();
+  if (distpfxidx) *distpfxidx = h->dist.as<u32>();
+  return 0;
+}
+
+int gtb_esa_split_ranges(gtb_esa *h, unsigned numofparts, uint64_t *out4, unsigned *nparts)
+{
+  if (!h || !out4 || !nparts) return -1;
+  ErrBuf &err = h->err;
+  if (!h->counted) { err.set("gtb_esa_split_ranges: no bucket table"); return -1; }
+  if (numofparts < 1 || numofparts > (unsigned) MAX_RANGES) { err.set("gtb_esa_split_ranges: 1..%d parts", MAX_RANGES); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  GTB_TRY(h->misc.ensure(sizeof(u64) * (4 * MAX_RANGES + 8), err));
+  unsigned long long *d = (unsigned long long *) h->misc.as<u64>();
+  unsigned *dn = (unsigned *) (d + 4 * MAX_RANGES);
+  k_split_ranges<<<1, 1, 0, h->st>>>(h->leftborder.as<u32>(), h->ncodes, numofparts, d, dn);
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches++;
+  unsigned np = 0;
+  GTB_CUDA(cudaMemcpyAsync(&np, dn, sizeof np, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaMemcpyAsync(out4, d, sizeof(u64) * 4 * numofparts, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  *nparts = np;
   return 0;
 }
 

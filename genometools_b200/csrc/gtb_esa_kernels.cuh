@@ -133,6 +133,9 @@ struct TextSrc {
 //                     key is unique, or shared only by suffixes that meet a special at
 //                     the same depth, which are stored in text order
 template <bool DNA>
+__device__ __forceinline__ u64 key_code(u64 key, unsigned pl, unsigned K, const KeyFmt &f);
+
+template <bool DNA>
 struct RankMap {
   TextSrc<DNA> src;
   const u64 *keys;           // first-level sorted keys of this range
@@ -141,6 +144,8 @@ struct RankMap {
   const u32 *tbits, *tpre;   // bitmap of the initially tied positions, popcount prefix
   u32 *trank;
   const u32 *spre;           // popcount prefix of the special mask (null if no specials)
+  const u32 *leftborder;     // bucket starts (global indices) or null: narrows the search
+  unsigned pl, K;
   u64 n, nonspecials, sa_offset;
 
   __device__ __forceinline__ bool tied(u64 p) const { return (tbits[p >> 5] >> (p & 31u)) & 1u; }
@@ -157,6 +162,11 @@ struct RankMap {
     u64 kq;
     src.make_key_fmt(q, kq, src.f);
     u64 lo = 0, hi = N;
+    if (leftborder) {          // the suffix lies in its bucket: a few dozen entries
+      const u64 c = key_code<DNA>(kq, pl, K, src.f);
+      lo = (u64) leftborder[c] - sa_offset;
+      hi = (u64) leftborder[c + 1] - sa_offset;
+    }
     while (lo < hi) {
       const u64 mid = (lo + hi) >> 1;
       const u64 km = keys[mid];
@@ -349,12 +359,13 @@ __device__ __forceinline__ u64 key_code(u64 key, unsigned pl, unsigned K, const 
 // from the sorted keys by k_analyze_keys -- no atomic per suffix)
 template <bool DNA, bool COUNT_ALL>
 __global__ void __launch_bounds__(256)
-k_count_codes(TextSrc<DNA> src, u64 n, unsigned pl, unsigned K,
+k_count_codes(TextSrc<DNA> src, u64 first, u64 n, unsigned pl, unsigned K,
               u32 *__restrict__ cnt, u32 *__restrict__ csc, u32 *__restrict__ dist,
               const u64 *__restrict__ distoff /* [pl] offsets of level u (u>=1) */)
 {
+  // positions [first, n)
   const KeyFmt f = src.f;
-  for (u64 pos = blockIdx.x * (u64) blockDim.x + threadIdx.x; ; pos += (u64) gridDim.x * blockDim.x) {
+  for (u64 pos = first + blockIdx.x * (u64) blockDim.x + threadIdx.x; ; pos += (u64) gridDim.x * blockDim.x) {
     const bool inb = pos < n;
     u64 key = 0;
     bool ok = false;
@@ -451,7 +462,7 @@ struct AnalyzeArgs {
 template <bool DNA, bool FILL_LB, bool INNER>
 __device__ __forceinline__ void
 analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &unres, u32 &lasthead,
-               u64 &lcpword, u32 &mx, unsigned long long &sum)
+               u64 &lcpword, u32 &mx, unsigned long long &sum, u32 &headbits, u32 &unresbits)
 {
   const KeyFmt f = a.f;
   const u64 N = a.N;
@@ -495,7 +506,8 @@ analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &
     if (FILL_LB && !INNER && j + 1 == N) {
       for (u64 c0 = key_code<DNA>(k[i + 1], a.pl, a.K, f) + 1; c0 <= a.ncodes; c0++) a.leftborder[c0] = (u32) N;
     }
-    if (!head || !nexthead) unres++;
+    if (head) headbits |= 1u << i;
+    if (!head || !nexthead) { unres++; unresbits |= 1u << i; }
   }
 }
 
@@ -509,9 +521,10 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
                u8 *__restrict__ lcp8, u32 *__restrict__ tile_unres,
                u32 *__restrict__ tile_lasthead, DevStats *stats, int seam_prev_valid,
                u64 seam_prev_key, u32 *__restrict__ leftborder, u64 ncodes,
-               u32 *__restrict__ csc, u32 *__restrict__ dist, const u64 *__restrict__ distoff)
+               u32 *__restrict__ csc, u32 *__restrict__ dist, const u64 *__restrict__ distoff,
+               u8 *__restrict__ hbits, u8 *__restrict__ ubits /* one byte per thread: bit i = element i */)
 {
-  static_assert(AN_IPT == 8, "one 8-byte lcp store per thread");
+  static_assert(AN_IPT == 8, "one 8-byte lcp store and one flag byte per thread");
   __shared__ u32 scratch[AN_NT / 32 + 1];
   __shared__ u32 s_max[AN_NT / 32];
   __shared__ unsigned long long s_sum[AN_NT / 32];
@@ -529,10 +542,12 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
     u32 unres = 0, lasthead = 0;
     u64 lcpword = 0;
     const AnalyzeArgs a{N, f, tmask, pl, K, seam_prev_valid, seam_prev_key, leftborder, ncodes, csc, dist, distoff};
+    u32 headbits = 0, unresbits = 0;
     if (tile > 0 && (tile + 1) * AN_TILE < N)      // inner tile: no bounds to check
-      analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum);
+      analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
     else
-      analyze_thread<DNA, FILL_LB, false>(k, base, a, unres, lasthead, lcpword, mx, sum);
+      analyze_thread<DNA, FILL_LB, false>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
+    if (base < N) { hbits[base >> 3] = (u8) headbits; ubits[base >> 3] = (u8) unresbits; }
     if (base + AN_IPT <= N) {
       *reinterpret_cast<u64 *>(lcp8 + base) = lcpword;
     } else {
@@ -597,34 +612,21 @@ k_scan_tiles_sum_max(u32 *tile_unres, u32 *tile_lasthead, u64 ntiles, u64 *total
   if (threadIdx.x == 0 && total_out) *total_out = grand;
 }
 
-// pass 2: compact the unresolved elements (SA index, position, group head)
+// pass 2: compact the unresolved elements (SA index, position, group head) from the flag
+// bytes of pass 1 -- the keys are not read again
 __global__ void __launch_bounds__(AN_NT)
-k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N, KeyFmt f,
+k_compact_keys(const u8 *__restrict__ hbits, const u8 *__restrict__ ubits, const u32 *__restrict__ pos, u64 N,
                const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
                u32 *__restrict__ uidx, u32 *__restrict__ upos, u32 *__restrict__ ugrp)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
-  __shared__ u64 s_k[AN_SMEM_KEYS];
-  const u64 tmask = f.tailmask();
   const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
-  u64 k[AN_IPT + 2];
-  load_keys_blocked(keys, N, blockIdx.x, s_k, k);
-  bool head[AN_IPT + 1];
-  u32 unres = 0, lasthead = 0;
-#pragma unroll
-  for (int i = 0; i < AN_IPT + 1; i++) {
-    const u64 j = base + i;
-    head[i] = j == 0 || j >= N || key_head(k[i], k[i + 1], tmask);
-  }
-#pragma unroll
-  for (int i = 0; i < AN_IPT; i++) {
-    const u64 j = base + i;
-    if (j >= N) break;
-    if (head[i]) lasthead = (u32) j + 1u;
-    if (!head[i] || !head[i + 1]) unres++;
-  }
+  const u32 hb8 = base < N ? hbits[base >> 3] : 0u, ub8 = base < N ? ubits[base >> 3] : 0u;
+  const u32 unres = (u32) __popc(ub8);
+  const u32 lasthead = hb8 ? (u32) base + (31u - (u32) __clz(hb8)) + 1u : 0u;
   u32 total;
   u32 off = block_exclusive_sum<AN_NT, u32>(unres, scratch, &total) + tile_off[blockIdx.x];
+  if (total == 0) return;                         // (uniform) nothing tied in this tile
   // head index carried into this thread = max over previous threads / tiles
   u32 incl = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
   u32 carry = __shfl_up_sync(FULL_MASK, incl, 1);
@@ -634,13 +636,12 @@ k_compact_keys(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N,
   if (lane_id() == 0) carry = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
   const u32 hb = tile_headbefore[blockIdx.x];
   carry = carry > hb ? carry : hb;          // "+1" encoded index of the current group head
+  if (!ub8) return;
 #pragma unroll
   for (int i = 0; i < AN_IPT; i++) {
     const u64 j = base + i;
-    if (j >= N) break;
-    if (head[i]) carry = (u32) j + 1u;
-    const u32 g = carry - 1u;
-    if (!head[i] || !head[i + 1]) { uidx[off] = (u32) j; upos[off] = pos[j]; ugrp[off] = g; off++; }
+    if ((hb8 >> i) & 1u) carry = (u32) j + 1u;
+    if ((ub8 >> i) & 1u) { uidx[off] = (u32) j; upos[off] = pos[j]; ugrp[off] = carry - 1u; off++; }
   }
 }
 
@@ -946,6 +947,47 @@ __global__ void k_find_longest(TextSrc<DNA> src, const u64 *__restrict__ keys, u
   u64 lo = 0, hi = N;
   while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (keys[mid] < key0) lo = mid + 1; else hi = mid; }
   if (lo < N && keys[lo] == key0) stats->longest = sa_offset + lo;
+}
+
+// gt_suftabparts_new (sfx-partssuf.c:172-347) on the bucket table in HBM: part p ends at
+// the first code whose right border reaches the running target (gt_bcktab_findfirstlarger,
+// bcktab.c:1322-1381).  out[4*p..] = mincode, maxcode, sa_offset, width; *nout = parts.
+__global__ void k_split_ranges(const u32 *__restrict__ lb, u64 ncodes, unsigned numofparts,
+                               unsigned long long *__restrict__ out, unsigned *__restrict__ nout)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const u64 total = lb[ncodes];
+  unsigned np = 0;
+  if (numofparts <= 1 || total <= numofparts || ncodes == 1) {
+    out[0] = 0; out[1] = ncodes - 1; out[2] = 0; out[3] = total; *nout = 1; return;
+  }
+  const u64 width = total / numofparts, rem = total % numofparts;
+  u64 mincode = 0, target = 0;
+  for (unsigned part = 0; part < numofparts && mincode < ncodes; part++) {
+    target += width + (part < rem ? 1 : 0);
+    u64 maxcode;
+    if (part == numofparts - 1) maxcode = ncodes - 1;
+    else {
+      u64 lo = 0, hi = ncodes;                 // first c with lb[c+1] >= target
+      while (lo < hi) { const u64 mid = (lo + hi) >> 1; if ((u64) lb[mid + 1] < target) lo = mid + 1; else hi = mid; }
+      maxcode = lo < mincode ? mincode : lo;
+      if (maxcode > ncodes - 1) maxcode = ncodes - 1;
+    }
+    const u64 w = (u64) lb[maxcode + 1] - (u64) lb[mincode];
+    if (w > 0 || part == numofparts - 1) {
+      out[4 * np] = mincode; out[4 * np + 1] = maxcode; out[4 * np + 2] = lb[mincode]; out[4 * np + 3] = w; np++;
+    }
+    mincode = maxcode + 1;
+  }
+  if (np > 0 && out[4 * (np - 1) + 1] != ncodes - 1) {   // the last part reaches the last code
+    out[4 * (np - 1) + 1] = ncodes - 1;
+    out[4 * (np - 1) + 3] = (u64) lb[ncodes] - (u64) lb[out[4 * (np - 1)]];
+  }
+  unsigned keep = 0;                                      // drop empty parts
+  for (unsigned p = 0; p < np; p++)
+    if (out[4 * p + 3] > 0) { for (int q = 0; q < 4; q++) out[4 * keep + q] = out[4 * p + q]; keep++; }
+  if (keep == 0) { out[0] = 0; out[1] = ncodes - 1; out[2] = 0; out[3] = total; keep = 1; }
+  *nout = keep;
 }
 
 __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)

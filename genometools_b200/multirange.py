@@ -113,6 +113,46 @@ def range_first_keys(numofchars, prefixlength, parts):
     return np.array([lib.gtb_code_first_key(numofchars, prefixlength, p[0]) for p in parts], dtype=np.uint64)
 
 
+class DeviceArray:
+    """a device pointer of the library seen as a CUDA array (torch.as_tensor accepts it)"""
+
+    def __init__(self, p, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (p, False), "version": 2}
+
+
+def count_allreduce_and_split(lib, handle, numofchars, prefixlength, totallength, dist, device):
+    """the bucket table of a text replicated on every rank: rank r counts the k-mers of its
+    1/world slice of the text positions, one all-reduce (NCCL over NVLink) per table sums the
+    raw counts in place, every rank finishes with the same partial sums and cuts the same
+    `world` code ranges (gt_suftabparts_new).  Returns [(mincode, maxcode, sa_offset, width)]."""
+    import torch
+    world, me = dist.get_world_size(), dist.get_rank()
+
+    def ck(rc):
+        if rc != 0:
+            raise GtbError(lib.gtb_esa_error(handle).decode())
+
+    lo, hi = totallength * me // world, totallength * (me + 1) // world
+    ck(lib.gtb_esa_count_partial(handle, prefixlength, lo, hi))
+    nall, nspecial, ndist = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.gtb_bck_sizes(numofchars, prefixlength, C.byref(nall), C.byref(nspecial), C.byref(ndist))
+    plb, pcs, pdi = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ck(lib.gtb_esa_dev_bcktab(handle, C.byref(plb), C.byref(pcs), C.byref(pdi)))
+    for p, cnt in ((plb, nall.value + 1), (pcs, nspecial.value), (pdi, ndist.value)):
+        if cnt and p.value:
+            # uint32 counters summed as int32: the same bits
+            t = torch.as_tensor(DeviceArray(p.value, cnt, "<i4"), device=device)
+            dist.all_reduce(t)
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    ck(lib.gtb_esa_count_finish(handle))
+    out = (C.c_uint64 * (4 * world))()
+    npart = C.c_uint()
+    ck(lib.gtb_esa_split_ranges(handle, world, out, C.byref(npart)))
+    return [(int(out[4 * p]), int(out[4 * p + 1]), int(out[4 * p + 2]), int(out[4 * p + 3]))
+            for p in range(npart.value)]
+
+
 # ---------------------------------------------------------------- all ranges in one process
 def run_ranges_local(workers, first_keys, want_lcp=True):
     """lock-step over ranges that live in this process (same GPU): positions and ranks

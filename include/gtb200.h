@@ -161,6 +161,23 @@ uint64_t gtb_code_first_key(unsigned numofchars, unsigned prefixlength, uint64_t
    (gt_suftabparts_new) before sorting. */
 int gtb_esa_count(gtb_esa *h, unsigned prefixlength);
 
+/* The same, split for several GPUs (north_star: "NCCL ... used only for the count
+   allreduce and the result gather"): every device counts the k-mers of the text positions
+   [first_pos, end_pos) only and leaves RAW counts in its three tables; the caller sums the
+   tables of all devices in place (ncclAllReduce on the pointers of gtb_esa_dev_bcktab;
+   uint32 sums, sizes from gtb_bck_sizes, leftborder has nall+1 entries) and then calls
+   gtb_esa_count_finish (gt_bcktab_leftborderpartialsums, bcktab.c:1274-1304) on each. */
+int gtb_esa_count_partial(gtb_esa *h, unsigned prefixlength, uint64_t first_pos, uint64_t end_pos);
+int gtb_esa_count_finish(gtb_esa *h);
+int gtb_esa_dev_bcktab(const gtb_esa *h, uint32_t **leftborder, uint32_t **countspecialcodes,
+                       uint32_t **distpfxidx);
+
+/* gt_suftabparts_new (sfx-partssuf.c:172-347) on the bucket table in HBM: cut the codes
+   into at most `numofparts` (<= 64) contiguous ranges of about equal suffix counts.
+   out4[4*p .. 4*p+3] = mincode, maxcode, sa_offset, width of part p; *nparts = parts made
+   (empty ones are dropped). out4 must hold 4*numofparts entries. */
+int gtb_esa_split_ranges(gtb_esa *h, unsigned numofparts, uint64_t *out4, unsigned *nparts);
+
 int gtb_esa_get_stats(const gtb_esa *h, gtb_stats *st);
 
 /* filled keys of the first / last sorted suffix of this handle's code range, and

@@ -236,3 +236,55 @@ def test_cuda_protein_key_lengths(monkeypatch, m, text_rounds):
     for pl in (1, 2):
         res = build_esa(encode_symbols(sym, 20), pl)
         check_against_oracle(sym, 20, pl, res, f"protein m={m} text_rounds={text_rounds} pl={pl}")
+
+
+def test_cuda_partial_counts_and_range_split():
+    """count allreduce building blocks: the raw counts of two halves of the text add up to the
+    bucket table of the whole, and the device-side range split equals the host mirror of
+    gt_suftabparts_new"""
+    import ctypes as C
+    import torch
+    from genometools_b200.multirange import DeviceArray
+    from genometools_b200.sharding import suftab_parts
+    lib = _lib.load()
+    sym = synth.reads(400, 70, 9, p_n=0.02)
+    enc = encode_symbols(sym, 4)
+    n, pl = enc.totallength, 5
+    words, ranges = enc.twobitencoding()
+    buf = C.create_string_buffer(512)
+    hs = [lib.gtb_esa_new(0, buf, 512) for _ in range(3)]
+    for h in hs:
+        assert lib.gtb_esa_set_input_2bit(h, _lib.ptr(words), words.shape[0], n, _lib.ptr(ranges) if ranges.shape[0] else None,
+                                          ranges.shape[0]) == 0
+    nall, nsp, nd = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.gtb_bck_sizes(4, pl, C.byref(nall), C.byref(nsp), C.byref(nd))
+    sizes = (nall.value + 1, nsp.value, nd.value)
+
+    def tables(h):
+        p = [C.c_void_p() for _ in range(3)]
+        assert lib.gtb_esa_dev_bcktab(h, *[C.byref(x) for x in p]) == 0
+        return [torch.as_tensor(DeviceArray(x.value, c, "<i4"), device="cuda") for x, c in zip(p, sizes)]
+
+    cut = n // 3
+    assert lib.gtb_esa_count_partial(hs[0], pl, 0, cut) == 0
+    assert lib.gtb_esa_count_partial(hs[1], pl, cut, n) == 0
+    for a, b in zip(tables(hs[0]), tables(hs[1])):
+        a += b                                       # what the all-reduce does
+    torch.cuda.synchronize()
+    assert lib.gtb_esa_count_finish(hs[0]) == 0
+    assert lib.gtb_esa_count(hs[2], pl) == 0
+    got, ref = [], []
+    for h, dst in ((hs[0], got), (hs[2], ref)):
+        lb = np.empty(sizes[0], np.uint32); cs = np.empty(sizes[1], np.uint32); di = np.empty(max(sizes[2], 1), np.uint32)
+        assert lib.gtb_esa_copy_bcktab(h, _lib.ptr(lb), _lib.ptr(cs), _lib.ptr(di)) == 0
+        dst.extend([lb, cs, di[:sizes[2]]])
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    for parts in (1, 2, 3, 5, 8, 64):
+        out = (C.c_uint64 * (4 * parts))()
+        k = C.c_uint()
+        assert lib.gtb_esa_split_ranges(hs[0], parts, out, C.byref(k)) == 0
+        mine = [tuple(int(out[4 * p + q]) for q in range(4)) for p in range(k.value)]
+        assert mine == suftab_parts(ref[0], parts), parts
+    for h in hs:
+        lib.gtb_esa_delete(h)

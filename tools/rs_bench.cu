@@ -12,7 +12,9 @@
 #include <string>
 #include <algorithm>
 
+#ifndef RSB_NOPROFILE
 #define GTB_RS_PROFILE 1
+#endif
 #include "../genometools_b200/csrc/gtb_common.cuh"
 #include "../genometools_b200/csrc/gtb_radix.cuh"
 
@@ -94,6 +96,7 @@ static Result run_cfg(const char *name, const std::vector<u64> &hk, int reps, bo
     R.ok = bad == 0;
   }
   R.ms_pass = best; R.gbs = 24.0 * N / (best * 1e-3) / 1e9;
+#ifdef GTB_RS_PROFILE
   {
     unsigned long long ph[8];
     cudaMemcpyFromSymbol(ph, g_rs_phase, sizeof ph);
@@ -103,6 +106,7 @@ static Result run_cfg(const char *name, const std::vector<u64> &hk, int reps, bo
     memset(ph, 0, sizeof ph);
     cudaMemcpyToSymbol(g_rs_phase, ph, sizeof ph);
   }
+#endif
   cudaFree(kin); cudaFree(vin);
   for (int i = 0; i < 2; i++) { cudaFree(kb[i]); cudaFree(vb[i]); }
   radix_work_free(rw);
@@ -133,18 +137,18 @@ int main(int argc, char **argv)
       //  NT IPT MINB VAL_EARLY LB
       RUN(256, 16, 3, false, 0);     // no look-back: wrong result, upper bound of the rest
       RUN(256, 16, 3, false, 1);
+      RUN(256, 16, 3, false, 2);
       RUN(256, 16, 3, false, 4);
       RUN(256, 16, 3, false, 8);
-      RUN(256, 16, 3, false, 16);
-      RUN(256, 16, 3, true, 8);
-      RUN(256, 12, 4, false, 8);
-      RUN(384, 12, 3, false, 8);
-      RUN(384, 16, 2, false, 8);
-      RUN(512, 12, 2, false, 8);
-      RUN(512, 16, 1, false, 8);
+      RUN(256, 16, 3, true, 4);
+      RUN(256, 12, 4, false, 4);
+      RUN(384, 12, 3, false, 4);
+      RUN(384, 16, 2, false, 4);
+      RUN(512, 12, 2, false, 4);
+      RUN(512, 16, 1, false, 4);
     } else {
-      RUN(256, 16, 3, false, 8);
-      RUN(384, 16, 2, false, 8);
+      RUN(256, 16, 3, false, 4);
+      RUN(384, 16, 2, false, 4);
     }
   }
   printf("failures: %d\n", failures);
