@@ -312,11 +312,11 @@ def main():
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (radix_ms / 1e3) / 1e9 if radix_ms > 0 else 0.0
-    traffic = None
+    traffic = None          # DRAM bytes per launch: ncu's bytes per pair (profiles/) x pairs per launch here
     tpath = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and radix_passes:
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = float(json.load(open(tpath))["dram_bytes_per_pair"]) * pairs / radix_passes
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel (one 8-bit LSD pass over (key64,pos32) pairs)",

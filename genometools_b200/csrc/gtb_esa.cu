@@ -68,7 +68,8 @@ struct gtb_esa {
   bool have_input = false, dna = true;
   u64 n = 0, S = 0;
   unsigned K = 4;
-  DevBuf words, bytes, spmask, ranges;
+  DevBuf words, bytes, spmask, ranges, sepbits, seppos;
+  bool have_sep = false;
   u64 nmaskwords = 0;
   // code range (shard)
   bool full_range = true;
@@ -856,7 +857,7 @@ void gtb_esa_delete(gtb_esa *h)
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
-  DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->leftborder, &h->csc, &h->dist,
+  DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->sepbits, &h->seppos, &h->leftborder, &h->csc, &h->dist,
                    &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->hbits, &h->ubits, &h->tbits, &h->tpre, &h->trank, &h->spre,
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
@@ -879,7 +880,7 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
   if (n + 1 >= 0xffffffffull) { err.set("totallength %llu needs 64-bit suffix tables: not supported by this build (u32 positions)", (unsigned long long) n); return -1; }
   if (nwords < (n + 31) / 32) { err.set("twobitencoding too short: %llu words for %llu bases", (unsigned long long) nwords, (unsigned long long) n); return -1; }
   PhaseTimer t(h, &h->stats.ms_upload);
-  h->dna = true; h->K = 4; h->n = n; h->counted = false; h->ran = false;
+  h->dna = true; h->K = 4; h->n = n; h->counted = false; h->ran = false; h->have_sep = false;
   const u64 need = (n >> 5) + 4;
   GTB_TRY(h->words.ensure(sizeof(u64) * need, err));
   GTB_CUDA(cudaMemsetAsync(h->words.p, 0, sizeof(u64) * need, h->st));
@@ -925,6 +926,7 @@ int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src)
   if (h->device != src->device) { h->err.set("gtb_esa_share_input: handles live on different devices"); return -1; }
   h->dna = src->dna; h->K = src->K; h->n = src->n; h->S = src->S; h->nmaskwords = src->nmaskwords;
   h->words.borrow(src->words); h->bytes.borrow(src->bytes); h->spmask.borrow(src->spmask);
+  h->sepbits.borrow(src->sepbits); h->have_sep = src->have_sep;
   h->counted = false; h->ran = false; h->have_input = true;
   return 0;
 }
@@ -1209,6 +1211,55 @@ int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count
   GTB_CUDA(cudaSetDevice(h->device));
   if (count) GTB_CUDA(cudaMemcpyAsync(dst, h->lcp8.as<u8>() + first, count, cudaMemcpyDeviceToHost, h->st));
   GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_set_separators(gtb_esa *h, const uint64_t *positions, uint64_t count)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input || !h->dna) { err.set("gtb_esa_set_separators: needs a 2-bit input (the byte path carries its separators)"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  for (u64 i = 0; i < count; i++)
+    if (positions[i] >= h->n || (i > 0 && positions[i] <= positions[i - 1])) {
+      err.set("separator %llu at %llu is unordered or beyond the text", (unsigned long long) i, (unsigned long long) positions[i]);
+      return -1;
+    }
+  const u64 nw = (h->n >> 5) + 2;
+  GTB_TRY(h->sepbits.ensure(sizeof(u32) * nw, err));
+  GTB_CUDA(cudaMemsetAsync(h->sepbits.p, 0, sizeof(u32) * nw, h->st));
+  if (count > 0) {
+    GTB_TRY(h->seppos.ensure(sizeof(u64) * count, err));
+    GTB_CUDA(cudaMemcpyAsync(h->seppos.p, positions, sizeof(u64) * count, cudaMemcpyHostToDevice, h->st));
+    k_set_bits<<<grid_for(count, 256), 256, 0, h->st>>>(h->seppos.as<u64>(), count, h->sepbits.as<u32>());
+    GTB_LAUNCH_CHECK();
+  }
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  h->have_sep = true;
+  return 0;
+}
+
+int gtb_esa_copy_bwttab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count)
+{
+  GTB_TRY(check_range(h, first, count));
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (count == 0) return 0;
+  // staged in the (dead) key buffer, copied in chunks
+  const u64 chunk = 1ull << 28;
+  GTB_TRY(h->kbuf[h->res ^ 1].ensure(chunk < count ? chunk : count, err));
+  u8 *stage = h->kbuf[h->res ^ 1].as<u8>();
+  for (u64 off = 0; off < count; off += chunk) {
+    const u64 c = count - off < chunk ? count - off : chunk;
+    const u32 *sa = h->vbuf[h->res].as<u32>() + first + off;
+    const u32 *sep = h->have_sep ? h->sepbits.as<u32>() : nullptr;
+    if (h->dna) k_bwt<true><<<grid_for(c, 256), 256, 0, h->st>>>(sa, c, h->words.as<u64>(), h->bytes.as<u8>(), h->spmask.as<u32>(), sep, stage);
+    else k_bwt<false><<<grid_for(c, 256), 256, 0, h->st>>>(sa, c, h->words.as<u64>(), h->bytes.as<u8>(), h->spmask.as<u32>(), sep, stage);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+    GTB_CUDA(cudaMemcpyAsync(dst + off, stage, c, cudaMemcpyDeviceToHost, h->st));
+    GTB_CUDA(cudaStreamSynchronize(h->st));
+  }
   return 0;
 }
 

@@ -990,6 +990,33 @@ __global__ void k_split_ranges(const u32 *__restrict__ lb, u64 ncodes, unsigned 
   *nout = keep;
 }
 
+// ---- bwttab (bwttab2file, /root/reference/src/match/sfx-run.c:173-210) -------------------
+// bwt[j] = encoded symbol before suffix suf[j] (0..K-1, 254 wildcard, 255 separator);
+// UNDEFBWTCHAR (= 254, chardef.h:65) for the suffix that starts at 0
+__global__ void k_set_bits(const u64 *__restrict__ positions, u64 count, u32 *__restrict__ bits)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)
+    atomicOr(&bits[positions[i] >> 5], 1u << (positions[i] & 31u));
+}
+
+template <bool DNA>
+__global__ void k_bwt(const u32 *__restrict__ sa, u64 count, const u64 *__restrict__ words,
+                      const u8 *__restrict__ bytes, const u32 *__restrict__ spmask,
+                      const u32 *__restrict__ sepbits, u8 *__restrict__ out)
+{
+  for (u64 j = blockIdx.x * (u64) blockDim.x + threadIdx.x; j < count; j += (u64) gridDim.x * blockDim.x) {
+    const u64 p = sa[j];
+    u8 c = 254;
+    if (p > 0) {
+      const u64 q = p - 1;
+      if (!DNA) c = bytes[q];
+      else if ((spmask[q >> 5] >> (q & 31u)) & 1u) c = (sepbits && ((sepbits[q >> 5] >> (q & 31u)) & 1u)) ? 255 : 254;
+      else c = (u8) ((words[q >> 5] >> (62u - 2u * (unsigned) (q & 31u))) & 3u);
+    }
+    out[j] = c;
+  }
+}
+
 __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)
 {
   for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)

@@ -93,12 +93,13 @@ class SuffixeratorOptions:
     suf: bool = False
     lcp: bool = False
     bck: bool = False
+    bwt: bool = False
     pl: int = None            # None: option absent; 0: "-pl" without argument (automatic)
     parts: int = 1
     device: int = 0
     verbose: bool = False
 
-    UNSUPPORTED = ("-dir", "-mirrored", "-dc", "-spmopt", "-bwt", "-sortmaxdepth", "-suftabuint",
+    UNSUPPORTED = ("-dir", "-mirrored", "-dc", "-spmopt", "-sortmaxdepth", "-suftabuint",
                    "-compressedoutput", "-genomediff", "-lcpdist", "-memlimit", "-algbds",
                    "-cmpcharbychar", "-maxdepth", "-ii", "-smap", "-sat", "-kys", "-dccheck",
                    "-samplewithprefixlengthnull", "-storespecialcodes", "-showprogress")
@@ -108,7 +109,7 @@ class SuffixeratorOptions:
         o = cls()
         i = 0
         flags = {"-dna": "dna", "-protein": "protein", "-suf": "suf", "-lcp": "lcp", "-bck": "bck",
-                 "-v": "verbose"}
+                 "-bwt": "bwt", "-v": "verbose"}
         ignorable_yes = ("-tis", "-des", "-sds", "-ssp", "-md5")   # written by the encoder, not this path
         while i < len(argv):
             a = argv[i]
@@ -171,6 +172,7 @@ class EsaResult:
     suftab: np.ndarray = None        # uint64[n+1]
     lcptab: np.ndarray = None        # uint8[n+1]
     llvtab: np.ndarray = None        # uint64[k,2]
+    bwttab: np.ndarray = None        # uint8[n+1] (option -bwt)
     leftborder: np.ndarray = None    # uint32
     countspecialcodes: np.ndarray = None
     distpfxidx: np.ndarray = None
@@ -190,6 +192,9 @@ class EsaResult:
 
     def lcp_bytes(self):
         return self.lcptab.tobytes()
+
+    def bwt_bytes(self):
+        return self.bwttab.tobytes()
 
     def llv_bytes(self):
         return self.llvtab.astype("<u8", copy=False).tobytes()
@@ -260,6 +265,8 @@ class Suffixerator:
             self._keep = (words, ranges)
             self._ck(self.lib.gtb_esa_set_input_2bit(self.h, ptr(words), words.shape[0], enc.totallength,
                                                      ptr(ranges) if ranges.shape[0] else None, ranges.shape[0]))
+            sep = np.ascontiguousarray(np.flatnonzero(enc.symbols == 255), dtype=np.uint64)
+            self._ck(self.lib.gtb_esa_set_separators(self.h, ptr(sep) if sep.shape[0] else None, sep.shape[0]))
         else:
             self._keep = enc.symbols
             self._ck(self.lib.gtb_esa_set_input_bytes(self.h, ptr(enc.symbols), enc.totallength, enc.numofchars))
@@ -283,9 +290,13 @@ class Suffixerator:
         return lb, csc, dist
 
     # ---- the sort ----
-    def _collect(self, h, res_lists, want_suf, want_lcp):
-        suf_parts, lcp_parts, llv_parts = res_lists
+    def _collect(self, h, res_lists, want_suf, want_lcp, want_bwt=False):
+        suf_parts, lcp_parts, llv_parts = res_lists[:3]
         e = self.lib.gtb_esa_num_entries(h)
+        if want_bwt:
+            a = np.empty(e, dtype=np.uint8)
+            self._ckh(h, self.lib.gtb_esa_copy_bwttab(h, ptr(a), 0, e))
+            res_lists[3].append(a)
         if want_suf:
             a = np.empty(e, dtype=np.uint64)
             self._ckh(h, self.lib.gtb_esa_copy_suftab_u64(h, ptr(a), 0, e))
@@ -309,7 +320,7 @@ class Suffixerator:
         self._ckh(h, self.lib.gtb_esa_get_stats(h, C.byref(st)))
         return st.as_dict()
 
-    def run(self, prefixlength, want_suf=True, want_lcp=True, want_bck=True, parts=1, copy=True):
+    def run(self, prefixlength, want_suf=True, want_lcp=True, want_bck=True, parts=1, copy=True, want_bwt=False):
         """gt_Sfxiterator_next over all parts.  parts > 1 (option -parts) cuts the bucket
         codes into ranges (gt_suftabparts_new) that are sorted as independent problems --
         the same code path that puts one range on each GPU -- and concatenated."""
@@ -322,7 +333,7 @@ class Suffixerator:
         if parts > 1 and prefixlength >= 1:
             lb, _, _ = self.bucket_table(prefixlength)
             plist = suftab_parts(lb, parts)
-        lists = ([], [], [])
+        lists = ([], [], [], [])
         if len(plist) <= 1:
             self._ck(self.lib.gtb_esa_run(self.h, prefixlength, flags))
             handles = [self.h]
@@ -357,7 +368,7 @@ class Suffixerator:
                 if st["longest"] != 0xFFFFFFFFFFFFFFFF:
                     longest = st["longest"]
                 if copy:
-                    self._collect(h, lists, want_suf, want_lcp)
+                    self._collect(h, lists, want_suf, want_lcp, want_bwt)
             if want_bck and prefixlength >= 1:
                 hb = handles[0]
                 a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -369,7 +380,9 @@ class Suffixerator:
         finally:
             for h in extra:
                 self.lib.gtb_esa_delete(h)
-        suf_parts, lcp_parts, llv_parts = lists
+        suf_parts, lcp_parts, llv_parts, bwt_parts = lists
+        if copy and want_bwt:
+            res.bwttab = np.concatenate(bwt_parts) if len(bwt_parts) > 1 else bwt_parts[0]
         if copy:
             if want_suf:
                 res.suftab = np.concatenate(suf_parts) if len(suf_parts) > 1 else suf_parts[0]
@@ -382,7 +395,7 @@ class Suffixerator:
 
 
 def build_esa(enc: EncodedSequence, prefixlength=None, device=0, parts=1, want_suf=True, want_lcp=True,
-              want_bck=True, filler=None):
+              want_bck=True, filler=None, want_bwt=False):
     """One call: encoded sequence -> EsaResult (the public entry the benchmarks time end to end)."""
     if prefixlength is None or prefixlength == 0:
         prefixlength = recommendedprefixlength(enc.numofchars, enc.totallength)
@@ -393,7 +406,7 @@ def build_esa(enc: EncodedSequence, prefixlength=None, device=0, parts=1, want_s
                            f"size and alphabet size is {maxpl}")          # gt_checkprefixlength, sfx-apfxlen.c:149
     with Suffixerator(device) as sfx:
         sfx.set_sequence(enc, filler)
-        return sfx.run(prefixlength, want_suf, want_lcp, want_bck, parts)
+        return sfx.run(prefixlength, want_suf, want_lcp, want_bck, parts, want_bwt=want_bwt)
 
 
 def suffixerator_main(argv, out=sys.stdout):
@@ -405,7 +418,11 @@ def suffixerator_main(argv, out=sys.stdout):
             raise GtbError("one of the options -dna or -protein is required (alphabet guessing is not on this path)")
         enc = encode_fasta(o.db, alphabet)
         pl = o.pl
-        res = build_esa(enc, pl if pl else None, o.device, o.parts, o.suf, o.lcp, o.bck or pl is not None)
+        res = build_esa(enc, pl if pl else None, o.device, o.parts, o.suf, o.lcp, o.bck or pl is not None,
+                        want_bwt=o.bwt)
+        if o.bwt:
+            with open(o.indexname + ".bwt", "wb") as fh:
+                fh.write(res.bwt_bytes())
         if o.suf:
             with open(o.indexname + ".suf", "wb") as fh:
                 fh.write(res.suf_bytes())

@@ -50,7 +50,6 @@ static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
 
   if (so->inputindex != NULL && gt_str_length(so->inputindex) > 0) what = "-ii";
   else if (gt_index_options_readmode_value(so->idxopts) != GT_READMODE_FORWARD) what = "-dir";
-  else if (gt_index_options_outbwttab_value(so->idxopts)) what = "-bwt";
   else if (gt_index_options_outkystab_value(so->idxopts)) what = "-kys";
   else if (gt_index_options_lcpdist_value(so->idxopts)) what = "-lcpdist";
   else if (gt_index_options_maximumspace_value(so->idxopts) > 0) what = "-memlimit";
@@ -131,18 +130,20 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   if (!had_err) {
     const bool want_suf = gt_index_options_outsuftab_value(so.idxopts),
                want_lcp = gt_index_options_outlcptab_value(so.idxopts),
-               want_bck = gt_index_options_outbcktab_value(so.idxopts);
+               want_bck = gt_index_options_outbcktab_value(so.idxopts),
+               want_bwt = gt_index_options_outbwttab_value(so.idxopts);
+    const bool want_any = want_suf || want_lcp || want_bck || want_bwt;
     const GtUword n = gt_encseq_total_length(encseq);
     const unsigned int numofchars = gt_encseq_alphabetnumofchars(encseq);
     unsigned int prefixlength = gt_index_options_prefixlength_value(so.idxopts);
     uint64_t *suftab = NULL, *llv = NULL, nllv = 0, nall = 0, nspec = 0, ndist = 0;
-    uint8_t *lcptab = NULL;
+    uint8_t *lcptab = NULL, *bwttab = NULL;
     uint32_t *leftborder = NULL, *csc = NULL, *dist = NULL;
     gtb_stats stats;
     char msg[512];
 
     memset(&stats, 0, sizeof stats);
-    if (want_suf || want_lcp || want_bck) {
+    if (want_any) {
       /* detpfxlen, src/match/sfx-run.c:319-367 */
       unsigned int rec = gt_recommendedprefixlength(numofchars, n,
                                                     GT_RECOMMENDED_MULTIPLIER_DEFAULT, true);
@@ -159,8 +160,11 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
                         "suffixerator path");
       had_err = -1;
     }
-    if (!had_err && (want_suf || want_lcp || want_bck)) {
-      int rc;
+    if (!had_err && want_any) {
+      int rc = 0;
+      gtb_esa *h = gtb_esa_new(0, msg, sizeof msg);
+      if (h == NULL) rc = -1;
+      if (want_bwt) bwttab = gt_malloc(sizeof *bwttab * (n + 1));
       if (want_suf) suftab = gt_malloc(sizeof *suftab * (n + 1));
       if (want_lcp) {
         lcptab = gt_malloc(sizeof *lcptab * (n + 1));
@@ -194,22 +198,46 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
           gt_specialrangeiterator_delete(sri);
           nranges = fill;
         }
-        rc = gtb_esa_build_2bit(0, (const uint64_t *) tbe, gt_unitsoftwobitencoding(n), n,
-                                ranges, nranges, prefixlength, suftab, lcptab, llv, n + 1, &nllv,
-                                leftborder, csc, dist, &stats, msg, sizeof msg);
+        if (rc == 0)
+          rc = gtb_esa_set_input_2bit(h, (const uint64_t *) tbe, gt_unitsoftwobitencoding(n), n,
+                                      ranges, nranges);
         gt_free(ranges);
+        if (rc == 0 && want_bwt) {
+          /* which special positions are separators: one before every sequence but the first */
+          const GtUword nseq = gt_encseq_num_of_sequences(encseq);
+          uint64_t *sep = gt_malloc(sizeof *sep * (nseq + 1));
+          GtUword i;
+          for (i = 1; i < nseq; i++) sep[i-1] = (uint64_t) gt_encseq_seqstartpos(encseq, i) - 1;
+          rc = gtb_esa_set_separators(h, sep, nseq - 1);
+          gt_free(sep);
+        }
       } else {
         GtUchar *symbols = gt_malloc(n + 1);
         if (n > 0) gt_encseq_extract_encoded(encseq, symbols, 0, n - 1);
-        rc = gtb_esa_build_bytes(0, symbols, n, numofchars, prefixlength, suftab, lcptab, llv,
-                                 n + 1, &nllv, leftborder, csc, dist, &stats, msg, sizeof msg);
+        if (rc == 0) rc = gtb_esa_set_input_bytes(h, symbols, n, numofchars);
         gt_free(symbols);
       }
+      if (rc == 0)
+        rc = gtb_esa_run(h, prefixlength, (want_suf ? GTB_WANT_SUF : 0u) | (want_lcp ? GTB_WANT_LCP : 0u) |
+                                          (want_bck ? GTB_WANT_BCK : 0u));
+      if (rc == 0) {
+        const uint64_t e = gtb_esa_num_entries(h);          /* = n + 1 */
+        if (want_suf) rc = gtb_esa_copy_suftab_u64(h, suftab, 0, e);
+        if (rc == 0 && want_lcp) rc = gtb_esa_copy_lcptab(h, lcptab, 0, e);
+        if (rc == 0 && want_lcp) { nllv = gtb_esa_num_llv(h); rc = gtb_esa_copy_llv(h, llv); }
+        if (rc == 0 && want_bck) rc = gtb_esa_copy_bcktab(h, leftborder, csc, dist);
+        if (rc == 0 && want_bwt) rc = gtb_esa_copy_bwttab(h, bwttab, 0, e);
+        if (rc == 0) rc = gtb_esa_get_stats(h, &stats);
+      }
+      if (rc != 0 && h != NULL) snprintf(msg, sizeof msg, "%s", gtb_esa_error(h));
+      gtb_esa_delete(h);
       if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
     }
     /* the reference's files */
     if (!had_err && want_suf)
       had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, err);
+    if (!had_err && want_bwt)
+      had_err = b200_write(gt_str_get(so.indexname), ".bwt", bwttab, 1, n + 1, 0, err);
     if (!had_err && want_lcp) {
       had_err = b200_write(gt_str_get(so.indexname), ".lcp", lcptab, 1, n + 1, 0, err);
       if (!had_err)
@@ -227,10 +255,10 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     }
     if (!had_err) {
       Definedunsignedlong longest;
-      longest.defined = want_suf || want_lcp || want_bck;
+      longest.defined = want_any;
       longest.valueunsignedlong = (GtUword) stats.longest;
       if (gt_outprjfile(gt_str_get(so.indexname), GT_READMODE_FORWARD, encseq,
-                        (want_suf || want_lcp || want_bck) ? n + 1 : 0, prefixlength,
+                        want_any ? n + 1 : 0, prefixlength,
                         want_lcp ? (GtUword) stats.numoflargelcpvalues : 0,
                         want_lcp ? stats.lcptabsum / (double) (n + 1) : 0.0,
                         want_lcp ? (GtUword) stats.maxbranchdepth : 0,
@@ -239,7 +267,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     }
     gt_logger_log(logger, "B200 device time %.3f ms, %u kernel launches, %u radix passes",
                   stats.ms_total, stats.kernel_launches, stats.radix_passes);
-    gt_free(suftab); gt_free(lcptab); gt_free(llv);
+    gt_free(suftab); gt_free(lcptab); gt_free(llv); gt_free(bwttab);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
   }
   gt_encseq_delete(encseq);

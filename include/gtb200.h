@@ -199,6 +199,14 @@ int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t 
 int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t count);
 /* outlcpvalues (sfx-lcpvalues.c:371-433) */
 int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count);
+/* -bwt (bwttab2file, src/match/sfx-run.c:173-210): one encoded symbol per suffix-table
+   entry, the symbol before the suffix (0..numofchars-1, 254 wildcard, 255 separator;
+   UNDEFBWTCHAR = 254 for the suffix that starts at 0, chardef.h:65).  The 2-bit input does
+   not say which special positions are separators: pass their positions (ascending; for
+   sequence i >= 1 that is gt_encseq_seqstartpos(encseq, i) - 1) before the run, otherwise
+   every special is reported as a wildcard. */
+int gtb_esa_set_separators(gtb_esa *h, const uint64_t *positions, uint64_t count);
+int gtb_esa_copy_bwttab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count);
 /* Largelcpvalue pairs (lcpoverflow.h:25-29): dst holds 2*gtb_esa_num_llv()
    uint64 {index, value}; index is global (sa_offset added). */
 int gtb_esa_copy_llv(gtb_esa *h, uint64_t *dst);

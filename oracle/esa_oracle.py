@@ -110,6 +110,17 @@ def file_images(o):
             "llv": llv.astype("<u8").tobytes(), "bck": bck}
 
 
+def bwt_image(o, symbols):
+    """the byte image of .bwt (bwttab2file, /root/reference/src/match/sfx-run.c:173-210): the
+    encoded symbol before each suffix, UNDEFBWTCHAR (254) for the suffix starting at 0"""
+    suf = o["suf"].astype(np.int64)
+    sym = np.asarray(symbols, dtype=np.uint8)
+    out = np.full(suf.shape[0], 254, dtype=np.uint8)
+    nz = suf > 0
+    out[nz] = sym[suf[nz] - 1]
+    return out.tobytes()
+
+
 def prj_sorter_lines(o):
     """the lines of the .prj file the sorter is responsible for (sfx-outprj.c:66-77)"""
     n = o["totallength"]
@@ -136,4 +147,7 @@ def run_reference(fasta_paths, workdir, alphabet="dna", pl=None, parts=1, indexn
     for ext in ("suf", "lcp", "llv", "bck", "prj"):
         with open(os.path.join(workdir, indexname + "." + ext), "rb") as fh:
             out[ext] = fh.read()
+    if "-bwt" in extra:
+        with open(os.path.join(workdir, indexname + ".bwt"), "rb") as fh:
+            out["bwt"] = fh.read()
     return out

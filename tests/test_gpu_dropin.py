@@ -24,6 +24,8 @@ def run_both(tmp_path, fasta, alphabet, extra=()):
         subprocess.check_call([exe, "suffixerator", "-" + alphabet, "-suf", "-lcp", "-bck", "-pl", *extra,
                                "-indexname", idx, "-db", *fasta], stdout=subprocess.DEVNULL)
         out[name] = {ext: open(idx + "." + ext, "rb").read() for ext in ("suf", "lcp", "llv", "bck", "prj", "esq")}
+        if "-bwt" in extra:
+            out[name]["bwt"] = open(idx + ".bwt", "rb").read()
     return out
 
 
@@ -51,13 +53,25 @@ def test_dropin_files_identical_to_reference(tmp_path, case):
 
 
 @need_bins
+@pytest.mark.parametrize("case", ["reads", "protein"])
+def test_dropin_bwt_identical_to_reference(tmp_path, case):
+    sym, alpha = (synth.reads(3000, 90, 12, 0.004), "dna") if case == "reads" else (synth.protein(60_000, 5), "protein")
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(sym, fa, alpha)
+    # "-pl" takes the optional numeric argument, so the extra options follow an explicit value
+    out = run_both(tmp_path, [fa], alpha, extra=("3" if alpha == "dna" else "2", "-bwt"))
+    for ext in ("bwt", "bck", "suf", "lcp", "llv", "prj"):
+        assert out["b200"][ext] == out["ref"][ext], ext
+
+
+@need_bins
 def test_dropin_explicit_prefixlength_and_errors(tmp_path):
     fa = str(tmp_path / "in.fa")
     synth.to_fasta(synth.random_dna(50_000, 3, 0.01), fa, "dna")
     out = run_both(tmp_path, [fa], "dna", extra=("4",))
     for ext in ("bck", "suf", "lcp", "llv", "prj"):
         assert out["b200"][ext] == out["ref"][ext], ext
-    for bad in (["-dir", "rev"], ["-dc", "32"], ["-bwt"]):
+    for bad in (["-dir", "rev"], ["-dc", "32"], ["-suftabuint"]):
         r = subprocess.run([GT_B200, "suffixerator", "-dna", "-suf", *bad, "-indexname", str(tmp_path / "x"), "-db", fa],
                            capture_output=True, text=True)
         assert r.returncode != 0 and "not supported by the B200" in r.stderr
