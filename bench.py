@@ -11,8 +11,10 @@ A step = one complete pass of the hot path over the workload: fused key generati
 from the sorted keys, text-driven / prefix-doubling refinement of the ties, lcp, special
 tail -- results left in HBM (`value`), or through the host-buffer C-ABI including the
 H2D copy of the packed sequence and the D2H copy of .suf/.lcp/.llv/.bck (`e2e`).
-With N > 1 ranks (torchrun) the bucket codes are sharded: count allreduce (NCCL), the
-rank's own code range sorted, rank exchange (all-to-all) in the doubling rounds.
+With N > 1 ranks (torchrun) the bucket codes are sharded: count allreduce (NCCL), key
+generation sharded by text position with an all-to-all of the (key, position) pairs to the
+owning code range, the rank's own range sorted, rank exchange (all-to-all) in the doubling
+rounds.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -242,8 +244,8 @@ def main():
     upload()
     flags = GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK
     # weak scaling: the sequence is replicated, the bucket codes are sharded over the ranks.
-    # Every step: count allreduce (each rank counts 1/world of the text), the same code ranges
-    # cut on every rank, then the lock-step sort of the rank's own range.
+    # Every step: count allreduce (each rank counts coarse codes over 1/world of the text), the
+    # same code ranges cut on every rank, then the lock-step sort of the rank's own range.
     dev = torch.device("cuda", local_rank)
 
     def sync_all():
@@ -255,17 +257,22 @@ def main():
     worker = None
     if world > 1:
         from genometools_b200.multirange import (GpuRangeWorker, run_range_distributed, range_first_keys,
-                                                 count_allreduce_and_split)
+                                                 coarse_allreduce_and_split, allreduce_bcktab, PairExchange)
         worker = GpuRangeWorker(h, pl, flags | GTB_REUSE_COUNTS, local_rank)
+        # sharding the text scan pays once the all-to-all is small against the scans it saves
+        use_x = os.environ.get("GTB_BENCH_EXCHANGE", "1" if world >= 4 else "0") == "1"
+        exchange = PairExchange(lib, h, pl, flags | GTB_REUSE_COUNTS, n, dist, dev) if use_x else None
 
     def step():
         if world > 1:
-            parts = count_allreduce_and_split(lib, h, w.numofchars, pl, n, dist, dev)
+            parts = coarse_allreduce_and_split(lib, h, pl, n, dist, dev)
             if len(parts) != world:
-                raise SystemExit("could not cut the bucket table into one part per rank")
-            mn, mx, off, _ = parts[rank]
-            ck(lib.gtb_esa_set_code_range(h, mn, mx, off, 1 if rank == world - 1 else 0))
-            run_range_distributed(worker, range_first_keys(w.numofchars, pl, parts), dist, dev)
+                raise SystemExit("could not cut the bucket codes into one part per rank")
+            mn, mx, off, width = parts[rank]
+            ck(lib.gtb_esa_set_code_range_known(h, mn, mx, off, width, 1 if rank == world - 1 else 0))
+            fk = range_first_keys(w.numofchars, pl, parts)
+            run_range_distributed(worker, fk, dist, dev,
+                                  begin=(lambda: exchange.begin(fk)) if exchange is not None else None)
         else:
             ck(lib.gtb_esa_run(h, pl, flags))
         ck(lib.gtb_esa_get_stats(h, C.byref(st)))
@@ -387,9 +394,21 @@ def main():
     mx = torch.tensor([last["maxbranchdepth"], last["doubling_rounds"]], dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    bck_ok = None
+    if dist is not None:
+        # the ranks' bucket tables hold their own codes only: sum them and check the total
+        allreduce_bcktab(lib, h, w.numofchars, pl, dist, dev)
+        a_, b_, c_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a_), C.byref(b_), C.byref(c_))
+        plb_ = C.c_void_p()
+        lib.gtb_esa_dev_bcktab(h, C.byref(plb_), None, None)
+        lbt = torch.as_tensor(_DevArr(plb_.value, a_.value + 1, "<u4"), device=dev)
+        bck_ok = int(lbt[-1].item()) == int(chk[2].item()) and bool((lbt[1:].to(torch.int64) >= lbt[:-1].to(torch.int64)).all().item())
     checks = {"suftab_is_permutation_sum": int(chk[0].item()) == n * (n + 1) // 2 and int(chk[1].item()) == n + 1,
               "lcptabsum": int(chk[3].item()), "largelcpvalues": int(chk[4].item()),
               "maxbranchdepth": int(mx[0].item()), "doubling_rounds": int(mx[1].item())}
+    if bck_ok is not None:
+        checks["merged_bucket_table_monotone_and_complete"] = bck_ok
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -55,6 +55,11 @@ SYMBOLS = {
     "gtb_esa_count_finish": (C.c_int, [_P]),
     "gtb_esa_dev_bcktab": (C.c_int, [_P, _P, _P, _P]),
     "gtb_esa_split_ranges": (C.c_int, [_P, C.c_uint, _P, _P]),
+    "gtb_esa_coarse_partial": (C.c_int, [_P, C.c_uint, _U64, _U64, _P, _P]),
+    "gtb_esa_coarse_split": (C.c_int, [_P, C.c_uint, _P, _P]),
+    "gtb_esa_set_code_range_known": (C.c_int, [_P, _U64, _U64, _U64, _U64, C.c_int]),
+    "gtb_esa_slice_partition": (C.c_int, [_P, C.c_uint, _U64, _U64, _P, C.c_int, _P, _P, _U64, _P]),
+    "gtb_esa_sort_begin_pairs": (C.c_int, [_P, C.c_uint, C.c_uint, _P, _P, _U64]),
     "gtb_esa_sort_begin": (C.c_int, [_P, C.c_uint, C.c_uint]),
     "gtb_esa_unresolved": (_U64, [_P]),
     "gtb_esa_ensure_ranks": (C.c_int, [_P]),

@@ -87,6 +87,10 @@ struct gtb_esa {
   int res = 0;              // which vbuf holds the suffix table
   u64 N = 0;                // sorted (non-special) suffixes of this shard
   u64 sa_offset = 0;        // global SA index of the shard's first entry
+  bool range_given = false; // sa_offset / width of the code range come from the caller (coarse counts)
+  u64 given_offset = 0, given_width = 0;
+  bool lb_own = false;      // leftborder holds (only) this range's own codes, filled from its sorted keys
+  DevBuf coarse; unsigned plc = 0; u32 ncoarse = 0;
   u64 entries = 0;          // N (+ S + 1 with tail)
   u64 nllv = 0;
   u64 first_key = 0, last_key = 0;
@@ -101,6 +105,9 @@ struct gtb_esa {
   int opt_text_rounds = -1; // GTB200_TEXT_ROUNDS = 0..8): override the automatic choices
   unsigned text_left = 0;   // text-driven rounds still allowed before ranks are built
   float ms_count_ext = 0;   // device time of gtb_esa_count_partial/_finish since the last run
+  float ms_part_ext = 0;    // ... and of gtb_esa_slice_partition (its pass counts as a radix pass)
+  u64 part_pairs_ext = 0; u32 part_launches_ext = 0;
+  float ext_ms_radix = 0; u64 ext_pairs = 0; u32 ext_launches = 0;   // carried into this run's stats
   u64 depth[64];            // depth[r] = common prefix of the groups entering round r
   DevBuf ranks, owner, sendidx, rcounts;
   gtb_stats stats;
@@ -173,6 +180,7 @@ TextSrc<DNA> make_src(gtb_esa *h, u64 klo, u64 khi)
   s.bytes = h->bytes.as<u8>();
   s.spmask = h->spmask.as<u32>();
   s.klo = klo; s.khi = khi;
+  s.pos0 = 0;
   s.f = h->fmt;
   return s;
 }
@@ -283,8 +291,10 @@ template <bool DNA> int build_ranks(gtb_esa *h);
 template <bool DNA> int round_local(gtb_esa *h);
 
 // ---- stage 1: bucket table, first-level sort, analysis, special tail, compaction of ties ----
+// ext != null: the (key, position) pairs of this range already lie in device memory in text
+// order (they were generated slice-wise on several GPUs and exchanged): no text scan here
 template <bool DNA>
-int stage_begin(gtb_esa *h, unsigned flags)
+int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 extcount = 0)
 {
   ErrBuf &err = h->err;
   gtb_stats &S = h->stats;
@@ -305,10 +315,13 @@ int stage_begin(gtb_esa *h, unsigned flags)
   // the table is much larger than the text; code ranges need them before the sort
   const bool want_table = h->pl > 0 && ((flags & GTB_WANT_BCK) || !h->full_range);
   bool lb_from_keys = false;
+  h->lb_own = false;
   {
     PhaseTimer t(h, &S.ms_count);
     if (want_table && !h->counted) {
-      lb_from_keys = h->full_range && ipow_u64(h->K, h->pl) <= 4 * (h->n - h->S) + 1024;
+      // a range whose offset and width the caller knows (coarse counts) also fills its own codes
+      lb_from_keys = (h->full_range && ipow_u64(h->K, h->pl) <= 4 * (h->n - h->S) + 1024) ||
+                     (!h->full_range && h->range_given);
       GTB_TRY(count_codes(h, h->pl, !lb_from_keys));
     }
     t.stop();
@@ -317,7 +330,10 @@ int stage_begin(gtb_esa *h, unsigned flags)
   code_range_to_keys(h, &klo, &khi);
   u64 Ncap = h->n - h->S;
   h->sa_offset = 0;
-  if (!h->full_range) {
+  if (!h->full_range && h->range_given && !h->counted) {
+    h->sa_offset = h->given_offset;
+    Ncap = h->given_width;
+  } else if (!h->full_range) {
     u32 lb[2];
     GTB_CUDA(cudaMemcpyAsync(&lb[0], h->leftborder.as<u32>() + h->mincode, sizeof(u32),
                              cudaMemcpyDeviceToHost, st));
@@ -352,7 +368,10 @@ int stage_begin(gtb_esa *h, unsigned flags)
   plan_add_bits(plan, f.lowbit() & ~7, 64);
   u64 N = 0;
   h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0; h->rw.ms_hist = 0; h->rw.ms_radix = 0;
-  GTB_TRY(radix_sort(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err));
+  if (ext) GTB_TRY(radix_sort(h->rw, st, *ext, extcount, kb, vb, plan, &h->res, &N, err));
+  else GTB_TRY(radix_sort(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err));
+  if (ext && N != Ncap) { err.set("exchanged pairs: %llu received, the code range holds %llu suffixes",
+                                  (unsigned long long) N, (unsigned long long) Ncap); return -1; }
   if (N > Ncap) { err.set("internal: sorted %llu suffixes, expected at most %llu",
                           (unsigned long long) N, (unsigned long long) Ncap); return -1; }
   h->N = N;
@@ -380,11 +399,13 @@ int stage_begin(gtb_esa *h, unsigned flags)
       if (lb_from_keys)
         k_analyze_keys<DNA, true><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes,
-            h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>(), h->hbits.as<u8>(), h->ubits.as<u8>());
+            h->csc.as<u32>(), h->dist.as<u32>(), h->distoff.as<u64>(), h->hbits.as<u8>(), h->ubits.as<u8>(),
+            h->full_range ? 0 : h->mincode,
+            (h->full_range || h->maxcode + 1 == h->ncodes) ? h->ncodes : h->maxcode, h->sa_offset);
       else
         k_analyze_keys<DNA, false><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0, nullptr, nullptr, nullptr,
-            h->hbits.as<u8>(), h->ubits.as<u8>());
+            h->hbits.as<u8>(), h->ubits.as<u8>(), 0, 0, 0);
       GTB_LAUNCH_CHECK();
       k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,
                                                h->misc.as<u64>());
@@ -395,7 +416,8 @@ int stage_begin(gtb_esa *h, unsigned flags)
       GTB_CUDA(cudaMemcpyAsync(&M0, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
       GTB_CUDA(cudaStreamSynchronize(st));
     }
-    if (lb_from_keys) h->counted = true;       // (N = 0: the zeroed table is already right)
+    if (lb_from_keys && h->full_range) h->counted = true;   // (N = 0: the zeroed table is already right)
+    if (lb_from_keys && !h->full_range) h->lb_own = true;   // own codes only: summed over the ranges by the caller
     t.stop();
   }
   S.unresolved_after_first_sort = M0;
@@ -478,7 +500,7 @@ RankMap<DNA> make_rankmap(gtb_esa *h)
   rm.N = h->N;
   rm.tbits = h->tbits.as<u32>(); rm.tpre = h->tpre.as<u32>(); rm.trank = h->trank.as<u32>();
   rm.spre = h->spre.as<u32>();
-  rm.leftborder = (h->counted && h->pl > 0) ? h->leftborder.as<u32>() : nullptr;
+  rm.leftborder = ((h->counted || h->lb_own) && h->pl > 0) ? h->leftborder.as<u32>() : nullptr;
   rm.pl = h->pl; rm.K = h->K;
   rm.n = h->n; rm.nonspecials = h->n - h->S; rm.sa_offset = h->sa_offset;
   return rm;
@@ -739,9 +761,11 @@ int stage_end(gtb_esa *h)
   S.maxbranchdepth = hs.maxlcp;
   S.lcptabsum = (double) hs.lcpsum;
   S.prefixlength = h->pl; S.numofchars = h->K;
-  S.radix_passes = h->rw.passes; S.radix_pairs_moved = h->rw.pairs_moved;
-  S.kernel_launches += h->rw.launches;
-  S.ms_hist = h->rw.ms_hist; S.ms_radix = h->rw.ms_radix;
+  // (a slice partition that preceded this run is one more pass of the same kernel)
+  S.radix_passes = h->rw.passes + (h->ext_pairs ? 1u : 0u);
+  S.radix_pairs_moved = h->rw.pairs_moved + h->ext_pairs;
+  S.kernel_launches += h->rw.launches + h->ext_launches;
+  S.ms_hist = h->rw.ms_hist; S.ms_radix = h->rw.ms_radix + h->ext_ms_radix;
   h->in_progress = false;
   return 0;
 }
@@ -766,8 +790,11 @@ static int check_run_args(gtb_esa *h, unsigned prefixlength, unsigned flags)
   const float up = h->stats.ms_upload;
   memset(&h->stats, 0, sizeof h->stats);
   h->stats.ms_upload = up;
-  if (flags & GTB_REUSE_COUNTS) { h->stats.ms_count = h->ms_count_ext; h->stats.ms_total = h->ms_count_ext; }
-  h->ms_count_ext = 0;
+  if (flags & GTB_REUSE_COUNTS) { h->stats.ms_count = h->ms_count_ext; h->stats.ms_total = h->ms_count_ext + h->ms_part_ext; }
+  h->ext_ms_radix = (flags & GTB_REUSE_COUNTS) ? h->ms_part_ext : 0;
+  h->ext_pairs = (flags & GTB_REUSE_COUNTS) ? h->part_pairs_ext : 0;
+  h->ext_launches = (flags & GTB_REUSE_COUNTS) ? h->part_launches_ext : 0;
+  h->ms_count_ext = 0; h->ms_part_ext = 0; h->part_pairs_ext = 0; h->part_launches_ext = 0;
   if (h->pl != prefixlength || !(flags & GTB_REUSE_COUNTS)) h->counted = false;
   h->pl = prefixlength;
   h->ran = false;
@@ -858,7 +885,7 @@ void gtb_esa_delete(gtb_esa *h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->sepbits, &h->seppos, &h->leftborder, &h->csc, &h->dist,
-                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->hbits, &h->ubits, &h->tbits, &h->tpre, &h->trank, &h->spre,
+                   &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->coarse, &h->hbits, &h->ubits, &h->tbits, &h->tpre, &h->trank, &h->spre,
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
@@ -935,9 +962,10 @@ int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint6
                            int emit_special_tail)
 {
   if (!h) return -1;
-  (void) sa_offset;   // derived from the bucket table; kept in the signature for callers that know it
+  // (the offset is derived from the bucket table when the handle has counted one)
   if (mincode > maxcode) { h->err.set("empty code range"); return -1; }
   h->full_range = false; h->mincode = mincode; h->maxcode = maxcode;
+  h->given_offset = sa_offset; h->range_given = false;
   h->emit_tail = emit_special_tail ? 1 : 0;
   return 0;
 }
@@ -960,6 +988,51 @@ int gtb_esa_sort_begin(gtb_esa *h, unsigned prefixlength, unsigned flags)
   if (!h) return -1;
   GTB_TRY(check_run_args(h, prefixlength, flags));
   return timed_stage(h, [&]() -> int { return h->dna ? stage_begin<true>(h, flags) : stage_begin<false>(h, flags); });
+}
+
+int gtb_esa_slice_partition(gtb_esa *h, unsigned prefixlength, uint64_t first_pos, uint64_t end_pos,
+                            const uint64_t *range_first_keys, int nranges, uint64_t *dev_keys,
+                            uint32_t *dev_positions, uint64_t capacity, uint64_t *counts_out)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input) { err.set("gtb_esa_slice_partition: no input set"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (end_pos > h->n) end_pos = h->n;
+  if (first_pos > end_pos) { err.set("gtb_esa_slice_partition: empty or reversed slice"); return -1; }
+  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  cudaEvent_t e0, e1;
+  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
+  GTB_CUDA(cudaEventRecord(e0, h->st));
+  int rc;
+  h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0;
+  if (h->dna) {
+    TextSrc<true> src = make_src<true>(h, 0, ~0ull); src.pos0 = first_pos;
+    rc = rs_partition_by_owner(h->rw, h->st, src, end_pos - first_pos, range_first_keys, nranges, dev_keys,
+                               dev_positions, capacity, counts_out, err);
+  } else {
+    TextSrc<false> src = make_src<false>(h, 0, ~0ull); src.pos0 = first_pos;
+    rc = rs_partition_by_owner(h->rw, h->st, src, end_pos - first_pos, range_first_keys, nranges, dev_keys,
+                               dev_positions, capacity, counts_out, err);
+  }
+  cudaEventRecord(e1, h->st);
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  h->ms_part_ext = ms; h->part_pairs_ext = h->rw.pairs_moved; h->part_launches_ext = h->rw.launches;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+
+int gtb_esa_sort_begin_pairs(gtb_esa *h, unsigned prefixlength, unsigned flags, const uint64_t *dev_keys,
+                             const uint32_t *dev_positions, uint64_t count)
+{
+  if (!h) return -1;
+  if (h->full_range) { h->err.set("gtb_esa_sort_begin_pairs needs a code range (gtb_esa_set_code_range)"); return -1; }
+  GTB_TRY(check_run_args(h, prefixlength, flags));
+  PairSrc ext{dev_keys, dev_positions};
+  return timed_stage(h, [&]() -> int {
+    return h->dna ? stage_begin<true>(h, flags, &ext, count) : stage_begin<false>(h, flags, &ext, count);
+  });
 }
 
 uint64_t gtb_esa_unresolved(const gtb_esa *h) { return h ? h->M : 0; }
@@ -1085,6 +1158,114 @@ int gtb_esa_count_finish(gtb_esa *h)
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (rc == 0) h->counted = true;
   return rc;
+}
+
+// ---- coarse counts: code ranges for several GPUs without a fine-grained counting pass ----
+static unsigned coarse_pl(const gtb_esa *h, unsigned pl)
+{
+  unsigned plc = 0;
+  u64 c = 1;
+  while (plc < pl && c * h->K <= (u64) CC_MAXCODES) { c *= h->K; plc++; }
+  return plc;
+}
+
+int gtb_esa_coarse_partial(gtb_esa *h, unsigned prefixlength, uint64_t first_pos, uint64_t end_pos,
+                           uint32_t **dev_counts, uint64_t *ncounts)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->have_input) { err.set("gtb_esa_coarse_partial: no input set"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
+  h->counted = false; h->lb_own = false;
+  h->pl = prefixlength;
+  h->ncodes = ipow_u64(h->K, prefixlength);
+  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  h->plc = coarse_pl(h, prefixlength);
+  h->ncoarse = (u32) ipow_u64(h->K, h->plc);
+  GTB_TRY(h->coarse.ensure(sizeof(u32) * (h->ncoarse + 1), err));
+  cudaEvent_t e0, e1;
+  GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
+  GTB_CUDA(cudaEventRecord(e0, h->st));
+  GTB_CUDA(cudaMemsetAsync(h->coarse.p, 0, sizeof(u32) * (h->ncoarse + 1), h->st));
+  if (end_pos > h->n) end_pos = h->n;
+  if (first_pos < end_pos) {
+    const unsigned grid = grid_for(end_pos - first_pos, 256, 148u * 8u);
+    if (h->dna) k_count_coarse<true><<<grid, 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), first_pos, end_pos, h->plc, h->K, h->ncoarse, h->coarse.as<u32>());
+    else k_count_coarse<false><<<grid, 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), first_pos, end_pos, h->plc, h->K, h->ncoarse, h->coarse.as<u32>());
+    GTB_LAUNCH_CHECK();
+  }
+  cudaEventRecord(e1, h->st);
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  h->ms_count_ext = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (dev_counts) *dev_counts = h->coarse.as<u32>();
+  if (ncounts) *ncounts = h->ncoarse;
+  return 0;
+}
+
+int gtb_esa_coarse_split(gtb_esa *h, unsigned numofparts, uint64_t *out4, unsigned *nparts)
+{
+  if (!h || !out4 || !nparts) return -1;
+  ErrBuf &err = h->err;
+  if (h->ncoarse == 0 || !h->coarse.p) { err.set("gtb_esa_coarse_split without gtb_esa_coarse_partial"); return -1; }
+  if (numofparts < 1 || numofparts > (unsigned) MAX_RANGES) { err.set("gtb_esa_coarse_split: 1..%d parts", MAX_RANGES); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  // the (summed) coarse table is tiny: cut on the host, gt_suftabparts_new on coarse buckets
+  u32 *cnt = (u32 *) malloc(sizeof(u32) * (h->ncoarse + 1));
+  u64 *lb = (u64 *) malloc(sizeof(u64) * (h->ncoarse + 2));
+  if (!cnt || !lb) { free(cnt); free(lb); err.set("out of host memory"); return -1; }
+  GTB_CUDA(cudaMemcpyAsync(cnt, h->coarse.p, sizeof(u32) * h->ncoarse, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  lb[0] = 0;
+  for (u32 c = 0; c < h->ncoarse; c++) lb[c + 1] = lb[c] + cnt[c];
+  const u64 total = lb[h->ncoarse], fine = h->ncodes / h->ncoarse;    // fine codes per coarse code
+  unsigned np = 0;
+  u64 mincode = 0, target = 0;
+  const u64 width = total / numofparts, rem = total % numofparts;
+  if (numofparts <= 1 || total <= numofparts || h->ncoarse == 1) {
+    out4[0] = 0; out4[1] = h->ncodes - 1; out4[2] = 0; out4[3] = total; np = 1;
+  } else {
+    for (unsigned part = 0; part < numofparts && mincode < h->ncoarse; part++) {
+      target += width + (part < rem ? 1 : 0);
+      u64 maxcode;
+      if (part == numofparts - 1) maxcode = h->ncoarse - 1;
+      else {
+        u64 lo = 0, hi = h->ncoarse;
+        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (lb[mid + 1] < target) lo = mid + 1; else hi = mid; }
+        maxcode = lo < mincode ? mincode : lo;
+        if (maxcode > h->ncoarse - 1) maxcode = h->ncoarse - 1;
+      }
+      const u64 w = lb[maxcode + 1] - lb[mincode];
+      if (w > 0 || part == numofparts - 1) {
+        out4[4 * np] = mincode * fine; out4[4 * np + 1] = (maxcode + 1) * fine - 1;
+        out4[4 * np + 2] = lb[mincode]; out4[4 * np + 3] = w; np++;
+      }
+      mincode = maxcode + 1;
+    }
+    if (np > 0 && out4[4 * (np - 1) + 1] != h->ncodes - 1) {
+      const u64 mc = out4[4 * (np - 1)] / fine;
+      out4[4 * (np - 1) + 1] = h->ncodes - 1;
+      out4[4 * (np - 1) + 3] = total - lb[mc];
+    }
+    unsigned keep = 0;
+    for (unsigned p = 0; p < np; p++)
+      if (out4[4 * p + 3] > 0) { for (int q = 0; q < 4; q++) out4[4 * keep + q] = out4[4 * p + q]; keep++; }
+    if (keep == 0) { out4[0] = 0; out4[1] = h->ncodes - 1; out4[2] = 0; out4[3] = total; keep = 1; }
+    np = keep;
+  }
+  free(cnt); free(lb);
+  *nparts = np;
+  return 0;
+}
+
+int gtb_esa_set_code_range_known(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint64_t sa_offset,
+                                 uint64_t width, int emit_special_tail)
+{
+  if (gtb_esa_set_code_range(h, mincode, maxcode, sa_offset, emit_special_tail) != 0) return -1;
+  h->range_given = true; h->given_offset = sa_offset; h->given_width = width;
+  return 0;
 }
 
 int gtb_esa_dev_bcktab(const gtb_esa *h, uint32_t **leftborder, uint32_t **countspecialcodes, uint32_t **distpfxidx)
@@ -1277,7 +1458,7 @@ int gtb_esa_copy_bcktab(gtb_esa *h, uint32_t *leftborder, uint32_t *countspecial
 {
   if (!h) return -1;
   ErrBuf &err = h->err;
-  if (!h->counted) { err.set("no bucket table: run with GTB_WANT_BCK or call gtb_esa_count first"); return -1; }
+  if (!h->counted && !h->lb_own) { err.set("no bucket table: run with GTB_WANT_BCK or call gtb_esa_count first"); return -1; }
   GTB_CUDA(cudaSetDevice(h->device));
   if (leftborder) GTB_CUDA(cudaMemcpyAsync(leftborder, h->leftborder.p, sizeof(u32) * (h->ncodes + 1), cudaMemcpyDeviceToHost, h->st));
   if (countspecialcodes) GTB_CUDA(cudaMemcpyAsync(countspecialcodes, h->csc.p, sizeof(u32) * h->nspecialcodes, cudaMemcpyDeviceToHost, h->st));

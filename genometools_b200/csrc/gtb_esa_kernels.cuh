@@ -88,6 +88,7 @@ struct TextSrc {
   const u8  *bytes;      // bytes path: symbols (padded by >= 16 bytes of 255)
   const u32 *spmask;     // bit i set <=> position i is special; bits >= n all set
   u64 klo, khi;          // inclusive key range of this shard
+  u64 pos0;              // item i of the source is text position pos0 + i
   KeyFmt f;
 
   // filled key of position pos in format g (any m <= 29 for DNA, m*b + tb <= 64)
@@ -116,9 +117,9 @@ struct TextSrc {
     if (!make_key_fmt(pos, key, f)) return false;
     return key >= klo && key <= khi;
   }
-  __device__ __forceinline__ bool load_key(u64 pos, u64 &k) const
-  { return make_key(pos, k); }
-  __device__ __forceinline__ u32 load_val(u64 pos) const { return (u32) pos; }
+  __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
+  { return make_key(pos0 + idx, k); }
+  __device__ __forceinline__ u32 load_val(u64 idx) const { return (u32) (pos0 + idx); }
 };
 
 // ---- ranks without an inverse suffix array -----------------------------------------------
@@ -456,6 +457,8 @@ __device__ __forceinline__ bool key_head(u64 kprev, u64 kcur, u64 tmask)
 struct AnalyzeArgs {
   u64 N; KeyFmt f; u64 tmask; unsigned pl, K; int seam_prev_valid; u64 seam_prev_key;
   u32 *leftborder; u64 ncodes; u32 *csc; u32 *dist; const u64 *distoff;
+  // a code range fills only its own codes [lbfirst, lblast] with global indices (sa_offset + j)
+  u64 lbfirst, lblast, sa_offset;
 };
 
 // the AN_IPT elements of one thread; INNER: the tile lies strictly inside the array
@@ -485,8 +488,8 @@ analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &
       if (FILL_LB && ((!INNER && j == 0) || l < a.pl)) {
         // a new bucket starts here: every code in (code of j-1, code of j] starts at j
         const u64 c1 = key_code<DNA>(k[i + 1], a.pl, a.K, f);
-        u64 c0 = (!INNER && j == 0) ? 0 : key_code<DNA>(k[i], a.pl, a.K, f) + 1;
-        for (; c0 <= c1; c0++) a.leftborder[c0] = (u32) j;
+        u64 c0 = (!INNER && j == 0) ? a.lbfirst : key_code<DNA>(k[i], a.pl, a.K, f) + 1;
+        for (; c0 <= c1; c0++) a.leftborder[c0] = (u32) (a.sa_offset + j);
       }
       if (FILL_LB && u < a.pl) {
         run++;
@@ -504,7 +507,8 @@ analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &
       }
     }                                   // else: pending, lcp byte 0 = refinement level 0
     if (FILL_LB && !INNER && j + 1 == N) {
-      for (u64 c0 = key_code<DNA>(k[i + 1], a.pl, a.K, f) + 1; c0 <= a.ncodes; c0++) a.leftborder[c0] = (u32) N;
+      for (u64 c0 = key_code<DNA>(k[i + 1], a.pl, a.K, f) + 1; c0 <= a.lblast; c0++)
+        a.leftborder[c0] = (u32) (a.sa_offset + N);
     }
     if (head) headbits |= 1u << i;
     if (!head || !nexthead) { unres++; unresbits |= 1u << i; }
@@ -522,7 +526,8 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
                u32 *__restrict__ tile_lasthead, DevStats *stats, int seam_prev_valid,
                u64 seam_prev_key, u32 *__restrict__ leftborder, u64 ncodes,
                u32 *__restrict__ csc, u32 *__restrict__ dist, const u64 *__restrict__ distoff,
-               u8 *__restrict__ hbits, u8 *__restrict__ ubits /* one byte per thread: bit i = element i */)
+               u8 *__restrict__ hbits, u8 *__restrict__ ubits /* one byte per thread: bit i = element i */,
+               u64 lbfirst, u64 lblast, u64 sa_offset)
 {
   static_assert(AN_IPT == 8, "one 8-byte lcp store and one flag byte per thread");
   __shared__ u32 scratch[AN_NT / 32 + 1];
@@ -541,7 +546,8 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
     load_keys_blocked(keys, N, tile, s_k, k);
     u32 unres = 0, lasthead = 0;
     u64 lcpword = 0;
-    const AnalyzeArgs a{N, f, tmask, pl, K, seam_prev_valid, seam_prev_key, leftborder, ncodes, csc, dist, distoff};
+    const AnalyzeArgs a{N, f, tmask, pl, K, seam_prev_valid, seam_prev_key, leftborder, ncodes, csc, dist, distoff,
+                        lbfirst, lblast, sa_offset};
     u32 headbits = 0, unresbits = 0;
     if (tile > 0 && (tile + 1) * AN_TILE < N)      // inner tile: no bounds to check
       analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
@@ -947,6 +953,35 @@ __global__ void k_find_longest(TextSrc<DNA> src, const u64 *__restrict__ keys, u
   u64 lo = 0, hi = N;
   while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (keys[mid] < key0) lo = mid + 1; else hi = mid; }
   if (lo < N && keys[lo] == key0) stats->longest = sa_offset + lo;
+}
+
+// Coarse bucket counts for cutting code ranges over several GPUs: the first `plc` symbols of
+// the filled key (at most 4096 codes), counted in shared memory -- no global atomic per
+// suffix.  Positions [first, end).
+constexpr int CC_MAXCODES = 4096;
+template <bool DNA>
+__global__ void __launch_bounds__(256)
+k_count_coarse(TextSrc<DNA> src, u64 first, u64 end, unsigned plc, unsigned K, u32 ncoarse,
+               u32 *__restrict__ cnt)
+{
+  __shared__ u32 s_c[CC_MAXCODES];
+  for (u32 i = threadIdx.x; i < ncoarse; i += blockDim.x) s_c[i] = 0;
+  __syncthreads();
+  for (u64 pos = first + blockIdx.x * (u64) blockDim.x + threadIdx.x; ; pos += (u64) gridDim.x * blockDim.x) {
+    const bool inb = pos < end;
+    u64 key = 0;
+    bool ok = false;
+    if (inb) ok = src.make_key(pos, key);
+    const unsigned act = __ballot_sync(FULL_MASK, ok);
+    if (ok) {
+      const u32 code = (u32) key_code<DNA>(key, plc, K, src.f);
+      const unsigned peers = __match_any_sync(act, code);
+      if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&s_c[code], (u32) __popc(peers));
+    }
+    if (!__any_sync(FULL_MASK, inb)) break;
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < ncoarse; i += blockDim.x) if (s_c[i]) atomicAdd(&cnt[i], s_c[i]);
 }
 
 // gt_suftabparts_new (sfx-partssuf.c:172-347) on the bucket table in HBM: part p ends at

@@ -173,13 +173,26 @@ __device__ __forceinline__ unsigned warp_peers(unsigned d, bool valid)
   return CHECK_VALID ? (valid ? peers : 0u) : peers;
 }
 
+// first keys of up to 64 key ranges (MODE 3: the "digit" of a key is the range that owns it)
+constexpr int RS_MAX_OWNERS = 64;
+__constant__ u64 c_rs_bounds[RS_MAX_OWNERS];
+__constant__ int c_rs_nbounds;
+
+__device__ __forceinline__ unsigned rs_owner(u64 key)
+{
+  unsigned d = 0;
+  for (int i = 1; i < c_rs_nbounds; i++) d += key >= c_rs_bounds[i] ? 1u : 0u;
+  return d;
+}
+
 // digit extraction.  MODE 0 / 1: the digit is byte `bsel` of the low / high half of the
-// key (one PRMT); MODE 2: any (shift, mask)
+// key (one PRMT); MODE 2: any (shift, mask); MODE 3: the owning key range
 template <int MODE>
 __device__ __forceinline__ unsigned rs_digit(u64 key, unsigned bsel, unsigned dmask)
 {
   if (MODE == 0) return __byte_perm((u32) key, 0u, bsel);
   if (MODE == 1) return __byte_perm((u32) (key >> 32), 0u, bsel);
+  if (MODE == 3) return rs_owner(key);
   return (unsigned) (key >> bsel) & dmask;
 }
 
@@ -504,6 +517,81 @@ static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
   }
   w.ticket_base += (u32) tiles;
   w.passes++; w.launches++;
+  return 0;
+}
+
+// number of items of `src` per owning key range (c_rs_bounds must be set)
+template <class Src>
+__global__ void __launch_bounds__(RH_NT)
+rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
+{
+  __shared__ u32 s_h[RS_BINS];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const u64 ntiles = (N + RH_TILE - 1) / RH_TILE;
+  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const u64 base = tile * RH_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RH_IPT; k++) {
+      const u64 idx = base + (u64) k * RH_NT + threadIdx.x;
+      u64 key = 0;
+      bool ok = idx < N;
+      if (ok) ok = src.load_key(idx, key);
+      const unsigned d = rs_owner(key);
+      // consecutive text positions mostly differ in their owner: aggregate what does coincide
+      const unsigned act = __ballot_sync(FULL_MASK, ok);
+      if (ok) {
+        const unsigned peers = __match_any_sync(act, d);
+        if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&s_h[d], (u32) __popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  if (s_h[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], (unsigned long long) s_h[threadIdx.x]);
+}
+
+// One stable partition pass: the valid items of `src` grouped by owning key range
+// (bounds[0..nranges) = first key of each range, bounds[0] is taken as 0), written to
+// okeys/ovals; counts_out[r] = items of range r.  Synchronises the stream.
+template <class Src, class Cfg = RsDefault>
+static int rs_partition_by_owner(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, const u64 *bounds,
+                                 int nranges, u64 *okeys, u32 *ovals, u64 capacity, u64 *counts_out, ErrBuf &err)
+{
+  if (nranges < 1 || nranges > RS_MAX_OWNERS) { err.set("partition: 1..%d ranges", RS_MAX_OWNERS); return -1; }
+  for (int r = 0; r < nranges; r++) counts_out[r] = 0;
+  if (nsrc == 0) return 0;
+  u64 hb[RS_MAX_OWNERS];
+  for (int r = 0; r < nranges; r++) hb[r] = r == 0 ? 0 : bounds[r];
+  GTB_CUDA(cudaMemcpyToSymbolAsync(c_rs_bounds, hb, sizeof(u64) * nranges, 0, cudaMemcpyHostToDevice, st));
+  GTB_CUDA(cudaMemcpyToSymbolAsync(c_rs_nbounds, &nranges, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+  GTB_TRY(radix_work_reserve(w, nsrc, err));
+  GTB_CUDA(cudaMemsetAsync(w.ghist, 0, sizeof(unsigned long long) * RS_BINS, st));
+  {
+    u64 tiles = div_up(nsrc, RH_TILE);
+    unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
+    rs_owner_hist_kernel<Src><<<grid, RH_NT, 0, st>>>(src, nsrc, w.ghist);
+    GTB_LAUNCH_CHECK();
+    rs_scan_kernel<<<1, RS_BINS, 0, st>>>(w.ghist, w.gbase);
+    GTB_LAUNCH_CHECK();
+    w.launches += 2;
+  }
+  GTB_CUDA(cudaMemcpyAsync(w.h_hist, w.ghist, sizeof(unsigned long long) * RS_BINS, cudaMemcpyDeviceToHost, st));
+  GTB_CUDA(cudaStreamSynchronize(st));
+  u64 total = 0;
+  for (int r = 0; r < nranges; r++) { counts_out[r] = w.h_hist[r]; total += w.h_hist[r]; }
+  if (total > capacity) { err.set("partition: %llu items for a buffer of %llu", (unsigned long long) total, (unsigned long long) capacity); return -1; }
+  if (total == 0) return 0;
+  const u64 tiles = div_up(nsrc, Cfg::TILE);
+  if (tiles > w.status_tiles) { err.set("radix: status array too small"); return -1; }
+  if (++w.epoch >= 0xffffu) {
+    GTB_CUDA(cudaMemsetAsync(w.status, 0, sizeof(u64) * RS_BINS * w.status_tiles, st));
+    w.epoch = 1;
+  }
+  GTB_TRY((rs_launch_mode<Src, Cfg, 3>(w, st, src, nsrc, tiles, okeys, ovals, 0u, 0xffu, 0, err)));
+  w.ticket_base += (u32) tiles;
+  w.passes++; w.launches++;
+  w.pairs_moved += total;
+  GTB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

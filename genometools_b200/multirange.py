@@ -153,13 +153,59 @@ def count_allreduce_and_split(lib, handle, numofchars, prefixlength, totallength
             for p in range(npart.value)]
 
 
+def coarse_allreduce_and_split(lib, handle, prefixlength, totallength, dist, device):
+    """code ranges without a fine-grained counting pass: rank r counts the first few symbols
+    of the filled keys (<= 4096 coarse codes, in shared memory) over its 1/world slice of the
+    text, one all-reduce sums the tiny table, every rank cuts the same `world` ranges of whole
+    coarse buckets.  Returns [(mincode, maxcode, sa_offset, width)] in fine-grained codes."""
+    import torch
+    world, me = dist.get_world_size(), dist.get_rank()
+
+    def ck(rc):
+        if rc != 0:
+            raise GtbError(lib.gtb_esa_error(handle).decode())
+
+    lo, hi = totallength * me // world, totallength * (me + 1) // world
+    pd, nc = C.c_void_p(), C.c_uint64()
+    ck(lib.gtb_esa_coarse_partial(handle, prefixlength, lo, hi, C.byref(pd), C.byref(nc)))
+    t = torch.as_tensor(DeviceArray(pd.value, nc.value, "<i4"), device=device)
+    dist.all_reduce(t)
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    out = (C.c_uint64 * (4 * world))()
+    npart = C.c_uint()
+    ck(lib.gtb_esa_coarse_split(handle, world, out, C.byref(npart)))
+    return [(int(out[4 * p]), int(out[4 * p + 1]), int(out[4 * p + 2]), int(out[4 * p + 3]))
+            for p in range(npart.value)]
+
+
+def allreduce_bcktab(lib, handle, numofchars, prefixlength, dist, device):
+    """every rank's run filled the bucket-table entries of its own codes only: sum the three
+    tables over the ranks in place (afterwards every rank holds the whole table)"""
+    import torch
+    nall, nspecial, ndist = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.gtb_bck_sizes(numofchars, prefixlength, C.byref(nall), C.byref(nspecial), C.byref(ndist))
+    plb, pcs, pdi = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    if lib.gtb_esa_dev_bcktab(handle, C.byref(plb), C.byref(pcs), C.byref(pdi)) != 0:
+        raise GtbError("no bucket table on this handle")
+    for p, cnt in ((plb, nall.value + 1), (pcs, nspecial.value), (pdi, ndist.value)):
+        if cnt and p.value:
+            dist.all_reduce(torch.as_tensor(DeviceArray(p.value, cnt, "<i4"), device=device))
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+
+
 # ---------------------------------------------------------------- all ranges in one process
-def run_ranges_local(workers, first_keys, want_lcp=True):
+def run_ranges_local(workers, first_keys, want_lcp=True, begins=None):
     """lock-step over ranges that live in this process (same GPU): positions and ranks
-    are read in place, nothing is copied"""
+    are read in place, nothing is copied.  begins[r] (optional) replaces worker r's
+    sort_begin (a range whose pairs were produced by slice partitions)."""
     R = len(workers)
-    for w in workers:
-        w.sort_begin()
+    for r, w in enumerate(workers):
+        if begins is not None and begins[r] is not None:
+            begins[r]()
+        else:
+            w.sort_begin()
     if any(w.unresolved() > 0 for w in workers):
         for w in workers:
             w.ensure_ranks()
@@ -201,9 +247,61 @@ def run_ranges_local(workers, first_keys, want_lcp=True):
 
 
 # ---------------------------------------------------------------- one range per process
-def run_range_distributed(worker, first_keys, dist, device, want_lcp=True):
+class PairExchange:
+    """Sharded text scan: this rank generates the (filled key, position) pairs of its 1/world
+    slice of the text positions, grouped by owning code range (gtb_esa_slice_partition: one
+    onesweep pass whose digit is the owner), all_to_all moves every group to its owner --
+    the owner receives its pairs in text order (slices in rank order) -- and the owner's sort
+    starts from those pairs (gtb_esa_sort_begin_pairs): no rank scans the whole text."""
+
+    def __init__(self, lib, handle, prefixlength, flags, totallength, dist, device):
+        import torch
+        self.torch, self.lib, self.h, self.pl, self.flags = torch, lib, handle, prefixlength, flags
+        self.n, self.dist, self.device = totallength, dist, device
+        self.buf = {}
+
+    def _tensor(self, name, count, dtype):
+        t = self.buf.get(name)
+        if t is None or t.numel() < count:
+            t = self.torch.empty(max(count, 1), dtype=dtype, device=self.device)
+            self.buf[name] = t
+        return t
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GtbError(self.lib.gtb_esa_error(self.h).decode())
+
+    def begin(self, first_keys):
+        torch, dist = self.torch, self.dist
+        world, me = dist.get_world_size(), dist.get_rank()
+        lo, hi = self.n * me // world, self.n * (me + 1) // world
+        cap = hi - lo
+        send_k = self._tensor("send_k", cap, torch.int64)
+        send_p = self._tensor("send_p", cap, torch.int32)
+        fk = np.ascontiguousarray(first_keys, dtype=np.uint64)
+        counts = np.zeros(world, dtype=np.uint64)
+        self._ck(self.lib.gtb_esa_slice_partition(self.h, self.pl, lo, hi, ptr(fk), world, send_k.data_ptr(),
+                                                  send_p.data_ptr(), max(cap, 1), ptr(counts)))
+        sc = [int(c) for c in counts]
+        sct = torch.tensor(sc, dtype=torch.int64, device=self.device)
+        rct = torch.empty_like(sct)
+        dist.all_to_all_single(rct, sct)
+        rc = [int(x) for x in rct.tolist()]
+        tot_s, tot_r = sum(sc), sum(rc)
+        recv_k = self._tensor("recv_k", tot_r, torch.int64)
+        recv_p = self._tensor("recv_p", tot_r, torch.int32)
+        dist.all_to_all_single(recv_k[:tot_r], send_k[:tot_s], output_split_sizes=rc, input_split_sizes=sc)
+        dist.all_to_all_single(recv_p[:tot_r], send_p[:tot_s], output_split_sizes=rc, input_split_sizes=sc)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        self._ck(self.lib.gtb_esa_sort_begin_pairs(self.h, self.pl, self.flags, recv_k.data_ptr(), recv_p.data_ptr(),
+                                                   tot_r))
+        return tot_s * 12, tot_r * 12
+
+
+def run_range_distributed(worker, first_keys, dist, device, want_lcp=True, begin=None):
     """lock-step over torch.distributed (NCCL on GPUs, gloo in the CPU tests): rank r of
-    the process group runs code range r"""
+    the process group runs code range r.  begin (optional) replaces worker.sort_begin()."""
     import torch
     world, me = dist.get_world_size(), dist.get_rank()
 
@@ -218,7 +316,10 @@ def run_range_distributed(worker, first_keys, dist, device, want_lcp=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return int(t.item())
 
-    worker.sort_begin()
+    if begin is not None:
+        begin()
+    else:
+        worker.sort_begin()
     rounds = 0
     if allmax(worker.unresolved()) > 0:
         worker.ensure_ranks()

@@ -172,6 +172,40 @@ int gtb_esa_count_finish(gtb_esa *h);
 int gtb_esa_dev_bcktab(const gtb_esa *h, uint32_t **leftborder, uint32_t **countspecialcodes,
                        uint32_t **distpfxidx);
 
+/* Code ranges for several GPUs WITHOUT a fine-grained counting pass (one atomic per suffix
+   into a table larger than L2 is the slowest way to learn where to cut): the first
+   plc <= prefixlength symbols of the filled keys (at most 4096 coarse codes) are counted
+   in shared memory over the text positions [first_pos, end_pos); the caller sums the tiny
+   table of all ranks in place (*dev_counts, *ncounts uint32 entries) and every rank cuts the
+   same ranges with gtb_esa_coarse_split -- fine-grained mincode/maxcode, global offset and
+   width of each part, whole coarse buckets per part.  A rank then takes its part with
+   gtb_esa_set_code_range_known; its run derives the bucket-table entries of its own codes
+   from its sorted keys (all other entries 0: the caller sums the tables of the ranks,
+   gtb_esa_dev_bcktab, when the whole table is wanted). */
+int gtb_esa_coarse_partial(gtb_esa *h, unsigned prefixlength, uint64_t first_pos, uint64_t end_pos,
+                           uint32_t **dev_counts, uint64_t *ncounts);
+int gtb_esa_coarse_split(gtb_esa *h, unsigned numofparts, uint64_t *out4, unsigned *nparts);
+int gtb_esa_set_code_range_known(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint64_t sa_offset,
+                                 uint64_t width, int emit_special_tail);
+
+/* Sharding the text SCAN as well (every rank holds the whole packed sequence, but key
+   generation is the expensive part of the first pass): rank r turns the text positions
+   [first_pos, end_pos) of its slice into (filled key, position) pairs and groups them,
+   stably, by the code range that owns the key (range_first_keys[g] = gtb_code_first_key of
+   range g's first code) -- one onesweep pass whose "digit" is the owner.  dev_keys /
+   dev_positions are caller-owned DEVICE buffers of `capacity` pairs; counts_out[g] = pairs
+   for range g (they lie in that order).  The caller moves the groups to their owners
+   (ncclAllToAll, or peer copies) so that every owner holds its pairs in text order -- slices
+   in rank order -- and starts the sort there with gtb_esa_sort_begin_pairs instead of
+   gtb_esa_sort_begin (same staged protocol afterwards).  The owner needs its code range:
+   gtb_esa_set_code_range after gtb_esa_count* (+ GTB_REUSE_COUNTS), or
+   gtb_esa_set_code_range_known after the coarse counts. */
+int gtb_esa_slice_partition(gtb_esa *h, unsigned prefixlength, uint64_t first_pos, uint64_t end_pos,
+                            const uint64_t *range_first_keys, int nranges, uint64_t *dev_keys,
+                            uint32_t *dev_positions, uint64_t capacity, uint64_t *counts_out);
+int gtb_esa_sort_begin_pairs(gtb_esa *h, unsigned prefixlength, unsigned flags, const uint64_t *dev_keys,
+                             const uint32_t *dev_positions, uint64_t count);
+
 /* gt_suftabparts_new (sfx-partssuf.c:172-347) on the bucket table in HBM: cut the codes
    into at most `numofparts` (<= 64) contiguous ranges of about equal suffix counts.
    out4[4*p .. 4*p+3] = mincode, maxcode, sa_offset, width of part p; *nparts = parts made

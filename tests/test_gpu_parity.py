@@ -288,3 +288,156 @@ def test_cuda_partial_counts_and_range_split():
         assert mine == suftab_parts(ref[0], parts), parts
     for h in hs:
         lib.gtb_esa_delete(h)
+
+
+def test_cuda_slice_partition_and_pair_exchange():
+    """the sharded text scan on one GPU: two "ranks" partition their halves of the text by
+    owning code range, the groups are concatenated per owner in rank order (what the
+    all-to-all delivers) and each range sorts its pairs -- same bytes as the oracle"""
+    import ctypes as C
+    import torch
+    from genometools_b200.multirange import GpuRangeWorker, run_ranges_local, range_first_keys
+    from genometools_b200._lib import GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS, ptr
+    from genometools_b200.sharding import suftab_parts
+    lib = _lib.load()
+    for sym, pl, R in ((synth.repeats_dna(50_000, 8, unit=1500, copies=5, exact_len=900, exact_copies=3), 5, 2),
+                       (synth.reads(500, 70, 3, p_n=0.02), 4, 3)):
+        enc = encode_symbols(sym, 4)
+        n = enc.totallength
+        words, ranges = enc.twobitencoding()
+        buf = C.create_string_buffer(512)
+        h0 = lib.gtb_esa_new(0, buf, 512)
+        assert lib.gtb_esa_set_input_2bit(h0, ptr(words), words.shape[0], n, ptr(ranges) if ranges.shape[0] else None,
+                                          ranges.shape[0]) == 0
+        assert lib.gtb_esa_count(h0, pl) == 0
+        nall, nsp, nd = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(4, pl, C.byref(nall), C.byref(nsp), C.byref(nd))
+        lb = np.empty(nall.value + 1, np.uint32)
+        assert lib.gtb_esa_copy_bcktab(h0, ptr(lb), None, None) == 0
+        parts = suftab_parts(lb, R)
+        assert len(parts) == R
+        fk = range_first_keys(4, pl, parts)
+        groups = [[] for _ in range(R)]          # groups[owner] = list over slices
+        for r in range(R):
+            lo, hi = n * r // R, n * (r + 1) // R
+            sk = torch.empty(max(hi - lo, 1), dtype=torch.int64, device="cuda")
+            sp = torch.empty(max(hi - lo, 1), dtype=torch.int32, device="cuda")
+            counts = np.zeros(R, np.uint64)
+            assert lib.gtb_esa_slice_partition(h0, pl, lo, hi, ptr(fk), R, sk.data_ptr(), sp.data_ptr(), max(hi - lo, 1),
+                                               ptr(counts)) == 0, lib.gtb_esa_error(h0)
+            off = 0
+            for g in range(R):
+                c = int(counts[g])
+                groups[g].append((sk[off:off + c].clone(), sp[off:off + c].clone()))
+                off += c
+        flags = GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK | GTB_REUSE_COUNTS
+        hs, workers, begins, keep = [], [], [], []
+        for g, (mn, mx, off, _w) in enumerate(parts):
+            h = lib.gtb_esa_new(0, buf, 512)
+            hs.append(h)
+            assert lib.gtb_esa_share_input(h, h0) == 0
+            assert lib.gtb_esa_count(h, pl) == 0
+            assert lib.gtb_esa_set_code_range(h, mn, mx, off, 1 if g == R - 1 else 0) == 0
+            k = torch.cat([x[0] for x in groups[g]]); p = torch.cat([x[1] for x in groups[g]])
+            keep.append((k, p))
+            workers.append(GpuRangeWorker(h, pl, flags, 0))
+            begins.append(lambda h=h, k=k, p=p: _ck0(lib, h, lib.gtb_esa_sort_begin_pairs(h, pl, flags, k.data_ptr(),
+                                                                                         p.data_ptr(), k.numel())))
+        run_ranges_local(workers, fk, True, begins)
+        suf, lcp = [], []
+        for h in hs:
+            e = lib.gtb_esa_num_entries(h)
+            a = np.empty(e, np.uint64); b = np.empty(e, np.uint8)
+            assert lib.gtb_esa_copy_suftab_u64(h, ptr(a), 0, e) == 0
+            assert lib.gtb_esa_copy_lcptab(h, ptr(b), 0, e) == 0
+            suf.append(a); lcp.append(b)
+        o = eo.esa(sym, 4, pl)
+        im = eo.file_images(o)
+        assert np.concatenate(suf).astype("<u8").tobytes() == im["suf"]
+        assert np.concatenate(lcp).tobytes() == im["lcp"]
+        for h in hs + [h0]:
+            lib.gtb_esa_delete(h)
+
+
+def _ck0(lib, h, rc):
+    assert rc == 0, lib.gtb_esa_error(h).decode()
+
+
+@pytest.mark.parametrize("exchange", [False, True])
+def test_cuda_coarse_ranges_and_merged_bucket_table(exchange):
+    """the multi-GPU flow on one GPU: coarse counts -> ranges of whole coarse buckets -> every
+    range sorts (from the text, or from exchanged pairs) and fills the bucket-table entries
+    of its own codes from its sorted keys; the summed tables and the concatenated suffix /
+    lcp tables equal the oracle's"""
+    import ctypes as C
+    import torch
+    from genometools_b200.multirange import GpuRangeWorker, run_ranges_local, range_first_keys
+    from genometools_b200._lib import GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS, ptr
+    lib = _lib.load()
+    for sym, pl, R in ((synth.repeats_dna(60_000, 18, unit=1500, copies=5, exact_len=900, exact_copies=3), 8, 3),
+                       (synth.reads(600, 70, 13, p_n=0.02), 7, 2), (synth.random_dna(30_000, 4, 0.01), 3, 4)):
+        enc = encode_symbols(sym, 4)
+        n = enc.totallength
+        words, ranges = enc.twobitencoding()
+        buf = C.create_string_buffer(512)
+        h0 = lib.gtb_esa_new(0, buf, 512)
+        assert lib.gtb_esa_set_input_2bit(h0, ptr(words), words.shape[0], n, ptr(ranges) if ranges.shape[0] else None,
+                                          ranges.shape[0]) == 0
+        pd, nc = C.c_void_p(), C.c_uint64()
+        assert lib.gtb_esa_coarse_partial(h0, pl, 0, n, C.byref(pd), C.byref(nc)) == 0
+        out4 = (C.c_uint64 * (4 * R))(); k = C.c_uint()
+        assert lib.gtb_esa_coarse_split(h0, R, out4, C.byref(k)) == 0
+        parts = [tuple(int(out4[4 * p + q]) for q in range(4)) for p in range(k.value)]
+        assert parts[0][0] == 0 and parts[-1][1] == 4 ** pl - 1 and sum(p[3] for p in parts) == int((sym < 4).sum())
+        fk = range_first_keys(4, pl, parts)
+        flags = GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK | GTB_REUSE_COUNTS
+        hs, workers, begins, keep = [], [], [], []
+        groups = [[] for _ in parts]
+        if exchange:
+            for r in range(2):                        # two slices of the text
+                lo, hi = n * r // 2, n * (r + 1) // 2
+                sk = torch.empty(max(hi - lo, 1), dtype=torch.int64, device="cuda")
+                sp = torch.empty(max(hi - lo, 1), dtype=torch.int32, device="cuda")
+                counts = np.zeros(len(parts), np.uint64)
+                assert lib.gtb_esa_slice_partition(h0, pl, lo, hi, ptr(fk), len(parts), sk.data_ptr(), sp.data_ptr(),
+                                                   max(hi - lo, 1), ptr(counts)) == 0
+                off = 0
+                for g in range(len(parts)):
+                    c = int(counts[g]); groups[g].append((sk[off:off + c].clone(), sp[off:off + c].clone())); off += c
+        for g, (mn, mx, off, width) in enumerate(parts):
+            h = lib.gtb_esa_new(0, buf, 512)
+            hs.append(h)
+            assert lib.gtb_esa_share_input(h, h0) == 0
+            assert lib.gtb_esa_set_code_range_known(h, mn, mx, off, width, 1 if g == len(parts) - 1 else 0) == 0
+            workers.append(GpuRangeWorker(h, pl, flags, 0))
+            if exchange:
+                kk = torch.cat([x[0] for x in groups[g]]); pp = torch.cat([x[1] for x in groups[g]])
+                keep.append((kk, pp))
+                begins.append(lambda h=h, kk=kk, pp=pp: _ck0(lib, h, lib.gtb_esa_sort_begin_pairs(
+                    h, pl, flags, kk.data_ptr(), pp.data_ptr(), kk.numel())))
+            else:
+                begins.append(None)
+        run_ranges_local(workers, fk, True, begins)
+        nall, nsp, nd = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(4, pl, C.byref(nall), C.byref(nsp), C.byref(nd))
+        tabs = [np.zeros(nall.value + 1, np.uint64), np.zeros(nsp.value, np.uint64), np.zeros(max(nd.value, 1), np.uint64)]
+        suf, lcp = [], []
+        for h in hs:
+            e = lib.gtb_esa_num_entries(h)
+            a = np.empty(e, np.uint64); b = np.empty(e, np.uint8)
+            assert lib.gtb_esa_copy_suftab_u64(h, ptr(a), 0, e) == 0
+            assert lib.gtb_esa_copy_lcptab(h, ptr(b), 0, e) == 0
+            suf.append(a); lcp.append(b)
+            t = [np.empty(nall.value + 1, np.uint32), np.empty(nsp.value, np.uint32), np.empty(max(nd.value, 1), np.uint32)]
+            assert lib.gtb_esa_copy_bcktab(h, ptr(t[0]), ptr(t[1]), ptr(t[2]) if nd.value else None) == 0
+            for x, y in zip(tabs, t):
+                x += y                                # what the all-reduce over the ranks does
+        o = eo.esa(sym, 4, pl)
+        im = eo.file_images(o)
+        assert np.concatenate(suf).astype("<u8").tobytes() == im["suf"]
+        assert np.concatenate(lcp).tobytes() == im["lcp"]
+        assert np.array_equal(tabs[0], o["leftborder"].astype(np.uint64))
+        assert np.array_equal(tabs[1], o["countspecialcodes"].astype(np.uint64))
+        assert np.array_equal(tabs[2][:nd.value], o["distpfxidx"].astype(np.uint64))
+        for h in hs + [h0]:
+            lib.gtb_esa_delete(h)
