@@ -59,6 +59,7 @@ SYMBOLS = {
     "gtb_esa_coarse_split": (C.c_int, [_P, C.c_uint, _P, _P]),
     "gtb_esa_set_code_range_known": (C.c_int, [_P, _U64, _U64, _U64, _U64, C.c_int]),
     "gtb_esa_slice_partition": (C.c_int, [_P, C.c_uint, _U64, _U64, _P, C.c_int, _P, _P, _U64, _P]),
+    "gtb_esa_sort_begin_positions": (C.c_int, [_P, C.c_uint, C.c_uint, _P, _U64]),
     "gtb_esa_sort_begin_pairs": (C.c_int, [_P, C.c_uint, C.c_uint, _P, _P, _U64]),
     "gtb_esa_sort_begin": (C.c_int, [_P, C.c_uint, C.c_uint]),
     "gtb_esa_unresolved": (_U64, [_P]),

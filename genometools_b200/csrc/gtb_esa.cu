@@ -107,7 +107,7 @@ struct gtb_esa {
   float ms_count_ext = 0;   // device time of gtb_esa_count_partial/_finish since the last run
   float ms_part_ext = 0;    // ... and of gtb_esa_slice_partition (its pass counts as a radix pass)
   u64 part_pairs_ext = 0; u32 part_launches_ext = 0;
-  float ext_ms_radix = 0; u64 ext_pairs = 0; u32 ext_launches = 0;   // carried into this run's stats
+  float ext_ms_radix = 0, ext_ms_keygen = 0; u64 ext_pairs = 0; u32 ext_launches = 0;   // carried into this run's stats
   u64 depth[64];            // depth[r] = common prefix of the groups entering round r
   DevBuf ranks, owner, sendidx, rcounts;
   gtb_stats stats;
@@ -501,6 +501,7 @@ RankMap<DNA> make_rankmap(gtb_esa *h)
   rm.tbits = h->tbits.as<u32>(); rm.tpre = h->tpre.as<u32>(); rm.trank = h->trank.as<u32>();
   rm.spre = h->spre.as<u32>();
   rm.leftborder = ((h->counted || h->lb_own) && h->pl > 0) ? h->leftborder.as<u32>() : nullptr;
+  rm.own_last = (h->lb_own && !h->counted) ? h->maxcode : ~0ull;
   rm.pl = h->pl; rm.K = h->K;
   rm.n = h->n; rm.nonspecials = h->n - h->S; rm.sa_offset = h->sa_offset;
   return rm;
@@ -765,7 +766,7 @@ int stage_end(gtb_esa *h)
   S.radix_passes = h->rw.passes + (h->ext_pairs ? 1u : 0u);
   S.radix_pairs_moved = h->rw.pairs_moved + h->ext_pairs;
   S.kernel_launches += h->rw.launches + h->ext_launches;
-  S.ms_hist = h->rw.ms_hist; S.ms_radix = h->rw.ms_radix + h->ext_ms_radix;
+  S.ms_hist = h->rw.ms_hist + h->ext_ms_keygen; S.ms_radix = h->rw.ms_radix + h->ext_ms_radix;
   h->in_progress = false;
   return 0;
 }
@@ -791,6 +792,7 @@ static int check_run_args(gtb_esa *h, unsigned prefixlength, unsigned flags)
   memset(&h->stats, 0, sizeof h->stats);
   h->stats.ms_upload = up;
   if (flags & GTB_REUSE_COUNTS) { h->stats.ms_count = h->ms_count_ext; h->stats.ms_total = h->ms_count_ext + h->ms_part_ext; }
+  h->ext_ms_keygen = 0;
   h->ext_ms_radix = (flags & GTB_REUSE_COUNTS) ? h->ms_part_ext : 0;
   h->ext_pairs = (flags & GTB_REUSE_COUNTS) ? h->part_pairs_ext : 0;
   h->ext_launches = (flags & GTB_REUSE_COUNTS) ? h->part_launches_ext : 0;
@@ -1031,6 +1033,31 @@ int gtb_esa_sort_begin_pairs(gtb_esa *h, unsigned prefixlength, unsigned flags, 
   GTB_TRY(check_run_args(h, prefixlength, flags));
   PairSrc ext{dev_keys, dev_positions};
   return timed_stage(h, [&]() -> int {
+    return h->dna ? stage_begin<true>(h, flags, &ext, count) : stage_begin<false>(h, flags, &ext, count);
+  });
+}
+
+int gtb_esa_sort_begin_positions(gtb_esa *h, unsigned prefixlength, unsigned flags,
+                                 const uint32_t *dev_positions, uint64_t count)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (h->full_range) { err.set("gtb_esa_sort_begin_positions needs a code range"); return -1; }
+  GTB_TRY(check_run_args(h, prefixlength, flags));
+  // the keys are regenerated once into the second key buffer: the first pass reads them
+  // there and writes the first buffer
+  for (int i = 0; i < 2; i++) GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * (count + 1), err));
+  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  PairSrc ext{h->kbuf[1].as<u64>(), dev_positions};
+  return timed_stage(h, [&]() -> int {
+    if (count > 0) {
+      PhaseTimer t(h, &h->ext_ms_keygen);       // (key generation: accounted with the histogram phase)
+      if (h->dna) k_keys_from_positions<true><<<grid_for(count, 256), 256, 0, h->st>>>(make_src<true>(h, 0, ~0ull), dev_positions, count, h->kbuf[1].as<u64>());
+      else k_keys_from_positions<false><<<grid_for(count, 256), 256, 0, h->st>>>(make_src<false>(h, 0, ~0ull), dev_positions, count, h->kbuf[1].as<u64>());
+      GTB_LAUNCH_CHECK();
+      h->stats.kernel_launches++;
+      t.stop();
+    }
     return h->dna ? stage_begin<true>(h, flags, &ext, count) : stage_begin<false>(h, flags, &ext, count);
   });
 }

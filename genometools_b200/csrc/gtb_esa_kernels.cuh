@@ -146,6 +146,8 @@ struct RankMap {
   u32 *trank;
   const u32 *spre;           // popcount prefix of the special mask (null if no specials)
   const u32 *leftborder;     // bucket starts (global indices) or null: narrows the search
+  u64 own_last;              // last code whose successor entry is not in this table (a code range
+                             // fills its own codes only), ~0 if the table is complete
   unsigned pl, K;
   u64 n, nonspecials, sa_offset;
 
@@ -166,7 +168,7 @@ struct RankMap {
     if (leftborder) {          // the suffix lies in its bucket: a few dozen entries
       const u64 c = key_code<DNA>(kq, pl, K, src.f);
       lo = (u64) leftborder[c] - sa_offset;
-      hi = (u64) leftborder[c + 1] - sa_offset;
+      hi = c == own_last ? N : (u64) leftborder[c + 1] - sa_offset;
     }
     while (lo < hi) {
       const u64 mid = (lo + hi) >> 1;
@@ -1023,6 +1025,18 @@ __global__ void k_split_ranges(const u32 *__restrict__ lb, u64 ncodes, unsigned 
     if (out[4 * p + 3] > 0) { for (int q = 0; q < 4; q++) out[4 * keep + q] = out[4 * p + q]; keep++; }
   if (keep == 0) { out[0] = 0; out[1] = ncodes - 1; out[2] = 0; out[3] = total; keep = 1; }
   *nout = keep;
+}
+
+// keys of a list of (valid, non-special) text positions
+template <bool DNA>
+__global__ void k_keys_from_positions(TextSrc<DNA> src, const u32 *__restrict__ pos, u64 count,
+                                      u64 *__restrict__ keys)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x) {
+    u64 k = 0;
+    src.make_key_fmt(pos[i], k, src.f);
+    keys[i] = k;
+  }
 }
 
 // ---- bwttab (bwttab2file, /root/reference/src/match/sfx-run.c:173-210) -------------------

@@ -388,7 +388,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
     if (FULL || i < total) {
       const u64 kk = s_keys[i];
       const unsigned d = rs_digit<MODE>(kk, bsel, dmask);
-      s_pk[d][i] = kk;
+      if (MODE != 3 || okeys != nullptr) s_pk[d][i] = kk;     // (a partition pass may keep the values only)
       s_pv[d][i] = s_vals[i];
     }
   }
@@ -552,7 +552,8 @@ rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
 
 // One stable partition pass: the valid items of `src` grouped by owning key range
 // (bounds[0..nranges) = first key of each range, bounds[0] is taken as 0), written to
-// okeys/ovals; counts_out[r] = items of range r.  Synchronises the stream.
+// okeys/ovals (okeys may be null: values only); counts_out[r] = items of range r.
+// Synchronises the stream.
 template <class Src, class Cfg = RsDefault>
 static int rs_partition_by_owner(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, const u64 *bounds,
                                  int nranges, u64 *okeys, u32 *ovals, u64 capacity, u64 *counts_out, ErrBuf &err)

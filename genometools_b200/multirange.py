@@ -254,11 +254,12 @@ class PairExchange:
     the owner receives its pairs in text order (slices in rank order) -- and the owner's sort
     starts from those pairs (gtb_esa_sort_begin_pairs): no rank scans the whole text."""
 
-    def __init__(self, lib, handle, prefixlength, flags, totallength, dist, device):
+    def __init__(self, lib, handle, prefixlength, flags, totallength, dist, device, positions_only=True):
         import torch
         self.torch, self.lib, self.h, self.pl, self.flags = torch, lib, handle, prefixlength, flags
         self.n, self.dist, self.device = totallength, dist, device
-        self.buf = {}
+        self.positions_only = positions_only     # 4 instead of 12 bytes per suffix over the links;
+        self.buf = {}                            # the owner regenerates the keys
 
     def _tensor(self, name, count, dtype):
         t = self.buf.get(name)
@@ -276,11 +277,12 @@ class PairExchange:
         world, me = dist.get_world_size(), dist.get_rank()
         lo, hi = self.n * me // world, self.n * (me + 1) // world
         cap = hi - lo
-        send_k = self._tensor("send_k", cap, torch.int64)
+        send_k = None if self.positions_only else self._tensor("send_k", cap, torch.int64)
         send_p = self._tensor("send_p", cap, torch.int32)
         fk = np.ascontiguousarray(first_keys, dtype=np.uint64)
         counts = np.zeros(world, dtype=np.uint64)
-        self._ck(self.lib.gtb_esa_slice_partition(self.h, self.pl, lo, hi, ptr(fk), world, send_k.data_ptr(),
+        self._ck(self.lib.gtb_esa_slice_partition(self.h, self.pl, lo, hi, ptr(fk), world,
+                                                  send_k.data_ptr() if send_k is not None else None,
                                                   send_p.data_ptr(), max(cap, 1), ptr(counts)))
         sc = [int(c) for c in counts]
         sct = torch.tensor(sc, dtype=torch.int64, device=self.device)
@@ -288,10 +290,15 @@ class PairExchange:
         dist.all_to_all_single(rct, sct)
         rc = [int(x) for x in rct.tolist()]
         tot_s, tot_r = sum(sc), sum(rc)
-        recv_k = self._tensor("recv_k", tot_r, torch.int64)
         recv_p = self._tensor("recv_p", tot_r, torch.int32)
-        dist.all_to_all_single(recv_k[:tot_r], send_k[:tot_s], output_split_sizes=rc, input_split_sizes=sc)
         dist.all_to_all_single(recv_p[:tot_r], send_p[:tot_s], output_split_sizes=rc, input_split_sizes=sc)
+        if self.positions_only:
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+            self._ck(self.lib.gtb_esa_sort_begin_positions(self.h, self.pl, self.flags, recv_p.data_ptr(), tot_r))
+            return tot_s * 4, tot_r * 4
+        recv_k = self._tensor("recv_k", tot_r, torch.int64)
+        dist.all_to_all_single(recv_k[:tot_r], send_k[:tot_s], output_split_sizes=rc, input_split_sizes=sc)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         self._ck(self.lib.gtb_esa_sort_begin_pairs(self.h, self.pl, self.flags, recv_k.data_ptr(), recv_p.data_ptr(),

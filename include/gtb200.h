@@ -205,6 +205,11 @@ int gtb_esa_slice_partition(gtb_esa *h, unsigned prefixlength, uint64_t first_po
                             uint32_t *dev_positions, uint64_t capacity, uint64_t *counts_out);
 int gtb_esa_sort_begin_pairs(gtb_esa *h, unsigned prefixlength, unsigned flags, const uint64_t *dev_keys,
                              const uint32_t *dev_positions, uint64_t count);
+/* the same with a third of the exchange volume: gtb_esa_slice_partition with dev_keys = NULL
+   keeps the positions only (4 bytes per suffix cross the links); the owner regenerates the
+   keys of its positions once (they arrive ascending per slice) */
+int gtb_esa_sort_begin_positions(gtb_esa *h, unsigned prefixlength, unsigned flags,
+                                 const uint32_t *dev_positions, uint64_t count);
 
 /* gt_suftabparts_new (sfx-partssuf.c:172-347) on the bucket table in HBM: cut the codes
    into at most `numofparts` (<= 64) contiguous ranges of about equal suffix counts.

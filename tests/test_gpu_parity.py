@@ -363,7 +363,7 @@ def _ck0(lib, h, rc):
     assert rc == 0, lib.gtb_esa_error(h).decode()
 
 
-@pytest.mark.parametrize("exchange", [False, True])
+@pytest.mark.parametrize("exchange", [False, True, "positions"])
 def test_cuda_coarse_ranges_and_merged_bucket_table(exchange):
     """the multi-GPU flow on one GPU: coarse counts -> ranges of whole coarse buckets -> every
     range sorts (from the text, or from exchanged pairs) and fills the bucket-table entries
@@ -375,7 +375,9 @@ def test_cuda_coarse_ranges_and_merged_bucket_table(exchange):
     from genometools_b200._lib import GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS, ptr
     lib = _lib.load()
     for sym, pl, R in ((synth.repeats_dna(60_000, 18, unit=1500, copies=5, exact_len=900, exact_copies=3), 8, 3),
-                       (synth.reads(600, 70, 13, p_n=0.02), 7, 2), (synth.random_dna(30_000, 4, 0.01), 3, 4)):
+                       (synth.reads(600, 70, 13, p_n=0.02), 7, 2), (synth.random_dna(30_000, 4, 0.01), 3, 4),
+                       (synth.low_complexity_dna(20_000, 5), 3, 4),      # ties whose partners end middle ranges
+                       (synth.repeats_dna(40_000, 2, unit=900, copies=12, exact_len=2500, exact_copies=4), 2, 5)):
         enc = encode_symbols(sym, 4)
         n = enc.totallength
         words, ranges = enc.twobitencoding()
@@ -399,7 +401,8 @@ def test_cuda_coarse_ranges_and_merged_bucket_table(exchange):
                 sk = torch.empty(max(hi - lo, 1), dtype=torch.int64, device="cuda")
                 sp = torch.empty(max(hi - lo, 1), dtype=torch.int32, device="cuda")
                 counts = np.zeros(len(parts), np.uint64)
-                assert lib.gtb_esa_slice_partition(h0, pl, lo, hi, ptr(fk), len(parts), sk.data_ptr(), sp.data_ptr(),
+                assert lib.gtb_esa_slice_partition(h0, pl, lo, hi, ptr(fk), len(parts),
+                                                   None if exchange == "positions" else sk.data_ptr(), sp.data_ptr(),
                                                    max(hi - lo, 1), ptr(counts)) == 0
                 off = 0
                 for g in range(len(parts)):
@@ -413,8 +416,12 @@ def test_cuda_coarse_ranges_and_merged_bucket_table(exchange):
             if exchange:
                 kk = torch.cat([x[0] for x in groups[g]]); pp = torch.cat([x[1] for x in groups[g]])
                 keep.append((kk, pp))
-                begins.append(lambda h=h, kk=kk, pp=pp: _ck0(lib, h, lib.gtb_esa_sort_begin_pairs(
-                    h, pl, flags, kk.data_ptr(), pp.data_ptr(), kk.numel())))
+                if exchange == "positions":
+                    begins.append(lambda h=h, pp=pp: _ck0(lib, h, lib.gtb_esa_sort_begin_positions(
+                        h, pl, flags, pp.data_ptr(), pp.numel())))
+                else:
+                    begins.append(lambda h=h, kk=kk, pp=pp: _ck0(lib, h, lib.gtb_esa_sort_begin_pairs(
+                        h, pl, flags, kk.data_ptr(), pp.data_ptr(), kk.numel())))
             else:
                 begins.append(None)
         run_ranges_local(workers, fk, True, begins)
