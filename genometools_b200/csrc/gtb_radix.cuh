@@ -47,13 +47,15 @@ struct RsCfg {
   static constexpr bool VAL_EARLY = VAL_EARLY_;
   static_assert(NT_ >= RS_BINS && NT_ % 32 == 0, "one thread per bin needed");
   static_assert(IPT_ * 32 < 4096, "warp-local ranks are kept in 12 bits");
-  static constexpr size_t SMEM = sizeof(u64) * TILE + sizeof(u32) * TILE +
-                                 sizeof(u32) * WARPS * RS_BINS + sizeof(u32) * (WARPS + 4);
+  // staged keys + values, warp histograms (16-bit: a warp ranks at most 32*IPT <= 65535 pairs;
+  // at least 4 KB because the per-bin output pointer tables reuse the space), scan scratch
+  static constexpr size_t HIST = sizeof(unsigned short) * WARPS * RS_BINS < 4096 ? 4096 : sizeof(unsigned short) * WARPS * RS_BINS;
+  static constexpr size_t SMEM = sizeof(u64) * TILE + sizeof(u32) * TILE + HIST + sizeof(u32) * (WARPS + 4);
 };
 
 // the shape the library uses (chosen with tools/rs_bench.cu on B200, see profiles/)
 #ifndef GTB_RS_DEFAULT_CFG
-#define GTB_RS_DEFAULT_CFG RsCfg<256, 16, 3, false>
+#define GTB_RS_DEFAULT_CFG RsCfg<384, 16, 2, false>
 #endif
 typedef GTB_RS_DEFAULT_CFG RsDefault;
 constexpr int RS_TILE = RsDefault::TILE;      // granularity the status array is sized for
@@ -232,11 +234,12 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
   constexpr int NT = Cfg::NT, IPT = Cfg::IPT, TILE = Cfg::TILE, WARPS = Cfg::WARPS;
   u64 *s_keys = reinterpret_cast<u64 *>(rs_smem);
   u32 *s_vals = reinterpret_cast<u32 *>(s_keys + TILE);
-  u32 *s_wh   = s_vals + TILE;                        // [WARPS][RS_BINS] warp histograms -> slots
+  typedef unsigned short hist_t;
+  hist_t *s_wh = reinterpret_cast<hist_t *>(s_vals + TILE);   // [WARPS][RS_BINS] warp histograms -> slots
   u64 **s_pk  = reinterpret_cast<u64 **>(s_wh);       // [RS_BINS] per-bin output pointers, reuse
-  u32 **s_pv  = reinterpret_cast<u32 **>(s_pk + RS_BINS);   // s_wh after staging (needs WARPS >= 4)
-  u32 *s_scan = s_wh + WARPS * RS_BINS;               // WARPS + 2
-  static_assert(WARPS >= 4, "pointer tables reuse the warp histograms");
+  u32 **s_pv  = reinterpret_cast<u32 **>(s_pk + RS_BINS);   // s_wh after staging
+  u32 *s_scan = reinterpret_cast<u32 *>(reinterpret_cast<unsigned char *>(s_wh) + Cfg::HIST);   // WARPS + 2
+  static_assert(TILE <= 65535, "16-bit slots");
 #ifdef GTB_RS_PROFILE
   long long t_phase_ = clock64();
 #endif
@@ -269,7 +272,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
   // stable ranking inside the warp (rows in order, lanes in order): every lane reads the
   // warp's bin counter, the first lane of each set of equal digits writes it back
   // bumped by the size of the set
-  u32 *wh = s_wh + warp * RS_BINS;
+  hist_t *wh = s_wh + warp * RS_BINS;
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
@@ -279,7 +282,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
     const unsigned lower = peers & lt;
     const u32 old = wh[d];
     __syncwarp();
-    if (ok && lower == 0u) wh[d] = old + (u32) __popc(peers);
+    if (ok && lower == 0u) wh[d] = (hist_t) (old + (u32) __popc(peers));
     __syncwarp();
     rk[k] = old + (u32) __popc(lower);
   }
@@ -301,7 +304,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
 #pragma unroll
       for (int w = 0; w < WARPS; w++) {
         const u32 c = s_wh[w * RS_BINS + tid];
-        s_wh[w * RS_BINS + tid] = run;
+        s_wh[w * RS_BINS + tid] = (hist_t) run;
         run += c;
       }
       RS_ST(status + tile * RS_BINS + tid, ep | (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | (u64) cnt);
@@ -407,7 +410,7 @@ rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u6
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
   {
     u32 *s_wh = reinterpret_cast<u32 *>(rs_smem + (sizeof(u64) + sizeof(u32)) * TILE);
-    for (int i = threadIdx.x; i < Cfg::WARPS * RS_BINS; i += Cfg::NT) s_wh[i] = 0;
+    for (int i = threadIdx.x; i < (int) (Cfg::HIST / 4); i += Cfg::NT) s_wh[i] = 0;
   }
   __syncthreads();
   const u64 tile = s_ticket;

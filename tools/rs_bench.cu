@@ -136,19 +136,18 @@ int main(int argc, char **argv)
     if (mode == 0) {
       //  NT IPT MINB VAL_EARLY LB
       RUN(256, 16, 3, false, 0);     // no look-back: wrong result, upper bound of the rest
-      RUN(256, 16, 3, false, 1);
-      RUN(256, 16, 3, false, 2);
       RUN(256, 16, 3, false, 4);
-      RUN(256, 16, 3, false, 8);
-      RUN(256, 16, 3, true, 4);
-      RUN(256, 12, 4, false, 4);
-      RUN(384, 12, 3, false, 4);
+      RUN(256, 16, 4, false, 4);
       RUN(384, 16, 2, false, 4);
       RUN(512, 12, 2, false, 4);
-      RUN(512, 16, 1, false, 4);
+      RUN(512, 16, 2, false, 4);
+      RUN(512, 16, 2, false, 2);
+      RUN(512, 16, 2, false, 8);
+      RUN(1024, 8, 1, false, 4);
+      RUN(1024, 12, 1, false, 4);
     } else {
       RUN(256, 16, 3, false, 4);
-      RUN(384, 16, 2, false, 4);
+      RUN(512, 16, 2, false, 4);
     }
   }
   printf("failures: %d\n", failures);
