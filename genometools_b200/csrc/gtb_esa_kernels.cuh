@@ -122,6 +122,67 @@ struct TextSrc {
   __device__ __forceinline__ u32 load_val(u64 idx) const { return (u32) (pos0 + idx); }
 };
 
+// ---- digit histograms of the whole DNA text with rolling keys -------------------------------
+// The generic histogram kernel rebuilds every key from the packed text (~135 instructions
+// per position).  Here a thread walks 32 consecutive positions (one 2-bit word): the key
+// of the next position is the 128-bit text window shifted by one base, the distance to the
+// next special the 64-bit mask window shifted by one bit.
+__global__ void __launch_bounds__(256)
+k_hist_text_dna(TextSrc<true> src, u64 n, PassPlan plan, unsigned long long *__restrict__ ghist)
+{
+  __shared__ u32 s_h[RS_MAXPASS * RS_BINS];
+  for (int i = threadIdx.x; i < RS_MAXPASS * RS_BINS; i += blockDim.x) s_h[i] = 0;
+  __syncthreads();
+  const KeyFmt f = src.f;
+  const unsigned m = (unsigned) f.m;
+  const u64 nchunks = (n + 31) >> 5;
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < nchunks; c += (u64) gridDim.x * blockDim.x) {
+    u64 hi = src.words[c], lo = src.words[c + 1];                       // bases c*32 .. c*32+63
+    u64 mw = (u64) src.spmask[c] | ((u64) src.spmask[c + 1] << 32);     // their special bits
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+      if (!(mw & 1ull)) {                                               // (positions >= n are marked special)
+        const unsigned z = mw ? (unsigned) __ffsll((long long) mw) - 1u : 64u;
+        const unsigned u = z < m ? z : m;
+        u64 sym = hi >> (64 - 2 * m);
+        if (u < m) sym |= (1ull << (2u * (m - u))) - 1ull;
+        const u64 key = (sym << (64 - 2 * m)) | ((u64) (m - u) << f.sh);
+        if (key >= src.klo && key <= src.khi) {
+#pragma unroll
+          for (int p = 0; p < RS_MAXPASS; p++)
+            if (p < plan.npass)
+              atomicAdd(&s_h[p * RS_BINS + ((unsigned) (key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+        }
+      }
+      hi = (hi << 2) | (lo >> 62);
+      lo <<= 2;
+      mw >>= 1;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&ghist[i], (unsigned long long) s_h[i]);
+}
+
+template <>
+struct RsHistLauncher<TextSrc<true>> {
+  static void launch(const TextSrc<true> &src, u64 nsrc, const PassPlan &plan, unsigned long long *ghist,
+                     cudaStream_t st)
+  {
+    if (src.pos0 == 0) {                 // the whole text: rolling keys
+      const u64 chunks = (nsrc + 31) >> 5;
+      u64 g = div_up(chunks, 256);
+      if (g > 148ull * 8) g = 148ull * 8;
+      if (g < 1) g = 1;
+      k_hist_text_dna<<<(unsigned) g, 256, 0, st>>>(src, nsrc, plan, ghist);
+    } else {
+      u64 tiles = div_up(nsrc, RH_TILE);
+      unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
+      rs_hist_kernel<TextSrc<true>, false><<<grid, RH_NT, 0, st>>>(src, nsrc, plan, ghist);
+    }
+  }
+};
+
 // ---- ranks without an inverse suffix array -----------------------------------------------
 // Prefix doubling needs rank(q) = suffix-array index of q (of its group head while q is
 // tied) for the positions q = p + h of the tied suffixes p only -- about 1 % of a genome.

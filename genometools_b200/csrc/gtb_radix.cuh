@@ -142,6 +142,17 @@ rs_hist_kernel(Src src, u64 N, PassPlan plan, unsigned long long *__restrict__ g
     if (s_h[i]) atomicAdd(&ghist[i], (unsigned long long) s_h[i]);
 }
 
+// launch of the histogram kernel: a source may bring a cheaper way to walk its keys
+template <class Src>
+struct RsHistLauncher {
+  static void launch(const Src &src, u64 nsrc, const PassPlan &plan, unsigned long long *ghist, cudaStream_t st)
+  {
+    u64 tiles = div_up(nsrc, RH_TILE);
+    unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
+    rs_hist_kernel<Src, Src::ALWAYS_VALID><<<grid, RH_NT, 0, st>>>(src, nsrc, plan, ghist);   // pairs in memory may be skewed
+  }
+};
+
 // exclusive scan of each pass's 256 counts -> global digit starts
 __global__ void __launch_bounds__(RS_BINS)
 rs_scan_kernel(const unsigned long long *__restrict__ ghist, u64 *__restrict__ gbase)
@@ -616,9 +627,7 @@ static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
   GTB_CUDA(cudaEventRecord(w.ev[0], st));
   GTB_CUDA(cudaMemsetAsync(w.ghist, 0, sizeof(unsigned long long) * RS_MAXPASS * RS_BINS, st));
   {
-    u64 tiles = div_up(nsrc, RH_TILE);
-    unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
-    rs_hist_kernel<Src, Src::ALWAYS_VALID><<<grid, RH_NT, 0, st>>>(src, nsrc, plan, w.ghist);   // pairs in memory may be skewed
+    RsHistLauncher<Src>::launch(src, nsrc, plan, w.ghist, st);
     GTB_LAUNCH_CHECK();
     rs_scan_kernel<<<plan.npass, RS_BINS, 0, st>>>(w.ghist, w.gbase);
     GTB_LAUNCH_CHECK();
