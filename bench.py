@@ -352,15 +352,19 @@ def main():
             ps = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
             ps[:] = w.symbols
         d2h = 0
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        parts_s = [0.0, 0.0, 0.0]                   # H2D, kernels, D2H of the timed steps
+
+        def e2e_step():
+            nonlocal d2h
+            ta = time.perf_counter()
             if w.is_dna:
                 ck(lib.gtb_esa_set_input_2bit(h, ptr(words_pinned), words_pinned.shape[0], n,
                                               ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
             else:
                 ck(lib.gtb_esa_set_input_bytes(h, ptr(ps), n, w.numofchars))
+            tb = time.perf_counter()
             step()
+            tc = time.perf_counter()
             e = lib.gtb_esa_num_entries(h)
             ck(lib.gtb_esa_copy_suftab_u64(h, ptr(suf), 0, e))
             ck(lib.gtb_esa_copy_lcptab(h, ptr(lcp), 0, e))
@@ -369,7 +373,19 @@ def main():
             if k:
                 ck(lib.gtb_esa_copy_llv(h, ptr(llv)))
             ck(lib.gtb_esa_copy_bcktab(h, ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
-            d2h = 8 * e + e + 16 * k + 4 * (a.value + 1 + b.value + c.value)
+            # bytes that cross the bus: the suffix table travels as uint32 and is widened to the
+            # file's uint64 by host threads (GTB200_SUF_COPY=wide: widened on the device, 8 B each)
+            sufb = 8 if os.environ.get("GTB200_SUF_COPY") == "wide" else 4
+            d2h = sufb * e + e + 16 * k + 4 * (a.value + 1 + b.value + c.value)
+            td = time.perf_counter()
+            return tb - ta, tc - tb, td - tc
+
+        e2e_step()                                  # untimed: pins the staging buffers of the copies
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            for i_, v_ in enumerate(e2e_step()):
+                parts_s[i_] += v_
         sync_all()
         ewall = time.perf_counter() - t0
         te = torch.tensor([ewall], dtype=torch.float64, device="cuda")
@@ -378,7 +394,10 @@ def main():
         e2e = {"value": (n + 1) * args.e2e_steps / te.item() / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": w.input_bytes(), "d2h_bytes_per_step": int(d2h),
                "steps": args.e2e_steps, "ms_per_step": te.item() / args.e2e_steps * 1e3,
-               "note": "pinned host buffers; suftab widened to the file's uint64 on the device"}
+               "breakdown_ms": {"h2d": parts_s[0] / args.e2e_steps * 1e3, "kernels": parts_s[1] / args.e2e_steps * 1e3,
+                                "d2h": parts_s[2] / args.e2e_steps * 1e3},
+               "note": "pinned host buffers; results delivered as the files hold them (uint64 suftab, "
+                       "uint8 lcptab, llv pairs, uint32 bucket tables); one untimed warm-up step"}
 
     # cheap global check: the shards together are a permutation of 0..n (sum of entries)
     class _DevArr:

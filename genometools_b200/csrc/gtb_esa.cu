@@ -19,6 +19,7 @@
 #include "gtb_common.cuh"
 #include "gtb_radix.cuh"
 #include "gtb_esa_kernels.cuh"
+#include "gtb_hostio.cuh"
 
 namespace gtb {
 
@@ -110,6 +111,7 @@ struct gtb_esa {
   float ext_ms_radix = 0, ext_ms_keygen = 0; u64 ext_pairs = 0; u32 ext_launches = 0;   // carried into this run's stats
   u64 depth[64];            // depth[r] = common prefix of the groups entering round r
   DevBuf ranks, owner, sendidx, rcounts;
+  HostStage hstage;         // pinned staging + host threads of the result copies
   gtb_stats stats;
 };
 
@@ -894,6 +896,7 @@ void gtb_esa_delete(gtb_esa *h)
                    &h->ranks, &h->owner, &h->sendidx, &h->rcounts};
   for (DevBuf *b : all) b->release();
   radix_work_free(h->rw);
+  h->hstage.release();
   cudaStreamDestroy(h->st);
   delete h;
 }
@@ -1378,8 +1381,11 @@ int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t 
   GTB_TRY(check_range(h, first, count));
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
-  if (count) GTB_CUDA(cudaMemcpyAsync(dst, h->vbuf[h->res].as<u32>() + first, sizeof(u32) * count,
-                                      cudaMemcpyDeviceToHost, h->st));
+  const u32 *src = h->vbuf[h->res].as<u32>() + first;
+  if (count && host_pointer_is_pinned(dst))
+    GTB_CUDA(cudaMemcpyAsync(dst, src, sizeof(u32) * count, cudaMemcpyDeviceToHost, h->st));
+  else
+    GTB_TRY(staged_d2h(h->hstage, h->st, src, dst, count, sizeof(u32), false, err));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;
 }
@@ -1389,7 +1395,15 @@ int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t 
   GTB_TRY(check_range(h, first, count));
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
-  // widen on the device into a staging buffer (the dead key buffers), copy in chunks
+  const char *mode = getenv("GTB200_SUF_COPY");
+  if (!(mode && strcmp(mode, "wide") == 0 && host_pointer_is_pinned(dst))) {
+    // 4 bytes per entry cross the bus; host threads widen them to the file's uint64 (gtb_hostio.cuh)
+    GTB_TRY(staged_d2h(h->hstage, h->st, h->vbuf[h->res].as<u32>() + first, dst, count, sizeof(u32), true, err));
+    GTB_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+  }
+  // GTB200_SUF_COPY=wide (hosts whose memory system is slower than the bus): widen on the device
+  // into the dead key buffers and move 8 bytes per entry into the caller's pinned buffer
   const u64 chunk = 1ull << 25;                 // 32 Mi entries = 256 MiB per chunk
   u64 *stage[2];
   for (int i = 0; i < 2; i++) {
@@ -1417,7 +1431,11 @@ int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count
   GTB_TRY(check_range(h, first, count));
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
-  if (count) GTB_CUDA(cudaMemcpyAsync(dst, h->lcp8.as<u8>() + first, count, cudaMemcpyDeviceToHost, h->st));
+  const u8 *src = h->lcp8.as<u8>() + first;
+  if (count && host_pointer_is_pinned(dst))
+    GTB_CUDA(cudaMemcpyAsync(dst, src, count, cudaMemcpyDeviceToHost, h->st));
+  else
+    GTB_TRY(staged_d2h(h->hstage, h->st, src, dst, count, 1, false, err));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;
 }

@@ -537,15 +537,22 @@ analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &
   for (int i = 0; i < AN_IPT; i++) {
     const u64 j = base + i;
     if (!INNER && j >= N) break;
-    const bool head = (!INNER && j == 0) || key_head(k[i], k[i + 1], a.tmask);
+    // the common case: both neighbours are full keys (no special within their m symbols)
+    const bool fullpair = ((k[i] | k[i + 1]) & a.tmask) == 0 && (INNER || j > 0);
+    const bool head = fullpair ? k[i] != k[i + 1] : ((!INNER && j == 0) || key_head(k[i], k[i + 1], a.tmask));
     const bool nexthead = (!INNER && j + 1 >= N) || key_head(k[i + 1], k[i + 2], a.tmask);
     if (head) {
       lasthead = (u32) j + 1u;
-      u32 l = 0;
-      if (INNER || j > 0) l = key_lcp<DNA>(k[i], k[i + 1], f);
-      else if (a.seam_prev_valid) l = key_lcp<DNA>(a.seam_prev_key, k[i + 1], f);
+      u32 l = 0, u = (u32) f.m;
+      if (fullpair) {
+        constexpr u32 B = DNA ? 2u : 5u;
+        l = (u32) __clzll((long long) (k[i] ^ k[i + 1])) / B;   // (they differ in a symbol)
+      } else {
+        if (INNER || j > 0) l = key_lcp<DNA>(k[i], k[i + 1], f);
+        else if (a.seam_prev_valid) l = key_lcp<DNA>(a.seam_prev_key, k[i + 1], f);
+        u = (u32) f.m - f.tail(k[i + 1]);
+      }
       lcpword |= (u64) l << (8 * i);
-      const u32 u = (u32) f.m - f.tail(k[i + 1]);
       if (u >= a.pl) sum += l;
       mx = l > mx ? l : mx;
       if (FILL_LB && ((!INNER && j == 0) || l < a.pl)) {

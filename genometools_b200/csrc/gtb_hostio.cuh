@@ -1,0 +1,175 @@
+// gtb_hostio.cuh -- moving results from HBM into the caller's host buffers.
+//
+// The suffix table lives in HBM as uint32 (n + 1 < 2^32) while the reference's .suf holds
+// uint64 entries (gt_suffixsortspace_to_file, /root/reference/src/match/sfx-suffixgetset.c:462-477).
+// PCIe is the bottleneck of every end-to-end run (c4: 24.8 GB of uint64 against 187 ms of
+// kernels), so only the 4 significant bytes per entry cross the bus: chunks are copied into
+// pinned staging buffers owned by the handle and widened into the caller's buffer by a few
+// host threads with streaming stores while the next chunks are in flight.  The same staging
+// serves byte tables (.lcp, .bwt) whose destination is pageable memory -- a cudaMemcpy straight
+// into pageable memory is bounced through one driver thread at a fraction of the bus rate.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <emmintrin.h>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "gtb_common.cuh"
+
+namespace gtb {
+
+struct HostStage {
+  static constexpr int NB = 3;                     // chunks in flight
+  static constexpr size_t CHUNK = size_t(64) << 20; // bytes of device data per chunk
+  void *buf[NB] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
+  bool ready = false;
+  int nthreads = 0;
+
+  int ensure(ErrBuf &err)
+  {
+    if (ready) return 0;
+    for (int i = 0; i < NB; i++) {
+      GTB_CUDA(cudaHostAlloc(&buf[i], CHUNK, cudaHostAllocDefault));
+      GTB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    int t = 0;
+    if (const char *e = getenv("GTB200_HOST_THREADS")) t = atoi(e);
+    if (t <= 0) {
+      const unsigned hw = std::thread::hardware_concurrency();
+      t = hw > 3 ? (int) hw - 2 : 1;
+      if (t > 32) t = 32;
+    }
+    nthreads = t > 128 ? 128 : t;
+    ready = true;
+    return 0;
+  }
+  void release()
+  {
+    for (int i = 0; i < NB; i++) {
+      if (buf[i]) cudaFreeHost(buf[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      buf[i] = nullptr; ev[i] = nullptr;
+    }
+    ready = false;
+  }
+};
+
+// dst[i] = src[i] for i < n, streaming (the destination is written once and not read here)
+static inline void widen_u32_u64_host(const u32 *src, u64 *dst, u64 n)
+{
+  u64 i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15u)) { dst[i] = src[i]; i++; }
+  const __m128i z = _mm_setzero_si128();
+  for (; i + 8 <= n; i += 8) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 4));
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_unpacklo_epi32(a, z));
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 2), _mm_unpackhi_epi32(a, z));
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_unpacklo_epi32(b, z));
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 6), _mm_unpackhi_epi32(b, z));
+  }
+  for (; i < n; i++) dst[i] = src[i];
+  _mm_sfence();
+}
+
+// Copy `count` elements of `elem` bytes from device memory to host memory through the pinned
+// staging buffers; widen = true turns uint32 elements into uint64 on the way.  All device work
+// is queued on `st` (the handle's stream), so the copy sees the finished results.
+static int staged_d2h(HostStage &hs, cudaStream_t st, const void *dsrc, void *hdst, u64 count,
+                      unsigned elem, bool widen, ErrBuf &err)
+{
+  if (count == 0) return 0;
+  GTB_TRY(hs.ensure(err));
+  const u64 per = HostStage::CHUNK / elem;                 // elements per chunk
+  const u64 nchunks = div_up(count, per);
+  const u64 outelem = widen ? 8 : elem;
+  // small transfers: one chunk, this thread
+  int T = hs.nthreads;
+  if (count * (u64) elem < (u64(4) << 20)) T = 1;
+
+  std::mutex mu;
+  std::condition_variable cv;
+  u64 arrived = 0;                                         // chunks whose bytes are in their staging buffer
+  bool failed = false;
+  std::atomic<u64> done[HostStage::NB];
+  for (auto &d : done) d.store(0);
+
+  auto work = [&](int t) {
+    for (u64 k = 0; k < nchunks; k++) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return arrived > k || failed; });
+        if (failed) return;
+      }
+      const u64 c = count - k * per < per ? count - k * per : per;
+      const u64 lo = c * (u64) t / (u64) T, hi = c * (u64) (t + 1) / (u64) T;
+      const u8 *s = static_cast<const u8 *>(hs.buf[k % HostStage::NB]) + lo * elem;
+      u8 *d = static_cast<u8 *>(hdst) + (k * per + lo) * outelem;
+      if (widen) widen_u32_u64_host(reinterpret_cast<const u32 *>(s), reinterpret_cast<u64 *>(d), hi - lo);
+      else memcpy(d, s, (hi - lo) * elem);
+      done[k % HostStage::NB].fetch_add(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+
+  int rc = 0;
+  u64 issued = 0;
+  auto fail = [&](cudaError_t e, const char *what) {
+    err.set("%s failed: %s", what, cudaGetErrorString(e));
+    { std::lock_guard<std::mutex> lk(mu); failed = true; }
+    cv.notify_all();
+    rc = -1;
+  };
+  for (u64 k = 0; k < nchunks && rc == 0; k++) {
+    while (issued < nchunks && issued < k + HostStage::NB && rc == 0) {
+      const int b = (int) (issued % HostStage::NB);
+      // the buffer's previous chunk must have left it (all T slices taken)
+      const u64 uses = issued / HostStage::NB;
+      if (T > 1) while (done[b].load(std::memory_order_acquire) < uses * (u64) T) std::this_thread::yield();
+      const u64 c = count - issued * per < per ? count - issued * per : per;
+      cudaError_t e = cudaMemcpyAsync(hs.buf[b], static_cast<const u8 *>(dsrc) + issued * per * elem, c * elem,
+                                      cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaEventRecord(hs.ev[b], st);
+      if (e != cudaSuccess) { fail(e, "staged device-to-host copy"); break; }
+      issued++;
+      if (T == 1) break;                                   // single thread: strictly one after the other
+    }
+    if (rc != 0) break;
+    cudaError_t e = cudaEventSynchronize(hs.ev[k % HostStage::NB]);
+    if (e != cudaSuccess) { fail(e, "cudaEventSynchronize"); break; }
+    if (T == 1) {
+      const u64 c = count - k * per < per ? count - k * per : per;
+      const u8 *s = static_cast<const u8 *>(hs.buf[k % HostStage::NB]);
+      u8 *d = static_cast<u8 *>(hdst) + k * per * outelem;
+      if (widen) widen_u32_u64_host(reinterpret_cast<const u32 *>(s), reinterpret_cast<u64 *>(d), c);
+      else memcpy(d, s, c * elem);
+      continue;
+    }
+    { std::lock_guard<std::mutex> lk(mu); arrived = k + 1; }
+    cv.notify_all();
+    // this thread takes slice 0 of the chunk
+    const u64 c = count - k * per < per ? count - k * per : per;
+    const u64 hi = c / (u64) T;
+    const u8 *s = static_cast<const u8 *>(hs.buf[k % HostStage::NB]);
+    u8 *d = static_cast<u8 *>(hdst) + k * per * outelem;
+    if (widen) widen_u32_u64_host(reinterpret_cast<const u32 *>(s), reinterpret_cast<u64 *>(d), hi);
+    else memcpy(d, s, hi * elem);
+    done[k % HostStage::NB].fetch_add(1, std::memory_order_release);
+  }
+  for (auto &th : pool) th.join();
+  return rc;
+}
+
+// true when `p` is page-locked host memory the copy engine can write directly
+static inline bool host_pointer_is_pinned(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+} // namespace gtb
