@@ -143,15 +143,43 @@ def time_oracle_port(w):
     return [time.perf_counter() - t0]
 
 
-def cpu_baseline(args, wl_name):
+def time_dropin_cli(w, workdir, device):
+    """SURVEY.md section 8d, t_cli: the drop-in binary (host/_build/gt_b200 = the reference's `gt` with
+    our gt_suffixerator object, FASTA parse and file writes included) on the FASTA sample the reference
+    was just timed on, and a byte comparison of the five index files of the two runs."""
+    exe = os.path.join(ROOT, "host", "_build", "gt_b200")
+    fa = os.path.join(workdir, "sample.fa")
+    if not (os.path.exists(exe) and os.path.exists(fa) and os.path.exists(os.path.join(workdir, "ref.suf"))):
+        return None
+    t0 = time.perf_counter()
+    subprocess.check_call([exe, "suffixerator", "-dna" if w.is_dna else "-protein", "-suf", "-lcp", "-bck", "-pl",
+                           "-indexname", os.path.join(workdir, "b200"), "-db", fa], stdout=subprocess.DEVNULL)
+    t = time.perf_counter() - t0
+    same = True
+    for ext in ("suf", "lcp", "llv", "bck", "prj"):
+        a, b = os.path.join(workdir, "ref." + ext), os.path.join(workdir, "b200." + ext)
+        same = same and subprocess.call(["cmp", "-s", a, b]) == 0
+    return {"seconds": t, "value": (w.totallength + 1) / t / 1e6, "unit": UNIT, "files_identical_to_reference": same,
+            "what": "host/_build/gt_b200 suffixerator -suf -lcp -bck -pl on the cpu_baseline FASTA sample: the "
+                    "reference's own CLI, FASTA encoder and .prj writer around libgtb200 (process start, "
+                    "CUDA context, encoding on one host core and the writes of .suf/.lcp/.llv/.bck included)"}
+
+
+def cpu_baseline(args, wl_name, device=None):
     w = reference_sample(wl_name, args.cpu_sample)
     tmp = tempfile.mkdtemp(prefix="gtb_ref_")
+    cli = None
     try:
         times = time_reference(w, tmp)
         kind = "reference"
         if times is None:
             times = time_oracle_port(w)
             kind = "port"
+        elif device is not None:
+            try:
+                cli = time_dropin_cli(w, tmp, device)
+            except Exception as ex:      # reported, never fatal
+                cli = {"error": str(ex)}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     t = min(times)
@@ -159,7 +187,7 @@ def cpu_baseline(args, wl_name):
             "seconds": t,
             "sample": f"{w.name} generator at n={w.totallength} ({w.description}); "
                       + ("oracle/_ref/gtref suffixerator -suf -lcp -bck -pl, 1 thread (lcp is wrong with -j N)"
-                         if kind == "reference" else "oracle/esa_oracle.c restatement")}
+                         if kind == "reference" else "oracle/esa_oracle.c restatement")}, cli
 
 
 def run_reference_arm(args, rank, world):
@@ -432,10 +460,10 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
-    cpu = None
-    if not args.no_cpu_baseline:
+    cpu, cli = None, None
+    if not args.no_cpu_baseline and world == 1:
         try:
-            cpu = cpu_baseline(args, args.workload)
+            cpu, cli = cpu_baseline(args, args.workload, local_rank)
         except Exception as ex:      # the baseline is reported, never fatal
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(ex)}
     line = {
@@ -448,7 +476,7 @@ def main():
                    "l2": "inputs_exceed_l2 (no flush needed)", "sharding": f"{world} bucket-code ranges"
                    if world > 1 else "single range", "scale": args.scale},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "cli": cli,
         "wall_ms_per_step": wall_ms_max / args.steps,
         "breakdown_ms_last_step": {k: last[k] for k in ("ms_count", "ms_hist", "ms_radix", "ms_analyze",
                                                          "ms_doubling", "ms_lcp", "ms_tail")},

@@ -45,6 +45,7 @@ SYMBOLS = {
     "gtb_esa_error": (C.c_char_p, [_P]),
     "gtb_esa_set_input_2bit": (C.c_int, [_P, _P, _U64, _U64, _P, _U64]),
     "gtb_esa_set_input_bytes": (C.c_int, [_P, _P, _U64, C.c_uint]),
+    "gtb_esa_set_readmode": (C.c_int, [_P, C.c_uint]),
     "gtb_esa_share_input": (C.c_int, [_P, _P]),
     "gtb_esa_set_separators": (C.c_int, [_P, _P, _U64]),
     "gtb_esa_copy_bwttab": (C.c_int, [_P, _P, _U64, _U64]),

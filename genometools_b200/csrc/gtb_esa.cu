@@ -72,6 +72,7 @@ struct gtb_esa {
   DevBuf words, bytes, spmask, ranges, sepbits, seppos;
   bool have_sep = false;
   u64 nmaskwords = 0;
+  unsigned readmode = 0;    // GtReadmode of the sequence in HBM: 0 fwd, 1 rev, 2 cpl, 3 rcl
   // code range (shard)
   bool full_range = true;
   u64 mincode = 0, maxcode = 0;
@@ -398,6 +399,8 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
       GTB_TRY(h->tile_b.ensure(sizeof(u32) * (h->atiles + 1), err));
       GTB_TRY(h->hbits.ensure(N / 8 + 16, err));
       GTB_TRY(h->ubits.ensure(N / 8 + 16, err));
+      GTB_CUDA(cudaMemsetAsync(h->tile_a.p, 0, sizeof(u32) * (h->atiles + 1), st));   // the warps of a tile add / max
+      GTB_CUDA(cudaMemsetAsync(h->tile_b.p, 0, sizeof(u32) * (h->atiles + 1), st));   // into these
       if (lb_from_keys)
         k_analyze_keys<DNA, true><<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, st>>>(keys, N, f, h->pl, h->K, lcp8,
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, h->leftborder.as<u32>(), h->ncodes,
@@ -903,6 +906,15 @@ void gtb_esa_delete(gtb_esa *h)
 
 const char *gtb_esa_error(const gtb_esa *h) { return h ? h->err.msg : "null handle"; }
 
+int gtb_esa_set_readmode(gtb_esa *h, unsigned readmode)
+{
+  if (!h) return -1;
+  if (readmode > 3) { h->err.set("unknown readmode, must be fwd or rev or cpl or rcl"); return -1; }
+  if (readmode != h->readmode) { h->have_input = false; h->counted = false; h->ran = false; }
+  h->readmode = readmode;
+  return 0;
+}
+
 int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nwords,
                            uint64_t n, const gtb_range *specials, uint64_t nranges)
 {
@@ -915,9 +927,20 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
   h->dna = true; h->K = 4; h->n = n; h->counted = false; h->ran = false; h->have_sep = false;
   const u64 need = (n >> 5) + 4;
   GTB_TRY(h->words.ensure(sizeof(u64) * need, err));
-  GTB_CUDA(cudaMemsetAsync(h->words.p, 0, sizeof(u64) * need, h->st));
   const u64 ncopy = nwords < need ? nwords : need;
-  if (ncopy) GTB_CUDA(cudaMemcpyAsync(h->words.p, twobitenc, sizeof(u64) * ncopy, cudaMemcpyHostToDevice, h->st));
+  const bool rev = (h->readmode & 1u) != 0, cpl = (h->readmode & 2u) != 0;
+  if (h->readmode == 0) {
+    GTB_CUDA(cudaMemsetAsync(h->words.p, 0, sizeof(u64) * need, h->st));
+    if (ncopy) GTB_CUDA(cudaMemcpyAsync(h->words.p, twobitenc, sizeof(u64) * ncopy, cudaMemcpyHostToDevice, h->st));
+  } else {
+    // -dir rev|cpl|rcl: the words go to scratch memory and are rewritten in the read direction
+    GTB_TRY(h->kbuf[0].ensure(sizeof(u64) * need, err));
+    GTB_CUDA(cudaMemsetAsync(h->kbuf[0].p, 0, sizeof(u64) * need, h->st));
+    if (ncopy) GTB_CUDA(cudaMemcpyAsync(h->kbuf[0].p, twobitenc, sizeof(u64) * ncopy, cudaMemcpyHostToDevice, h->st));
+    k_readmode_words<<<grid_for(need, 256), 256, 0, h->st>>>(h->kbuf[0].as<u64>(), h->words.as<u64>(), n, need,
+                                                             rev ? 1 : 0, cpl ? 1 : 0);
+    GTB_LAUNCH_CHECK();
+  }
   for (u64 r = 0; r < nranges; r++) {
     if (specials[r].start >= specials[r].end || specials[r].end > n ||
         (r > 0 && specials[r].start < specials[r - 1].end)) {
@@ -926,7 +949,21 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
       return -1;
     }
   }
-  GTB_TRY(build_mask(h, specials, nranges));
+  if (rev && nranges > 0) {
+    // the special runs in read direction: mirrored and in reverse order
+    gtb_range *mir = static_cast<gtb_range *>(malloc(sizeof(gtb_range) * nranges));
+    if (!mir) { err.set("out of host memory for %llu special ranges", (unsigned long long) nranges); return -1; }
+    for (u64 r = 0; r < nranges; r++) {
+      mir[r].start = n - specials[nranges - 1 - r].end;
+      mir[r].end = n - specials[nranges - 1 - r].start;
+    }
+    const int rc = build_mask(h, mir, nranges);
+    if (rc == 0) cudaStreamSynchronize(h->st);      // (the upload of `mir` is asynchronous)
+    free(mir);
+    GTB_TRY(rc);
+  } else {
+    GTB_TRY(build_mask(h, specials, nranges));
+  }
   t.stop();
   h->have_input = true;
   return 0;
@@ -939,12 +976,23 @@ int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols, uint64_t n, unsi
   GTB_CUDA(cudaSetDevice(h->device));
   if (n + 1 >= 0xffffffffull) { err.set("totallength %llu needs 64-bit suffix tables: not supported by this build", (unsigned long long) n); return -1; }
   if (K < 1 || K > 31) { err.set("numofchars %u not supported by the byte path (1..31)", K); return -1; }
+  if ((h->readmode & 2u) && K != 4) {     // sfx-run.c:541-549
+    err.set("option -%s only can be used for DNA alphabets", h->readmode == 2 ? "cpl" : "rcl");
+    return -1;
+  }
   PhaseTimer t(h, &h->stats.ms_upload);
   h->dna = false; h->K = K; h->n = n; h->counted = false; h->ran = false;
   const u64 need = ((n + 31) / 32) * 32 + 64;
   GTB_TRY(h->bytes.ensure(need, err));
   GTB_CUDA(cudaMemsetAsync(h->bytes.p, 0xff, need, h->st));
-  if (n) GTB_CUDA(cudaMemcpyAsync(h->bytes.p, symbols, n, cudaMemcpyHostToDevice, h->st));
+  if (n && h->readmode == 0) GTB_CUDA(cudaMemcpyAsync(h->bytes.p, symbols, n, cudaMemcpyHostToDevice, h->st));
+  if (n && h->readmode != 0) {
+    GTB_TRY(h->kbuf[0].ensure(n, err));
+    GTB_CUDA(cudaMemcpyAsync(h->kbuf[0].p, symbols, n, cudaMemcpyHostToDevice, h->st));
+    k_readmode_bytes<<<grid_for(n, 256), 256, 0, h->st>>>(h->kbuf[0].as<u8>(), h->bytes.as<u8>(), n,
+                                                          (h->readmode & 1u) ? 1 : 0, (h->readmode & 2u) ? 1 : 0);
+    GTB_LAUNCH_CHECK();
+  }
   GTB_TRY(build_mask(h, nullptr, 0));
   t.stop();
   h->have_input = true;
@@ -957,6 +1005,7 @@ int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src)
   if (!src->have_input) { h->err.set("gtb_esa_share_input: source has no input"); return -1; }
   if (h->device != src->device) { h->err.set("gtb_esa_share_input: handles live on different devices"); return -1; }
   h->dna = src->dna; h->K = src->K; h->n = src->n; h->S = src->S; h->nmaskwords = src->nmaskwords;
+  h->readmode = src->readmode;
   h->words.borrow(src->words); h->bytes.borrow(src->bytes); h->spmask.borrow(src->spmask);
   h->sepbits.borrow(src->sepbits); h->have_sep = src->have_sep;
   h->counted = false; h->ran = false; h->have_input = true;
@@ -1451,6 +1500,14 @@ int gtb_esa_set_separators(gtb_esa *h, const uint64_t *positions, uint64_t count
       err.set("separator %llu at %llu is unordered or beyond the text", (unsigned long long) i, (unsigned long long) positions[i]);
       return -1;
     }
+  u64 *mirrored = nullptr;
+  if ((h->readmode & 1u) && count > 0) {          // forward coordinates -> read direction
+    mirrored = static_cast<u64 *>(malloc(sizeof(u64) * count));
+    if (!mirrored) { err.set("out of host memory for %llu separators", (unsigned long long) count); return -1; }
+    for (u64 i = 0; i < count; i++) mirrored[i] = h->n - 1 - positions[count - 1 - i];
+    positions = mirrored;
+  }
+  struct FreeLater { u64 *p; ~FreeLater() { free(p); } } free_later{mirrored};
   const u64 nw = (h->n >> 5) + 2;
   GTB_TRY(h->sepbits.ensure(sizeof(u32) * nw, err));
   GTB_CUDA(cudaMemsetAsync(h->sepbits.p, 0, sizeof(u32) * nw, h->st));

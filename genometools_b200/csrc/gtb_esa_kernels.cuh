@@ -84,6 +84,7 @@ __device__ __forceinline__ u64 dna_window(const u64 *__restrict__ words, u64 pos
 template <bool DNA>
 struct TextSrc {
   static constexpr bool ALWAYS_VALID = false;
+  static constexpr bool BLOCKED_GEN = DNA;   // rolling keys over the 2-bit words (gen_block)
   const u64 *words;      // DNA: packed 2-bit words (padded by >= 2 words)
   const u8  *bytes;      // bytes path: symbols (padded by >= 16 bytes of 255)
   const u32 *spmask;     // bit i set <=> position i is special; bits >= n all set
@@ -120,6 +121,51 @@ struct TextSrc {
   __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
   { return make_key(pos0 + idx, k); }
   __device__ __forceinline__ u32 load_val(u64 idx) const { return (u32) (pos0 + idx); }
+  // keys of the `cnt` <= 16 consecutive items idx .. idx + cnt - 1 into out[0 .. 15] (the rest
+  // and every item that is special or outside [klo, khi] becomes ~0, which no filled key equals).
+  // DNA only.  The 16 + m - 1 <= 44 bases and the 64 mask bits a thread needs are loaded once
+  // into 32-bit registers; key i is two funnel shifts by the constant 2i and two ANDs, its
+  // distance to the next special one funnel shift of the mask -- about 8 instructions per key
+  // unless a special lies within its m symbols.
+  __device__ __forceinline__ void gen_block(u64 idx, u32 cnt, u64 *out) const
+  {
+    const u64 p0 = pos0 + idx;
+    const unsigned m = (unsigned) f.m;
+    if (cnt < 16u) {                                    // the ragged end of the source
+#pragma unroll 1
+      for (u32 i = 0; i < 16u; i++) {
+        u64 key = ~0ull;
+        if (i < cnt && !make_key(p0 + i, key)) key = ~0ull;
+        out[i] = key;
+      }
+      return;
+    }
+    const u64 h64 = dna_window(words, p0);              // bases p0 .. p0+31
+    const u32 w0 = (u32) (h64 >> 32), w1 = (u32) h64;
+    const u32 w2 = (u32) (dna_window(words, p0 + 32) >> 32);   // bases p0+32 .. p0+47
+    const u32 mlo = mask_window(spmask, p0), mhi = mask_window(spmask, p0 + 32);
+    const u64 sm = f.symmask();
+    const u32 smhi = (u32) (sm >> 32), smlo = (u32) sm;
+    const u32 mmask = (1u << m) - 1u;                   // m <= 29
+    const bool filter = klo != 0ull || khi != ~0ull;
+#pragma unroll
+    for (u32 i = 0; i < 16u; i++) {
+      const u32 khi32 = __funnelshift_l(w1, w0, 2u * i) & smhi;
+      const u32 klo32 = __funnelshift_l(w2, w1, 2u * i) & smlo;
+      u64 key = ((u64) khi32 << 32) | klo32;
+      const u32 win = __funnelshift_r(mlo, mhi, i) & mmask;     // specials among positions i .. i+m-1
+      if (win != 0u) {
+        if (win & 1u) key = ~0ull;                      // a special position is no item
+        else {
+          const unsigned u = (unsigned) __ffs(win) - 1u;        // regular symbols before the special
+          key |= (1ull << (64u - 2u * u)) - (1ull << (64u - 2u * m));   // filler over symbols u .. m-1
+          key |= (u64) (m - u) << f.sh;
+        }
+      }
+      if (filter && (key < klo || key > khi)) key = ~0ull;
+      out[i] = key;
+    }
+  }
 };
 
 // ---- digit histograms of the whole DNA text with rolling keys -------------------------------
@@ -479,27 +525,6 @@ struct DevStats {
 
 constexpr int AN_NT = 256, AN_IPT = 8, AN_TILE = AN_NT * AN_IPT;
 
-// Every thread of a tile needs AN_IPT consecutive keys plus one on either side.  The
-// tile is read coalesced into shared memory (one padding word per 8 keys: the blocked
-// reads are then free of bank conflicts) and handed out: k[i] = keys[base + i - 1].
-constexpr int AN_SMEM_KEYS = AN_TILE + 2 + (AN_TILE + 2) / 8 + 1;
-__device__ __forceinline__ void load_keys_blocked(const u64 *__restrict__ keys, u64 N, u64 tile, u64 *s_k,
-                                                  u64 (&k)[AN_IPT + 2])
-{
-  const u64 tilebase = tile * AN_TILE;
-  __syncthreads();                                // (s_k may still be read for the previous tile)
-  for (int e = threadIdx.x; e < AN_TILE + 2; e += AN_NT) {
-    const u64 j = tilebase + e;                   // element e = keys[tilebase + e - 1]
-    s_k[e + (e >> 3)] = (j >= 1 && j - 1 < N) ? keys[j - 1] : 0;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < AN_IPT + 2; i++) {
-    const int e = threadIdx.x * AN_IPT + i;
-    k[i] = s_k[e + (e >> 3)];
-  }
-}
-
 template <bool DNA>
 __device__ __forceinline__ u32 key_lcp(u64 ka, u64 kb, const KeyFmt &f)
 {
@@ -588,7 +613,14 @@ analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &
 // pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head; with
 // FILL_LB also the whole bucket table from the sorted keys: leftborder[c] = index of the
 // first key with code >= c; countspecialcodes / distpfxidx from the keys that met a special
-// within their first pl symbols (equal ones are adjacent: one atomic per run and thread)
+// within their first pl symbols (equal ones are adjacent: one atomic per run and thread).
+//
+// A warp owns 32 * AN_IPT consecutive keys, a thread AN_IPT of them: four 128-bit loads, the
+// two neighbours by shuffle, no shared memory and no block barrier.  A warp whose keys are
+// all full (no special within their m symbols -- all but ~1e-4 of a genome) takes a lean
+// path of about 16 instructions per key; anything else (tail fields, the two ends of the
+// array) goes through analyze_thread.  tile_unres / tile_lasthead must be zero on entry (the
+// warps of a tile add / max into them).
 template <bool DNA, bool FILL_LB>
 __global__ void __launch_bounds__(AN_NT)
 k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsigned K,
@@ -600,41 +632,105 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
                u64 lbfirst, u64 lblast, u64 sa_offset)
 {
   static_assert(AN_IPT == 8, "one 8-byte lcp store and one flag byte per thread");
-  __shared__ u32 scratch[AN_NT / 32 + 1];
+  constexpr u32 WCHUNK = 32 * AN_IPT;                      // keys per warp and iteration
+  constexpr u32 B = DNA ? 2u : 5u;
   __shared__ u32 s_max[AN_NT / 32];
   __shared__ unsigned long long s_sum[AN_NT / 32];
-  __shared__ u64 s_k[AN_SMEM_KEYS];
   const u64 tmask = f.tailmask();
-  const u64 ntiles = (N + AN_TILE - 1) / AN_TILE;
+  const AnalyzeArgs a{N, f, tmask, pl, K, seam_prev_valid, seam_prev_key, leftborder, ncodes, csc, dist, distoff,
+                      lbfirst, lblast, sa_offset};
+  const unsigned lane = lane_id();
+  const u64 nchunks = (N + WCHUNK - 1) / WCHUNK;
+  const u64 nwarps = (u64) gridDim.x * (AN_NT / 32);
   u32 mx = 0;
   unsigned long long sum = 0;
-  // a CTA walks over many tiles and keeps the statistics in registers: one atomic per CTA
-  // (one per warp and tile would serialise on the two addresses in L2)
-  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const u64 base = tile * AN_TILE + (u64) threadIdx.x * AN_IPT;
+  for (u64 c = (u64) blockIdx.x * (AN_NT / 32) + (threadIdx.x >> 5); c < nchunks; c += nwarps) {
+    const u64 base = c * WCHUNK + (u64) lane * AN_IPT;
     u64 k[AN_IPT + 2];                   // k[i] = keys[base + i - 1]
-    load_keys_blocked(keys, N, tile, s_k, k);
-    u32 unres = 0, lasthead = 0;
+    if (base + AN_IPT <= N) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(keys + base);
+#pragma unroll
+      for (int q = 0; q < AN_IPT / 2; q++) {
+        const uint4 v = ld_stream_v4(p + q);
+        k[1 + 2 * q] = (u64) v.x | ((u64) v.y << 32);
+        k[2 + 2 * q] = (u64) v.z | ((u64) v.w << 32);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < AN_IPT; i++) k[1 + i] = base + i < N ? keys[base + i] : 0;
+    }
+    k[0] = __shfl_up_sync(FULL_MASK, k[AN_IPT], 1);
+    k[AN_IPT + 1] = __shfl_down_sync(FULL_MASK, k[1], 1);
+    if (lane == 0) k[0] = (base >= 1 && base - 1 < N) ? keys[base - 1] : 0;
+    if (lane == 31) k[AN_IPT + 1] = base + AN_IPT < N ? keys[base + AN_IPT] : 0;
+
+    u64 orall = k[0];
+#pragma unroll
+    for (int i = 1; i < AN_IPT + 2; i++) orall |= k[i];
+    u32 unres = 0, lasthead = 0, headbits = 0, unresbits = 0;
     u64 lcpword = 0;
-    const AnalyzeArgs a{N, f, tmask, pl, K, seam_prev_valid, seam_prev_key, leftborder, ncodes, csc, dist, distoff,
-                        lbfirst, lblast, sa_offset};
-    u32 headbits = 0, unresbits = 0;
-    if (tile > 0 && (tile + 1) * AN_TILE < N)      // inner tile: no bounds to check
-      analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
-    else
+    // (warp-uniform choices: a warp that runs two of the paths pays for both)
+    if (c == 0 || (c + 1) * WCHUNK + 1 > N) {                   // the two ends of the array
       analyze_thread<DNA, FILL_LB, false>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
+    } else if (__any_sync(FULL_MASK, (orall & tmask) != 0)) {   // some key met a special
+      analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
+    } else {
+      // all ten keys are full and inside the array: head <=> the keys differ (then in a symbol)
+      u32 hb = 0, gapbits = 0, lsum = 0;
+      const unsigned codesh = 64u - B * pl;             // DNA: the bucket code is the top 2*pl bits
+#pragma unroll
+      for (int i = 0; i < AN_IPT; i++) {
+        const u64 x = k[i] ^ k[i + 1];
+        const u32 l = x ? (u32) __clzll((long long) x) / B : 0u;
+        lcpword |= (u64) l << (8 * i);
+        lsum += l;
+        mx = l > mx ? l : mx;
+        if (x) hb |= 1u << i;
+        if (FILL_LB && pl > 0 && (x >> codesh) != 0) {
+          // a new bucket starts at element i: every code in (code of i-1, code of i] starts there.
+          // DNA: one predicated store; empty buckets in between (rare) are filled below
+          if (DNA) {
+            const u32 c1 = (u32) (k[i + 1] >> codesh), c0 = (u32) (k[i] >> codesh);
+            leftborder[c1] = (u32) (sa_offset + base + i);
+            if (c1 - c0 > 1u) gapbits |= 1u << i;
+          } else {
+            const u64 c1 = key_code<DNA>(k[i + 1], pl, K, f);
+            for (u64 c0 = key_code<DNA>(k[i], pl, K, f) + 1; c0 <= c1; c0++)
+              leftborder[c0] = (u32) (sa_offset + base + i);
+          }
+        }
+      }
+      sum += lsum;
+      if (k[AN_IPT] != k[AN_IPT + 1]) hb |= 1u << AN_IPT;
+      headbits = hb & 0xffu;
+      unresbits = (~hb | ~(hb >> 1)) & 0xffu;
+      unres = (u32) __popc(unresbits);
+      lasthead = headbits ? (u32) base + (31u - (u32) __clz(headbits)) + 1u : 0u;
+      if (FILL_LB && DNA && gapbits) {
+#pragma unroll
+        for (int i = 0; i < AN_IPT; i++)
+          if ((gapbits >> i) & 1u) {
+            const u32 c1 = (u32) (k[i + 1] >> codesh);
+            for (u32 c0 = (u32) (k[i] >> codesh) + 1u; c0 < c1; c0++)
+              leftborder[c0] = (u32) (sa_offset + base + i);
+          }
+      }
+    }
     if (base < N) { hbits[base >> 3] = (u8) headbits; ubits[base >> 3] = (u8) unresbits; }
     if (base + AN_IPT <= N) {
       *reinterpret_cast<u64 *>(lcp8 + base) = lcpword;
     } else {
       for (int i = 0; i < AN_IPT && base + i < N; i++) lcp8[base + i] = (u8) (lcpword >> (8 * i));
     }
-    u32 total;
-    block_exclusive_sum<AN_NT, u32>(unres, scratch, &total);
-    const u32 lh = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
-    if (threadIdx.x == AN_NT - 1) { tile_unres[tile] = total; tile_lasthead[tile] = lh; }
+    const u32 wsum = __reduce_add_sync(FULL_MASK, unres);
+    const u32 wmax = __reduce_max_sync(FULL_MASK, lasthead);
+    if (lane == 0) {
+      const u64 tile = c / (AN_TILE / WCHUNK);
+      if (wsum) atomicAdd(&tile_unres[tile], wsum);
+      if (wmax) atomicMax(&tile_lasthead[tile], wmax);
+    }
   }
-  // stats
+  // stats: one atomic per CTA
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     sum += __shfl_xor_sync(FULL_MASK, sum, d);
@@ -653,32 +749,44 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
 }
 
 // single block: exclusive sum of tile_unres (in place) and exclusive running max of
-// tile_lasthead (in place: becomes "last head before this tile", +1 encoded)
+// tile_lasthead (in place: becomes "last head before this tile", +1 encoded); a thread
+// takes 8 consecutive tiles per iteration
 __global__ void __launch_bounds__(1024)
 k_scan_tiles_sum_max(u32 *tile_unres, u32 *tile_lasthead, u64 ntiles, u64 *total_out)
 {
+  constexpr int PT = 8;
   __shared__ u32 scratch[1024 / 32 + 1];
+  __shared__ u32 s_wlast[32];
   __shared__ u32 carry_sum, carry_max;
   if (threadIdx.x == 0) { carry_sum = 0; carry_max = 0; }
   __syncthreads();
   u64 grand = 0;
-  for (u64 base = 0; base < ntiles; base += 1024) {
-    const u64 i = base + threadIdx.x;
-    const u32 v = i < ntiles ? tile_unres[i] : 0u;
-    const u32 h = i < ntiles ? tile_lasthead[i] : 0u;
+  for (u64 base = 0; base < ntiles; base += 1024 * PT) {
+    const u64 i0 = base + (u64) threadIdx.x * PT;
+    u32 v[PT], h[PT], tsum = 0, tmax = 0;
+#pragma unroll
+    for (int q = 0; q < PT; q++) {
+      v[q] = i0 + q < ntiles ? tile_unres[i0 + q] : 0u;
+      h[q] = i0 + q < ntiles ? tile_lasthead[i0 + q] : 0u;
+      tsum += v[q];
+      tmax = h[q] > tmax ? h[q] : tmax;
+    }
     u32 total;
-    const u32 ex = block_exclusive_sum<1024, u32>(v, scratch, &total);
-    const u32 incl = block_inclusive_max<1024, u32>(h, scratch);
-    // exclusive max = inclusive max of the previous element
+    u32 ex = block_exclusive_sum<1024, u32>(tsum, scratch, &total);
+    const u32 incl = block_inclusive_max<1024, u32>(tmax, scratch);
+    // exclusive max = inclusive max of the previous thread
     u32 prev = __shfl_up_sync(FULL_MASK, incl, 1);
-    __shared__ u32 s_wlast[32];
     if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
     __syncthreads();
     if (lane_id() == 0) prev = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
     const u32 cs = carry_sum, cm = carry_max;
-    if (i < ntiles) {
-      tile_unres[i] = ex + cs;
-      tile_lasthead[i] = prev > cm ? prev : cm;
+    ex += cs;
+    prev = prev > cm ? prev : cm;
+#pragma unroll
+    for (int q = 0; q < PT; q++) {
+      if (i0 + q < ntiles) { tile_unres[i0 + q] = ex; tile_lasthead[i0 + q] = prev; }
+      ex += v[q];
+      prev = h[q] > prev ? h[q] : prev;
     }
     grand += total;
     __syncthreads();
@@ -1138,6 +1246,49 @@ __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ ou
 {
   for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)
     out[i] = in[i];
+}
+
+// ---- read modes (-dir rev | cpl | rcl) ----------------------------------------------------
+// The reference reads the sequence through a GtReadmode (gt_encseq_get_encoded_char,
+// /root/reference/src/core/encseq.c:6094-6140; extraction of k-mers in reverse / complement,
+// src/match/sfx-mapped4.gen:33-86): position i of the text the suffixes are taken from is
+// text[n-1-i] (rev, rcl), complemented (cpl, rcl: A<->T, C<->G, i.e. 3 - c; specials stay).
+// Here the transformed sequence is materialised once in HBM and everything downstream is
+// unchanged.
+__device__ __forceinline__ u64 reverse_bases(u64 w)      // order of the 32 2-bit symbols reversed
+{
+  w = __brevll(w);
+  return ((w & 0x5555555555555555ull) << 1) | ((w >> 1) & 0x5555555555555555ull);
+}
+// `in`: n bases, zero padded by >= 2 words; `out`: nwords_out words, zero beyond base n-1
+__global__ void k_readmode_words(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, u64 nwords_out,
+                                 int rev, int cpl)
+{
+  for (u64 w = blockIdx.x * (u64) blockDim.x + threadIdx.x; w < nwords_out; w += (u64) gridDim.x * blockDim.x) {
+    u64 v = 0;
+    const u64 first = w * 32;                    // output bases first .. first + 31
+    if (first < n) {
+      if (!rev) v = in[w];
+      else {
+        const u64 hi = n - 1 - first;            // input base of output base `first`; the word
+        const u64 win = hi >= 31 ? dna_window(in, hi - 31)            // holds input bases hi-31 .. hi
+                                 : in[0] >> (2u * (unsigned) (31 - hi));
+        v = reverse_bases(win);
+      }
+      if (cpl) v = ~v;
+      const u64 valid = n - first;
+      if (valid < 32) v &= ~0ull << (2u * (unsigned) (32 - valid));
+    }
+    out[w] = v;
+  }
+}
+// byte path: one symbol per byte; cpl only for the 4-letter alphabet (regular symbols 0..3)
+__global__ void k_readmode_bytes(const u8 *__restrict__ in, u8 *__restrict__ out, u64 n, int rev, int cpl)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+    const u8 c = in[rev ? n - 1 - i : i];
+    out[i] = (cpl && c < 4) ? (u8) (3 - c) : c;
+  }
 }
 
 __global__ void k_set_u32(u32 *p, u32 v) { *p = v; }

@@ -83,8 +83,15 @@ static inline void plan_add_bits(PassPlan &p, int begin_bit, int end_bit)
 }
 
 // ---- key sources -------------------------------------------------------------
+// A source may generate the keys of consecutive items much cheaper than one by one (rolling
+// keys over the packed text): BLOCKED_GEN sources fill a thread's IPT consecutive items with
+// gen_block(first item, items, out) -- RS_INVALID_KEY marks items that do not take part --
+// and the tile is transposed through shared memory into the warp-striped order of the ranking.
+constexpr u64 RS_INVALID_KEY = ~0ull;
+
 struct PairSrc {                 // pairs already in memory
   static constexpr bool ALWAYS_VALID = true;
+  static constexpr bool BLOCKED_GEN = false;
   const u64 *keys;
   const u32 *vals;
   __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
@@ -235,12 +242,77 @@ __device__ __forceinline__ bool rs_status_ready(u64 s, u32 epoch)
 #endif
 
 // ---- one onesweep pass ---------------------------------------------------------
-// FULL: the tile is complete and the source has no invalid items: no guards at all.
+// FULL: the tile is complete and every item takes part: no guards at all.
+// rs_tile = the load of a tile (warp-striped, or generated and transposed) + rs_tile_sort.
+template <class Src, class Cfg, int MODE, bool FULL>
+__device__ __forceinline__ void
+rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? Cfg::IPT : 1], unsigned okmask,
+             u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u64 tile, unsigned bsel, unsigned dmask,
+             const u64 *__restrict__ gbase, u64 *status, u32 epoch, unsigned char *rs_smem);
+
 template <class Src, class Cfg, int MODE, bool FULL>
 __device__ __forceinline__ void
 rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u32 count,
         u64 tile, unsigned bsel, unsigned dmask, const u64 *__restrict__ gbase,
         u64 *status, u32 epoch, unsigned char *rs_smem)
+{
+  constexpr int IPT = Cfg::IPT, TILE = Cfg::TILE;
+  u64 *s_keys = reinterpret_cast<u64 *>(rs_smem);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const u32 wbase = warp * (32u * IPT) + lane;        // index of this thread's row-0 item
+
+  u64 key[IPT];
+  u32 val[Cfg::VAL_EARLY ? IPT : 1];
+  unsigned okmask = FULL ? ~0u : 0u;
+
+  // warp-striped load: warp w owns [w*32*IPT, (w+1)*32*IPT), lane-contiguous rows
+  if constexpr (Src::BLOCKED_GEN) {
+    // thread t generates items [t*IPT, (t+1)*IPT) into a padded row (IPT + 1 words: the
+    // blocked writes and the striped reads are both free of bank conflicts); the staging
+    // area is still unused at this point
+    static_assert(!FULL, "generated tiles carry invalid items");
+    static_assert(IPT == 16, "gen_block fills rows of 16 items");
+    static_assert(!Cfg::VAL_EARLY, "values of a generated tile are computed when they are staged");
+    static_assert(sizeof(u64) * (TILE + TILE / IPT) <= (sizeof(u64) + sizeof(u32)) * TILE, "row padding fits the staging area");
+    const u32 first = tid * (u32) IPT;
+    src.gen_block(base + first, first < count ? (count - first < (u32) IPT ? count - first : (u32) IPT) : 0u,
+                  s_keys + first + tid);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const u32 idx = wbase + (u32) k * 32u;
+      key[k] = s_keys[idx + idx / (u32) IPT];
+      if (key[k] != RS_INVALID_KEY) okmask |= 1u << k;
+    }
+    __syncthreads();              // separates the reads above from the staging writes
+    // (a guard-free variant for tiles without invalid items does not pay: two inlined copies of
+    // rs_tile_sort in one kernel also make ptxas 12.9 fail with C7600)
+    rs_tile_sort<Src, Cfg, MODE, false>(src, key, val, okmask, okeys, ovals, base, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+    return;
+  } else {
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const u32 idx = wbase + (u32) k * 32u;
+      if (FULL) {
+        src.load_key(base + idx, key[k]);
+        if (Cfg::VAL_EARLY) val[k] = src.load_val(base + idx);
+      } else {
+        bool ok = idx < count;
+        key[k] = 0;
+        if (ok) ok = src.load_key(base + idx, key[k]);
+        if (Cfg::VAL_EARLY) val[k] = idx < count ? src.load_val(base + idx) : 0u;
+        okmask |= (ok ? 1u : 0u) << k;
+      }
+    }
+    rs_tile_sort<Src, Cfg, MODE, FULL>(src, key, val, okmask, okeys, ovals, base, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+  }
+}
+
+template <class Src, class Cfg, int MODE, bool FULL>
+__device__ __forceinline__ void
+rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? Cfg::IPT : 1], unsigned okmask,
+             u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u64 tile, unsigned bsel, unsigned dmask,
+             const u64 *__restrict__ gbase, u64 *status, u32 epoch, unsigned char *rs_smem)
 {
   constexpr int NT = Cfg::NT, IPT = Cfg::IPT, TILE = Cfg::TILE, WARPS = Cfg::WARPS;
   u64 *s_keys = reinterpret_cast<u64 *>(rs_smem);
@@ -258,27 +330,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const u64 ep = (u64) epoch << 48;
   const u32 wbase = warp * (32u * IPT) + lane;        // index of this thread's row-0 item
-
-  u64 key[IPT];
-  u32 val[Cfg::VAL_EARLY ? IPT : 1];
   u32 rk[IPT];                  // warp-local rank, later the staging slot
-  unsigned okmask = FULL ? ~0u : 0u;
-
-  // warp-striped load: warp w owns [w*32*IPT, (w+1)*32*IPT), lane-contiguous rows
-#pragma unroll
-  for (int k = 0; k < IPT; k++) {
-    const u32 idx = wbase + (u32) k * 32u;
-    if (FULL) {
-      src.load_key(base + idx, key[k]);
-      if (Cfg::VAL_EARLY) val[k] = src.load_val(base + idx);
-    } else {
-      bool ok = idx < count;
-      key[k] = 0;
-      if (ok) ok = src.load_key(base + idx, key[k]);
-      if (Cfg::VAL_EARLY) val[k] = idx < count ? src.load_val(base + idx) : 0u;
-      okmask |= (ok ? 1u : 0u) << k;
-    }
-  }
 
   // stable ranking inside the warp (rows in order, lanes in order): every lane reads the
   // warp's bin counter, the first lane of each set of equal digits writes it back
@@ -427,10 +479,13 @@ rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u6
   const u64 tile = s_ticket;
   const u64 base = tile * (u64) TILE;
   const u32 count = (N - base) < (u64) TILE ? (u32) (N - base) : (u32) TILE;
-  if (Src::ALWAYS_VALID && count == (u32) TILE)
-    rs_tile<Src, Cfg, MODE, true>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
-  else
-    rs_tile<Src, Cfg, MODE, false>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+  if constexpr (Src::ALWAYS_VALID) {
+    if (count == (u32) TILE) {
+      rs_tile<Src, Cfg, MODE, true>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+      return;
+    }
+  }
+  rs_tile<Src, Cfg, MODE, false>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
 }
 
 // ---- host-side driver ------------------------------------------------------------

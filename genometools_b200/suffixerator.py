@@ -1,7 +1,7 @@
 """Host mirror of the `gt suffixerator` interface for the accelerated path.
 
-  gt suffixerator -db F.. (-dna|-protein) [-suf] [-lcp] [-bck] [-pl [k]] [-parts p]
-                  -indexname I                 (/root/reference/src/match/sfx-opt.c:34-122,
+  gt suffixerator -db F.. (-dna|-protein) [-suf] [-lcp] [-bck] [-bwt] [-pl [k]] [-parts p]
+                  [-dir fwd|rev|cpl|rcl] -indexname I                (/root/reference/src/match/sfx-opt.c:34-122,
                                                 index_options.c:274-521, encseq_options.c:181-326)
 
 Same option names, same meaning, same error behaviour for the options this path
@@ -31,6 +31,7 @@ GT_RECOMMENDED_MULTIPLIER_DEFAULT = 0.25       # sfx-apfxlen.h:23
 GT_MAXMULTIPLIEROFTOTALLENGTH = 4.0            # sfx-apfxlen.c:44
 LCPOVERFLOW = 255                              # lcpoverflow.h:23
 UINT32_MAX = 0xFFFFFFFF
+READMODES = ("fwd", "rev", "cpl", "rcl")       # GtReadmode, src/core/readmode.c:25-30
 
 
 # ---------------------------------------------------------------- a14: prefix length policy
@@ -96,10 +97,11 @@ class SuffixeratorOptions:
     bwt: bool = False
     pl: int = None            # None: option absent; 0: "-pl" without argument (automatic)
     parts: int = 1
+    dir: str = "fwd"
     device: int = 0
     verbose: bool = False
 
-    UNSUPPORTED = ("-dir", "-mirrored", "-dc", "-spmopt", "-sortmaxdepth", "-suftabuint",
+    UNSUPPORTED = ("-mirrored", "-dc", "-spmopt", "-sortmaxdepth", "-suftabuint",
                    "-compressedoutput", "-genomediff", "-lcpdist", "-memlimit", "-algbds",
                    "-cmpcharbychar", "-maxdepth", "-ii", "-smap", "-sat", "-kys", "-dccheck",
                    "-samplewithprefixlengthnull", "-storespecialcodes", "-showprogress")
@@ -139,6 +141,13 @@ class SuffixeratorOptions:
                 if i >= len(argv) or not argv[i].isdigit() or int(argv[i]) < 1:
                     raise GtbError("argument to option \"-parts\" must be a positive integer")
                 o.parts = int(argv[i])
+            elif a == "-dir":
+                i += 1
+                if i >= len(argv):
+                    raise GtbError("missing argument to option \"-dir\"")
+                if argv[i] not in READMODES:
+                    raise GtbError("unknown readmode, must be fwd or rev or cpl or rcl")   # readmode.c:44
+                o.dir = argv[i]
             elif a == "-device":
                 i += 1; o.device = int(argv[i])
             elif a in ignorable_yes:
@@ -161,6 +170,11 @@ class SuffixeratorOptions:
             o.indexname = os.path.basename(o.db[0])
         if o.bck and o.pl is None:
             o.pl = 0
+        if o.dir in ("cpl", "rcl") and o.protein:          # sfx-run.c:541-549
+            raise GtbError(f"option -{o.dir} only can be used for DNA alphabets")
+        if o.dir != "fwd" and not (o.suf or o.lcp or o.bwt):   # sfx-run.c:586-593
+            raise GtbError(f"option '-dir {o.dir}' only makes sense in combination with at least one of "
+                           "the options -suf, -lcp, or -bwt")
         return o
 
 
@@ -180,6 +194,7 @@ class EsaResult:
     numoflargelcpvalues: int = 0
     maxbranchdepth: int = 0
     lcptabsum: float = 0.0
+    readmode: int = 0
     stats: list = field(default_factory=list)   # one gtb_stats dict per part
 
     @property
@@ -222,7 +237,7 @@ class EsaResult:
         L.append(f"largelcpvalues={self.numoflargelcpvalues if with_lcp else 0}")
         L.append("averagelcp=%.2f" % (self.averagelcp if with_lcp else 0.0))
         L.append(f"maxbranchdepth={self.maxbranchdepth if with_lcp else 0}")
-        L += ["integersize=64", "littleendian=1", "readmode=0", "mirrored=0"]
+        L += ["integersize=64", "littleendian=1", f"readmode={self.readmode}", "mirrored=0"]
         return "\n".join(L) + "\n"
 
 
@@ -257,8 +272,13 @@ class Suffixerator:
             raise GtbError(self.lib.gtb_esa_error(self.h).decode())
 
     # ---- input ----
-    def set_sequence(self, enc: EncodedSequence, filler=None):
+    def set_sequence(self, enc: EncodedSequence, filler=None, readmode="fwd"):
+        """readmode: -dir fwd|rev|cpl|rcl -- the library rewrites the sequence in read direction"""
+        if readmode not in READMODES:
+            raise GtbError("unknown readmode, must be fwd or rev or cpl or rcl")
         self.enc = enc
+        self.readmode = READMODES.index(readmode)
+        self._ck(self.lib.gtb_esa_set_readmode(self.h, self.readmode))
         if enc.is_dna:
             words, ranges = enc.twobitencoding(filler)
             ranges = np.ascontiguousarray(ranges, dtype=np.uint64)
@@ -328,7 +348,7 @@ class Suffixerator:
         n = enc.totallength
         flags = (GTB_WANT_SUF if want_suf else 0) | (GTB_WANT_LCP if want_lcp else 0) | \
                 (GTB_WANT_BCK if want_bck else 0)
-        res = EsaResult(n, enc.numofchars, prefixlength)
+        res = EsaResult(n, enc.numofchars, prefixlength, readmode=getattr(self, "readmode", 0))
         plist = []
         if parts > 1 and prefixlength >= 1:
             lb, _, _ = self.bucket_table(prefixlength)
@@ -395,7 +415,7 @@ class Suffixerator:
 
 
 def build_esa(enc: EncodedSequence, prefixlength=None, device=0, parts=1, want_suf=True, want_lcp=True,
-              want_bck=True, filler=None, want_bwt=False):
+              want_bck=True, filler=None, want_bwt=False, readmode="fwd"):
     """One call: encoded sequence -> EsaResult (the public entry the benchmarks time end to end)."""
     if prefixlength is None or prefixlength == 0:
         prefixlength = recommendedprefixlength(enc.numofchars, enc.totallength)
@@ -405,7 +425,7 @@ def build_esa(enc: EncodedSequence, prefixlength=None, device=0, parts=1, want_s
             raise GtbError(f"prefix length {prefixlength} is too large, maximal prefix length for this input "
                            f"size and alphabet size is {maxpl}")          # gt_checkprefixlength, sfx-apfxlen.c:149
     with Suffixerator(device) as sfx:
-        sfx.set_sequence(enc, filler)
+        sfx.set_sequence(enc, filler, readmode)
         return sfx.run(prefixlength, want_suf, want_lcp, want_bck, parts, want_bwt=want_bwt)
 
 
@@ -419,7 +439,7 @@ def suffixerator_main(argv, out=sys.stdout):
         enc = encode_fasta(o.db, alphabet)
         pl = o.pl
         res = build_esa(enc, pl if pl else None, o.device, o.parts, o.suf, o.lcp, o.bck or pl is not None,
-                        want_bwt=o.bwt)
+                        want_bwt=o.bwt, readmode=o.dir)
         if o.bwt:
             with open(o.indexname + ".bwt", "wb") as fh:
                 fh.write(res.bwt_bytes())

@@ -27,6 +27,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include "core/alphabet.h"
 #include "core/encseq.h"
 #include "core/error_api.h"
 #include "core/fa.h"
@@ -49,7 +50,6 @@ static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
   const char *what = NULL;
 
   if (so->inputindex != NULL && gt_str_length(so->inputindex) > 0) what = "-ii";
-  else if (gt_index_options_readmode_value(so->idxopts) != GT_READMODE_FORWARD) what = "-dir";
   else if (gt_index_options_outkystab_value(so->idxopts)) what = "-kys";
   else if (gt_index_options_lcpdist_value(so->idxopts)) what = "-lcpdist";
   else if (gt_index_options_maximumspace_value(so->idxopts) > 0) what = "-memlimit";
@@ -134,6 +134,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
                want_bwt = gt_index_options_outbwttab_value(so.idxopts);
     const bool want_any = want_suf || want_lcp || want_bck || want_bwt;
     const GtUword n = gt_encseq_total_length(encseq);
+    const GtReadmode readmode = gt_index_options_readmode_value(so.idxopts);
     const unsigned int numofchars = gt_encseq_alphabetnumofchars(encseq);
     unsigned int prefixlength = gt_index_options_prefixlength_value(so.idxopts);
     uint64_t *suftab = NULL, *llv = NULL, nllv = 0, nall = 0, nspec = 0, ndist = 0;
@@ -143,7 +144,19 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     char msg[512];
 
     memset(&stats, 0, sizeof stats);
-    if (want_any) {
+    /* the two -dir checks of gt_runsuffixerator, src/match/sfx-run.c:541-549,586-593 */
+    if ((readmode == GT_READMODE_COMPL || readmode == GT_READMODE_REVCOMPL) &&
+        !gt_alphabet_is_dna(gt_encseq_alphabet(encseq))) {
+      gt_error_set(err, "option -%s only can be used for DNA alphabets",
+                   readmode == GT_READMODE_COMPL ? "cpl" : "rcl");
+      had_err = -1;
+    }
+    if (!had_err && !want_any && readmode != GT_READMODE_FORWARD) {
+      gt_error_set(err, "option '-dir %s' only makes sense in combination with at least one of the "
+                        "options -suf, -lcp, or -bwt", gt_readmode_show(readmode));
+      had_err = -1;
+    }
+    if (!had_err && want_any) {
       /* detpfxlen, src/match/sfx-run.c:319-367 */
       unsigned int rec = gt_recommendedprefixlength(numofchars, n,
                                                     GT_RECOMMENDED_MULTIPLIER_DEFAULT, true);
@@ -164,6 +177,8 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       int rc = 0;
       gtb_esa *h = gtb_esa_new(0, msg, sizeof msg);
       if (h == NULL) rc = -1;
+      /* GtReadmode values are the library's: fwd 0, rev 1, cpl 2, rcl 3 (src/core/readmode.h) */
+      if (rc == 0) rc = gtb_esa_set_readmode(h, (unsigned) readmode);
       if (want_bwt) bwttab = gt_malloc(sizeof *bwttab * (n + 1));
       if (want_suf) suftab = gt_malloc(sizeof *suftab * (n + 1));
       if (want_lcp) {
@@ -257,7 +272,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       Definedunsignedlong longest;
       longest.defined = want_any;
       longest.valueunsignedlong = (GtUword) stats.longest;
-      if (gt_outprjfile(gt_str_get(so.indexname), GT_READMODE_FORWARD, encseq,
+      if (gt_outprjfile(gt_str_get(so.indexname), readmode, encseq,
                         want_any ? n + 1 : 0, prefixlength,
                         want_lcp ? (GtUword) stats.numoflargelcpvalues : 0,
                         want_lcp ? stats.lcptabsum / (double) (n + 1) : 0.0,

@@ -105,6 +105,17 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
 int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols,
                             uint64_t totallength, unsigned numofchars);
 
+/* -dir fwd|rev|cpl|rcl (GtReadmode, src/core/readmode.h; the first argument of
+   gt_Sfxiterator_new_withadditionalvalues, sfx-suffixer.h:39): the direction the sequence is
+   read in.  0 forward, 1 reverse, 2 complement, 3 reverse complement; position i of the
+   sorted text is then text[n-1-i] (1, 3), complemented (2, 3) -- what
+   gt_encseq_get_encoded_char(encseq, i, readmode) returns (encseq.c:6094-6140).  Call it
+   BEFORE gtb_esa_set_input_*: the inputs are still given in forward coordinates (as the
+   GtEncseq exports them) and rewritten in read direction while they are uploaded;
+   gtb_esa_set_separators takes forward coordinates as well.  Complement modes on the byte
+   path fail like the reference ("only can be used for DNA alphabets", sfx-run.c:541-549). */
+int gtb_esa_set_readmode(gtb_esa *h, unsigned readmode);
+
 /* let `h` use the sequence `src` already holds in HBM (same device; `src` must outlive
    the use): several code ranges processed on one GPU share one copy of the input */
 int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src);

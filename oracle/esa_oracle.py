@@ -95,6 +95,23 @@ def esa(symbols, numofchars, prefixlength):
             "prefixlength": prefixlength, "numofchars": numofchars}
 
 
+def apply_readmode(symbols, mode):
+    """the sequence as gt_encseq_get_encoded_char(encseq, i, readmode) reads it
+    (/root/reference/src/core/encseq.c:6094-6140): rev/rcl mirror the positions, cpl/rcl
+    complement the regular DNA symbols (a<->t, c<->g = 3 - c); specials are kept.  Verified
+    against the reference: its -dir output equals its forward output on this sequence
+    (tests/golden/readmode_vectors.npz)."""
+    s = np.array(symbols, dtype=np.uint8, copy=True)
+    if mode in ("rev", "rcl"):
+        s = s[::-1].copy()
+    if mode in ("cpl", "rcl"):
+        reg = s < 4
+        s[reg] = 3 - s[reg]
+    elif mode not in ("fwd", "rev"):
+        raise ValueError("unknown readmode, must be fwd or rev or cpl or rcl")
+    return s
+
+
 def file_images(o):
     """the byte images of .suf .lcp .llv .bck implied by an oracle result
     (formats: SURVEY.md appendix A; u32 bucket table since n+1 <= UINT_MAX)"""

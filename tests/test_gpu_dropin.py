@@ -71,7 +71,7 @@ def test_dropin_explicit_prefixlength_and_errors(tmp_path):
     out = run_both(tmp_path, [fa], "dna", extra=("4",))
     for ext in ("bck", "suf", "lcp", "llv", "prj"):
         assert out["b200"][ext] == out["ref"][ext], ext
-    for bad in (["-dir", "rev"], ["-dc", "32"], ["-suftabuint"]):
+    for bad in (["-dc", "32"], ["-suftabuint"]):
         r = subprocess.run([GT_B200, "suffixerator", "-dna", "-suf", *bad, "-indexname", str(tmp_path / "x"), "-db", fa],
                            capture_output=True, text=True)
         assert r.returncode != 0 and "not supported by the B200" in r.stderr
@@ -81,3 +81,35 @@ def test_dropin_explicit_prefixlength_and_errors(tmp_path):
                         capture_output=True, text=True)
     assert r.returncode != 0 and r2.returncode != 0
     assert r.stderr.split("error:")[1] == r2.stderr.split("error:")[1]      # same message as the reference
+
+
+@need_bins
+@pytest.mark.parametrize("case,mode", [("reads", "rev"), ("reads", "cpl"), ("reads", "rcl"), ("repeats", "rcl"),
+                                       ("protein", "rev")])
+def test_dropin_readmodes_identical_to_reference(tmp_path, case, mode):
+    """-dir rev|cpl|rcl: all files incl. .bwt and the readmode line of .prj"""
+    if case == "reads":
+        sym, alpha = synth.reads(2500, 100, 17, 0.003), "dna"
+    elif case == "repeats":
+        sym, alpha = synth.repeats_dna(200_000, 5, unit=5000, copies=8, exact_len=20000, exact_copies=3), "dna"
+    else:
+        sym, alpha = synth.protein(80_000, 9), "protein"
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(sym, fa, alpha)
+    out = run_both(tmp_path, [fa], alpha, extra=("3" if alpha == "dna" else "2", "-bwt", "-dir", mode))
+    for ext in ("bwt", "bck", "suf", "lcp", "llv", "prj"):
+        assert out["b200"][ext] == out["ref"][ext], ext
+
+
+@need_bins
+def test_dropin_readmode_errors_like_the_reference(tmp_path):
+    fa = str(tmp_path / "p.fa")
+    synth.to_fasta(synth.protein(5_000, 2), fa, "protein")
+    for args in (["-protein", "-suf", "-dir", "cpl"], ["-protein", "-dir", "rev"]):
+        msgs = []
+        for exe in (GT_B200, GTREF):
+            r = subprocess.run([exe, "suffixerator", *args, "-indexname", str(tmp_path / "x"), "-db", fa],
+                               capture_output=True, text=True)
+            assert r.returncode != 0
+            msgs.append(r.stderr.split("error:")[1])
+        assert msgs[0] == msgs[1]

@@ -133,6 +133,14 @@ def test_option_parser_mirrors_reference_errors():
     assert o.pl == 0 and o.suf and o.lcp and o.bck and o.db == ["x.fna"]
     assert P(["-db", "a", "-dna", "-pl", "5", "-parts", "3"]).pl == 5
     for bad in (["-dna"], ["-db", "a", "b", "-dna"], ["-db", "a", "-dna", "-protein"],
-                ["-db", "a", "-dir", "rev"], ["-db", "a", "-dc", "32"], ["-db", "a", "-bogus"]):
+                ["-db", "a", "-dir", "rev"], ["-db", "a", "-dc", "32"], ["-db", "a", "-bogus"],
+                ["-db", "a", "-dna", "-suf", "-dir", "up"], ["-db", "a", "-protein", "-suf", "-dir", "rcl"]):
         with pytest.raises(_lib.GtbError):
             P(bad)
+    # -dir (src/core/readmode.c:25-46, sfx-run.c:541-549,586-593)
+    assert P(["-db", "a", "-dna", "-suf", "-dir", "rcl"]).dir == "rcl"
+    assert P(["-db", "a", "-protein", "-lcp", "-dir", "rev"]).dir == "rev"
+    with pytest.raises(_lib.GtbError, match="only makes sense"):
+        P(["-db", "a", "-dna", "-bck", "-dir", "rev"])
+    with pytest.raises(_lib.GtbError, match="only can be used for DNA"):
+        P(["-db", "a", "-protein", "-suf", "-dir", "cpl"])
