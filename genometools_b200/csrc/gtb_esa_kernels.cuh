@@ -465,6 +465,20 @@ __device__ __forceinline__ u64 key_code(u64 key, unsigned pl, unsigned K, const 
   return code;
 }
 
+// code of the first `len` <= pl symbols of a filled key (= key_code / K^(pl-len)); codes fit 32 bits
+template <bool DNA>
+__device__ __forceinline__ u32 key_code_prefix(u64 key, unsigned len, unsigned K, const KeyFmt &f)
+{
+  if (DNA) return len ? (u32) (key >> (64u - 2u * len)) : 0u;
+  u32 code = 0;
+  for (unsigned k = 0; k < len; k++) {
+    u32 s = (u32) (key >> (64u - (unsigned) f.b * (k + 1u))) & 31u;
+    if (s >= K) s = K - 1u;
+    code = code * K + s;
+  }
+  return code;
+}
+
 // COUNT_ALL = false: only the two special-code tables (the bucket starts are then taken
 // from the sorted keys by k_analyze_keys -- no atomic per suffix)
 template <bool DNA, bool COUNT_ALL>
@@ -610,6 +624,80 @@ analyze_thread(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &
   }
 }
 
+// The AN_IPT elements of a thread whose ten keys lie inside the array, some with tail fields
+// (reads, proteins: every warp meets some).  The per-element part is branch-free -- about 30
+// instructions; what is rare per element (a bucket start, the end of a run of equal keys that
+// met a special within pl symbols) is collected in bit masks and handled after the loop, so a
+// warp runs those bodies once per thread run instead of once per element.
+template <bool DNA, bool FILL_LB>
+__device__ __forceinline__ void
+analyze_thread_inner(const u64 (&k)[AN_IPT + 2], u64 base, const AnalyzeArgs &a, u32 &unres, u32 &lasthead,
+                     u64 &lcpword, u32 &mx, unsigned long long &sum, u32 &headbits, u32 &unresbits)
+{
+  constexpr u32 B = DNA ? 2u : 5u;
+  const KeyFmt f = a.f;
+  const u32 m = (u32) f.m, pl = a.pl;
+  const u64 symmask = f.symmask();
+  const unsigned codesh = 64u - B * pl;
+  u32 hb = 0, xnz = 0, spbits = 0, lbbits = 0, lsum = 0;
+  u32 tprev = f.tail(k[0]);
+#pragma unroll
+  for (int i = 0; i < AN_IPT; i++) {
+    const u64 x = k[i] ^ k[i + 1];
+    const u32 tcur = f.tail(k[i + 1]);
+    const u64 xs = x & symmask;
+    u32 l = xs ? (u32) __clzll((long long) xs) / B : m;
+    const u32 ua = m - tprev, ub = m - tcur;
+    l = l < ua ? l : ua;
+    l = l < ub ? l : ub;
+    const bool head = x != 0 || tcur != 0;
+    if (x != 0) xnz |= 1u << i;
+    if (head) {
+      hb |= 1u << i;
+      lcpword |= (u64) l << (8 * i);
+      if (ub >= pl) lsum += l;
+      mx = l > mx ? l : mx;
+      if (FILL_LB && pl > 0 && (x >> codesh) != 0) lbbits |= 1u << i;   // the top pl symbols differ
+      if (FILL_LB && ub < pl) spbits |= 1u << i;
+    }
+    tprev = tcur;
+  }
+  sum += lsum;
+  const u64 xlast = k[AN_IPT] ^ k[AN_IPT + 1];
+  if (xlast != 0) xnz |= 1u << AN_IPT;
+  if (xlast != 0 || (k[AN_IPT + 1] & a.tmask) != 0) hb |= 1u << AN_IPT;
+  headbits = hb & 0xffu;
+  unresbits = (~hb | ~(hb >> 1)) & 0xffu;
+  unres = (u32) __popc(unresbits);
+  lasthead = headbits ? (u32) base + (31u - (u32) __clz(headbits)) + 1u : 0u;
+  if (FILL_LB && lbbits) {
+    // a new bucket may start at these elements: every code in (code of j-1, code of j] starts at j
+    // (the filler counts as the largest symbol, so different top symbols can still be one code)
+#pragma unroll
+    for (int i = 0; i < AN_IPT; i++)
+      if ((lbbits >> i) & 1u) {
+        const u32 c1 = key_code_prefix<DNA>(k[i + 1], pl, a.K, f);
+        for (u32 c0 = key_code_prefix<DNA>(k[i], pl, a.K, f) + 1u; c0 <= c1 && c0 != 0u; c0++)
+          a.leftborder[c0] = (u32) (a.sa_offset + base + i);
+      }
+  }
+  if (FILL_LB && spbits) {
+    // keys that met a special within their first pl symbols: equal ones are adjacent; one atomic per
+    // run of equal keys inside this thread.  A run ends where the next key differs or the thread ends
+    const u32 runend = spbits & ((xnz >> 1) | (1u << (AN_IPT - 1)));
+    const u32 runstart = spbits & (xnz | 1u);
+#pragma unroll
+    for (int i = 0; i < AN_IPT; i++)
+      if ((runend >> i) & 1u) {
+        const u32 first = 31u - (u32) __clz(runstart & ((2u << i) - 1u));
+        const u32 run = (u32) i - first + 1u;
+        const u32 u = m - f.tail(k[i + 1]);
+        atomicAdd(&a.csc[key_code_prefix<DNA>(k[i + 1], pl - 1u, a.K, f)], run);
+        if (u + 1u < pl) atomicAdd(&a.dist[a.distoff[u] + key_code_prefix<DNA>(k[i + 1], u, a.K, f)], run);
+      }
+  }
+}
+
 // pass 1: lcp of resolved neighbours, per-tile count of unresolved + last head; with
 // FILL_LB also the whole bucket table from the sorted keys: leftborder[c] = index of the
 // first key with code >= c; countspecialcodes / distpfxidx from the keys that met a special
@@ -673,7 +761,7 @@ k_analyze_keys(const u64 *__restrict__ keys, u64 N, KeyFmt f, unsigned pl, unsig
     if (c == 0 || (c + 1) * WCHUNK + 1 > N) {                   // the two ends of the array
       analyze_thread<DNA, FILL_LB, false>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
     } else if (__any_sync(FULL_MASK, (orall & tmask) != 0)) {   // some key met a special
-      analyze_thread<DNA, FILL_LB, true>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
+      analyze_thread_inner<DNA, FILL_LB>(k, base, a, unres, lasthead, lcpword, mx, sum, headbits, unresbits);
     } else {
       // all ten keys are full and inside the array: head <=> the keys differ (then in a symbol)
       u32 hb = 0, gapbits = 0, lsum = 0;
