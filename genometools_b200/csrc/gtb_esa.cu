@@ -111,7 +111,7 @@ struct gtb_esa {
   u64 part_pairs_ext = 0; u32 part_launches_ext = 0;
   float ext_ms_radix = 0, ext_ms_keygen = 0; u64 ext_pairs = 0; u32 ext_launches = 0;   // carried into this run's stats
   u64 depth[64];            // depth[r] = common prefix of the groups entering round r
-  DevBuf ranks, owner, sendidx, rcounts;
+  DevBuf ranks, owner, sendidx, rcounts, rankwords;
   HostStage hstage;         // pinned staging + host threads of the result copies
   gtb_stats stats;
 };
@@ -503,8 +503,7 @@ RankMap<DNA> make_rankmap(gtb_esa *h)
   rm.keys = h->kbuf[h->res].as<u64>();
   rm.sa = h->vbuf[h->res].as<u32>();
   rm.N = h->N;
-  rm.tbits = h->tbits.as<u32>(); rm.tpre = h->tpre.as<u32>(); rm.trank = h->trank.as<u32>();
-  rm.spre = h->spre.as<u32>();
+  rm.rw = h->rankwords.as<uint4>(); rm.trank = h->trank.as<u32>();
   rm.leftborder = ((h->counted || h->lb_own) && h->pl > 0) ? h->leftborder.as<u32>() : nullptr;
   rm.own_last = (h->lb_own && !h->counted) ? h->maxcode : ~0ull;
   rm.pl = h->pl; rm.K = h->K;
@@ -548,6 +547,13 @@ int build_ranks(gtb_esa *h)
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
     GTB_TRY(popcount_prefix(h, h->tbits.as<u32>(), h->tpre.as<u32>(), nw));
+  }
+  GTB_TRY(h->rankwords.ensure(sizeof(uint4) * nw, err));
+  k_pack_rankwords<<<grid_for(nw, 256), 256, 0, st>>>(h->spmask.as<u32>(), h->S > 0 ? h->spre.as<u32>() : nullptr,
+      h->tbits.as<u32>(), h->M0 > 0 ? h->tpre.as<u32>() : nullptr, nw, h->rankwords.as<uint4>());
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches++;
+  if (h->M0 > 0) {
     RankMap<DNA> rm = make_rankmap<DNA>(h);
     if (h->round > 0) {          // text-driven rounds have resolved some of the initial ties
       k_trank_resolved<DNA><<<grid_for(h->M0, 256), 256, 0, st>>>(rm, h->uidx0.as<u32>(), h->M0);
@@ -896,7 +902,7 @@ void gtb_esa_delete(gtb_esa *h)
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
-                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts};
+                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts, &h->rankwords};
   for (DevBuf *b : all) b->release();
   radix_work_free(h->rw);
   h->hstage.release();

@@ -84,7 +84,7 @@ __device__ __forceinline__ u64 dna_window(const u64 *__restrict__ words, u64 pos
 template <bool DNA>
 struct TextSrc {
   static constexpr bool ALWAYS_VALID = false;
-  static constexpr bool BLOCKED_GEN = DNA;   // rolling keys over the 2-bit words (gen_block)
+  static constexpr bool BLOCKED_GEN = true;  // keys of 16 consecutive positions at once (gen_block)
   const u64 *words;      // DNA: packed 2-bit words (padded by >= 2 words)
   const u8  *bytes;      // bytes path: symbols (padded by >= 16 bytes of 255)
   const u32 *spmask;     // bit i set <=> position i is special; bits >= n all set
@@ -123,26 +123,51 @@ struct TextSrc {
   __device__ __forceinline__ u32 load_val(u64 idx) const { return (u32) (pos0 + idx); }
   // keys of the `cnt` <= 16 consecutive items idx .. idx + cnt - 1 into out[0 .. 15] (the rest
   // and every item that is special or outside [klo, khi] becomes ~0, which no filled key equals).
-  // DNA only.  The 16 + m - 1 <= 44 bases and the 64 mask bits a thread needs are loaded once
-  // into 32-bit registers; key i is two funnel shifts by the constant 2i and two ANDs, its
-  // distance to the next special one funnel shift of the mask -- about 8 instructions per key
-  // unless a special lies within its m symbols.
+  // The 16 + m - 1 symbols a thread needs are loaded once and laid out as one big-endian bit
+  // string in 32-bit registers (DNA: three words of the packed text; bytes: 27 symbols of 5
+  // bits from two 128-bit loads); key i is then two funnel shifts by the constant i*b and two
+  // ANDs, its distance to the next special one funnel shift of the mask -- about 8 instructions
+  // per key unless a special lies within its m symbols.
+  __device__ __forceinline__ bool can_gen_fast(u64 idx, u32 cnt) const
+  { return cnt >= 16u && (DNA || ((pos0 + idx) & 15u) == 0); }
   __device__ __forceinline__ void gen_block(u64 idx, u32 cnt, u64 *out) const
   {
-    const u64 p0 = pos0 + idx;
-    const unsigned m = (unsigned) f.m;
-    if (cnt < 16u) {                                    // the ragged end of the source
+    if (!can_gen_fast(idx, cnt)) {                      // the ragged end of the source; unaligned slices
 #pragma unroll 1
       for (u32 i = 0; i < 16u; i++) {
         u64 key = ~0ull;
-        if (i < cnt && !make_key(p0 + i, key)) key = ~0ull;
+        if (i < cnt && !make_key(pos0 + idx + i, key)) key = ~0ull;
         out[i] = key;
       }
       return;
     }
-    const u64 h64 = dna_window(words, p0);              // bases p0 .. p0+31
-    const u32 w0 = (u32) (h64 >> 32), w1 = (u32) h64;
-    const u32 w2 = (u32) (dna_window(words, p0 + 32) >> 32);   // bases p0+32 .. p0+47
+    gen_block_fast(idx, out);
+  }
+  // (only constant indices into out: it may live in registers)
+  __device__ __forceinline__ void gen_block_fast(u64 idx, u64 *out) const
+  {
+    constexpr unsigned B = DNA ? 2u : 5u;
+    const u64 p0 = pos0 + idx;
+    const unsigned m = (unsigned) f.m;
+    u32 S[DNA ? 3 : 5];
+    if (DNA) {
+      const u64 h64 = dna_window(words, p0);            // bases p0 .. p0+31
+      S[0] = (u32) (h64 >> 32); S[1] = (u32) h64;
+      S[2] = (u32) (dna_window(words, p0 + 32) >> 32);  // bases p0+32 .. p0+47
+    } else {
+      const uint4 a = *reinterpret_cast<const uint4 *>(bytes + p0);
+      const uint4 c = *reinterpret_cast<const uint4 *>(bytes + p0 + 16);
+      const u32 wv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int w = 0; w < 5; w++) S[w] = 0;
+#pragma unroll
+      for (int j = 0; j < 27; j++) {                    // symbol j at bits [160-5(j+1), 160-5j) of S
+        const u32 sy = (wv[j >> 2] >> (8 * (j & 3))) & 31u;
+        const int pos = 160 - 5 * (j + 1), word = 4 - pos / 32, off = pos % 32;
+        S[word] |= sy << off;
+        if (off > 27) S[word - 1] |= sy >> (32 - off);
+      }
+    }
     const u32 mlo = mask_window(spmask, p0), mhi = mask_window(spmask, p0 + 32);
     const u64 sm = f.symmask();
     const u32 smhi = (u32) (sm >> 32), smlo = (u32) sm;
@@ -150,15 +175,16 @@ struct TextSrc {
     const bool filter = klo != 0ull || khi != ~0ull;
 #pragma unroll
     for (u32 i = 0; i < 16u; i++) {
-      const u32 khi32 = __funnelshift_l(w1, w0, 2u * i) & smhi;
-      const u32 klo32 = __funnelshift_l(w2, w1, 2u * i) & smlo;
+      const u32 w = (B * i) >> 5, sh = (B * i) & 31u;   // (compile-time after unrolling)
+      const u32 khi32 = __funnelshift_l(S[w + 1], S[w], sh) & smhi;
+      const u32 klo32 = __funnelshift_l(S[w + 2], S[w + 1], sh) & smlo;
       u64 key = ((u64) khi32 << 32) | klo32;
       const u32 win = __funnelshift_r(mlo, mhi, i) & mmask;     // specials among positions i .. i+m-1
       if (win != 0u) {
         if (win & 1u) key = ~0ull;                      // a special position is no item
         else {
           const unsigned u = (unsigned) __ffs(win) - 1u;        // regular symbols before the special
-          key |= (1ull << (64u - 2u * u)) - (1ull << (64u - 2u * m));   // filler over symbols u .. m-1
+          key |= (1ull << (64u - B * u)) - (1ull << (64u - B * m));   // filler over symbols u .. m-1
           key |= (u64) (m - u) << f.sh;
         }
       }
@@ -210,6 +236,57 @@ k_hist_text_dna(TextSrc<true> src, u64 n, PassPlan plan, unsigned long long *__r
     if (s_h[i]) atomicAdd(&ghist[i], (unsigned long long) s_h[i]);
 }
 
+// the same for any text source, keys from gen_block_fast (used for the byte path: ~135
+// instructions per position in the generic kernel, mostly byte loads)
+template <bool DNA>
+__global__ void __launch_bounds__(256)
+k_hist_text_blocked(TextSrc<DNA> src, u64 n, PassPlan plan, unsigned long long *__restrict__ ghist)
+{
+  __shared__ u32 s_h[RS_MAXPASS * RS_BINS];
+  for (int i = threadIdx.x; i < RS_MAXPASS * RS_BINS; i += blockDim.x) s_h[i] = 0;
+  __syncthreads();
+  const u64 nchunks = (n + 15) >> 4;
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < nchunks; c += (u64) gridDim.x * blockDim.x) {
+    const u64 idx = c << 4;
+    const u32 cnt = n - idx < 16 ? (u32) (n - idx) : 16u;
+    if (src.can_gen_fast(idx, cnt)) {
+      u64 keys[16];
+      src.gen_block_fast(idx, keys);
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        if (keys[i] == ~0ull) continue;
+#pragma unroll
+        for (int p = 0; p < RS_MAXPASS; p++)
+          if (p < plan.npass)
+            atomicAdd(&s_h[p * RS_BINS + ((unsigned) (keys[i] >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+      }
+    } else {
+      for (u32 i = 0; i < cnt; i++) {
+        u64 key;
+        if (!src.load_key(idx + i, key)) continue;
+        for (int p = 0; p < plan.npass; p++)
+          atomicAdd(&s_h[p * RS_BINS + ((unsigned) (key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&ghist[i], (unsigned long long) s_h[i]);
+}
+
+template <>
+struct RsHistLauncher<TextSrc<false>> {
+  static void launch(const TextSrc<false> &src, u64 nsrc, const PassPlan &plan, unsigned long long *ghist,
+                     cudaStream_t st)
+  {
+    const u64 chunks = (nsrc + 15) >> 4;
+    u64 g = div_up(chunks, 256);
+    if (g > 148ull * 8) g = 148ull * 8;
+    if (g < 1) g = 1;
+    k_hist_text_blocked<false><<<(unsigned) g, 256, 0, st>>>(src, nsrc, plan, ghist);
+  }
+};
+
 template <>
 struct RsHistLauncher<TextSrc<true>> {
   static void launch(const TextSrc<true> &src, u64 nsrc, const PassPlan &plan, unsigned long long *ghist,
@@ -249,26 +326,29 @@ struct RankMap {
   const u64 *keys;           // first-level sorted keys of this range
   const u32 *sa;             // its suffix table
   u64 N;
-  const u32 *tbits, *tpre;   // bitmap of the initially tied positions, popcount prefix
+  // per 32 text positions one 16-byte word {special bits, specials before, tied bits, tied
+  // before}: a rank query is one random 16-byte load (+ one into trank) instead of four loads
+  // from four arrays
+  const uint4 *rw;
   u32 *trank;
-  const u32 *spre;           // popcount prefix of the special mask (null if no specials)
   const u32 *leftborder;     // bucket starts (global indices) or null: narrows the search
   u64 own_last;              // last code whose successor entry is not in this table (a code range
                              // fills its own codes only), ~0 if the table is complete
   unsigned pl, K;
   u64 n, nonspecials, sa_offset;
 
-  __device__ __forceinline__ bool tied(u64 p) const { return (tbits[p >> 5] >> (p & 31u)) & 1u; }
-  __device__ __forceinline__ u32 dense(u64 p) const
-  { return tpre[p >> 5] + (u32) __popc(tbits[p >> 5] & ((1u << (p & 31u)) - 1u)); }
-  __device__ __forceinline__ void set(u64 p, u32 r) const { trank[dense(p)] = r; }
+  __device__ __forceinline__ void set(u64 p, u32 r) const
+  {
+    const uint4 w = __ldg(rw + (p >> 5));
+    trank[w.w + (u32) __popc(w.z & ((1u << (p & 31u)) - 1u))] = r;
+  }
   __device__ u32 get(u64 q) const
   {
     if (q >= n) return (u32) n;
-    const u32 mw = src.spmask[q >> 5];
-    if ((mw >> (q & 31u)) & 1u)
-      return (u32) (nonspecials + spre[q >> 5] + (u32) __popc(mw & ((1u << (q & 31u)) - 1u)));
-    if (tied(q)) return trank[dense(q)];
+    const uint4 w = __ldg(rw + (q >> 5));
+    const u32 bit = 1u << (q & 31u), below = bit - 1u;
+    if (w.x & bit) return (u32) (nonspecials + w.y + (u32) __popc(w.x & below));
+    if (w.z & bit) return trank[w.w + (u32) __popc(w.z & below)];
     u64 kq;
     src.make_key_fmt(q, kq, src.f);
     u64 lo = 0, hi = N;
@@ -935,6 +1015,15 @@ __global__ void k_tied_bits(const u32 *__restrict__ uidx0, u64 M0, const u32 *__
     const u32 p = sa[uidx0[c]];
     atomicOr(&tbits[p >> 5], 1u << (p & 31u));
   }
+}
+// the 16-byte words of the rank map (RankMap::rw); spre / tbits / tpre may be null (no specials,
+// no ties)
+__global__ void k_pack_rankwords(const u32 *__restrict__ spmask, const u32 *__restrict__ spre,
+                                 const u32 *__restrict__ tbits, const u32 *__restrict__ tpre, u64 nw,
+                                 uint4 *__restrict__ rw)
+{
+  for (u64 w = blockIdx.x * (u64) blockDim.x + threadIdx.x; w < nw; w += (u64) gridDim.x * blockDim.x)
+    rw[w] = make_uint4(spmask[w], spre ? spre[w] : 0u, tbits ? tbits[w] : 0u, tpre ? tpre[w] : 0u);
 }
 // ranks of the initially tied suffixes: first each as if resolved (its own index), then
 // the still tied ones with their group head
