@@ -738,11 +738,21 @@ int stage_end(gtb_esa *h)
     GTB_TRY(h->ulcp.ensure(sizeof(u32) * (M0 > h->S + 1 ? M0 : h->S + 1), err));
     DepthTab dt;
     for (int i = 0; i < 64; i++) dt.d[i] = i <= (int) h->round ? h->depth[i] : 0;
+    // (the refinement keys are dead: their buffer queues the pairs with long extensions)
+    GTB_TRY(h->dkeys.ensure(sizeof(u64) * M0, err));
+    unsigned long long *qcount = reinterpret_cast<unsigned long long *>(h->misc.as<u64>() + 8);
+    GTB_CUDA(cudaMemsetAsync(qcount, 0, sizeof(unsigned long long), st));
     k_deep_lcp<DNA><<<grid_for(M0, 128), 128, 0, st>>>(h->uidx0.as<u32>(), h->ugrp0.as<u32>(), M0, sa,
         h->words.as<u64>(), h->bytes.as<u8>(), h->spmask.as<u32>(), h->n, dt, lcp8,
-        h->ulcp.as<u32>(), dstats);
+        h->ulcp.as<u32>(), dstats, h->dkeys.as<u64>(), qcount);
     GTB_LAUNCH_CHECK();
     S.kernel_launches++;
+    if (DNA) {
+      k_deep_lcp_long<<<148 * 8, 256, 0, st>>>(h->dkeys.as<u64>(), qcount, h->uidx0.as<u32>(), sa,
+          h->words.as<u64>(), h->spmask.as<u32>(), h->n, lcp8, h->ulcp.as<u32>(), dstats);
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches++;
+    }
     DevStats hs;
     GTB_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
     GTB_CUDA(cudaStreamSynchronize(st));

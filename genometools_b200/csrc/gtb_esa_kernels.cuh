@@ -1222,12 +1222,18 @@ __global__ void k_build_dkeys_ranks(const u32 *__restrict__ ugrp, const u32 *__r
 // depth[r] = common prefix proven for a pair that was separated in refinement round r
 struct DepthTab { u64 d[64]; };
 
+// A thread walks at most DEEP_SOLO windows of 32 bases on its own; pairs that are still equal
+// then (long exact repeats: thousands of windows) are queued as (c : 32 | offset : 32) and
+// finished by k_deep_lcp_long, one warp per pair and 32 windows per step.
+constexpr int DEEP_SOLO = 8;
+constexpr u32 DEEP_PENDING = 0xfffffffeu;
+
 template <bool DNA>
 __global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict__ ugrp0, u64 M0,
                            const u32 *__restrict__ sa, const u64 *__restrict__ words,
                            const u8 *__restrict__ bytes, const u32 *__restrict__ spmask,
                            u64 n, DepthTab depth, u8 *__restrict__ lcp8, u32 *__restrict__ ulcp,
-                           DevStats *stats)
+                           DevStats *stats, u64 *__restrict__ queue, unsigned long long *qcount)
 {
   u32 mx = 0;
   unsigned long long sum = 0, large = 0;
@@ -1237,15 +1243,16 @@ __global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict_
     if (ugrp0[c] != j) {
       const u64 a = sa[j - 1], b = sa[j];
       u64 off = depth.d[lcp8[j] & 63u];        // proven common prefix
+      bool done = false;
       if (DNA) {
-        for (;;) {
+        for (int it = 0; it < DEEP_SOLO; it++) {
           const u32 wa = mask_window(spmask, a + off), wb = mask_window(spmask, b + off);
           const u32 wab = wa | wb;
           const unsigned lim = wab ? (unsigned) __ffs(wab) - 1u : 32u;
           const u64 x = dna_window(words, a + off) ^ dna_window(words, b + off);
           const unsigned common = x ? (unsigned) (__clzll((long long) x) >> 1) : 32u;
-          if (common < lim) { off += common; break; }
-          if (lim < 32u) { off += lim; break; }
+          if (common < lim) { off += common; done = true; break; }
+          if (lim < 32u) { off += lim; done = true; break; }
           off += 32;
         }
       } else {
@@ -1254,12 +1261,18 @@ __global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict_
           if (ca >= 254u || cb >= 254u || ca != cb) break;
           off++;
         }
+        done = true;
       }
-      l = (u32) off;
-      lcp8[j] = (u8) (l < 255u ? l : 255u);
-      mx = l > mx ? l : mx;
-      sum += l;
-      if (l >= 255u) large++;
+      if (done) {
+        l = (u32) off;
+        lcp8[j] = (u8) (l < 255u ? l : 255u);
+        mx = l > mx ? l : mx;
+        sum += l;
+        if (l >= 255u) large++;
+      } else {
+        l = DEEP_PENDING;
+        queue[atomicAdd(qcount, 1ull)] = (c << 32) | off;
+      }
     }
     ulcp[c] = l;
   }
@@ -1271,6 +1284,57 @@ __global__ void k_deep_lcp(const u32 *__restrict__ uidx0, const u32 *__restrict_
     mx = o > mx ? o : mx;
   }
   if (lane_id() == 0) {
+    if (sum) atomicAdd(&stats->lcpsum, sum);
+    if (large) atomicAdd(&stats->numlarge, large);
+    if (mx) atomicMax(&stats->maxlcp, mx);
+  }
+}
+
+// one warp per queued pair: lane i compares the window 32*i bases further
+__global__ void k_deep_lcp_long(const u64 *__restrict__ queue, const unsigned long long *__restrict__ qcount,
+                                const u32 *__restrict__ uidx0, const u32 *__restrict__ sa,
+                                const u64 *__restrict__ words, const u32 *__restrict__ spmask, u64 n,
+                                u8 *__restrict__ lcp8, u32 *__restrict__ ulcp, DevStats *stats)
+{
+  const unsigned lane = lane_id();
+  const u64 nq = *qcount;
+  const u64 warps = ((u64) gridDim.x * blockDim.x) >> 5;
+  u32 mx = 0;
+  unsigned long long sum = 0, large = 0;
+  for (u64 q = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
+    const u64 e = queue[q];
+    const u64 c = e >> 32;
+    u64 off = e & 0xffffffffull;
+    const u32 j = uidx0[c];
+    const u64 a = sa[j - 1], b = sa[j];
+    for (;;) {
+      const u64 pa = a + off + 32u * lane, pb = b + off + 32u * lane;
+      unsigned stop = 0;                         // equal regular bases in this lane's window
+      if (pa < n && pb < n) {                    // (the end of the text acts as a special)
+        const u32 wab = mask_window(spmask, pa) | mask_window(spmask, pb);
+        const unsigned lim = wab ? (unsigned) __ffs(wab) - 1u : 32u;
+        const u64 x = dna_window(words, pa) ^ dna_window(words, pb);
+        const unsigned common = x ? (unsigned) (__clzll((long long) x) >> 1) : 32u;
+        stop = common < lim ? common : lim;
+      }
+      const unsigned ended = __ballot_sync(FULL_MASK, stop < 32u);
+      if (ended) {
+        const unsigned first = (unsigned) __ffs(ended) - 1u;
+        off += 32u * first + __shfl_sync(FULL_MASK, stop, first);
+        break;
+      }
+      off += 1024;
+    }
+    if (lane == 0) {
+      const u32 l = (u32) off;
+      lcp8[j] = (u8) (l < 255u ? l : 255u);
+      ulcp[c] = l;
+      mx = l > mx ? l : mx;
+      sum += l;
+      if (l >= 255u) large++;
+    }
+  }
+  if (lane == 0) {
     if (sum) atomicAdd(&stats->lcpsum, sum);
     if (large) atomicAdd(&stats->numlarge, large);
     if (mx) atomicMax(&stats->maxlcp, mx);
