@@ -65,6 +65,7 @@ struct gtb_esa {
   ErrBuf err;
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;   // second copy stream of gtb_esa_copy_suftab_u64
   // input
   bool have_input = false, dna = true;
   u64 n = 0, S = 0;
@@ -916,6 +917,7 @@ void gtb_esa_delete(gtb_esa *h)
   for (DevBuf *b : all) b->release();
   radix_work_free(h->rw);
   h->hstage.release();
+  if (h->st2) cudaStreamDestroy(h->st2);
   cudaStreamDestroy(h->st);
   delete h;
 }
@@ -1455,39 +1457,74 @@ int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t 
   return 0;
 }
 
+// the wide half of gtb_esa_copy_suftab_u64: chunks from the back of the dealer are widened on the
+// device (into the dead key buffers) and copied as uint64 straight into the caller's pinned buffer
+static int suftab_wide_chunks(gtb_esa *h, cudaStream_t st2, uint64_t *dst, uint64_t first, uint64_t count,
+                              u64 per, ChunkDealer *dealer, ErrBuf &err)
+{
+  GTB_CUDA(cudaSetDevice(h->device));
+  u64 *stage[2];
+  cudaEvent_t done[2];
+  for (int i = 0; i < 2; i++) {
+    stage[i] = h->kbuf[i].as<u64>();
+    GTB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  int b = 0, rc = 0;
+  u64 k;
+  while (rc == 0 && dealer->take_back(&k)) {
+    const u64 off = k * per, c = count - off < per ? count - off : per;
+    cudaError_t e = cudaEventSynchronize(done[b]);          // (a fresh event is complete)
+    if (e == cudaSuccess) {
+      k_widen_u32_u64<<<grid_for(c, 256), 256, 0, st2>>>(h->vbuf[h->res].as<u32>() + first + off, stage[b], c);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst + off, stage[b], sizeof(u64) * c, cudaMemcpyDeviceToHost, st2);
+    if (e == cudaSuccess) e = cudaEventRecord(done[b], st2);
+    if (e != cudaSuccess) { err.set("wide suffix-table copy failed: %s", cudaGetErrorString(e)); rc = -1; }
+    b ^= 1;
+  }
+  if (cudaStreamSynchronize(st2) != cudaSuccess && rc == 0) { err.set("wide suffix-table copy failed"); rc = -1; }
+  for (int i = 0; i < 2; i++) cudaEventDestroy(done[i]);
+  return rc;
+}
+
 int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t count)
 {
   GTB_TRY(check_range(h, first, count));
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
+  // The .suf entries are uint64, the table in HBM uint32.  Two ways to the host: "narrow" (default)
+  // -- 4 bytes per entry cross PCIe into small pinned staging buffers (they stay in the host's last
+  // level cache) and host threads widen them into the destination; "wide" -- widened on the device,
+  // 8 bytes per entry by DMA straight into a pinned destination (bound by PCIe).
+  // GTB200_SUF_COPY = wide selects the second, = both deals the chunks from both ends to both paths
+  // (measured on the pool's 16-core hosts: narrow 334 ms, both 392 ms, wide 463 ms for c4's 24.8 GB).
   const char *mode = getenv("GTB200_SUF_COPY");
-  if (!(mode && strcmp(mode, "wide") == 0 && host_pointer_is_pinned(dst))) {
-    // 4 bytes per entry cross the bus; host threads widen them to the file's uint64 (gtb_hostio.cuh)
+  const bool pinned = host_pointer_is_pinned(dst);
+  const bool want_wide = pinned && mode && (strcmp(mode, "wide") == 0 || strcmp(mode, "both") == 0);
+  const bool want_narrow = !(pinned && mode && strcmp(mode, "wide") == 0);
+  GTB_TRY(h->hstage.ensure(err));
+  const u64 per = h->hstage.chunk / sizeof(u32);
+  const u64 nchunks = div_up(count, per);
+  if (!want_wide || nchunks < 4) {
     GTB_TRY(staged_d2h(h->hstage, h->st, h->vbuf[h->res].as<u32>() + first, dst, count, sizeof(u32), true, err));
     GTB_CUDA(cudaStreamSynchronize(h->st));
     return 0;
   }
-  // GTB200_SUF_COPY=wide (hosts whose memory system is slower than the bus): widen on the device
-  // into the dead key buffers and move 8 bytes per entry into the caller's pinned buffer
-  const u64 chunk = 1ull << 25;                 // 32 Mi entries = 256 MiB per chunk
-  u64 *stage[2];
-  for (int i = 0; i < 2; i++) {
-    GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * (chunk < count ? chunk : count), err));
-    stage[i] = h->kbuf[i].as<u64>();
-  }
-  cudaEvent_t done[2];
-  for (int i = 0; i < 2; i++) GTB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-  int b = 0;
-  for (u64 off = 0; off < count; off += chunk, b ^= 1) {
-    const u64 c = count - off < chunk ? count - off : chunk;
-    GTB_CUDA(cudaEventSynchronize(done[b]));
-    k_widen_u32_u64<<<grid_for(c, 256), 256, 0, h->st>>>(h->vbuf[h->res].as<u32>() + first + off, stage[b], c);
-    GTB_LAUNCH_CHECK();
-    GTB_CUDA(cudaMemcpyAsync(dst + off, stage[b], sizeof(u64) * c, cudaMemcpyDeviceToHost, h->st));
-    GTB_CUDA(cudaEventRecord(done[b], h->st));
-  }
+  for (int i = 0; i < 2; i++) GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * per, err));
+  if (!h->st2) GTB_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+  GTB_CUDA(cudaStreamSynchronize(h->st));                  // the results are final; both streams may read them
+  ChunkDealer dealer(nchunks);
+  ErrBuf err2;
+  int rc2 = 0;
+  std::thread wide([&] { rc2 = suftab_wide_chunks(h, h->st2, dst, first, count, per, &dealer, err2); });
+  int rc = 0;
+  if (want_narrow)
+    rc = staged_d2h(h->hstage, h->st, h->vbuf[h->res].as<u32>() + first, dst, count, sizeof(u32), true, err, &dealer);
+  wide.join();
+  if (rc == 0 && rc2 != 0) { err = err2; rc = -1; }
+  GTB_TRY(rc);
   GTB_CUDA(cudaStreamSynchronize(h->st));
-  for (int i = 0; i < 2; i++) cudaEventDestroy(done[i]);
   return 0;
 }
 
@@ -1578,9 +1615,16 @@ int gtb_esa_copy_bcktab(gtb_esa *h, uint32_t *leftborder, uint32_t *countspecial
   ErrBuf &err = h->err;
   if (!h->counted && !h->lb_own) { err.set("no bucket table: run with GTB_WANT_BCK or call gtb_esa_count first"); return -1; }
   GTB_CUDA(cudaSetDevice(h->device));
-  if (leftborder) GTB_CUDA(cudaMemcpyAsync(leftborder, h->leftborder.p, sizeof(u32) * (h->ncodes + 1), cudaMemcpyDeviceToHost, h->st));
-  if (countspecialcodes) GTB_CUDA(cudaMemcpyAsync(countspecialcodes, h->csc.p, sizeof(u32) * h->nspecialcodes, cudaMemcpyDeviceToHost, h->st));
-  if (distpfxidx && h->ndist) GTB_CUDA(cudaMemcpyAsync(distpfxidx, h->dist.p, sizeof(u32) * h->ndist, cudaMemcpyDeviceToHost, h->st));
+  // (pageable destinations go through the pinned staging buffers and host threads)
+  auto table = [&](uint32_t *dst, const void *src, u64 cnt) -> int {
+    if (!dst || cnt == 0) return 0;
+    if (host_pointer_is_pinned(dst)) GTB_CUDA(cudaMemcpyAsync(dst, src, sizeof(u32) * cnt, cudaMemcpyDeviceToHost, h->st));
+    else GTB_TRY(staged_d2h(h->hstage, h->st, src, dst, cnt, sizeof(u32), false, err));
+    return 0;
+  };
+  GTB_TRY(table(leftborder, h->leftborder.p, h->ncodes + 1));
+  GTB_TRY(table(countspecialcodes, h->csc.p, h->nspecialcodes));
+  GTB_TRY(table(distpfxidx, h->dist.p, h->ndist));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;
 }

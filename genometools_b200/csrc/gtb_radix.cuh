@@ -27,6 +27,7 @@
 // sfx-bltrie.c; as a stand-alone pair sort it is the counterpart of
 // gt_radixsort_inplace_GtUwordPair (/root/reference/src/core/radix_sort.h:107).
 #pragma once
+#include <atomic>
 #include "gtb_common.cuh"
 
 namespace gtb {
@@ -547,12 +548,16 @@ static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
                           u64 *okeys, u32 *ovals, unsigned bsel, unsigned dmask, int passidx,
                           ErrBuf &err)
 {
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  // (the attribute is per device: one bit per device and instantiation)
+  static std::atomic<unsigned long long> attr_set{0};
+  int dev = 0;
+  GTB_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(attr_set.load(std::memory_order_relaxed) & bit)) {
     GTB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<Src, Cfg, MODE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int) Cfg::SMEM));
-    attr_set = true;
+    attr_set.fetch_or(bit, std::memory_order_relaxed);
   }
   rs_onesweep_kernel<Src, Cfg, MODE><<<(unsigned) tiles, Cfg::NT, Cfg::SMEM, st>>>(
       src, okeys, ovals, nsrc, bsel, dmask, w.gbase + passidx * RS_BINS,
