@@ -1378,6 +1378,8 @@ __global__ void k_find_longest(TextSrc<DNA> src, const u64 *__restrict__ keys, u
 // the filled key (at most 4096 codes), counted in shared memory -- no global atomic per
 // suffix.  Positions [first, end).
 constexpr int CC_MAXCODES = 4096;
+// A thread takes a chunk of 16 consecutive positions (keys from TextSrc::gen_block_fast); equal
+// codes of neighbouring positions (low-complexity sequence) are added as one run.
 template <bool DNA>
 __global__ void __launch_bounds__(256)
 k_count_coarse(TextSrc<DNA> src, u64 first, u64 end, unsigned plc, unsigned K, u32 ncoarse,
@@ -1386,18 +1388,30 @@ k_count_coarse(TextSrc<DNA> src, u64 first, u64 end, unsigned plc, unsigned K, u
   __shared__ u32 s_c[CC_MAXCODES];
   for (u32 i = threadIdx.x; i < ncoarse; i += blockDim.x) s_c[i] = 0;
   __syncthreads();
-  for (u64 pos = first + blockIdx.x * (u64) blockDim.x + threadIdx.x; ; pos += (u64) gridDim.x * blockDim.x) {
-    const bool inb = pos < end;
-    u64 key = 0;
-    bool ok = false;
-    if (inb) ok = src.make_key(pos, key);
-    const unsigned act = __ballot_sync(FULL_MASK, ok);
-    if (ok) {
-      const u32 code = (u32) key_code<DNA>(key, plc, K, src.f);
-      const unsigned peers = __match_any_sync(act, code);
-      if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&s_c[code], (u32) __popc(peers));
+  const u64 c0 = first >> 4, c1 = (end + 15) >> 4;          // chunks [16c, 16c + 16) that meet [first, end)
+  for (u64 c = c0 + blockIdx.x * (u64) blockDim.x + threadIdx.x; c < c1; c += (u64) gridDim.x * blockDim.x) {
+    const u64 p = c << 4;
+    u32 prev = 0, run = 0;
+    if (p >= first && p + 16 <= end) {
+      u64 keys[16];
+      src.gen_block_fast(p, keys);                           // (pos0 = 0: item = position; p is 16-aligned)
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        if (keys[i] == ~0ull) continue;
+        const u32 code = key_code_prefix<DNA>(keys[i], plc, K, src.f);
+        if (run && code == prev) run++;
+        else { if (run) atomicAdd(&s_c[prev], run); prev = code; run = 1; }
+      }
+    } else {
+      for (u64 q = p < first ? first : p; q < end && q < p + 16; q++) {
+        u64 key;
+        if (!src.make_key(q, key)) continue;
+        const u32 code = key_code_prefix<DNA>(key, plc, K, src.f);
+        if (run && code == prev) run++;
+        else { if (run) atomicAdd(&s_c[prev], run); prev = code; run = 1; }
+      }
     }
-    if (!__any_sync(FULL_MASK, inb)) break;
+    if (run) atomicAdd(&s_c[prev], run);
   }
   __syncthreads();
   for (u32 i = threadIdx.x; i < ncoarse; i += blockDim.x) if (s_c[i]) atomicAdd(&cnt[i], s_c[i]);

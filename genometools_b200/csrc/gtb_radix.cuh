@@ -602,21 +602,54 @@ rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
   __shared__ u32 s_h[RS_BINS];
   s_h[threadIdx.x] = 0;
   __syncthreads();
-  const u64 ntiles = (N + RH_TILE - 1) / RH_TILE;
-  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const u64 base = tile * RH_TILE;
+  if constexpr (Src::BLOCKED_GEN) {
+    // a thread takes 16 consecutive items; with at most 16 ranges their counts fit two registers of
+    // eight 8-bit fields, summed over the warp before they touch shared memory
+    const int nb = c_rs_nbounds;
+    const u64 nchunks = (N + 15) >> 4;
+    for (u64 c0 = (u64) blockIdx.x * RH_NT; c0 < nchunks; c0 += (u64) gridDim.x * RH_NT) {
+      const u64 c = c0 + threadIdx.x;
+      const u64 idx = c << 4;
+      const u32 cnt = c < nchunks ? (N - idx < 16 ? (u32) (N - idx) : 16u) : 0u;
+      unsigned long long packed[2] = {0ull, 0ull};
+      if (cnt > 0 && src.can_gen_fast(idx, cnt) && nb <= 16) {
+        u64 keys[16];
+        src.gen_block_fast(idx, keys);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          if (keys[i] == RS_INVALID_KEY) continue;
+          const unsigned d = rs_owner(keys[i]);
+          if (d < 8u) packed[0] += 1ull << (8u * d); else packed[1] += 1ull << (8u * (d - 8u));
+        }
+      } else {
+        for (u32 i = 0; i < cnt; i++) {
+          u64 key;
+          if (src.load_key(idx + i, key)) atomicAdd(&s_h[rs_owner(key)], 1u);
+        }
+      }
+      for (int g = 0; g < nb && g < 16; g++) {               // (uniform trip count)
+        const u32 mine = (u32) ((g < 8 ? packed[0] : packed[1]) >> (8 * (g & 7))) & 0xffu;
+        const u32 sum = __reduce_add_sync(FULL_MASK, mine);
+        if (lane_id() == 0 && sum) atomicAdd(&s_h[g], sum);
+      }
+    }
+  } else {
+    const u64 ntiles = (N + RH_TILE - 1) / RH_TILE;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const u64 base = tile * RH_TILE;
 #pragma unroll 4
-    for (int k = 0; k < RH_IPT; k++) {
-      const u64 idx = base + (u64) k * RH_NT + threadIdx.x;
-      u64 key = 0;
-      bool ok = idx < N;
-      if (ok) ok = src.load_key(idx, key);
-      const unsigned d = rs_owner(key);
-      // consecutive text positions mostly differ in their owner: aggregate what does coincide
-      const unsigned act = __ballot_sync(FULL_MASK, ok);
-      if (ok) {
-        const unsigned peers = __match_any_sync(act, d);
-        if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&s_h[d], (u32) __popc(peers));
+      for (int k = 0; k < RH_IPT; k++) {
+        const u64 idx = base + (u64) k * RH_NT + threadIdx.x;
+        u64 key = 0;
+        bool ok = idx < N;
+        if (ok) ok = src.load_key(idx, key);
+        const unsigned d = rs_owner(key);
+        // consecutive text positions mostly differ in their owner: aggregate what does coincide
+        const unsigned act = __ballot_sync(FULL_MASK, ok);
+        if (ok) {
+          const unsigned peers = __match_any_sync(act, d);
+          if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&s_h[d], (u32) __popc(peers));
+        }
       }
     }
   }
@@ -642,7 +675,7 @@ static int rs_partition_by_owner(RadixWork &w, cudaStream_t st, const Src &src, 
   GTB_TRY(radix_work_reserve(w, nsrc, err));
   GTB_CUDA(cudaMemsetAsync(w.ghist, 0, sizeof(unsigned long long) * RS_BINS, st));
   {
-    u64 tiles = div_up(nsrc, RH_TILE);
+    u64 tiles = div_up(nsrc, RH_TILE);     // (a blocked source takes 16 items per thread: the same 4096 per CTA)
     unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
     rs_owner_hist_kernel<Src><<<grid, RH_NT, 0, st>>>(src, nsrc, w.ghist);
     GTB_LAUNCH_CHECK();
