@@ -448,3 +448,33 @@ def test_cuda_coarse_ranges_and_merged_bucket_table(exchange):
         assert np.array_equal(tabs[2][:nd.value], o["distpfxidx"].astype(np.uint64))
         for h in hs + [h0]:
             lib.gtb_esa_delete(h)
+
+
+@pytest.mark.parametrize("mode", ["", "wide", "both"])
+@pytest.mark.parametrize("stage_kb", ["64", "8192"])
+def test_result_copy_paths_agree(mode, stage_kb, monkeypatch):
+    """gtb_esa_copy_suftab_u64 into PINNED memory: staged uint32 + host widening (default), widened
+    on the device (GTB200_SUF_COPY=wide), both dealt from the two ends (=both); staging chunks
+    smaller and larger than the table.  All must deliver the table the pageable path delivers."""
+    import torch
+    if mode:
+        monkeypatch.setenv("GTB200_SUF_COPY", mode)
+    monkeypatch.setenv("GTB200_STAGE_KB", stage_kb)
+    monkeypatch.setenv("GTB200_HOST_THREADS", "5")
+    lib = _lib.load()
+    n = 3_000_001                                    # 12 MB of uint32: 184 chunks of 64 KiB, 2 of 8 MiB
+    sym = synth.random_dna(n, 77, p_n=0.001)
+    enc = encode_symbols(sym, 4)
+    with Suffixerator(0) as s:
+        s.set_sequence(enc)
+        res = s.run(8, want_bck=True)                # the library's pageable path (numpy buffers)
+        e = int(lib.gtb_esa_num_entries(s.h))
+        for first, count in ((0, e), (12345, e - 20000), (e - 1, 1), (7, 0)):
+            pinned = torch.empty(max(count, 1), dtype=torch.int64, pin_memory=True)
+            pinned.fill_(-1)
+            assert lib.gtb_esa_copy_suftab_u64(s.h, pinned.data_ptr(), first, count) == 0, lib.gtb_esa_error(s.h)
+            got = pinned.numpy().view(np.uint64)[:count]
+            assert np.array_equal(got, res.suftab[first:first + count]), (mode, first, count)
+            lp = torch.empty(max(count, 1), dtype=torch.uint8, pin_memory=True)
+            assert lib.gtb_esa_copy_lcptab(s.h, lp.data_ptr(), first, count) == 0
+            assert np.array_equal(lp.numpy()[:count], res.lcptab[first:first + count])
