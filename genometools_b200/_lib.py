@@ -91,6 +91,9 @@ SYMBOLS = {
     "gtb_esa_build_bytes": (C.c_int, [C.c_int, _P, _U64, C.c_uint, C.c_uint, _P, _P, _P, _U64,
                                       C.POINTER(_U64), _P, _P, _P, C.POINTER(GtbStats), C.c_char_p, C.c_size_t]),
     "gtb_radixsort_pairs_u64_u32": (C.c_int, [C.c_int, _P, _P, _U64, C.c_uint, C.c_uint, C.c_char_p, C.c_size_t]),
+    "gtb_radixsort_u64": (C.c_int, [C.c_int, _P, _U64, C.c_char_p, C.c_size_t]),
+    "gtb_radixsort_u64pair": (C.c_int, [C.c_int, _P, _U64, C.c_char_p, C.c_size_t]),
+    "gtb_radixsort_u64keypair": (C.c_int, [C.c_int, _P, _U64, C.c_char_p, C.c_size_t]),
 }
 
 GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS = 1, 2, 4, 8

@@ -1737,4 +1737,79 @@ int gtb_radixsort_pairs_u64_u32(int device, uint64_t *keys, uint32_t *values, ui
   return rc;
 }
 
+// records of `width` uint64 (1: plain keys; 2: pairs), sorted by component 0 (nkeys = 1) or by
+// (component 0, component 1) (nkeys = 2): LSD over the components with the onesweep engine on
+// (key, record index) pairs, then one gather of the records.  Stable.
+static int sort_u64_records(int device, uint64_t *rec, uint64_t count, unsigned width, unsigned nkeys, ErrBuf &err)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    err.set("libgtb200: no CUDA device available; there is no CPU fallback"); return -1;
+  }
+  if (count >= 0xffffffffull) { err.set("more than 2^32-2 records are not supported"); return -1; }
+  GTB_CUDA(cudaSetDevice(device));
+  if (count <= 1) return 0;
+  cudaStream_t st;
+  GTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  RadixWork rw;
+  DevBuf k[2], v[2], kin, vin, drec, dout;
+  int rc = radix_work_init(rw, err);
+  for (int i = 0; i < 2 && rc == 0; i++) { rc |= k[i].ensure(sizeof(u64) * count, err); rc |= v[i].ensure(sizeof(u32) * count, err); }
+  if (rc == 0) { rc |= kin.ensure(sizeof(u64) * count, err); rc |= vin.ensure(sizeof(u32) * count, err); }
+  if (rc == 0) rc |= drec.ensure(sizeof(u64) * width * count, err);
+  if (rc == 0) rc |= dout.ensure(sizeof(u64) * width * count, err);
+  if (rc == 0 && cudaMemcpyAsync(drec.p, rec, sizeof(u64) * width * count, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    err.set("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1;
+  }
+  u64 *kk[2] = {k[0].as<u64>(), k[1].as<u64>()};
+  u32 *vv[2] = {v[0].as<u32>(), v[1].as<u32>()};
+  const u32 *perm = nullptr;
+  for (int comp = (int) nkeys - 1; comp >= 0 && rc == 0; comp--) {     // least significant component first
+    k_records_to_pairs<<<grid_for(count, 256), 256, 0, st>>>(drec.as<u64>(), width, (unsigned) comp, perm, count,
+                                                           kin.as<u64>(), vin.as<u32>());
+    if (cudaGetLastError() != cudaSuccess) { err.set("kernel launch failed"); rc = -1; break; }
+    PassPlan plan; plan.npass = 0;
+    plan_add_bits(plan, 0, 64);
+    PairSrc ps{kin.as<u64>(), vin.as<u32>()};
+    int res = 0; u64 nout = 0;
+    rc = radix_sort(rw, st, ps, count, kk, vv, plan, &res, &nout, err);
+    perm = vv[res];
+    if (rc == 0 && comp > 0) {
+      // the next sort overwrites both value buffers: keep this order aside
+      if (cudaMemcpyAsync(dout.p, perm, sizeof(u32) * count, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { err.set("copy failed"); rc = -1; }
+      perm = dout.as<u32>();
+    }
+  }
+  if (rc == 0) {
+    // (the order of the last sort lies in a value buffer; dout is free again)
+    k_gather_records<<<grid_for(count, 256), 256, 0, st>>>(drec.as<u64>(), width, perm, count, dout.as<u64>());
+    if (cudaGetLastError() != cudaSuccess) { err.set("kernel launch failed"); rc = -1; }
+  }
+  if (rc == 0 && (cudaMemcpyAsync(rec, dout.p, sizeof(u64) * width * count, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                  cudaStreamSynchronize(st) != cudaSuccess)) {
+    err.set("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1;
+  }
+  kin.release(); vin.release(); drec.release(); dout.release();
+  for (int i = 0; i < 2; i++) { k[i].release(); v[i].release(); }
+  radix_work_free(rw);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+static int sort_u64_records_entry(int device, uint64_t *rec, uint64_t count, unsigned width, unsigned nkeys,
+                                  char *errbuf, size_t errlen)
+{
+  ErrBuf err;
+  const int rc = sort_u64_records(device, rec, count, width, nkeys, err);
+  if (rc != 0 && errbuf && errlen) snprintf(errbuf, errlen, "%s", err.msg);
+  return rc;
+}
+
+int gtb_radixsort_u64(int device, uint64_t *keys, uint64_t count, char *errbuf, size_t errlen)
+{ return sort_u64_records_entry(device, keys, count, 1, 1, errbuf, errlen); }
+int gtb_radixsort_u64pair(int device, uint64_t *pairs, uint64_t count, char *errbuf, size_t errlen)
+{ return sort_u64_records_entry(device, pairs, count, 2, 1, errbuf, errlen); }
+int gtb_radixsort_u64keypair(int device, uint64_t *pairs, uint64_t count, char *errbuf, size_t errlen)
+{ return sort_u64_records_entry(device, pairs, count, 2, 2, errbuf, errlen); }
+
 } // extern "C"

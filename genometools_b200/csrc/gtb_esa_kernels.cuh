@@ -1497,6 +1497,28 @@ __global__ void k_bwt(const u32 *__restrict__ sa, u64 count, const u64 *__restri
   }
 }
 
+// ---- stand-alone sorts of 64-bit records (gt_radixsort_inplace_*, src/core/radix_sort.h) ----
+// keys[i] = component `comp` of record perm[i] (perm null: record i), vals[i] = its record index
+__global__ void k_records_to_pairs(const u64 *__restrict__ rec, unsigned width, unsigned comp,
+                                   const u32 *__restrict__ perm, u64 count, u64 *__restrict__ keys,
+                                   u32 *__restrict__ vals)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x) {
+    const u32 r = perm ? perm[i] : (u32) i;
+    keys[i] = rec[(u64) r * width + comp];
+    vals[i] = r;
+  }
+}
+// out[i] = record perm[i]
+__global__ void k_gather_records(const u64 *__restrict__ rec, unsigned width, const u32 *__restrict__ perm,
+                                 u64 count, u64 *__restrict__ out)
+{
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x) {
+    const u64 r = perm[i];
+    for (unsigned c = 0; c < width; c++) out[i * width + c] = rec[r * width + c];
+  }
+}
+
 __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)
 {
   for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)

@@ -307,6 +307,18 @@ int gtb_radixsort_pairs_u64_u32(int device, uint64_t *keys, uint32_t *values,
                                 uint64_t count, unsigned begin_bit,
                                 unsigned end_bit, char *errbuf, size_t errlen);
 
+/* The record sorts of src/core/radix_sort.h on the same engine (host buffers, sorted in place;
+   fewer than 2^32-1 records):
+     gtb_radixsort_u64        gt_radixsort_inplace_ulong (radix_sort.h:91): plain 64-bit keys
+     gtb_radixsort_u64pair    gt_radixsort_inplace_GtUwordPair (:107): records {a, b}, a is the key;
+                              equal keys keep their input order (the reference's in-place MSD sort
+                              leaves that order unspecified)
+     gtb_radixsort_u64keypair gt_radixsort_inplace_Gtuint64keyPair (:125): records {a, b}, both
+                              components are keys (a first) */
+int gtb_radixsort_u64(int device, uint64_t *keys, uint64_t count, char *errbuf, size_t errlen);
+int gtb_radixsort_u64pair(int device, uint64_t *pairs, uint64_t count, char *errbuf, size_t errlen);
+int gtb_radixsort_u64keypair(int device, uint64_t *pairs, uint64_t count, char *errbuf, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,10 @@
                                    (/root/reference/src/match/sfx-run.c:719)
     gtref sfxmap <args>         -> gt_sfxmap (brute-force ESA verifier,
                                    /root/reference/src/tools/gt_sfxmap.c)
+    gtref radixsort ulong|ulongpair|keypair <in> <out>
+                                -> gt_radixsort_inplace_ulong / _GtUwordPair /
+                                   _Gtuint64keyPair (/root/reference/src/core/radix_sort.h:91,107,125)
+                                   on a file of raw uint64 values; prints the seconds of the call
 
   It replaces src/gt.c + the toolbox so that only the files on the
   suffixerator path have to be compiled.  No reference source is copied.
@@ -19,7 +23,42 @@
 #include "core/init_api.h"
 #include "core/error_api.h"
 #include "core/tool_api.h"
+#include "core/ma_api.h"
+#include "core/radix_sort.h"
+#include "core/timer_api.h"
 #include "match/sfx-run.h"
+#include <sys/time.h>
+
+static int ref_radixsort(int argc, char **argv)
+{
+  FILE *fp;
+  long bytes;
+  size_t n;
+  uint64_t *buf;
+  struct timeval t0, t1;
+
+  if (argc != 5) { fprintf(stderr, "usage: radixsort ulong|ulongpair|keypair <in> <out>\n"); return 1; }
+  fp = fopen(argv[3], "rb");
+  if (fp == NULL) { perror(argv[3]); return 1; }
+  fseek(fp, 0, SEEK_END); bytes = ftell(fp); fseek(fp, 0, SEEK_SET);
+  n = (size_t) bytes / sizeof (uint64_t);
+  buf = gt_malloc(bytes > 0 ? (size_t) bytes : 8);
+  if (fread(buf, sizeof (uint64_t), n, fp) != n) { fclose(fp); return 1; }
+  fclose(fp);
+  gettimeofday(&t0, NULL);
+  if (strcmp(argv[2], "ulong") == 0) gt_radixsort_inplace_ulong((GtUword*) buf, (GtUword) n);
+  else if (strcmp(argv[2], "ulongpair") == 0) gt_radixsort_inplace_GtUwordPair((GtUwordPair*) buf, (GtUword) (n / 2));
+  else if (strcmp(argv[2], "keypair") == 0) gt_radixsort_inplace_Gtuint64keyPair((Gtuint64keyPair*) buf, (GtUword) (n / 2));
+  else { fprintf(stderr, "unknown kind %s\n", argv[2]); return 1; }
+  gettimeofday(&t1, NULL);
+  printf("%.6f\n", (double) (t1.tv_sec - t0.tv_sec) + 1e-6 * (double) (t1.tv_usec - t0.tv_usec));
+  fp = fopen(argv[4], "wb");
+  if (fp == NULL) { perror(argv[4]); return 1; }
+  fwrite(buf, sizeof (uint64_t), n, fp);
+  fclose(fp);
+  gt_free(buf);
+  return 0;
+}
 
 GtTool* gt_sfxmap(void);  /* /root/reference/src/tools/gt_sfxmap.c:1530 */
 
@@ -35,7 +74,9 @@ int main(int argc, char **argv)
   gt_lib_init();
   err = gt_error_new();
   gt_error_set_progname(err, argv[0]);
-  if (strcmp(argv[1], "suffixerator") == 0)
+  if (strcmp(argv[1], "radixsort") == 0)
+    rval = ref_radixsort(argc, argv);
+  else if (strcmp(argv[1], "suffixerator") == 0)
     rval = gt_parseargsandcallsuffixerator(true, argc - 1,
                                            (const char**) argv + 1, err);
 #ifdef GTREF_WITH_SFXMAP
