@@ -66,6 +66,7 @@ struct gtb_esa {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;   // second copy stream of gtb_esa_copy_suftab_u64
+  cudaStream_t st3 = nullptr;   // lcp bytes beside the suffix table (gtb_esa_copy_tables)
   // input
   bool have_input = false, dna = true;
   u64 n = 0, S = 0;
@@ -918,6 +919,7 @@ void gtb_esa_delete(gtb_esa *h)
   radix_work_free(h->rw);
   h->hstage.release();
   if (h->st2) cudaStreamDestroy(h->st2);
+  if (h->st3) cudaStreamDestroy(h->st3);
   cudaStreamDestroy(h->st);
   delete h;
 }
@@ -1542,6 +1544,26 @@ int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count
   return 0;
 }
 
+// suffix table and lcp table together: the suffix-table copy is bound by the host's memory system,
+// not by the bus, so the lcp bytes travel on a second stream at the same time
+int gtb_esa_copy_tables(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t first, uint64_t count)
+{
+  GTB_TRY(check_range(h, first, count));
+  if (!suftab || !lcptab || count == 0 || !host_pointer_is_pinned(lcptab)) {
+    if (suftab) GTB_TRY(gtb_esa_copy_suftab_u64(h, suftab, first, count));
+    if (lcptab) GTB_TRY(gtb_esa_copy_lcptab(h, lcptab, first, count));
+    return 0;
+  }
+  ErrBuf &err = h->err;
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (!h->st3) GTB_CUDA(cudaStreamCreateWithFlags(&h->st3, cudaStreamNonBlocking));
+  GTB_CUDA(cudaStreamSynchronize(h->st));                  // the results are final
+  GTB_CUDA(cudaMemcpyAsync(lcptab, h->lcp8.as<u8>() + first, count, cudaMemcpyDeviceToHost, h->st3));
+  const int rc = gtb_esa_copy_suftab_u64(h, suftab, first, count);
+  GTB_CUDA(cudaStreamSynchronize(h->st3));
+  return rc;
+}
+
 int gtb_esa_set_separators(gtb_esa *h, const uint64_t *positions, uint64_t count)
 {
   if (!h) return -1;
@@ -1645,8 +1667,7 @@ static int one_shot(gtb_esa *h, unsigned pl, uint64_t *suftab, uint8_t *lcptab, 
   if (leftborder || csc || dist) flags |= GTB_WANT_BCK;
   GTB_TRY(gtb_esa_run(h, pl, flags));
   const u64 e = gtb_esa_num_entries(h);
-  if (suftab) GTB_TRY(gtb_esa_copy_suftab_u64(h, suftab, 0, e));
-  if (lcptab) GTB_TRY(gtb_esa_copy_lcptab(h, lcptab, 0, e));
+  GTB_TRY(gtb_esa_copy_tables(h, suftab, lcptab, 0, e));
   if (nllv) *nllv = h->nllv;
   if (llv) {
     if (h->nllv > llv_capacity) { h->err.set("llv buffer too small: %llu entries needed", (unsigned long long) h->nllv); return -1; }

@@ -249,6 +249,9 @@ int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t 
 int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t count);
 /* outlcpvalues (sfx-lcpvalues.c:371-433) */
 int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count);
+/* both tables of the same entries in one call (either pointer may be NULL): with pinned buffers the lcp
+   bytes cross the bus while host threads still widen the suffix table */
+int gtb_esa_copy_tables(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t first, uint64_t count);
 /* -bwt (bwttab2file, src/match/sfx-run.c:173-210): one encoded symbol per suffix-table
    entry, the symbol before the suffix (0..numofchars-1, 254 wildcard, 255 separator;
    UNDEFBWTCHAR = 254 for the suffix that starts at 0, chardef.h:65).  The 2-bit input does

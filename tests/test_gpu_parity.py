@@ -478,3 +478,7 @@ def test_result_copy_paths_agree(mode, stage_kb, monkeypatch):
             lp = torch.empty(max(count, 1), dtype=torch.uint8, pin_memory=True)
             assert lib.gtb_esa_copy_lcptab(s.h, lp.data_ptr(), first, count) == 0
             assert np.array_equal(lp.numpy()[:count], res.lcptab[first:first + count])
+            pinned.fill_(-1); lp.fill_(7)                 # both tables in one call (lcp on a second stream)
+            assert lib.gtb_esa_copy_tables(s.h, pinned.data_ptr(), lp.data_ptr(), first, count) == 0
+            assert np.array_equal(pinned.numpy().view(np.uint64)[:count], res.suftab[first:first + count])
+            assert np.array_equal(lp.numpy()[:count], res.lcptab[first:first + count])
