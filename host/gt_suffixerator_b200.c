@@ -24,6 +24,7 @@
   Build: see host/Makefile (needs the reference tree for headers and libgenometools.a).
 */
 #include <limits.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -68,6 +69,21 @@ static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
   return 0;
 }
 
+/* Creating the sorter object means creating a CUDA context (a few hundred milliseconds in a fresh
+   process): it is started on a thread of its own before the FASTA files are encoded, so that it
+   costs nothing next to the reference's encoder. */
+typedef struct {
+  gtb_esa *handle;
+  char msg[512];
+} B200Init;
+
+static void *b200_init_thread(void *p)
+{
+  B200Init *init = p;
+  init->handle = gtb_esa_new(0, init->msg, sizeof init->msg);
+  return NULL;
+}
+
 static int b200_write(const char *indexname, const char *suffix, const void *data,
                       size_t size, size_t nmemb, size_t pad_to, GtError *err)
 {
@@ -95,6 +111,9 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   Suffixeratoroptions so;
   GtEncseq *encseq = NULL;
   GtLogger *logger = NULL;
+  B200Init init;
+  pthread_t init_tid;
+  bool init_started = false;
   int retval, had_err = 0;
 
   gt_error_check(err);
@@ -105,6 +124,11 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   }
   logger = gt_logger_new(so.beverbose, GT_LOGGER_DEFLT_PREFIX, stdout);
   had_err = b200_unsupported(&so, err);
+  if (!had_err && (gt_index_options_outsuftab_value(so.idxopts) || gt_index_options_outlcptab_value(so.idxopts) ||
+                   gt_index_options_outbcktab_value(so.idxopts) || gt_index_options_outbwttab_value(so.idxopts))) {
+    memset(&init, 0, sizeof init);
+    init_started = pthread_create(&init_tid, NULL, b200_init_thread, &init) == 0;
+  }
 
   if (!had_err) {                        /* encode + load, exactly the reference's calls */
     GtEncseqEncoder *ee = gt_encseq_encoder_new_from_options(so.encopts, err);
@@ -175,7 +199,14 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     }
     if (!had_err && want_any) {
       int rc = 0;
-      gtb_esa *h = gtb_esa_new(0, msg, sizeof msg);
+      gtb_esa *h = NULL;
+      if (init_started) {                       /* created while the sequences were being encoded */
+        pthread_join(init_tid, NULL);
+        init_started = false;
+        h = init.handle;
+        if (h == NULL) snprintf(msg, sizeof msg, "%s", init.msg);
+      } else
+        h = gtb_esa_new(0, msg, sizeof msg);
       if (h == NULL) rc = -1;
       /* GtReadmode values are the library's: fwd 0, rev 1, cpl 2, rcl 3 (src/core/readmode.h) */
       if (rc == 0) rc = gtb_esa_set_readmode(h, (unsigned) readmode);
@@ -284,6 +315,10 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
                   stats.ms_total, stats.kernel_launches, stats.radix_passes);
     gt_free(suftab); gt_free(lcptab); gt_free(llv); gt_free(bwttab);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
+  }
+  if (init_started) {                           /* an error came first: the object was never used */
+    pthread_join(init_tid, NULL);
+    gtb_esa_delete(init.handle);
   }
   gt_encseq_delete(encseq);
   gt_logger_delete(logger);
