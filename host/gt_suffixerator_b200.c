@@ -28,6 +28,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/time.h>
 #include "core/alphabet.h"
 #include "core/encseq.h"
 #include "core/error_api.h"
@@ -67,6 +68,13 @@ static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
     return -1;
   }
   return 0;
+}
+
+static double b200_now(void)
+{
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return (double) tv.tv_sec + 1e-6 * (double) tv.tv_usec;
 }
 
 /* Creating the sorter object means creating a CUDA context (a few hundred milliseconds in a fresh
@@ -115,6 +123,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   pthread_t init_tid;
   bool init_started = false;
   int retval, had_err = 0;
+  double t_start = b200_now(), t_encoded = 0, t_uploaded = 0, t_sorted = 0, t_copied = 0;
 
   gt_error_check(err);
   retval = gt_suffixeratoroptions(&so, true, argc, argv, err);
@@ -151,6 +160,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     }
   }
 
+  t_encoded = b200_now();
   if (!had_err) {
     const bool want_suf = gt_index_options_outsuftab_value(so.idxopts),
                want_lcp = gt_index_options_outlcptab_value(so.idxopts),
@@ -263,9 +273,11 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
         if (rc == 0) rc = gtb_esa_set_input_bytes(h, symbols, n, numofchars);
         gt_free(symbols);
       }
+      t_uploaded = b200_now();
       if (rc == 0)
         rc = gtb_esa_run(h, prefixlength, (want_suf ? GTB_WANT_SUF : 0u) | (want_lcp ? GTB_WANT_LCP : 0u) |
                                           (want_bck ? GTB_WANT_BCK : 0u));
+      t_sorted = b200_now();
       if (rc == 0) {
         const uint64_t e = gtb_esa_num_entries(h);          /* = n + 1 */
         if (want_suf) rc = gtb_esa_copy_suftab_u64(h, suftab, 0, e);
@@ -279,6 +291,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       gtb_esa_delete(h);
       if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
     }
+    t_copied = b200_now();
     /* the reference's files */
     if (!had_err && want_suf)
       had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, err);
@@ -313,6 +326,11 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     }
     gt_logger_log(logger, "B200 device time %.3f ms, %u kernel launches, %u radix passes",
                   stats.ms_total, stats.kernel_launches, stats.radix_passes);
+    if (t_copied > 0)
+      gt_logger_log(logger, "wall seconds: encode+load %.3f, export+upload (incl. waiting for the CUDA context) "
+                            "%.3f, sort %.3f, copy to host %.3f, write files %.3f",
+                    t_encoded - t_start, t_uploaded - t_encoded, t_sorted - t_uploaded, t_copied - t_sorted,
+                    b200_now() - t_copied);
     gt_free(suftab); gt_free(lcptab); gt_free(llv); gt_free(bwttab);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
   }
