@@ -331,12 +331,17 @@ def run_range_distributed(worker, first_keys, dist, device, want_lcp=True, begin
     if allmax(worker.unresolved()) > 0:
         worker.ensure_ranks()
         dist.barrier()                                  # every range can answer from here on
-        while allmax(worker.unresolved()) > 0:
-            send, counts = worker.round_prepare(first_keys, me)
-            sc = torch.tensor(counts, dtype=torch.int64, device=device)
-            rc = torch.empty_like(sc)
-            dist.all_to_all_single(rc, sc)
-            rcl = [int(x) for x in rc.tolist()]
+        while True:
+            # one collective carries the loop condition and the exchange sizes: every rank
+            # gathers (positions it asks of each range ..., its own number of tied suffixes)
+            send, counts = worker.round_prepare(first_keys, me)        # (nothing to ask when nothing is tied)
+            mine = torch.tensor(list(counts) + [worker.unresolved()], dtype=torch.int64, device=device)
+            rows = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(rows, mine)
+            table = torch.stack(rows).tolist()
+            if max(int(row[world]) for row in table) == 0:
+                break
+            rcl = [int(table[r][me]) for r in range(world)]
             recv_q = torch.empty(sum(rcl), dtype=send.dtype, device=device)
             dist.all_to_all_single(recv_q, send.contiguous(), output_split_sizes=rcl, input_split_sizes=counts)
             wait()
