@@ -113,3 +113,27 @@ def test_dropin_readmode_errors_like_the_reference(tmp_path):
             assert r.returncode != 0
             msgs.append(r.stderr.split("error:")[1])
         assert msgs[0] == msgs[1]
+
+
+@need_bins
+@pytest.mark.parametrize("mode", ["fwd", "rcl"])
+def test_dropin_index_passes_the_reference_verifier(tmp_path, mode):
+    """`gt dev sfxmap -suf -lcp -bck -esa` -- the reference's own brute-force checker
+    (/root/reference/src/tools/gt_sfxmap.c, src/match/esa-map.c) reads OUR index files and accepts them"""
+    sym = np.concatenate([synth.reads(400, 90, 3, 0.004), np.array([255], dtype=np.uint8),
+                          synth.repeats_dna(60_000, 6, unit=3000, copies=6, exact_len=9000, exact_copies=3)])
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(sym, fa, "dna")
+    idx = str(tmp_path / "b200")
+    subprocess.check_call([GT_B200, "suffixerator", "-dna", "-tis", "-suf", "-lcp", "-bck", "-ssp", "-des", "-sds",
+                           "-pl", "-dir", mode, "-indexname", idx, "-db", fa], stdout=subprocess.DEVNULL)
+    r = subprocess.run([GTREF, "sfxmap", "-tis", "-suf", "-lcp", "-bck", "-ssp", "-v", "-esa", idx],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "compare lcp-values against reference" in r.stdout and r.stdout.strip().endswith("okay")
+    # and it does notice a wrong table: swap two suffix-table entries
+    suf = np.fromfile(idx + ".suf", dtype=np.uint64)
+    suf[[1000, 1001]] = suf[[1001, 1000]]
+    suf.tofile(idx + ".suf")
+    r = subprocess.run([GTREF, "sfxmap", "-tis", "-suf", "-lcp", "-bck", "-ssp", "-esa", idx], capture_output=True, text=True)
+    assert r.returncode != 0
