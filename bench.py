@@ -10,9 +10,13 @@ A step = one complete pass of the hot path over the workload: fused key generati
 5-8 radix passes (key length chosen from the text length), group analysis + bucket table
 from the sorted keys, text-driven / prefix-doubling refinement of the ties, lcp, special
 tail -- results left in HBM (`value`), or through the host-buffer C-ABI including the
-H2D copy of the packed sequence and the D2H copy of .suf/.lcp/.llv/.bck (`e2e`).
-With N > 1 ranks (torchrun) the bucket codes are sharded: count allreduce (NCCL), key
-generation sharded by text position with an all-to-all of the (key, position) pairs to the
+H2D copy of the packed sequence and the D2H copy of .suf/.lcp/.llv/.bck (`e2e`: pinned host
+buffers, one untimed warm-up step, per-phase breakdown).  At N = 1 the line also carries
+`cpu_baseline` (the unmodified reference, one host core, bounded sample of the same generator)
+and `cli` (the drop-in binary host/_build/gt_b200 on the same FASTA sample, index files compared
+byte for byte with the reference's).
+With N > 1 ranks (torchrun) the bucket codes are sharded: count allreduce (NCCL), from 4
+ranks on key generation sharded by text position with an all-to-all of the positions to the
 owning code range, the rank's own range sorted, rank exchange (all-to-all) in the doubling
 rounds.
 Prints ONE JSON line on rank 0.
