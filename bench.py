@@ -388,9 +388,11 @@ def main():
         else:
             ps = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
             ps[:] = w.symbols
+        llv_pinned = torch.empty((max(int(lib.gtb_esa_num_llv(h)) * 2, 1024), 2), dtype=torch.int64,
+                                 pin_memory=True).numpy().view(np.uint64)
         d2h = 0
         parts_s = [0.0, 0.0, 0.0]                   # H2D, kernels, D2H of the timed steps
-        d2h_parts = [0.0, 0.0, 0.0]                 # suftab, lcptab, llv + bucket table (incl. the warm-up step)
+        d2h_parts = [0.0]                           # gtb_esa_copy_results (incl. the warm-up step)
 
         def e2e_step():
             nonlocal d2h
@@ -405,14 +407,19 @@ def main():
             tc = time.perf_counter()
             e = lib.gtb_esa_num_entries(h)
             t1 = time.perf_counter()
-            ck(lib.gtb_esa_copy_tables(h, ptr(suf), ptr(lcp), 0, e))    # (the lcp bytes travel beside the suffix table)
-            t2 = t3 = time.perf_counter()
             k = lib.gtb_esa_num_llv(h)
-            llv = np.empty((max(k, 1), 2), dtype=np.uint64)
-            if k:
-                ck(lib.gtb_esa_copy_llv(h, ptr(llv)))
-            ck(lib.gtb_esa_copy_bcktab(h, ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
-            d2h_parts[0] += t2 - t1; d2h_parts[1] += t3 - t2; d2h_parts[2] += time.perf_counter() - t3
+            if k > llv_pinned.shape[0]:
+                raise SystemExit("bench.py: llv buffer too small")
+            if os.environ.get("GTB_BENCH_COPY") == "tables":   # (A/B: suffix + lcp table together, the rest afterwards)
+                ck(lib.gtb_esa_copy_tables(h, ptr(suf), ptr(lcp), 0, e))
+                if k:
+                    ck(lib.gtb_esa_copy_llv(h, ptr(llv_pinned)))
+                ck(lib.gtb_esa_copy_bcktab(h, ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
+            else:
+                # one call: lcptab, llv and the bucket table travel beside the suffix table
+                ck(lib.gtb_esa_copy_results(h, ptr(suf), ptr(lcp), ptr(llv_pinned) if k else None,
+                                            ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
+            d2h_parts[0] += time.perf_counter() - t1
             # bytes of the host tensors that are filled (uint64 suftab, uint8 lcptab, llv, bucket
             # tables).  Fewer cross the bus: part of the suffix table travels as uint32 and is
             # widened by host threads, the rest is widened on the device (gtb_esa_copy_suftab_u64)
@@ -436,8 +443,7 @@ def main():
                "steps": args.e2e_steps, "ms_per_step": te.item() / args.e2e_steps * 1e3,
                "breakdown_ms": {"h2d": parts_s[0] / args.e2e_steps * 1e3, "kernels": parts_s[1] / args.e2e_steps * 1e3,
                                 "d2h": parts_s[2] / args.e2e_steps * 1e3,
-                                "d2h_suftab_lcptab": d2h_parts[0] / (args.e2e_steps + 1) * 1e3,
-                                "d2h_llv_bck": d2h_parts[2] / (args.e2e_steps + 1) * 1e3},
+                                "d2h_all_tables_one_call": d2h_parts[0] / (args.e2e_steps + 1) * 1e3},
                "note": "pinned host buffers; results delivered as the files hold them (uint64 suftab, "
                        "uint8 lcptab, llv pairs, uint32 bucket tables); one untimed warm-up step"}
 

@@ -1564,6 +1564,48 @@ int gtb_esa_copy_tables(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t 
   return rc;
 }
 
+// everything suffixeratorwithoutput() writes, in one call: the small tables (lcp, llv, bucket table)
+// cross the bus on a second stream while the suffix table is copied and widened.  Any pointer may be
+// NULL; pageable destinations are served one after the other.
+int gtb_esa_copy_results(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
+                         uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx)
+{
+  if (!h) return -1;
+  ErrBuf &err = h->err;
+  if (!h->ran) { err.set("no results: gtb_esa_run has not succeeded"); return -1; }
+  const u64 e = h->entries;
+  const bool want_bck = leftborder || countspecialcodes || distpfxidx;
+  if (want_bck && !h->counted && !h->lb_own) { err.set("no bucket table: run with GTB_WANT_BCK or call gtb_esa_count first"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  if (!h->st3) GTB_CUDA(cudaStreamCreateWithFlags(&h->st3, cudaStreamNonBlocking));
+  GTB_CUDA(cudaStreamSynchronize(h->st));                  // the results are final
+  // what the copy engine can write directly goes to the second stream now ...
+  bool later_lcp = false, later_llv = false, later_lb = false, later_csc = false, later_dist = false;
+  auto side = [&](void *dst, const void *src, size_t bytes, bool *later) -> int {
+    if (!dst || bytes == 0) return 0;
+    if (!host_pointer_is_pinned(dst)) { *later = true; return 0; }
+    GTB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st3));
+    return 0;
+  };
+  GTB_TRY(side(lcptab, h->lcp8.p, e, &later_lcp));
+  GTB_TRY(side(llv, h->llv.p, sizeof(u64) * 2 * h->nllv, &later_llv));
+  if (want_bck) {
+    GTB_TRY(side(leftborder, h->leftborder.p, sizeof(u32) * (h->ncodes + 1), &later_lb));
+    GTB_TRY(side(countspecialcodes, h->csc.p, sizeof(u32) * h->nspecialcodes, &later_csc));
+    GTB_TRY(side(distpfxidx, h->dist.p, sizeof(u32) * h->ndist, &later_dist));
+  }
+  // ... while the suffix table takes the main path
+  int rc = suftab ? gtb_esa_copy_suftab_u64(h, suftab, 0, e) : 0;
+  if (cudaStreamSynchronize(h->st3) != cudaSuccess && rc == 0) { err.set("result copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+  GTB_TRY(rc);
+  if (later_lcp) GTB_TRY(gtb_esa_copy_lcptab(h, lcptab, 0, e));
+  if (later_llv) GTB_TRY(gtb_esa_copy_llv(h, llv));
+  if (later_lb || later_csc || later_dist)
+    GTB_TRY(gtb_esa_copy_bcktab(h, later_lb ? leftborder : nullptr, later_csc ? countspecialcodes : nullptr,
+                                later_dist ? distpfxidx : nullptr));
+  return 0;
+}
+
 int gtb_esa_set_separators(gtb_esa *h, const uint64_t *positions, uint64_t count)
 {
   if (!h) return -1;

@@ -252,6 +252,11 @@ int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count
 /* both tables of the same entries in one call (either pointer may be NULL): with pinned buffers the lcp
    bytes cross the bus while host threads still widen the suffix table */
 int gtb_esa_copy_tables(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t first, uint64_t count);
+/* all results of this handle in one call -- what suffixeratorwithoutput() (sfx-run.c:212-317) writes:
+   with pinned buffers lcptab, llv (2*gtb_esa_num_llv() uint64) and the bucket table cross the bus on a
+   second stream while the suffix table is copied and widened.  Any pointer may be NULL. */
+int gtb_esa_copy_results(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
+                         uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx);
 /* -bwt (bwttab2file, src/match/sfx-run.c:173-210): one encoded symbol per suffix-table
    entry, the symbol before the suffix (0..numofchars-1, 254 wildcard, 255 separator;
    UNDEFBWTCHAR = 254 for the suffix that starts at 0, chardef.h:65).  The 2-bit input does

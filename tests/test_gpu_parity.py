@@ -478,6 +478,16 @@ def test_result_copy_paths_agree(mode, stage_kb, monkeypatch):
             lp = torch.empty(max(count, 1), dtype=torch.uint8, pin_memory=True)
             assert lib.gtb_esa_copy_lcptab(s.h, lp.data_ptr(), first, count) == 0
             assert np.array_equal(lp.numpy()[:count], res.lcptab[first:first + count])
+            if first == 0 and count == e:                 # every table in one call, small ones on a second stream
+                pinned.fill_(-1); lp.fill_(7)
+                lbp = torch.empty(res.leftborder.shape[0], dtype=torch.int32, pin_memory=True)
+                cs = np.empty_like(res.countspecialcodes)                 # (pageable: served afterwards)
+                assert lib.gtb_esa_copy_results(s.h, pinned.data_ptr(), lp.data_ptr(), None, lbp.data_ptr(),
+                                                cs.ctypes.data, None) == 0, lib.gtb_esa_error(s.h)
+                assert np.array_equal(pinned.numpy().view(np.uint64)[:count], res.suftab)
+                assert np.array_equal(lp.numpy()[:count], res.lcptab)
+                assert np.array_equal(lbp.numpy().view(np.uint32), res.leftborder)
+                assert np.array_equal(cs, res.countspecialcodes)
             pinned.fill_(-1); lp.fill_(7)                 # both tables in one call (lcp on a second stream)
             assert lib.gtb_esa_copy_tables(s.h, pinned.data_ptr(), lp.data_ptr(), first, count) == 0
             assert np.array_equal(pinned.numpy().view(np.uint64)[:count], res.suftab[first:first + count])
