@@ -35,6 +35,9 @@ def test_no_cpu_fallback_without_device():
     k = np.arange(4, dtype=np.uint64)
     v = np.arange(4, dtype=np.uint32)
     assert lib.gtb_radixsort_pairs_u64_u32(0, k.ctypes.data, v.ctypes.data, 4, 0, 64, buf, 256) == -1
+    for fn in (lib.gtb_radixsort_u64, lib.gtb_radixsort_u64pair, lib.gtb_radixsort_u64keypair):
+        buf2 = ctypes.create_string_buffer(256)
+        assert fn(0, k.ctypes.data, 2, buf2, 256) == -1 and b"no CPU fallback" in buf2.value
 
 
 @pytest.mark.parametrize("case", golden_cases())
