@@ -222,7 +222,7 @@ def run_reference_arm(args, rank, world):
     val = (w.totallength + 1) * len(times) / tot / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
             "config": {"workload": wl, "sample_totallength": w.totallength, "description": w.description,
                        "command": "suffixerator -suf -lcp -bck -pl (1 thread: the reference computes no lcp "
@@ -471,7 +471,39 @@ def main():
         lib.gtb_esa_dev_bcktab(h, C.byref(plb_), None, None)
         lbt = torch.as_tensor(_DevArr(plb_.value, a_.value + 1, "<u4"), device=dev)
         bck_ok = int(lbt[-1].item()) == int(chk[2].item()) and bool((lbt[1:].to(torch.int64) >= lbt[:-1].to(torch.int64)).all().item())
-    checks = {"suftab_is_permutation_sum": int(chk[0].item()) == n * (n + 1) // 2 and int(chk[1].item()) == n + 1,
+    # order-dependent checksums of the tables in HBM (gtb_esa_hash_results; shards add up) against the
+    # checksums of the files the unmodified reference wrote for this workload at this size
+    # (tests/golden/config_md5.json, tests/golden/make_golden_configs.py)
+    def as_i64(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+    nllv_mine = int(lib.gtb_esa_num_llv(h))
+    llv_before = 0
+    if dist is not None:
+        allk = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allk, torch.tensor([nllv_mine], dtype=torch.int64, device=dev))
+        llv_before = sum(int(t.item()) for t in allk[:rank])
+    out3 = (C.c_uint64 * 3)()
+    ck(lib.gtb_esa_hash_results(h, llv_before, out3))
+    hs = torch.tensor([as_i64(int(out3[i])) for i in range(3)], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(hs)             # (int64 sums wrap: the checksum is a sum mod 2^64)
+    hb = C.c_uint64()
+    ck(lib.gtb_esa_hash_bcktab(h, C.byref(hb)))       # (N > 1: the tables were summed over the ranks above)
+    hashes = {"suf": int(hs[0].item()) % (1 << 64), "lcp": int(hs[1].item()) % (1 << 64),
+              "llv": int(hs[2].item()) % (1 << 64), "bck": int(hb.value)}
+    golden_key = args.workload if args.scale == 1.0 else f"{args.workload}@{args.scale:g}"
+    gpath = os.path.join(ROOT, "tests", "golden", "config_md5.json")
+    golden = json.load(open(gpath)).get(golden_key) if os.path.exists(gpath) else None
+    identical = None
+    if golden is not None and golden["totallength"] == n:
+        identical = all(hashes[e] == golden["files"][e]["mixhash"] for e in ("suf", "lcp", "llv", "bck"))
+    checks = {"identical_to_reference": identical,
+              "identical_to_reference_how": "order-dependent 64-bit checksums (genometools_b200/mixhash.py) of "
+              "suftab/lcptab/llv/bucket table in HBM, summed over the shards, equal to the checksums of the "
+              "files `gtref suffixerator` wrote for this workload (tests/golden/config_md5.json)"
+              if golden is not None else "no golden checksums for this workload/scale",
+              "suf_hash": hashes["suf"], "lcp_hash": hashes["lcp"], "llv_hash": hashes["llv"], "bck_hash": hashes["bck"],
+              "suftab_is_permutation_sum": int(chk[0].item()) == n * (n + 1) // 2 and int(chk[1].item()) == n + 1,
               "lcptabsum": int(chk[3].item()), "largelcpvalues": int(chk[4].item()),
               "maxbranchdepth": int(mx[0].item()), "doubling_rounds": int(mx[1].item())}
     if bck_ok is not None:
@@ -489,10 +521,12 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": args.workload, "description": w.description, "totallength": n,
                    "specialcharacters": int(last["specialcharacters"]), "prefixlength": pl,
-                   "numofchars": w.numofchars, "outputs": "-suf -lcp -bck (results resident in HBM)",
+                   "numofchars": w.numofchars, "outputs": "-suf -lcp -bck (results resident in HBM; `value` excludes the H2D copy of the packed "
+                              "sequence -- inputs resident when the timed region starts -- `e2e` includes it)",
+                   "dtype_note": "u32 positions in HBM (n + 1 < 2^32), widened to the file's uint64 on copy-out",
                    "l2": "inputs_exceed_l2 (no flush needed)", "sharding": f"{world} bucket-code ranges"
                    if world > 1 else "single range", "scale": args.scale},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

@@ -84,6 +84,8 @@ SYMBOLS = {
     "gtb_esa_copy_llv": (C.c_int, [_P, _P]),
     "gtb_esa_copy_bcktab": (C.c_int, [_P, _P, _P, _P]),
     "gtb_bck_sizes": (None, [C.c_uint, C.c_uint, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "gtb_esa_hash_results": (C.c_int, [_P, _U64, C.POINTER(_U64)]),
+    "gtb_esa_hash_bcktab": (C.c_int, [_P, C.POINTER(_U64)]),
     "gtb_esa_stream": (_P, [_P]),
     "gtb_esa_dev_suftab": (_P, [_P]),
     "gtb_esa_dev_lcptab": (_P, [_P]),

@@ -848,6 +848,24 @@ static int timed_stage(gtb_esa *h, F body)
   return rc;
 }
 
+// checksum of `count` entries at device pointer v (global index of the first = index_base), added to *acc
+template <typename T>
+static int hash_table(gtb_esa *h, const T *v, u64 count, u64 index_base, u64 *acc)
+{
+  ErrBuf &err = h->err;
+  if (count == 0) return 0;
+  GTB_TRY(h->misc.ensure(256, err));
+  unsigned long long *d = reinterpret_cast<unsigned long long *>(h->misc.as<u64>() + 16);
+  GTB_CUDA(cudaMemsetAsync(d, 0, sizeof *d, h->st));
+  k_mixhash<T><<<grid_for(count, 256, 148u * 8u), 256, 0, h->st>>>(v, count, index_base, d);
+  GTB_LAUNCH_CHECK();
+  unsigned long long r = 0;
+  GTB_CUDA(cudaMemcpyAsync(&r, d, sizeof r, cudaMemcpyDeviceToHost, h->st));
+  GTB_CUDA(cudaStreamSynchronize(h->st));
+  *acc += (u64) r;
+  return 0;
+}
+
 // =============================== C-ABI =================================================
 extern "C" {
 
@@ -1690,6 +1708,40 @@ int gtb_esa_copy_bcktab(gtb_esa *h, uint32_t *leftborder, uint32_t *countspecial
   GTB_TRY(table(countspecialcodes, h->csc.p, h->nspecialcodes));
   GTB_TRY(table(distpfxidx, h->dist.p, h->ndist));
   GTB_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int gtb_esa_hash_results(gtb_esa *h, uint64_t llv_pairs_before, uint64_t out3[3])
+{
+  if (!h || !out3) return -1;
+  ErrBuf &err = h->err;
+  if (!h->ran) { err.set("no results: gtb_esa_run has not succeeded"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  out3[0] = out3[1] = out3[2] = 0;
+  GTB_TRY(hash_table(h, h->vbuf[h->res].as<u32>(), h->entries, h->sa_offset, &out3[0]));
+  if (h->flags & GTB_WANT_LCP) {
+    GTB_TRY(hash_table(h, h->lcp8.as<u8>(), h->entries, h->sa_offset, &out3[1]));
+    GTB_TRY(hash_table(h, h->llv.as<u64>(), 2 * h->nllv, 2 * llv_pairs_before, &out3[2]));
+  }
+  return 0;
+}
+
+int gtb_esa_hash_bcktab(gtb_esa *h, uint64_t *out)
+{
+  if (!h || !out) return -1;
+  ErrBuf &err = h->err;
+  if (!h->counted && !h->lb_own) { err.set("no bucket table: run with GTB_WANT_BCK or call gtb_esa_count first"); return -1; }
+  GTB_CUDA(cudaSetDevice(h->device));
+  // the .bck file: three uint32 tables, each padded to 8 bytes (gt_mapspec_write, mapspec.c:350-365)
+  u64 acc = 0, word = 0;
+  const u64 counts[3] = {h->ncodes + 1, h->nspecialcodes, h->ndist};
+  const u32 *tabs[3] = {h->leftborder.as<u32>(), h->csc.as<u32>(), h->dist.as<u32>()};
+  for (int t = 0; t < 3; t++) {
+    GTB_TRY(hash_table(h, tabs[t], counts[t], word, &acc));
+    word += counts[t];
+    if (word & 1ull) { acc += mh_term(word, 0); word++; }
+  }
+  *out = acc;
   return 0;
 }
 

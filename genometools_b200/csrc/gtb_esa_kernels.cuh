@@ -1570,6 +1570,34 @@ __global__ void k_readmode_bytes(const u8 *__restrict__ in, u8 *__restrict__ out
 
 __global__ void k_set_u32(u32 *p, u32 v) { *p = v; }
 
+// ---- order-dependent checksum of a result table (genometools_b200/mixhash.py) -------------
+//   H = sum_i fin((i + 1) * C1 xor fin(v_i + C2))  mod 2^64,  i = global index of entry v_i,
+// fin = splitmix64 finaliser.  The sum composes across shards (each GPU hashes its own part
+// with its global offset), the index makes it order-dependent: the same function over the
+// reference's files is what a full-size run is compared with (tests/golden/config_md5.json).
+__host__ __device__ __forceinline__ u64 mh_fin(u64 z)
+{
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+__host__ __device__ __forceinline__ u64 mh_term(u64 index, u64 value)
+{
+  return mh_fin(((index + 1ull) * 0x9E3779B97F4A7C15ull) ^ mh_fin(value + 0xC2B2AE3D27D4EB4Full));
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_mixhash(const T *__restrict__ v, u64 count, u64 index_base, unsigned long long *__restrict__ out)
+{
+  u64 sum = 0;
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)
+    sum += mh_term(index_base + i, (u64) v[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, d);
+  if (lane_id() == 0 && sum) atomicAdd(out, (unsigned long long) sum);
+}
+
 // leftborder: after the scan entry c holds the start of bucket c; entry C = number of
 // non-special suffixes (bcktab.c:1274-1304 keeps the same convention on file)
 } // namespace gtb

@@ -277,6 +277,21 @@ void gtb_bck_sizes(unsigned numofchars, unsigned prefixlength,
                    uint64_t *numofallcodes, uint64_t *numofspecialcodes,
                    uint64_t *numofdistpfxidx);
 
+/* Order-dependent 64-bit checksums of the results AS THEY LIE IN HBM (no copy to the host):
+     H = sum_i fin((i + 1) * C1 xor fin(v_i + C2)) mod 2^64,   i = global index of entry v_i
+   (genometools_b200/mixhash.py states the same function over the reference's files).  The sum
+   composes across code ranges: add the values of all shards.  out3[0]: suftab entries (index =
+   global suffix-array index, value = position -- what .suf holds as uint64), out3[1]: lcptab bytes,
+   out3[2]: the flat uint64 sequence of this shard's .llv pairs, the first pair being pair number
+   llv_pairs_before of the whole file (= sum of gtb_esa_num_llv over the preceding ranges).
+   gtb_esa_hash_bcktab: the uint32 words of the .bck file (gt_bcktab_flush_to_file, bcktab.c:519-577,
+   every table padded to 8 bytes) from the three tables of this handle -- call it on a handle that
+   holds the WHOLE table (single range, or after the tables of the ranges were summed).
+   This is how a 3.1 Gbp run at 1/2/4/8 GPUs is compared with the reference's files without moving
+   28 GB: tests/golden/config_md5.json holds the same checksums of the unmodified reference's output. */
+int gtb_esa_hash_results(gtb_esa *h, uint64_t llv_pairs_before, uint64_t out3[3]);
+int gtb_esa_hash_bcktab(gtb_esa *h, uint64_t *out);
+
 /* the CUDA stream (cudaStream_t) all work of this handle is launched on, so that a caller
    can record its own timing events on it */
 void *gtb_esa_stream(const gtb_esa *h);

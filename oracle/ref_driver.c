@@ -26,6 +26,7 @@
 #include "core/ma_api.h"
 #include "core/radix_sort.h"
 #include "core/timer_api.h"
+#include "core/thread_api.h"
 #include "match/sfx-run.h"
 #include <sys/time.h>
 
@@ -66,12 +67,22 @@ int main(int argc, char **argv)
 {
   GtError *err;
   int rval = 1;
+  unsigned int jobs = 1;
 
+  /* `gtref -j N <tool> ...`: the global option of `gt` (/root/reference/src/gtr.c:181) that sets
+     gt_jobs, the number of sorter threads (the SA-only multi-core figure of bench.py) */
+  if (argc >= 4 && strcmp(argv[1], "-j") == 0) {
+    int j = atoi(argv[2]);
+    jobs = j > 0 ? (unsigned int) j : 1u;
+    argv[2] = argv[0];
+    argv += 2; argc -= 2;
+  }
   if (argc < 2) {
-    fprintf(stderr, "usage: %s suffixerator|sfxmap [options]\n", argv[0]);
+    fprintf(stderr, "usage: %s [-j N] suffixerator|sfxmap [options]\n", argv[0]);
     return 2;
   }
   gt_lib_init();
+  gt_jobs = jobs;
   err = gt_error_new();
   gt_error_set_progname(err, argv[0]);
   if (strcmp(argv[1], "radixsort") == 0)
