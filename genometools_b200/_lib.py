@@ -86,6 +86,24 @@ SYMBOLS = {
     "gtb_bck_sizes": (None, [C.c_uint, C.c_uint, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "gtb_esa_hash_results": (C.c_int, [_P, _U64, C.POINTER(_U64)]),
     "gtb_esa_hash_bcktab": (C.c_int, [_P, C.POINTER(_U64)]),
+    "gtb_esa_run_sharded": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_int, C.c_int, _P, _P, C.c_int]),
+    "gtb_esa_llv_before": (_U64, [_P]),
+    "gtb_group_new": (_P, [C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_size_t]),
+    "gtb_group_delete": (None, [_P]),
+    "gtb_group_error": (C.c_char_p, [_P]),
+    "gtb_group_size": (C.c_int, [_P]),
+    "gtb_group_range": (_P, [_P, C.c_int]),
+    "gtb_group_set_readmode": (C.c_int, [_P, C.c_uint]),
+    "gtb_group_set_input_2bit": (C.c_int, [_P, _P, _U64, _U64, _P, _U64]),
+    "gtb_group_set_input_bytes": (C.c_int, [_P, _P, _U64, C.c_uint]),
+    "gtb_group_set_separators": (C.c_int, [_P, _P, _U64]),
+    "gtb_group_run": (C.c_int, [_P, C.c_uint, C.c_uint]),
+    "gtb_group_get_stats": (C.c_int, [_P, C.POINTER(GtbStats)]),
+    "gtb_group_num_entries": (_U64, [_P]),
+    "gtb_group_num_llv": (_U64, [_P]),
+    "gtb_group_copy_results": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "gtb_group_copy_bwttab": (C.c_int, [_P, _P]),
+    "gtb_group_hash_results": (C.c_int, [_P, C.POINTER(_U64)]),
     "gtb_esa_stream": (_P, [_P]),
     "gtb_esa_dev_suftab": (_P, [_P]),
     "gtb_esa_dev_lcptab": (_P, [_P]),
@@ -101,6 +119,7 @@ SYMBOLS = {
 }
 
 GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS = 1, 2, 4, 8
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 _lib = None
 

@@ -13,13 +13,18 @@
 //   K7 special tail
 #include <stdarg.h>
 #include <stdlib.h>
+#include <map>
 #include <new>
+#include <string>
+#include <type_traits>
+#include <vector>
 
 #include "../../include/gtb200.h"
 #include "gtb_common.cuh"
 #include "gtb_radix.cuh"
 #include "gtb_esa_kernels.cuh"
 #include "gtb_hostio.cuh"
+#include "gtb_shard.cuh"
 
 namespace gtb {
 
@@ -114,6 +119,12 @@ struct gtb_esa {
   float ext_ms_radix = 0, ext_ms_keygen = 0; u64 ext_pairs = 0; u32 ext_launches = 0;   // carried into this run's stats
   u64 depth[64];            // depth[r] = common prefix of the groups entering round r
   DevBuf ranks, owner, sendidx, rcounts, rankwords;
+  // sharded job (gtb_shard_host.cuh): peer mappings, the rank maps of all ranges as this GPU sees them
+  DevBuf peertab;
+  u64 peer_enabled = 0;     // devices this handle's device has peer access to (bit per device)
+  std::map<std::string, void *> ipc_maps;   // CUDA IPC handle -> mapping in this process
+  u64 llv_before = 0;       // .llv pairs of the preceding ranges of the job
+  int shard_np = 1;         // code ranges the last sharded run cut
   HostStage hstage;         // pinned staging + host threads of the result copies
   gtb_stats stats;
 };
@@ -866,6 +877,8 @@ static int hash_table(gtb_esa *h, const T *v, u64 count, u64 index_base, u64 *ac
   return 0;
 }
 
+#include "gtb_shard_host.cuh"
+
 // =============================== C-ABI =================================================
 extern "C" {
 
@@ -932,8 +945,10 @@ void gtb_esa_delete(gtb_esa *h)
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
-                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts, &h->rankwords};
+                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts, &h->rankwords, &h->peertab};
   for (DevBuf *b : all) b->release();
+  for (auto &m : h->ipc_maps) cudaIpcCloseMemHandle(m.second);
+  h->ipc_maps.clear();
   radix_work_free(h->rw);
   h->hstage.release();
   if (h->st2) cudaStreamDestroy(h->st2);
@@ -1330,50 +1345,11 @@ int gtb_esa_coarse_split(gtb_esa *h, unsigned numofparts, uint64_t *out4, unsign
   if (numofparts < 1 || numofparts > (unsigned) MAX_RANGES) { err.set("gtb_esa_coarse_split: 1..%d parts", MAX_RANGES); return -1; }
   GTB_CUDA(cudaSetDevice(h->device));
   // the (summed) coarse table is tiny: cut on the host, gt_suftabparts_new on coarse buckets
-  u32 *cnt = (u32 *) malloc(sizeof(u32) * (h->ncoarse + 1));
-  u64 *lb = (u64 *) malloc(sizeof(u64) * (h->ncoarse + 2));
-  if (!cnt || !lb) { free(cnt); free(lb); err.set("out of host memory"); return -1; }
-  GTB_CUDA(cudaMemcpyAsync(cnt, h->coarse.p, sizeof(u32) * h->ncoarse, cudaMemcpyDeviceToHost, h->st));
+  std::vector<u32> cnt((size_t) h->ncoarse + 1);
+  GTB_CUDA(cudaMemcpyAsync(cnt.data(), h->coarse.p, sizeof(u32) * h->ncoarse, cudaMemcpyDeviceToHost, h->st));
   GTB_CUDA(cudaStreamSynchronize(h->st));
-  lb[0] = 0;
-  for (u32 c = 0; c < h->ncoarse; c++) lb[c + 1] = lb[c] + cnt[c];
-  const u64 total = lb[h->ncoarse], fine = h->ncodes / h->ncoarse;    // fine codes per coarse code
-  unsigned np = 0;
-  u64 mincode = 0, target = 0;
-  const u64 width = total / numofparts, rem = total % numofparts;
-  if (numofparts <= 1 || total <= numofparts || h->ncoarse == 1) {
-    out4[0] = 0; out4[1] = h->ncodes - 1; out4[2] = 0; out4[3] = total; np = 1;
-  } else {
-    for (unsigned part = 0; part < numofparts && mincode < h->ncoarse; part++) {
-      target += width + (part < rem ? 1 : 0);
-      u64 maxcode;
-      if (part == numofparts - 1) maxcode = h->ncoarse - 1;
-      else {
-        u64 lo = 0, hi = h->ncoarse;
-        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (lb[mid + 1] < target) lo = mid + 1; else hi = mid; }
-        maxcode = lo < mincode ? mincode : lo;
-        if (maxcode > h->ncoarse - 1) maxcode = h->ncoarse - 1;
-      }
-      const u64 w = lb[maxcode + 1] - lb[mincode];
-      if (w > 0 || part == numofparts - 1) {
-        out4[4 * np] = mincode * fine; out4[4 * np + 1] = (maxcode + 1) * fine - 1;
-        out4[4 * np + 2] = lb[mincode]; out4[4 * np + 3] = w; np++;
-      }
-      mincode = maxcode + 1;
-    }
-    if (np > 0 && out4[4 * (np - 1) + 1] != h->ncodes - 1) {
-      const u64 mc = out4[4 * (np - 1)] / fine;
-      out4[4 * (np - 1) + 1] = h->ncodes - 1;
-      out4[4 * (np - 1) + 3] = total - lb[mc];
-    }
-    unsigned keep = 0;
-    for (unsigned p = 0; p < np; p++)
-      if (out4[4 * p + 3] > 0) { for (int q = 0; q < 4; q++) out4[4 * keep + q] = out4[4 * p + q]; keep++; }
-    if (keep == 0) { out4[0] = 0; out4[1] = h->ncodes - 1; out4[2] = 0; out4[3] = total; keep = 1; }
-    np = keep;
-  }
-  free(cnt); free(lb);
-  *nparts = np;
+  std::vector<u64> cnt64(cnt.begin(), cnt.end());
+  *nparts = coarse_cut(cnt64.data(), h->ncoarse, h->ncodes, numofparts, out4);
   return 0;
 }
 
@@ -1742,6 +1718,192 @@ int gtb_esa_hash_bcktab(gtb_esa *h, uint64_t *out)
     if (word & 1ull) { acc += mh_term(word, 0); word++; }
   }
   *out = acc;
+  return 0;
+}
+
+// ---- one job sharded over several code ranges (gtb_shard_host.cuh) ----
+int gtb_esa_run_sharded(gtb_esa *h, unsigned prefixlength, unsigned flags, int rank, int world,
+                        gtb_allgather_fn allgather, void *ctx, int separate_processes)
+{
+  if (!h) return -1;
+  if (!allgather) { h->err.set("gtb_esa_run_sharded needs an all-gather function"); return -1; }
+  if (!h->have_input) { h->err.set("no input set"); return -1; }
+  ShardComm c;
+  c.me = rank; c.world = world; c.ag = allgather; c.ctx = ctx; c.ipc = separate_processes != 0;
+  h->ran = false;
+  return run_sharded(h, c, prefixlength, flags);
+}
+
+uint64_t gtb_esa_llv_before(const gtb_esa *h) { return h && h->ran ? h->llv_before : 0; }
+
+gtb_group *gtb_group_new(const int *devices, int nranges, char *errbuf, size_t errlen)
+{
+  if (nranges < 1 || nranges > MAX_RANGES || !devices) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "gtb_group_new: 1..%d code ranges", MAX_RANGES);
+    return nullptr;
+  }
+  gtb_group *g = new (std::nothrow) gtb_group();
+  if (!g) { if (errbuf && errlen) snprintf(errbuf, errlen, "out of host memory"); return nullptr; }
+  memset(&g->stats, 0, sizeof g->stats);
+  for (int i = 0; i < nranges; i++) {
+    gtb_esa *h = gtb_esa_new(devices[i], errbuf, errlen);
+    if (!h) { gtb_group_delete(g); return nullptr; }
+    h->hstage.thread_div = nranges;       // the host threads of the result copies are shared by the ranges
+    g->hs.push_back(h);
+  }
+  g->comm.world = nranges;
+  return g;
+}
+
+void gtb_group_delete(gtb_group *g)
+{
+  if (!g) return;
+  // borrowers first: they only drop their references to the input of the first handle of their device
+  for (size_t i = g->hs.size(); i-- > 0;) gtb_esa_delete(g->hs[i]);
+  delete g;
+}
+
+const char *gtb_group_error(const gtb_group *g) { return g ? g->err.msg : "null group"; }
+int gtb_group_size(const gtb_group *g) { return g ? (int) g->hs.size() : 0; }
+gtb_esa *gtb_group_range(gtb_group *g, int i) { return g && i >= 0 && i < (int) g->hs.size() ? g->hs[(size_t) i] : nullptr; }
+
+int gtb_group_set_readmode(gtb_group *g, unsigned readmode)
+{
+  if (!g) return -1;
+  for (gtb_esa *h : g->hs)
+    if (gtb_esa_set_readmode(h, readmode) != 0) { snprintf(g->err.msg, sizeof g->err.msg, "%s", h->err.msg); return -1; }
+  return 0;
+}
+
+int gtb_group_set_input_2bit(gtb_group *g, const uint64_t *twobitenc, uint64_t nwords, uint64_t n,
+                             const gtb_range *specials, uint64_t nranges)
+{
+  if (!g) return -1;
+  return group_set_input(g, [&](gtb_esa *h) { return gtb_esa_set_input_2bit(h, twobitenc, nwords, n, specials, nranges); });
+}
+
+int gtb_group_set_input_bytes(gtb_group *g, const uint8_t *symbols, uint64_t n, unsigned K)
+{
+  if (!g) return -1;
+  return group_set_input(g, [&](gtb_esa *h) { return gtb_esa_set_input_bytes(h, symbols, n, K); });
+}
+
+int gtb_group_set_separators(gtb_group *g, const uint64_t *positions, uint64_t count)
+{
+  if (!g) return -1;
+  for (size_t i = 0; i < g->hs.size(); i++) {
+    gtb_esa *h = g->hs[i], *owner = nullptr;
+    for (size_t j = 0; j < i; j++) if (g->hs[j]->device == h->device) { owner = g->hs[j]; break; }
+    int rc;
+    if (!owner) rc = gtb_esa_set_separators(h, positions, count);
+    else { h->sepbits.borrow(owner->sepbits); h->have_sep = owner->have_sep; rc = 0; }
+    if (rc != 0) { snprintf(g->err.msg, sizeof g->err.msg, "%s", h->err.msg); return -1; }
+  }
+  return 0;
+}
+
+int gtb_group_run(gtb_group *g, unsigned prefixlength, unsigned flags)
+{
+  if (!g) return -1;
+  g->ran = false; g->bck_merged = false;
+  g->pl = prefixlength; g->flags = flags;
+  const int n = (int) g->hs.size();
+  std::vector<LocalCtx> ctx((size_t) n);
+  for (int i = 0; i < n; i++) ctx[(size_t) i] = LocalCtx{&g->comm, i};
+  GTB_TRY(group_parallel(g, [&](int i) -> int {
+    return gtb_esa_run_sharded(g->hs[(size_t) i], prefixlength, flags, i, n, local_allgather, &ctx[(size_t) i], 0);
+  }));
+  // the job's numbers: what gt_Sfxiterator_longest and the GtOutlcpinfo getters report (sfx-run.c:300,676-680)
+  gtb_stats &S = g->stats;
+  memset(&S, 0, sizeof S);
+  S.longest = ~0ull;
+  for (gtb_esa *h : g->hs) {
+    const gtb_stats &t = h->stats;
+    S.totallength = t.totallength; S.specialcharacters = t.specialcharacters;
+    S.prefixlength = prefixlength; S.numofchars = h->K;
+    S.nonspecials += t.nonspecials;
+    if (t.longest != ~0ull) S.longest = t.longest;
+    S.numoflargelcpvalues += t.numoflargelcpvalues;
+    if (t.maxbranchdepth > S.maxbranchdepth) S.maxbranchdepth = t.maxbranchdepth;
+    S.lcptabsum += t.lcptabsum;
+    S.unresolved_after_first_sort += t.unresolved_after_first_sort;
+    if (t.doubling_rounds > S.doubling_rounds) S.doubling_rounds = t.doubling_rounds;
+    S.radix_passes += t.radix_passes; S.radix_pairs_moved += t.radix_pairs_moved;
+    S.kernel_launches += t.kernel_launches;
+    float *dst[] = {&S.ms_total, &S.ms_upload, &S.ms_count, &S.ms_hist, &S.ms_radix, &S.ms_analyze, &S.ms_doubling, &S.ms_lcp, &S.ms_tail};
+    const float src[] = {t.ms_total, t.ms_upload, t.ms_count, t.ms_hist, t.ms_radix, t.ms_analyze, t.ms_doubling, t.ms_lcp, t.ms_tail};
+    for (int k = 0; k < 9; k++) if (src[k] > *dst[k]) *dst[k] = src[k];     // device times: the slowest range
+  }
+  g->ran = true;
+  return 0;
+}
+
+int gtb_group_get_stats(const gtb_group *g, gtb_stats *st)
+{
+  if (!g || !st || !g->ran) return -1;
+  *st = g->stats;
+  return 0;
+}
+
+uint64_t gtb_group_num_entries(const gtb_group *g)
+{
+  u64 e = 0;
+  if (g && g->ran) for (gtb_esa *h : g->hs) e += h->entries;
+  return e;
+}
+uint64_t gtb_group_num_llv(const gtb_group *g)
+{
+  u64 e = 0;
+  if (g && g->ran) for (gtb_esa *h : g->hs) e += h->nllv;
+  return e;
+}
+
+// the result gather: every range copies its shard straight to its place in the caller's tables
+// (offset sa_offset of the global suffix / lcp table, its pairs of the .llv list), all at once
+int gtb_group_copy_results(gtb_group *g, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
+                           uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx)
+{
+  if (!g) return -1;
+  if (!g->ran) { g->err.set("no results: gtb_group_run has not succeeded"); return -1; }
+  if (g->hs.size() == 1)
+    return group_parallel(g, [&](int) { return gtb_esa_copy_results(g->hs[0], suftab, lcptab, llv, leftborder, countspecialcodes, distpfxidx); });
+  GTB_TRY(group_parallel(g, [&](int i) -> int {
+    gtb_esa *h = g->hs[(size_t) i];
+    if (h->entries == 0) return 0;
+    return gtb_esa_copy_results(h, suftab ? suftab + h->sa_offset : nullptr, lcptab ? lcptab + h->sa_offset : nullptr,
+                                (llv && h->nllv) ? llv + 2 * h->llv_before : nullptr, nullptr, nullptr, nullptr);
+  }));
+  if (leftborder || countspecialcodes || distpfxidx) {
+    GTB_TRY(group_merge_bck(g));
+    if (gtb_esa_copy_bcktab(g->hs[0], leftborder, countspecialcodes, distpfxidx) != 0) {
+      snprintf(g->err.msg, sizeof g->err.msg, "%s", g->hs[0]->err.msg); return -1;
+    }
+  }
+  return 0;
+}
+
+int gtb_group_copy_bwttab(gtb_group *g, uint8_t *dst)
+{
+  if (!g || !dst) return -1;
+  if (!g->ran) { g->err.set("no results: gtb_group_run has not succeeded"); return -1; }
+  return group_parallel(g, [&](int i) -> int {
+    gtb_esa *h = g->hs[(size_t) i];
+    return h->entries ? gtb_esa_copy_bwttab(h, dst + (g->hs.size() == 1 ? 0 : h->sa_offset), 0, h->entries) : 0;
+  });
+}
+
+int gtb_group_hash_results(gtb_group *g, uint64_t out4[4])
+{
+  if (!g || !out4) return -1;
+  if (!g->ran) { g->err.set("no results: gtb_group_run has not succeeded"); return -1; }
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  for (gtb_esa *h : g->hs) {
+    u64 o[3];
+    if (gtb_esa_hash_results(h, g->hs.size() == 1 ? 0 : h->llv_before, o) != 0) { snprintf(g->err.msg, sizeof g->err.msg, "%s", h->err.msg); return -1; }
+    for (int k = 0; k < 3; k++) out4[k] += o[k];
+  }
+  GTB_TRY(group_merge_bck(g));
+  if (gtb_esa_hash_bcktab(g->hs[0], &out4[3]) != 0) { snprintf(g->err.msg, sizeof g->err.msg, "%s", g->hs[0]->err.msg); return -1; }
   return 0;
 }
 

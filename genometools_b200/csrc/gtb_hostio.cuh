@@ -30,6 +30,7 @@ struct HostStage {
   cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr, nullptr};
   bool ready = false;
   int nthreads = 0;
+  int thread_div = 1;          // handles of one job that copy at the same time share the host's cores
 
   int ensure(ErrBuf &err)
   {
@@ -48,6 +49,7 @@ struct HostStage {
       const unsigned hw = std::thread::hardware_concurrency();
       t = hw > 3 ? (int) hw - 2 : 1;
       if (t > 32) t = 32;
+      if (thread_div > 1) t = t / thread_div > 0 ? t / thread_div : 1;
     }
     nthreads = t > 128 ? 128 : t;
     ready = true;

@@ -194,26 +194,32 @@ __device__ __forceinline__ unsigned warp_peers(unsigned d, bool valid)
   return CHECK_VALID ? (valid ? peers : 0u) : peers;
 }
 
-// first keys of up to 64 key ranges (MODE 3: the "digit" of a key is the range that owns it)
+// first keys of up to 64 key ranges (MODE 3: the "digit" of a key is the range that owns it).
+// The bounds live in a device buffer of the RadixWork (per handle: two handles partitioning
+// at the same time on one GPU do not share them) and are staged in shared memory by the CTA.
 constexpr int RS_MAX_OWNERS = 64;
-__constant__ u64 c_rs_bounds[RS_MAX_OWNERS];
-__constant__ int c_rs_nbounds;
 
-__device__ __forceinline__ unsigned rs_owner(u64 key)
+__device__ __forceinline__ unsigned rs_owner(u64 key, const u64 *bnd, int nb)
 {
   unsigned d = 0;
-  for (int i = 1; i < c_rs_nbounds; i++) d += key >= c_rs_bounds[i] ? 1u : 0u;
+  for (int i = 1; i < nb; i++) d += key >= bnd[i] ? 1u : 0u;
   return d;
 }
 
 // digit extraction.  MODE 0 / 1: the digit is byte `bsel` of the low / high half of the
 // key (one PRMT); MODE 2: any (shift, mask); MODE 3: the owning key range
+struct RsOwners {               // MODE 3 only
+  const u64 *bnd;               // first keys of the ranges (shared memory inside the pass)
+  int nb;
+  const u64 *binbase;           // null, or per range the address its values are stored to (peer memory)
+};
+
 template <int MODE>
-__device__ __forceinline__ unsigned rs_digit(u64 key, unsigned bsel, unsigned dmask)
+__device__ __forceinline__ unsigned rs_digit(u64 key, unsigned bsel, unsigned dmask, const RsOwners &ow)
 {
   if (MODE == 0) return __byte_perm((u32) key, 0u, bsel);
   if (MODE == 1) return __byte_perm((u32) (key >> 32), 0u, bsel);
-  if (MODE == 3) return rs_owner(key);
+  if (MODE == 3) return rs_owner(key, ow.bnd, ow.nb);
   return (unsigned) (key >> bsel) & dmask;
 }
 
@@ -249,13 +255,13 @@ template <class Src, class Cfg, int MODE, bool FULL>
 __device__ __forceinline__ void
 rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? Cfg::IPT : 1], unsigned okmask,
              u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u64 tile, unsigned bsel, unsigned dmask,
-             const u64 *__restrict__ gbase, u64 *status, u32 epoch, unsigned char *rs_smem);
+             const u64 *__restrict__ gbase, u64 *status, u32 epoch, unsigned char *rs_smem, const RsOwners &ow);
 
 template <class Src, class Cfg, int MODE, bool FULL>
 __device__ __forceinline__ void
 rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u32 count,
         u64 tile, unsigned bsel, unsigned dmask, const u64 *__restrict__ gbase,
-        u64 *status, u32 epoch, unsigned char *rs_smem)
+        u64 *status, u32 epoch, unsigned char *rs_smem, const RsOwners &ow)
 {
   constexpr int IPT = Cfg::IPT, TILE = Cfg::TILE;
   u64 *s_keys = reinterpret_cast<u64 *>(rs_smem);
@@ -288,7 +294,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
     __syncthreads();              // separates the reads above from the staging writes
     // (a guard-free variant for tiles without invalid items does not pay: two inlined copies of
     // rs_tile_sort in one kernel also make ptxas 12.9 fail with C7600)
-    rs_tile_sort<Src, Cfg, MODE, false>(src, key, val, okmask, okeys, ovals, base, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+    rs_tile_sort<Src, Cfg, MODE, false>(src, key, val, okmask, okeys, ovals, base, tile, bsel, dmask, gbase, status, epoch, rs_smem, ow);
     return;
   } else {
 #pragma unroll
@@ -305,7 +311,7 @@ rs_tile(const Src &src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 ba
         okmask |= (ok ? 1u : 0u) << k;
       }
     }
-    rs_tile_sort<Src, Cfg, MODE, FULL>(src, key, val, okmask, okeys, ovals, base, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+    rs_tile_sort<Src, Cfg, MODE, FULL>(src, key, val, okmask, okeys, ovals, base, tile, bsel, dmask, gbase, status, epoch, rs_smem, ow);
   }
 }
 
@@ -313,7 +319,7 @@ template <class Src, class Cfg, int MODE, bool FULL>
 __device__ __forceinline__ void
 rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? Cfg::IPT : 1], unsigned okmask,
              u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 base, u64 tile, unsigned bsel, unsigned dmask,
-             const u64 *__restrict__ gbase, u64 *status, u32 epoch, unsigned char *rs_smem)
+             const u64 *__restrict__ gbase, u64 *status, u32 epoch, unsigned char *rs_smem, const RsOwners &ow)
 {
   constexpr int NT = Cfg::NT, IPT = Cfg::IPT, TILE = Cfg::TILE, WARPS = Cfg::WARPS;
   u64 *s_keys = reinterpret_cast<u64 *>(rs_smem);
@@ -341,7 +347,7 @@ rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? C
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     const bool ok = FULL || ((okmask >> k) & 1u);
-    const unsigned d = rs_digit<MODE>(key[k], bsel, dmask);
+    const unsigned d = rs_digit<MODE>(key[k], bsel, dmask, ow);
     const unsigned peers = warp_peers<!FULL>(d, ok);
     const unsigned lower = peers & lt;
     const u32 old = wh[d];
@@ -382,7 +388,7 @@ rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? C
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     if (FULL || ((okmask >> k) & 1u)) {
-      const unsigned d = rs_digit<MODE>(key[k], bsel, dmask);
+      const unsigned d = rs_digit<MODE>(key[k], bsel, dmask, ow);
       rk[k] += wh[d];
       s_keys[rk[k]] = key[k];
     }
@@ -443,7 +449,10 @@ rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? C
     }
     const u64 adj = prefix - (u64) excl;   // output index of slot 0 of this bin
     s_pk[tid] = okeys + adj;
-    s_pv[tid] = ovals + adj;
+    if (MODE == 3 && ow.binbase != nullptr)    // partition straight into the owners' buffers (peer memory): gbase is
+      s_pv[tid] = reinterpret_cast<u32 *>(ow.binbase[tid]) + adj;   // zero, the prefix counts inside the bin
+    else
+      s_pv[tid] = ovals + adj;
   }
   __syncthreads();
   RS_PHASE(3);                  // look-back
@@ -454,7 +463,7 @@ rs_tile_sort(const Src &src, u64 (&key)[Cfg::IPT], u32 (&val)[Cfg::VAL_EARLY ? C
     const u32 i = tid + (u32) k * NT;
     if (FULL || i < total) {
       const u64 kk = s_keys[i];
-      const unsigned d = rs_digit<MODE>(kk, bsel, dmask);
+      const unsigned d = rs_digit<MODE>(kk, bsel, dmask, ow);
       if (MODE != 3 || okeys != nullptr) s_pk[d][i] = kk;     // (a partition pass may keep the values only)
       s_pv[d][i] = s_vals[i];
     }
@@ -466,11 +475,15 @@ template <class Src, class Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 N,
                    unsigned bsel, unsigned dmask, const u64 *__restrict__ gbase,
-                   u64 *status, u32 epoch, u32 *ticket, u32 ticket_base)
+                   u64 *status, u32 epoch, u32 *ticket, u32 ticket_base,
+                   const u64 *__restrict__ owner_bounds, int nowners, const u64 *__restrict__ binbase)
 {
   constexpr int TILE = Cfg::TILE;
   extern __shared__ __align__(16) unsigned char rs_smem[];
   __shared__ u32 s_ticket;
+  __shared__ u64 s_bnd[MODE == 3 ? RS_MAX_OWNERS : 1];
+  if (MODE == 3 && threadIdx.x < (unsigned) nowners) s_bnd[threadIdx.x] = owner_bounds[threadIdx.x];
+  const RsOwners ow{s_bnd, nowners, binbase};
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
   {
     u32 *s_wh = reinterpret_cast<u32 *>(rs_smem + (sizeof(u64) + sizeof(u32)) * TILE);
@@ -482,11 +495,11 @@ rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u6
   const u32 count = (N - base) < (u64) TILE ? (u32) (N - base) : (u32) TILE;
   if constexpr (Src::ALWAYS_VALID) {
     if (count == (u32) TILE) {
-      rs_tile<Src, Cfg, MODE, true>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+      rs_tile<Src, Cfg, MODE, true>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem, ow);
       return;
     }
   }
-  rs_tile<Src, Cfg, MODE, false>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem);
+  rs_tile<Src, Cfg, MODE, false>(src, okeys, ovals, base, count, tile, bsel, dmask, gbase, status, epoch, rs_smem, ow);
 }
 
 // ---- host-side driver ------------------------------------------------------------
@@ -499,6 +512,9 @@ struct RadixWork {
   unsigned long long *ghist = nullptr;   // [8][256] device
   u64 *gbase = nullptr;                  // [8][256] device
   unsigned long long *h_hist = nullptr;  // pinned host copy
+  u64 *bounds = nullptr;                 // [RS_MAX_OWNERS] first keys of the owning ranges (partition passes)
+  int nbounds = 0;
+  u64 *binbase = nullptr;                // [RS_BINS] per range the address its values go to (peer stores)
   // statistics
   u32 passes = 0;
   u64 pairs_moved = 0;
@@ -514,6 +530,9 @@ static inline int radix_work_init(RadixWork &w, ErrBuf &err)
   GTB_CUDA(cudaMalloc(&w.ghist, sizeof(unsigned long long) * RS_MAXPASS * RS_BINS));
   GTB_CUDA(cudaMalloc(&w.gbase, sizeof(u64) * RS_MAXPASS * RS_BINS));
   GTB_CUDA(cudaMallocHost(&w.h_hist, sizeof(unsigned long long) * RS_MAXPASS * RS_BINS));
+  GTB_CUDA(cudaMalloc(&w.bounds, sizeof(u64) * RS_MAX_OWNERS));
+  GTB_CUDA(cudaMalloc(&w.binbase, sizeof(u64) * RS_BINS));
+  GTB_CUDA(cudaMemset(w.binbase, 0, sizeof(u64) * RS_BINS));
   for (int i = 0; i < 4; i++) GTB_CUDA(cudaEventCreate(&w.ev[i]));
   return 0;
 }
@@ -521,6 +540,7 @@ static inline int radix_work_init(RadixWork &w, ErrBuf &err)
 static inline void radix_work_free(RadixWork &w)
 {
   cudaFree(w.status); cudaFree(w.ticket); cudaFree(w.ghist); cudaFree(w.gbase);
+  cudaFree(w.bounds); cudaFree(w.binbase);
   if (w.h_hist) cudaFreeHost(w.h_hist);
   for (int i = 0; i < 4; i++) if (w.ev[i]) cudaEventDestroy(w.ev[i]);
   w = RadixWork();
@@ -546,7 +566,7 @@ static inline int radix_work_reserve(RadixWork &w, u64 nitems, ErrBuf &err)
 template <class Src, class Cfg, int MODE>
 static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, u64 tiles,
                           u64 *okeys, u32 *ovals, unsigned bsel, unsigned dmask, int passidx,
-                          ErrBuf &err)
+                          ErrBuf &err, bool peer_bins = false)
 {
   // (the attribute is per device: one bit per device and instantiation)
   static std::atomic<unsigned long long> attr_set{0};
@@ -561,7 +581,8 @@ static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
   }
   rs_onesweep_kernel<Src, Cfg, MODE><<<(unsigned) tiles, Cfg::NT, Cfg::SMEM, st>>>(
       src, okeys, ovals, nsrc, bsel, dmask, w.gbase + passidx * RS_BINS,
-      w.status, w.epoch, w.ticket, w.ticket_base);
+      w.status, w.epoch, w.ticket, w.ticket_base, w.bounds, MODE == 3 ? w.nbounds : 0,
+      peer_bins ? w.binbase : nullptr);
   GTB_LAUNCH_CHECK();
   return 0;
 }
@@ -594,18 +615,20 @@ static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
   return 0;
 }
 
-// number of items of `src` per owning key range (c_rs_bounds must be set)
+// number of items of `src` per owning key range
 template <class Src>
 __global__ void __launch_bounds__(RH_NT)
-rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
+rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist,
+                     const u64 *__restrict__ owner_bounds, int nb)
 {
   __shared__ u32 s_h[RS_BINS];
+  __shared__ u64 s_bnd[RS_MAX_OWNERS];
   s_h[threadIdx.x] = 0;
+  if (threadIdx.x < (unsigned) nb) s_bnd[threadIdx.x] = owner_bounds[threadIdx.x];
   __syncthreads();
   if constexpr (Src::BLOCKED_GEN) {
     // a thread takes 16 consecutive items; with at most 16 ranges their counts fit two registers of
     // eight 8-bit fields, summed over the warp before they touch shared memory
-    const int nb = c_rs_nbounds;
     const u64 nchunks = (N + 15) >> 4;
     for (u64 c0 = (u64) blockIdx.x * RH_NT; c0 < nchunks; c0 += (u64) gridDim.x * RH_NT) {
       const u64 c = c0 + threadIdx.x;
@@ -618,13 +641,13 @@ rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           if (keys[i] == RS_INVALID_KEY) continue;
-          const unsigned d = rs_owner(keys[i]);
+          const unsigned d = rs_owner(keys[i], s_bnd, nb);
           if (d < 8u) packed[0] += 1ull << (8u * d); else packed[1] += 1ull << (8u * (d - 8u));
         }
       } else {
         for (u32 i = 0; i < cnt; i++) {
           u64 key;
-          if (src.load_key(idx + i, key)) atomicAdd(&s_h[rs_owner(key)], 1u);
+          if (src.load_key(idx + i, key)) atomicAdd(&s_h[rs_owner(key, s_bnd, nb)], 1u);
         }
       }
       for (int g = 0; g < nb && g < 16; g++) {               // (uniform trip count)
@@ -643,7 +666,7 @@ rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
         u64 key = 0;
         bool ok = idx < N;
         if (ok) ok = src.load_key(idx, key);
-        const unsigned d = rs_owner(key);
+        const unsigned d = rs_owner(key, s_bnd, nb);
         // consecutive text positions mostly differ in their owner: aggregate what does coincide
         const unsigned act = __ballot_sync(FULL_MASK, ok);
         if (ok) {
@@ -657,48 +680,80 @@ rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist)
   if (s_h[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], (unsigned long long) s_h[threadIdx.x]);
 }
 
-// One stable partition pass: the valid items of `src` grouped by owning key range
-// (bounds[0..nranges) = first key of each range, bounds[0] is taken as 0), written to
-// okeys/ovals (okeys may be null: values only); counts_out[r] = items of range r.
-// Synchronises the stream.
-template <class Src, class Cfg = RsDefault>
-static int rs_partition_by_owner(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, const u64 *bounds,
-                                 int nranges, u64 *okeys, u32 *ovals, u64 capacity, u64 *counts_out, ErrBuf &err)
+// A stable partition of the valid items of `src` by owning key range, in two steps so that a
+// caller can learn the group sizes of ALL slices (an all-gather) before anything is stored:
+//   rs_owner_counts   counts_out[r] = items of range r (bounds[0..nranges) = first key of each
+//                     range, bounds[0] is taken as 0); synchronises the stream
+//   rs_owner_scatter  one onesweep pass whose digit is the owner.  binbase_host == null: the groups
+//                     are written one after the other to okeys/ovals (okeys may be null: values
+//                     only).  binbase_host[r] != 0: the values of range r are stored, in source
+//                     order, from that device address on -- a buffer of the OWNER, mapped into this
+//                     GPU's address space (peer access / CUDA IPC): the exchange of the partitioned
+//                     positions is fused into the pass, the stores travel over NVLink.
+template <class Src>
+static int rs_owner_counts(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, const u64 *bounds,
+                           int nranges, u64 *counts_out, ErrBuf &err)
 {
   if (nranges < 1 || nranges > RS_MAX_OWNERS) { err.set("partition: 1..%d ranges", RS_MAX_OWNERS); return -1; }
   for (int r = 0; r < nranges; r++) counts_out[r] = 0;
-  if (nsrc == 0) return 0;
   u64 hb[RS_MAX_OWNERS];
   for (int r = 0; r < nranges; r++) hb[r] = r == 0 ? 0 : bounds[r];
-  GTB_CUDA(cudaMemcpyToSymbolAsync(c_rs_bounds, hb, sizeof(u64) * nranges, 0, cudaMemcpyHostToDevice, st));
-  GTB_CUDA(cudaMemcpyToSymbolAsync(c_rs_nbounds, &nranges, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+  GTB_CUDA(cudaMemcpyAsync(w.bounds, hb, sizeof(u64) * nranges, cudaMemcpyHostToDevice, st));
+  GTB_CUDA(cudaStreamSynchronize(st));            // (hb lives on this stack frame)
+  w.nbounds = nranges;
+  if (nsrc == 0) return 0;
   GTB_TRY(radix_work_reserve(w, nsrc, err));
   GTB_CUDA(cudaMemsetAsync(w.ghist, 0, sizeof(unsigned long long) * RS_BINS, st));
-  {
-    u64 tiles = div_up(nsrc, RH_TILE);     // (a blocked source takes 16 items per thread: the same 4096 per CTA)
-    unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
-    rs_owner_hist_kernel<Src><<<grid, RH_NT, 0, st>>>(src, nsrc, w.ghist);
-    GTB_LAUNCH_CHECK();
-    rs_scan_kernel<<<1, RS_BINS, 0, st>>>(w.ghist, w.gbase);
-    GTB_LAUNCH_CHECK();
-    w.launches += 2;
-  }
+  u64 tiles = div_up(nsrc, RH_TILE);     // (a blocked source takes 16 items per thread: the same 4096 per CTA)
+  unsigned grid = (unsigned) (tiles < 148ull * 8 ? tiles : 148ull * 8);
+  rs_owner_hist_kernel<Src><<<grid, RH_NT, 0, st>>>(src, nsrc, w.ghist, w.bounds, nranges);
+  GTB_LAUNCH_CHECK();
+  w.launches += 1;
   GTB_CUDA(cudaMemcpyAsync(w.h_hist, w.ghist, sizeof(unsigned long long) * RS_BINS, cudaMemcpyDeviceToHost, st));
   GTB_CUDA(cudaStreamSynchronize(st));
-  u64 total = 0;
-  for (int r = 0; r < nranges; r++) { counts_out[r] = w.h_hist[r]; total += w.h_hist[r]; }
-  if (total > capacity) { err.set("partition: %llu items for a buffer of %llu", (unsigned long long) total, (unsigned long long) capacity); return -1; }
-  if (total == 0) return 0;
+  for (int r = 0; r < nranges; r++) counts_out[r] = w.h_hist[r];
+  return 0;
+}
+
+template <class Src, class Cfg = RsDefault>
+static int rs_owner_scatter(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, int nranges, u64 total,
+                            u64 *okeys, u32 *ovals, const u64 *binbase_host, ErrBuf &err)
+{
+  if (nsrc == 0 || total == 0) return 0;
+  if (binbase_host) {
+    u64 bb[RS_BINS];
+    for (int r = 0; r < RS_BINS; r++) bb[r] = r < nranges ? binbase_host[r] : 0ull;
+    GTB_CUDA(cudaMemcpyAsync(w.binbase, bb, sizeof bb, cudaMemcpyHostToDevice, st));
+    GTB_CUDA(cudaMemsetAsync(w.gbase, 0, sizeof(u64) * RS_BINS, st));     // offsets count inside each bin
+    GTB_CUDA(cudaStreamSynchronize(st));          // (bb lives on this stack frame)
+  } else {
+    rs_scan_kernel<<<1, RS_BINS, 0, st>>>(w.ghist, w.gbase);
+    GTB_LAUNCH_CHECK();
+    w.launches += 1;
+  }
   const u64 tiles = div_up(nsrc, Cfg::TILE);
   if (tiles > w.status_tiles) { err.set("radix: status array too small"); return -1; }
   if (++w.epoch >= 0xffffu) {
     GTB_CUDA(cudaMemsetAsync(w.status, 0, sizeof(u64) * RS_BINS * w.status_tiles, st));
     w.epoch = 1;
   }
-  GTB_TRY((rs_launch_mode<Src, Cfg, 3>(w, st, src, nsrc, tiles, okeys, ovals, 0u, 0xffu, 0, err)));
+  GTB_TRY((rs_launch_mode<Src, Cfg, 3>(w, st, src, nsrc, tiles, okeys, ovals, 0u, 0xffu, 0, err, binbase_host != nullptr)));
   w.ticket_base += (u32) tiles;
   w.passes++; w.launches++;
   w.pairs_moved += total;
+  return 0;
+}
+
+// both steps for one caller-owned buffer.  Synchronises the stream.
+template <class Src, class Cfg = RsDefault>
+static int rs_partition_by_owner(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, const u64 *bounds,
+                                 int nranges, u64 *okeys, u32 *ovals, u64 capacity, u64 *counts_out, ErrBuf &err)
+{
+  GTB_TRY(rs_owner_counts(w, st, src, nsrc, bounds, nranges, counts_out, err));
+  u64 total = 0;
+  for (int r = 0; r < nranges; r++) total += counts_out[r];
+  if (total > capacity) { err.set("partition: %llu items for a buffer of %llu", (unsigned long long) total, (unsigned long long) capacity); return -1; }
+  GTB_TRY((rs_owner_scatter<Src, Cfg>(w, st, src, nsrc, nranges, total, okeys, ovals, nullptr, err)));
   GTB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -19,6 +19,7 @@ Outputs (byte-identical to the reference):
 """
 from dataclasses import dataclass, field
 import ctypes as C
+import os
 import sys
 import numpy as np
 
@@ -191,6 +192,7 @@ class EsaResult:
     countspecialcodes: np.ndarray = None
     distpfxidx: np.ndarray = None
     longest: int = None
+    device_hashes: dict = None       # checksums of the tables in HBM (gtb_group_hash_results)
     numoflargelcpvalues: int = 0
     maxbranchdepth: int = 0
     lcptabsum: float = 0.0
@@ -414,9 +416,83 @@ class Suffixerator:
         return res
 
 
+def build_esa_group(enc: EncodedSequence, prefixlength, devices, want_suf=True, want_lcp=True, want_bck=True,
+                    filler=None, want_bwt=False, readmode="fwd"):
+    """The job sharded over len(devices) code ranges inside this process (gtb_group, include/gtb200.h):
+    range i runs on CUDA device devices[i] -- one range per GPU (`gt -j N`), or several ranges on one
+    GPU (-parts).  The ranges reach each other's HBM directly (peer access); the results are gathered
+    into one table by every range copying its shard to its offset."""
+    lib = _lib.load()
+    if readmode not in READMODES:
+        raise GtbError("unknown readmode, must be fwd or rev or cpl or rcl")
+    buf = C.create_string_buffer(512)
+    devs = (C.c_int * len(devices))(*devices)
+    g = lib.gtb_group_new(devs, len(devices), buf, 512)
+    if not g:
+        raise GtbError(buf.value.decode() or "gtb_group_new failed")
+
+    def ck(rc):
+        if rc != 0:
+            raise GtbError(lib.gtb_group_error(g).decode())
+    try:
+        n = enc.totallength
+        ck(lib.gtb_group_set_readmode(g, READMODES.index(readmode)))
+        if enc.is_dna:
+            words, ranges = enc.twobitencoding(filler)
+            ranges = np.ascontiguousarray(ranges, dtype=np.uint64)
+            ck(lib.gtb_group_set_input_2bit(g, ptr(words), words.shape[0], n,
+                                            ptr(ranges) if ranges.shape[0] else None, ranges.shape[0]))
+            sep = np.ascontiguousarray(np.flatnonzero(enc.symbols == 255), dtype=np.uint64)
+            ck(lib.gtb_group_set_separators(g, ptr(sep) if sep.shape[0] else None, sep.shape[0]))
+        else:
+            ck(lib.gtb_group_set_input_bytes(g, ptr(enc.symbols), n, enc.numofchars))
+        flags = (GTB_WANT_SUF if want_suf else 0) | (GTB_WANT_LCP if want_lcp else 0) | (GTB_WANT_BCK if want_bck else 0)
+        ck(lib.gtb_group_run(g, prefixlength, flags))
+        res = EsaResult(n, enc.numofchars, prefixlength, readmode=READMODES.index(readmode))
+        st = GtbStats()
+        ck(lib.gtb_group_get_stats(g, C.byref(st)))
+        res.stats.append(st.as_dict())
+        for i in range(lib.gtb_group_size(g)):
+            sti = GtbStats()
+            lib.gtb_esa_get_stats(lib.gtb_group_range(g, i), C.byref(sti))
+            res.stats.append(sti.as_dict())
+        e = int(lib.gtb_group_num_entries(g))
+        if e != n + 1:
+            raise GtbError(f"the code ranges hold {e} entries, expected {n + 1}")
+        k = int(lib.gtb_group_num_llv(g))
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(enc.numofchars, prefixlength, C.byref(a), C.byref(b), C.byref(c))
+        suf = np.empty(e, dtype=np.uint64) if want_suf else None
+        lcp = np.empty(e, dtype=np.uint8) if want_lcp else None
+        llv = np.empty((k, 2), dtype=np.uint64) if want_lcp else None
+        lb = np.empty(a.value + 1, dtype=np.uint32) if want_bck else None
+        csc = np.empty(b.value, dtype=np.uint32) if want_bck else None
+        dist = np.empty(c.value, dtype=np.uint32) if want_bck else None
+        ck(lib.gtb_group_copy_results(g, ptr(suf), ptr(lcp), ptr(llv) if (want_lcp and k) else None, ptr(lb),
+                                      ptr(csc) if (want_bck and b.value) else None,
+                                      ptr(dist) if (want_bck and c.value) else None))
+        if want_bwt:
+            res.bwttab = np.empty(e, dtype=np.uint8)
+            ck(lib.gtb_group_copy_bwttab(g, ptr(res.bwttab)))
+        res.suftab, res.lcptab, res.llvtab = suf, lcp, llv
+        res.leftborder, res.countspecialcodes, res.distpfxidx = lb, csc, dist
+        res.longest = None if st.longest == 0xFFFFFFFFFFFFFFFF else st.longest
+        res.lcptabsum, res.maxbranchdepth, res.numoflargelcpvalues = st.lcptabsum, st.maxbranchdepth, st.numoflargelcpvalues
+        h4 = (C.c_uint64 * 4)()
+        if want_suf and want_lcp and want_bck:
+            ck(lib.gtb_group_hash_results(g, h4))
+            res.device_hashes = {"suf": h4[0], "lcp": h4[1], "llv": h4[2], "bck": h4[3]}
+        return res
+    finally:
+        lib.gtb_group_delete(g)
+
+
 def build_esa(enc: EncodedSequence, prefixlength=None, device=0, parts=1, want_suf=True, want_lcp=True,
-              want_bck=True, filler=None, want_bwt=False, readmode="fwd"):
-    """One call: encoded sequence -> EsaResult (the public entry the benchmarks time end to end)."""
+              want_bck=True, filler=None, want_bwt=False, readmode="fwd", devices=None, protocol=None):
+    """One call: encoded sequence -> EsaResult (the public entry the benchmarks time end to end).
+    devices: a list of CUDA devices, one code range on each (times `parts`).  protocol="exchange"
+    keeps the request/answer rank exchange of genometools_b200/multirange.py for -parts on one GPU
+    (the single-GPU twin of the NCCL protocol); the default for several ranges is the gtb_group path."""
     if prefixlength is None or prefixlength == 0:
         prefixlength = recommendedprefixlength(enc.numofchars, enc.totallength)
     else:
@@ -424,6 +500,13 @@ def build_esa(enc: EncodedSequence, prefixlength=None, device=0, parts=1, want_s
         if prefixlength > maxpl:
             raise GtbError(f"prefix length {prefixlength} is too large, maximal prefix length for this input "
                            f"size and alphabet size is {maxpl}")          # gt_checkprefixlength, sfx-apfxlen.c:149
+    if protocol is None:
+        protocol = os.environ.get("GTB200_PARTS_PROTOCOL", "group")
+    if devices is not None or (parts > 1 and prefixlength >= 1 and protocol != "exchange"):
+        devs = [d for d in (devices if devices is not None else [device]) for _ in range(max(parts, 1))]
+        if len(devs) > 1:
+            return build_esa_group(enc, prefixlength, devs, want_suf, want_lcp, want_bck, filler, want_bwt, readmode)
+        device = devs[0]
     with Suffixerator(device) as sfx:
         sfx.set_sequence(enc, filler, readmode)
         return sfx.run(prefixlength, want_suf, want_lcp, want_bck, parts, want_bwt=want_bwt)

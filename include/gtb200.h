@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define GTB200_ABI_VERSION 1
+#define GTB200_ABI_VERSION 2
 
 typedef struct gtb_esa gtb_esa;              /* stands in for Sfxiterator   */
 
@@ -291,6 +291,54 @@ void gtb_bck_sizes(unsigned numofchars, unsigned prefixlength,
    28 GB: tests/golden/config_md5.json holds the same checksums of the unmodified reference's output. */
 int gtb_esa_hash_results(gtb_esa *h, uint64_t llv_pairs_before, uint64_t out3[3]);
 int gtb_esa_hash_bcktab(gtb_esa *h, uint64_t *out);
+
+/* ---- one job sharded over several GPUs (north_star: "contiguous .bck code
+   ranges balanced by bucket counts are assigned to the 8 GPUs of one box, each holding the full
+   replicated encseq") ------------------------------------------------------------------------
+   Every code range -- one handle on one GPU -- executes gtb_esa_run_sharded with its rank: as a
+   thread of one process (gtb_group below: what the C host does for `gt -j N`, src/gtr.c:181) or as a
+   process of its own (bench.py under torchrun, separate_processes = 1: buffers are mapped with CUDA
+   IPC).  The ranges meet at a handful of all-gathers of small host structs, the one collective the
+   caller provides (in-process: a shared buffer; across processes: NCCL).  The heavy exchanges go
+   through peer memory inside the kernels: the partition pass of the position-sharded text scan
+   stores every position straight into the owning range's HBM over NVLink, and a doubling round
+   reads rank(p + h) of a foreign suffix from the owner's rank map in place.  Partitioning as
+   gt_suftabparts_new (src/match/sfx-partssuf.c:172-347) on coarse buckets; seam lcp as
+   computelocallcpvalue (src/match/sfx-lcpvalues.c:91-111).  Ranks beyond the number of parts that
+   could be cut (tiny or one-bucket inputs) end with an empty result.  prefixlength >= 1.
+   allgather(ctx, mine, bytes, all): all[r * bytes ..] = block of rank r, 0 on success. */
+typedef int (*gtb_allgather_fn)(void *ctx, const void *mine, size_t bytes, void *all);
+int gtb_esa_run_sharded(gtb_esa *h, unsigned prefixlength, unsigned flags, int rank, int world,
+                        gtb_allgather_fn allgather, void *ctx, int separate_processes);
+/* .llv pairs of the ranges before this one (the shard's place in the .llv file) */
+uint64_t gtb_esa_llv_before(const gtb_esa *h);
+
+/* The ranges of one job inside ONE process: nranges handles, handle i on CUDA device devices[i] (a
+   device may be named several times: -parts on one GPU, sfx-suffixer.c:1791-1838; all ranges are
+   resident at once).  The packed sequence is uploaded once per device.  gtb_group_run = the threads
+   of the process run gtb_esa_run_sharded; gtb_group_copy_results is the result gather: every range
+   copies its shard straight to its offset in the caller's tables, all GPUs at once (the bucket
+   table is summed over the ranges through peer memory first). */
+typedef struct gtb_group gtb_group;
+gtb_group *gtb_group_new(const int *devices, int nranges, char *errbuf, size_t errlen);
+void gtb_group_delete(gtb_group *g);
+const char *gtb_group_error(const gtb_group *g);
+int gtb_group_size(const gtb_group *g);
+gtb_esa *gtb_group_range(gtb_group *g, int i);
+int gtb_group_set_readmode(gtb_group *g, unsigned readmode);
+int gtb_group_set_input_2bit(gtb_group *g, const uint64_t *twobitenc, uint64_t nwords, uint64_t totallength,
+                             const gtb_range *specials, uint64_t nspecialranges);
+int gtb_group_set_input_bytes(gtb_group *g, const uint8_t *symbols, uint64_t totallength, unsigned numofchars);
+int gtb_group_set_separators(gtb_group *g, const uint64_t *positions, uint64_t count);
+int gtb_group_run(gtb_group *g, unsigned prefixlength, unsigned flags);
+int gtb_group_get_stats(const gtb_group *g, gtb_stats *st);   /* the job: sums / maxima over the ranges */
+uint64_t gtb_group_num_entries(const gtb_group *g);
+uint64_t gtb_group_num_llv(const gtb_group *g);
+int gtb_group_copy_results(gtb_group *g, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
+                           uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx);
+int gtb_group_copy_bwttab(gtb_group *g, uint8_t *dst);
+/* out4 = checksums of suftab, lcptab, llv, bucket table of the whole job (gtb_esa_hash_results) */
+int gtb_group_hash_results(gtb_group *g, uint64_t out4[4]);
 
 /* the CUDA stream (cudaStream_t) all work of this handle is launched on, so that a caller
    can record its own timing events on it */
