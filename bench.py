@@ -290,17 +290,28 @@ def main():
         torch.cuda.synchronize()
 
     st = GtbStats()
-    worker = None
+    protocol = os.environ.get("GTB_BENCH_PROTOCOL", "sharded")     # "exchange": the round-1 NCCL request/answer protocol
+    worker = gather = None
     if world > 1:
         from genometools_b200.multirange import (GpuRangeWorker, run_range_distributed, range_first_keys,
-                                                 coarse_allreduce_and_split, allreduce_bcktab, PairExchange)
-        worker = GpuRangeWorker(h, pl, flags | GTB_REUSE_COUNTS, local_rank)
-        # sharding the text scan pays once the all-to-all is small against the scans it saves
-        use_x = os.environ.get("GTB_BENCH_EXCHANGE", "1" if world >= 4 else "0") == "1"
-        exchange = PairExchange(lib, h, pl, flags | GTB_REUSE_COUNTS, n, dist, dev) if use_x else None
+                                                 coarse_allreduce_and_split, allreduce_bcktab, PairExchange,
+                                                 DistAllgather, run_sharded)
+        # the host threads that widen the suffix table are shared by the ranks of the box
+        os.environ.setdefault("GTB200_HOST_THREADS", str(max(1, ((os.cpu_count() or 4) - 2) // world)))
+        if protocol == "sharded":
+            gather = DistAllgather(dist, dev)
+        else:
+            worker = GpuRangeWorker(h, pl, flags | GTB_REUSE_COUNTS, local_rank)
+            # sharding the text scan pays once the all-to-all is small against the scans it saves
+            use_x = os.environ.get("GTB_BENCH_EXCHANGE", "1" if world >= 4 else "0") == "1"
+            exchange = PairExchange(lib, h, pl, flags | GTB_REUSE_COUNTS, n, dist, dev) if use_x else None
 
     def step():
-        if world > 1:
+        if world > 1 and protocol == "sharded":
+            # the C entry the drop-in's `gt -j N` runs with threads, here one process per GPU: NCCL carries
+            # the count gather and the small sync blocks, peer memory (CUDA IPC) everything heavy
+            run_sharded(lib, h, pl, flags, dist, dev, gather)
+        elif world > 1:
             parts = coarse_allreduce_and_split(lib, h, pl, n, dist, dev)
             if len(parts) != world:
                 raise SystemExit("could not cut the bucket codes into one part per rank")
@@ -312,7 +323,16 @@ def main():
         else:
             ck(lib.gtb_esa_run(h, pl, flags))
         ck(lib.gtb_esa_get_stats(h, C.byref(st)))
+        bck_state["summed"] = False
         return st.as_dict()
+
+    bck_state = {"summed": False}
+
+    def sum_bck():
+        # a rank's run fills the bucket-table entries of its own codes: the job's table is their sum
+        if dist is not None and not bck_state["summed"]:
+            allreduce_bcktab(lib, h, w.numofchars, pl, dist, dev)
+            bck_state["summed"] = True
 
     lib_stream = torch.cuda.ExternalStream(lib.gtb_esa_stream(h), device=dev)
 
@@ -410,20 +430,19 @@ def main():
             k = lib.gtb_esa_num_llv(h)
             if k > llv_pinned.shape[0]:
                 raise SystemExit("bench.py: llv buffer too small")
-            if os.environ.get("GTB_BENCH_COPY") == "tables":   # (A/B: suffix + lcp table together, the rest afterwards)
-                ck(lib.gtb_esa_copy_tables(h, ptr(suf), ptr(lcp), 0, e))
-                if k:
-                    ck(lib.gtb_esa_copy_llv(h, ptr(llv_pinned)))
-                ck(lib.gtb_esa_copy_bcktab(h, ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
-            else:
-                # one call: lcptab, llv and the bucket table travel beside the suffix table
-                ck(lib.gtb_esa_copy_results(h, ptr(suf), ptr(lcp), ptr(llv_pinned) if k else None,
-                                            ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
+            # the gather: every rank copies its shard (its part of .suf/.lcp/.llv); the bucket table of the
+            # job is the sum of the ranks' tables (NCCL all-reduce) and leaves from rank 0.
+            # One call: lcptab, llv and the bucket table travel beside the suffix table
+            with_bck = rank == 0
+            sum_bck()
+            ck(lib.gtb_esa_copy_results(h, ptr(suf), ptr(lcp), ptr(llv_pinned) if k else None,
+                                        ptr(lbh) if with_bck else None, ptr(csch) if with_bck else None,
+                                        ptr(disth) if (c.value and with_bck) else None))
             d2h_parts[0] += time.perf_counter() - t1
             # bytes of the host tensors that are filled (uint64 suftab, uint8 lcptab, llv, bucket
             # tables).  Fewer cross the bus: part of the suffix table travels as uint32 and is
             # widened by host threads, the rest is widened on the device (gtb_esa_copy_suftab_u64)
-            d2h = 8 * e + e + 16 * k + 4 * (a.value + 1 + b.value + c.value)
+            d2h = 8 * e + e + 16 * k + (4 * (a.value + 1 + b.value + c.value) if with_bck else 0)
             td = time.perf_counter()
             return tb - ta, tc - tb, td - tc
 
@@ -438,8 +457,11 @@ def main():
         te = torch.tensor([ewall], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        tb_ = torch.tensor([int(d2h)], dtype=torch.int64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tb_)
         e2e = {"value": (n + 1) * args.e2e_steps / te.item() / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": w.input_bytes(), "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": w.input_bytes() * world, "d2h_bytes_per_step": int(tb_.item()),
                "steps": args.e2e_steps, "ms_per_step": te.item() / args.e2e_steps * 1e3,
                "breakdown_ms": {"h2d": parts_s[0] / args.e2e_steps * 1e3, "kernels": parts_s[1] / args.e2e_steps * 1e3,
                                 "d2h": parts_s[2] / args.e2e_steps * 1e3,
@@ -464,7 +486,7 @@ def main():
     bck_ok = None
     if dist is not None:
         # the ranks' bucket tables hold their own codes only: sum them and check the total
-        allreduce_bcktab(lib, h, w.numofchars, pl, dist, dev)
+        sum_bck()
         a_, b_, c_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
         lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a_), C.byref(b_), C.byref(c_))
         plb_ = C.c_void_p()
@@ -527,7 +549,10 @@ def main():
                    "numofchars": w.numofchars, "outputs": "-suf -lcp -bck (results resident in HBM; `value` excludes the H2D copy of the packed "
                               "sequence -- inputs resident when the timed region starts -- `e2e` includes it)",
                    "dtype_note": "u32 positions in HBM (n + 1 < 2^32), widened to the file's uint64 on copy-out",
-                   "l2": "inputs_exceed_l2 (no flush needed)", "sharding": f"{world} bucket-code ranges"
+                   "l2": "inputs_exceed_l2 (no flush needed)", "sharding": f"{world} bucket-code ranges, one per GPU "
+                   f"({protocol}: " + ("gtb_esa_run_sharded -- NCCL all-gathers of small host blocks, positions and "
+                                       "rank lookups through peer memory (CUDA IPC)" if protocol == "sharded" else
+                                       "NCCL all-to-all request/answer protocol") + ")"
                    if world > 1 else "single range", "scale": args.scale},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "cli": cli,

@@ -384,15 +384,16 @@ int run_sharded(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
 {
   ErrBuf &err = h->err;
   if (c.world < 1 || c.world > MAX_RANGES || c.me < 0 || c.me >= c.world) { err.set("bad rank %d of %d code ranges (1..%d)", c.me, c.world, MAX_RANGES); return -1; }
-  if (pl == 0) { err.set("a sharded run needs prefixlength >= 1"); return -1; }
-  int rc = check_run_args(h, pl, flags | GTB_WANT_BCK);
-  if (rc == 0 && cudaSetDevice(h->device) != cudaSuccess) { err.set("cudaSetDevice(%d) failed", h->device); rc = -1; }
-  h->ext_ms_keygen = 0; h->ext_ms_radix = 0; h->ext_pairs = 0; h->ext_launches = 0;
-  GTB_TRY(sync_barrier(h, c, rc));
   if (c.world == 1) {                     // one range: the plain run
     h->full_range = true; h->range_given = false; h->emit_tail = 1; h->llv_before = 0; h->shard_np = 1;
     return gtb_esa_run(h, pl, flags);
   }
+  int rc = 0;
+  if (pl == 0) { err.set("a sharded run needs prefixlength >= 1"); rc = -1; }
+  if (rc == 0) rc = check_run_args(h, pl, flags | GTB_WANT_BCK);
+  if (rc == 0 && cudaSetDevice(h->device) != cudaSuccess) { err.set("cudaSetDevice(%d) failed", h->device); rc = -1; }
+  h->ext_ms_keygen = 0; h->ext_ms_radix = 0; h->ext_pairs = 0; h->ext_launches = 0;
+  GTB_TRY(sync_barrier(h, c, rc));
   return h->dna ? sharded_body<true>(h, c, pl, flags | GTB_WANT_BCK) : sharded_body<false>(h, c, pl, flags | GTB_WANT_BCK);
 }
 

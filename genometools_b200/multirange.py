@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import GtbError, GtbStats, ptr
+from ._lib import GtbError, GtbStats, ptr, ALLGATHER_FN
 
 
 class RangeWorker:
@@ -368,3 +368,68 @@ def run_range_distributed(worker, first_keys, dist, device, want_lcp=True, begin
         if nonempty and prev is not None:
             worker.fix_seam(prev)
     return rounds
+
+
+# ---------------------------------------------------------------- the sharded C entry, one process per GPU
+class DistAllgather:
+    """The one collective gtb_esa_run_sharded asks of its caller -- an all-gather of a small host
+    block -- over torch.distributed (NCCL on the GPUs of a box, gloo in the CPU tests).  This is all
+    NCCL carries: the coarse count tables (the count "allreduce": gathered, summed by every rank),
+    group sizes, buffer handles and the loop condition of the doubling rounds.  The bulk of a step
+    -- partitioned positions, rank lookups -- moves through peer memory inside the kernels."""
+
+    def __init__(self, dist, device):
+        import torch
+        self.torch, self.dist, self.device = torch, dist, device
+        self.world = dist.get_world_size()
+        self.cuda = device is not None and device.type == "cuda"
+        self.cap = 0
+        self.calls = 0
+        self.error = None
+        self.fn = ALLGATHER_FN(self._call)
+
+    def _reserve(self, nbytes):
+        torch = self.torch
+        if nbytes <= self.cap:
+            return
+        cap = max(2 * nbytes, 1 << 16)
+        self.h_in = torch.empty(cap, dtype=torch.uint8, pin_memory=self.cuda)
+        self.h_out = torch.empty(cap * self.world, dtype=torch.uint8, pin_memory=self.cuda)
+        if self.cuda:
+            self.d_in = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self.d_out = torch.empty(cap * self.world, dtype=torch.uint8, device=self.device)
+        self.cap = cap
+
+    def _call(self, ctx, mine, nbytes, allp):
+        try:
+            self._reserve(nbytes)
+            total = nbytes * self.world
+            C.memmove(self.h_in.data_ptr(), mine, nbytes)
+            if self.cuda:
+                self.d_in[:nbytes].copy_(self.h_in[:nbytes], non_blocking=True)
+                self.dist.all_gather_into_tensor(self.d_out[:total], self.d_in[:nbytes])
+                self.h_out[:total].copy_(self.d_out[:total], non_blocking=True)
+                self.torch.cuda.current_stream(self.device).synchronize()
+            else:
+                self.dist.all_gather_into_tensor(self.h_out[:total], self.h_in[:nbytes])
+            C.memmove(allp, self.h_out.data_ptr(), total)
+            self.calls += 1
+            return 0
+        except Exception as ex:          # never let an exception cross the C frames
+            self.error = ex
+            return -1
+
+
+def run_sharded(lib, handle, prefixlength, flags, dist, device, gather=None):
+    """rank r of the process group runs code range r of the job: gtb_esa_run_sharded with a NCCL
+    all-gather, buffers of the other ranks mapped with CUDA IPC.  The same C entry the drop-in's
+    gtb_group drives with threads."""
+    gather = gather or DistAllgather(dist, device)
+    rc = lib.gtb_esa_run_sharded(handle, prefixlength, flags, dist.get_rank(), dist.get_world_size(),
+                                 gather.fn, None, 1)
+    if rc != 0:
+        msg = lib.gtb_esa_error(handle).decode()
+        if gather.error is not None:
+            msg += f" ({gather.error!r})"
+        raise GtbError(msg)
+    return gather

@@ -20,6 +20,13 @@
   C-ABI of include/gtb200.h, and the tables that come back are written in the reference's
   file formats (.suf .lcp .llv .bck).  Written from scratch; no reference code is copied.
 
+  Several GPUs: `gt -j N suffixerator ...` (the global option that sets gt_jobs, src/gtr.c:181;
+  environment GTB200_GPUS overrides it) puts one bucket-code range on each of N GPUs of the
+  box; `-parts p` cuts p ranges per GPU.  All ranges run inside this process (gtb_group): the
+  packed sequence is replicated to every GPU, the ranges reach each other's HBM through peer
+  access, and every GPU copies its shard straight to its offset in the one host table -- the
+  concatenated shards are the global suffix array (src/match/sfx-partssuf.c:172-347).
+
   Options outside the accelerated path fail loudly (no silent CPU fallback).
   Build: see host/Makefile (needs the reference tree for headers and libgenometools.a).
 */
@@ -38,6 +45,7 @@
 #include "core/range_api.h"
 #include "core/readmode.h"
 #include "core/str_api.h"
+#include "core/thread_api.h"
 #include "core/xansi_api.h"
 #include "match/bcktab.h"
 #include "match/sfx-apfxlen.h"
@@ -52,6 +60,8 @@ static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
   const char *what = NULL;
 
   if (so->inputindex != NULL && gt_str_length(so->inputindex) > 0) what = "-ii";
+  /* a mirrored GtEncseq reports 2n+1 symbols while gt_encseq_twobitencoding_export holds n */
+  else if (gt_encseq_options_mirrored_value(so->loadopts)) what = "-mirrored";
   else if (gt_index_options_outkystab_value(so->idxopts)) what = "-kys";
   else if (gt_index_options_lcpdist_value(so->idxopts)) what = "-lcpdist";
   else if (gt_index_options_maximumspace_value(so->idxopts) > 0) what = "-memlimit";
@@ -81,14 +91,27 @@ static double b200_now(void)
    process): it is started on a thread of its own before the FASTA files are encoded, so that it
    costs nothing next to the reference's encoder. */
 typedef struct {
-  gtb_esa *handle;
+  gtb_group *group;
+  int ndevices, nranges;
   char msg[512];
 } B200Init;
+
+/* GPUs of this run: GTB200_GPUS, else `gt -j N` (gt_jobs), never more than the box has */
+static int b200_gpu_count(void)
+{
+  const char *e = getenv("GTB200_GPUS");
+  int want = e != NULL ? atoi(e) : (int) gt_jobs, have = gtb_device_count();
+  if (want < 1) want = 1;
+  if (have >= 1 && want > have) want = have;
+  return want;
+}
 
 static void *b200_init_thread(void *p)
 {
   B200Init *init = p;
-  init->handle = gtb_esa_new(0, init->msg, sizeof init->msg);
+  int devices[64], i, nranges = init->nranges;
+  for (i = 0; i < nranges; i++) devices[i] = i % init->ndevices;   /* range i on GPU i mod N */
+  init->group = gtb_group_new(devices, nranges, init->msg, sizeof init->msg);
   return NULL;
 }
 
@@ -121,7 +144,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   GtLogger *logger = NULL;
   B200Init init;
   pthread_t init_tid;
-  bool init_started = false;
+  bool init_started = false, init_ever = false;
   int retval, had_err = 0;
   double t_start = b200_now(), t_encoded = 0, t_uploaded = 0, t_sorted = 0, t_copied = 0;
 
@@ -135,13 +158,29 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   had_err = b200_unsupported(&so, err);
   if (!had_err && (gt_index_options_outsuftab_value(so.idxopts) || gt_index_options_outlcptab_value(so.idxopts) ||
                    gt_index_options_outbcktab_value(so.idxopts) || gt_index_options_outbwttab_value(so.idxopts))) {
+    /* one code range per GPU, times -parts (at most 64 ranges; they are all resident at once: unlike
+       the reference's parts loop, src/match/sfx-suffixer.c:1791-1838, -parts does not bound memory) */
+    unsigned int parts = gt_index_options_numofparts_value(so.idxopts);
     memset(&init, 0, sizeof init);
+    init.ndevices = b200_gpu_count();
+    if (parts < 1) parts = 1;
+    if ((unsigned int) init.ndevices * parts > 64u) parts = 64u / (unsigned int) init.ndevices;
+    init.nranges = init.ndevices * (int) parts;
+    gt_logger_log(logger, "B200: %d GPU(s), %d bucket-code range(s) (gt -j %u, -parts %u)", init.ndevices,
+                  init.nranges, gt_jobs, gt_index_options_numofparts_value(so.idxopts));
+    init_ever = true;
     init_started = pthread_create(&init_tid, NULL, b200_init_thread, &init) == 0;
+    if (!init_started) b200_init_thread(&init);
   }
 
   if (!had_err) {                        /* encode + load, exactly the reference's calls */
     GtEncseqEncoder *ee = gt_encseq_encoder_new_from_options(so.encopts, err);
     if (ee == NULL) had_err = -1;
+    /* '-plain' implies no description support (src/match/sfx-run.c:498-502) */
+    if (!had_err && gt_encseq_options_plain_value(so.loadopts)) {
+      gt_encseq_encoder_do_not_create_des_tab(ee);
+      gt_encseq_encoder_do_not_create_sds_tab(ee);
+    }
     if (!had_err) {
       gt_encseq_encoder_set_logger(ee, logger);
       if (gt_encseq_encoder_encode(ee, so.db, gt_str_get(so.indexname), err) != 0)
@@ -157,6 +196,11 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       encseq = gt_encseq_loader_load(el, gt_str_get(so.indexname), err);
       gt_encseq_loader_delete(el);
       if (encseq == NULL) had_err = -1;
+      else if (gt_encseq_is_mirrored(encseq)) {
+        gt_error_set(err, "option -mirrored is not supported by the B200 suffixerator path "
+                          "(no silent fallback); use the CPU build of gt for it");
+        had_err = -1;
+      }
     }
   }
 
@@ -209,30 +253,17 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     }
     if (!had_err && want_any) {
       int rc = 0;
-      gtb_esa *h = NULL;
+      gtb_group *g = NULL;
       if (init_started) {                       /* created while the sequences were being encoded */
         pthread_join(init_tid, NULL);
         init_started = false;
-        h = init.handle;
-        if (h == NULL) snprintf(msg, sizeof msg, "%s", init.msg);
-      } else
-        h = gtb_esa_new(0, msg, sizeof msg);
-      if (h == NULL) rc = -1;
+      }
+      g = init.group;
+      init.group = NULL;
+      if (g == NULL) { snprintf(msg, sizeof msg, "%s", init.msg); rc = -1; }
       /* GtReadmode values are the library's: fwd 0, rev 1, cpl 2, rcl 3 (src/core/readmode.h) */
-      if (rc == 0) rc = gtb_esa_set_readmode(h, (unsigned) readmode);
-      if (want_bwt) bwttab = gt_malloc(sizeof *bwttab * (n + 1));
-      if (want_suf) suftab = gt_malloc(sizeof *suftab * (n + 1));
-      if (want_lcp) {
-        lcptab = gt_malloc(sizeof *lcptab * (n + 1));
-        llv = gt_malloc(sizeof *llv * 2 * (n + 1));    /* worst case; mostly untouched pages */
-      }
-      if (want_bck) {
-        gtb_bck_sizes(numofchars, prefixlength, &nall, &nspec, &ndist);
-        leftborder = gt_malloc(sizeof *leftborder * (nall + 1));
-        csc = gt_malloc(sizeof *csc * (nspec + 1));
-        dist = gt_malloc(sizeof *dist * (ndist + 1));
-      }
-      if (gt_encseq_has_twobitencoding(encseq)) {
+      if (rc == 0) rc = gtb_group_set_readmode(g, (unsigned) readmode);
+      if (rc == 0 && gt_encseq_has_twobitencoding(encseq)) {
         /* the 2-bit words and the special ranges as the reference's own sorter reads them */
         const GtTwobitencoding *tbe = gt_encseq_twobitencoding_export(encseq);
         GtUword nranges = 0, fill = 0;
@@ -254,8 +285,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
           gt_specialrangeiterator_delete(sri);
           nranges = fill;
         }
-        if (rc == 0)
-          rc = gtb_esa_set_input_2bit(h, (const uint64_t *) tbe, gt_unitsoftwobitencoding(n), n,
+        rc = gtb_group_set_input_2bit(g, (const uint64_t *) tbe, gt_unitsoftwobitencoding(n), n,
                                       ranges, nranges);
         gt_free(ranges);
         if (rc == 0 && want_bwt) {
@@ -264,31 +294,49 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
           uint64_t *sep = gt_malloc(sizeof *sep * (nseq + 1));
           GtUword i;
           for (i = 1; i < nseq; i++) sep[i-1] = (uint64_t) gt_encseq_seqstartpos(encseq, i) - 1;
-          rc = gtb_esa_set_separators(h, sep, nseq - 1);
+          rc = gtb_group_set_separators(g, sep, nseq - 1);
           gt_free(sep);
         }
-      } else {
+      } else if (rc == 0) {
         GtUchar *symbols = gt_malloc(n + 1);
         if (n > 0) gt_encseq_extract_encoded(encseq, symbols, 0, n - 1);
-        if (rc == 0) rc = gtb_esa_set_input_bytes(h, symbols, n, numofchars);
+        rc = gtb_group_set_input_bytes(g, symbols, n, numofchars);
         gt_free(symbols);
       }
       t_uploaded = b200_now();
       if (rc == 0)
-        rc = gtb_esa_run(h, prefixlength, (want_suf ? GTB_WANT_SUF : 0u) | (want_lcp ? GTB_WANT_LCP : 0u) |
-                                          (want_bck ? GTB_WANT_BCK : 0u));
+        rc = gtb_group_run(g, prefixlength, (want_suf ? GTB_WANT_SUF : 0u) | (want_lcp ? GTB_WANT_LCP : 0u) |
+                                            (want_bck ? GTB_WANT_BCK : 0u));
       t_sorted = b200_now();
-      if (rc == 0) {
-        const uint64_t e = gtb_esa_num_entries(h);          /* = n + 1 */
-        if (want_suf) rc = gtb_esa_copy_suftab_u64(h, suftab, 0, e);
-        if (rc == 0 && want_lcp) rc = gtb_esa_copy_lcptab(h, lcptab, 0, e);
-        if (rc == 0 && want_lcp) { nllv = gtb_esa_num_llv(h); rc = gtb_esa_copy_llv(h, llv); }
-        if (rc == 0 && want_bck) rc = gtb_esa_copy_bcktab(h, leftborder, csc, dist);
-        if (rc == 0 && want_bwt) rc = gtb_esa_copy_bwttab(h, bwttab, 0, e);
-        if (rc == 0) rc = gtb_esa_get_stats(h, &stats);
+      if (rc == 0 && gtb_group_num_entries(g) != (uint64_t) n + 1) {
+        snprintf(msg, sizeof msg, "internal: the code ranges hold %llu entries, expected %llu",
+                 (unsigned long long) gtb_group_num_entries(g), (unsigned long long) n + 1);
+        rc = -2;
       }
-      if (rc != 0 && h != NULL) snprintf(msg, sizeof msg, "%s", gtb_esa_error(h));
-      gtb_esa_delete(h);
+      if (rc == 0) {
+        /* the result tables, sized from what the run produced */
+        if (want_suf) suftab = gt_malloc(sizeof *suftab * (n + 1));
+        if (want_lcp) {
+          nllv = gtb_group_num_llv(g);
+          lcptab = gt_malloc(sizeof *lcptab * (n + 1));
+          llv = gt_malloc(sizeof *llv * 2 * (nllv + 1));
+        }
+        if (want_bck) {
+          gtb_bck_sizes(numofchars, prefixlength, &nall, &nspec, &ndist);
+          leftborder = gt_malloc(sizeof *leftborder * (nall + 1));
+          csc = gt_malloc(sizeof *csc * (nspec + 1));
+          dist = gt_malloc(sizeof *dist * (ndist + 1));
+        }
+        /* the gather: every range copies its shard to its offset of the one table, all tables in one call */
+        rc = gtb_group_copy_results(g, suftab, lcptab, nllv > 0 ? llv : NULL, leftborder, csc, dist);
+        if (rc == 0 && want_bwt) {
+          bwttab = gt_malloc(sizeof *bwttab * (n + 1));
+          rc = gtb_group_copy_bwttab(g, bwttab);
+        }
+        if (rc == 0) rc = gtb_group_get_stats(g, &stats);
+      }
+      if (rc == -1 && g != NULL) snprintf(msg, sizeof msg, "%s", gtb_group_error(g));
+      gtb_group_delete(g);
       if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
     }
     t_copied = b200_now();
@@ -334,10 +382,8 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     gt_free(suftab); gt_free(lcptab); gt_free(llv); gt_free(bwttab);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
   }
-  if (init_started) {                           /* an error came first: the object was never used */
-    pthread_join(init_tid, NULL);
-    gtb_esa_delete(init.handle);
-  }
+  if (init_started) pthread_join(init_tid, NULL);
+  if (init_ever && init.group != NULL) gtb_group_delete(init.group);   /* an error came first: never used */
   gt_encseq_delete(encseq);
   gt_logger_delete(logger);
   gt_sfxoptions_delete(&so);

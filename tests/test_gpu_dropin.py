@@ -137,3 +137,74 @@ def test_dropin_index_passes_the_reference_verifier(tmp_path, mode):
     suf.tofile(idx + ".suf")
     r = subprocess.run([GTREF, "sfxmap", "-tis", "-suf", "-lcp", "-bck", "-ssp", "-esa", idx], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+@need_bins
+def test_dropin_rejects_mirrored_loudly(tmp_path):
+    """-mirrored is outside the path (a mirrored GtEncseq reports 2n+1 symbols over n exported bases):
+    non-zero exit, the library is never called, no index tables are written"""
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(synth.random_dna(20_000, 5, 0.001), fa, "dna")
+    idx = str(tmp_path / "m")
+    r = subprocess.run([GT_B200, "suffixerator", "-dna", "-suf", "-lcp", "-mirrored", "-indexname", idx, "-db", fa],
+                       capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "option -mirrored is not supported by the B200 suffixerator path" in r.stderr
+    assert not os.path.exists(idx + ".suf") and not os.path.exists(idx + ".lcp")
+
+
+@need_bins
+def test_dropin_plain_input_like_the_reference(tmp_path):
+    """-plain (src/match/sfx-run.c:498-502: no description tables): same files as the reference"""
+    raw = str(tmp_path / "in.txt")
+    rng = np.random.default_rng(8)
+    open(raw, "wb").write(bytes(rng.choice(np.frombuffer(b"acgt", dtype=np.uint8), size=30_000)))
+    outs = {}
+    for name, exe in (("b200", GT_B200), ("ref", GTREF)):
+        idx = str(tmp_path / name)
+        subprocess.check_call([exe, "suffixerator", "-dna", "-plain", "-suf", "-lcp", "-bck", "-pl", "-indexname", idx,
+                               "-db", raw], stdout=subprocess.DEVNULL)
+        outs[name] = {ext: open(idx + "." + ext, "rb").read() for ext in ("suf", "lcp", "llv", "bck", "prj", "esq")}
+        outs[name]["files"] = sorted(f.split(".", 1)[1] for f in os.listdir(tmp_path) if f.startswith(name + "."))
+    assert outs["b200"] == outs["ref"]
+
+
+@need_bins
+@pytest.mark.parametrize("opts", [("-parts", "3"), ("-parts", "7")])
+def test_dropin_parts_identical_to_reference(tmp_path, opts):
+    """-parts p: p bucket-code ranges, the same files (testsuite/gt_suffixerator_include.rb:64-68)"""
+    sym = np.concatenate([synth.reads(1500, 100, 5, 0.003), np.array([255], dtype=np.uint8),
+                          synth.repeats_dna(250_000, 2, unit=6000, copies=9, exact_len=20000, exact_copies=3)])
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(sym, fa, "dna")
+    out = run_both(tmp_path, [fa], "dna", extra=("6", "-bwt") + opts)
+    for ext in ("bwt", "bck", "suf", "lcp", "llv", "prj"):
+        assert out["b200"][ext] == out["ref"][ext], ext
+
+
+def _ngpus():
+    from genometools_b200 import _lib
+    return _lib.load().gtb_device_count()
+
+
+@need_bins
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+def test_dropin_multi_gpu_identical_to_reference(tmp_path, ngpu):
+    """`gt -j N suffixerator`: one bucket-code range on each of N GPUs of the box, inside the drop-in
+    binary; all five files byte-identical to the reference's"""
+    if _ngpus() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    sym = np.concatenate([synth.reads(3000, 120, 15, 0.002), np.array([255], dtype=np.uint8),
+                          synth.repeats_dna(1_500_000, 12, unit=30_000, copies=12, exact_len=120_000, exact_copies=4)])
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(sym, fa, "dna")
+    ref = str(tmp_path / "ref")
+    subprocess.check_call([GTREF, "suffixerator", "-dna", "-suf", "-lcp", "-bck", "-pl", "-bwt", "-indexname", ref,
+                           "-db", fa], stdout=subprocess.DEVNULL)
+    idx = str(tmp_path / "b200")
+    r = subprocess.run([GT_B200, "-j", str(ngpu), "suffixerator", "-dna", "-suf", "-lcp", "-bck", "-pl", "-bwt", "-v",
+                        "-indexname", idx, "-db", fa], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert f"B200: {ngpu} GPU(s), {ngpu} bucket-code range(s)" in r.stdout
+    for ext in ("suf", "lcp", "llv", "bck", "bwt", "prj"):
+        assert open(f"{idx}.{ext}", "rb").read() == open(f"{ref}.{ext}", "rb").read(), ext

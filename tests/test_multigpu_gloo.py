@@ -70,3 +70,43 @@ def test_lockstep_protocol_world2(case):
     assert out[0][3] == out[1][3]                                      # same number of rounds on both ranks
     if case == "repeat_across_border":
         assert out[0][3] >= 2
+
+
+def _gather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        from genometools_b200.multirange import DistAllgather
+        ag = DistAllgather(dist, torch.device("cpu"))
+        ok = True
+        # the block sizes gtb_esa_run_sharded uses: a status word, the tied count, the 16.5 KB coarse table
+        for nbytes in (4, 136, 16512, 40, 70000, 8):
+            mine = (np.arange(nbytes, dtype=np.uint32) * 7 + rank * 131 + nbytes).astype(np.uint8)
+            out = np.zeros(nbytes * world, dtype=np.uint8)
+            rc = ag.fn(None, mine.ctypes.data, nbytes, out.ctypes.data)
+            ok = ok and rc == 0
+            for r in range(world):
+                exp = (np.arange(nbytes, dtype=np.uint32) * 7 + r * 131 + nbytes).astype(np.uint8)
+                ok = ok and bool((out[r * nbytes:(r + 1) * nbytes] == exp).all())
+        q.put((rank, ok, ag.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_entry_allgather_over_gloo_world2():
+    """the one collective gtb_esa_run_sharded needs from its caller (multirange.DistAllgather), driven
+    through the C callback type exactly as the library calls it, world_size 2 over gloo"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out == [(0, True, 6), (1, True, 6)]
