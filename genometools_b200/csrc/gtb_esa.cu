@@ -24,6 +24,7 @@
 #include "gtb_radix.cuh"
 #include "gtb_esa_kernels.cuh"
 #include "gtb_hostio.cuh"
+#include "gtb_vmm.cuh"
 #include "gtb_shard.cuh"
 
 namespace gtb {
@@ -41,12 +42,24 @@ struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   bool borrowed = false;     // memory owned by another handle (gtb_esa_share_input)
+  // share_dev >= 0: the buffer is allocated with the virtual-memory API on that device so that the
+  // other processes of a sharded job can map it (gtb_vmm.cuh); alloc_id names the allocation
+  int share_dev = -1;
+  bool vmm = false;
+  CUmemGenericAllocationHandle mh = 0;
+  u64 alloc_id = 0;
   int ensure(size_t bytes, ErrBuf &err)
   {
-    if (bytes <= cap && !borrowed) return 0;
-    if (p && !borrowed) cudaFree(p);
-    p = nullptr; cap = 0; borrowed = false;
+    if (bytes <= cap && !borrowed && (share_dev < 0 || vmm)) return 0;
+    release();
     size_t want = bytes + (bytes >> 6) + 256;
+    if (share_dev >= 0) {
+      static std::atomic<unsigned long long> next_id{0};
+      size_t got = 0;
+      if (vmm_alloc(share_dev, want, &p, &mh, &got, err) != 0) { p = nullptr; return -1; }
+      cap = got; vmm = true; alloc_id = ++next_id;
+      return 0;
+    }
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
       err.set("cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
@@ -55,7 +68,11 @@ struct DevBuf {
     cap = want;
     return 0;
   }
-  void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
+  void release()
+  {
+    if (p && !borrowed) { if (vmm) vmm_free(p, mh, cap); else cudaFree(p); }
+    p = nullptr; cap = 0; borrowed = false; vmm = false; mh = 0; alloc_id = 0;
+  }
   void borrow(const DevBuf &o) { release(); p = o.p; cap = o.cap; borrowed = o.p != nullptr; }
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -122,7 +139,14 @@ struct gtb_esa {
   // sharded job (gtb_shard_host.cuh): peer mappings, the rank maps of all ranges as this GPU sees them
   DevBuf peertab;
   u64 peer_enabled = 0;     // devices this handle's device has peer access to (bit per device)
-  std::map<std::string, void *> ipc_maps;   // CUDA IPC handle -> mapping in this process
+  // ranges in other processes (bench.py under torchrun): their buffers mapped here (gtb_vmm.cuh)
+  struct PeerImport { u64 alloc_id; void *ptr; size_t size; CUmemGenericAllocationHandle mh; };
+  std::map<std::pair<int, int>, PeerImport> imports;      // (rank, slot) -> mapping on this GPU
+  struct PendingFd { FdMsg msg; int fd; };
+  std::vector<PendingFd> pending_fds;                      // descriptors received before they were asked for
+  int ipc_sock = -1;
+  std::string ipc_key;
+  u64 sent_id[8] = {0, 0, 0, 0, 0, 0, 0, 0};              // allocation of each shareable buffer the peers hold
   u64 llv_before = 0;       // .llv pairs of the preceding ranges of the job
   int shard_np = 1;         // code ranges the last sharded run cut
   HostStage hstage;         // pinned staging + host threads of the result copies
@@ -947,8 +971,11 @@ void gtb_esa_delete(gtb_esa *h)
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
                    &h->ranks, &h->owner, &h->sendidx, &h->rcounts, &h->rankwords, &h->peertab};
   for (DevBuf *b : all) b->release();
-  for (auto &m : h->ipc_maps) cudaIpcCloseMemHandle(m.second);
-  h->ipc_maps.clear();
+  for (auto &m : h->imports) vmm_free(m.second.ptr, m.second.mh, m.second.size);
+  h->imports.clear();
+  for (auto &f : h->pending_fds) close(f.fd);
+  h->pending_fds.clear();
+  if (h->ipc_sock >= 0) close(h->ipc_sock);
   radix_work_free(h->rw);
   h->hstage.release();
   if (h->st2) cudaStreamDestroy(h->st2);

@@ -34,7 +34,8 @@ namespace gtb {
 struct PeerPtr {
   u64 ptr;                        // address in the exporting process (allocation base)
   int device, valid;
-  unsigned char ipc[64];          // cudaIpcMemHandle_t, when the ranges are separate processes
+  int slot, pad;                  // which shareable buffer of the exporter (separate processes:
+  u64 alloc_id, size;             // the importer maps allocation alloc_id of `size` bytes, gtb_vmm.cuh)
 };
 
 struct RankView {                 // the rank map of one range (RankMap, gtb_esa_kernels.cuh)

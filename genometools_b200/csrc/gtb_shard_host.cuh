@@ -54,18 +54,69 @@ int sync_barrier(gtb_esa *h, ShardComm &c, int rc)
 }
 
 // ---- peer pointers ---------------------------------------------------------------------------
-int export_ptr(gtb_esa *h, const ShardComm &c, const void *p, PeerPtr *out)
+// the buffers other ranges read or write: in a job of separate processes they are allocated with
+// the virtual-memory API (DevBuf::share_dev) and travel as file descriptors (gtb_vmm.cuh)
+constexpr int SHARE_SLOTS = 7;
+DevBuf *share_slot(gtb_esa *h, int slot)
+{
+  DevBuf *t[SHARE_SLOTS] = {&h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->rankwords, &h->trank, &h->leftborder};
+  return slot >= 0 && slot < SHARE_SLOTS ? t[slot] : nullptr;
+}
+int slot_of(gtb_esa *h, const DevBuf *b)
+{
+  for (int i = 0; i < SHARE_SLOTS; i++) if (share_slot(h, i) == b) return i;
+  return -1;
+}
+
+// descriptors that arrived: keep them until the mapping is asked for
+void drain_fds(gtb_esa *h, bool block_once)
+{
+  for (bool first = true;; first = false) {
+    if (!(block_once && first) && !fd_sock_readable(h->ipc_sock)) return;
+    gtb_esa::PendingFd pf;
+    ErrBuf e2;
+    if (fd_recv(h->ipc_sock, &pf.msg, &pf.fd, e2) != 0) return;
+    h->pending_fds.push_back(pf);
+  }
+}
+
+int send_fd_everywhere(gtb_esa *h, const ShardComm &c, int slot, const DevBuf &b)
+{
+  ErrBuf &err = h->err;
+  int fd = -1;
+  GTB_TRY(vmm_export_fd(b.mh, &fd, err));
+  FdMsg m; m.from = c.me; m.slot = slot; m.alloc_id = b.alloc_id; m.size = b.cap;
+  int rc = 0;
+  for (int r = 0; r < c.world && rc == 0; r++) {
+    if (r == c.me) continue;
+    for (int waited = 0;; waited++) {
+      drain_fds(h, false);                // (everybody sends before anybody asks: keep the queues short)
+      rc = fd_send(h->ipc_sock, h->ipc_key.c_str(), r, m, fd, err);
+      if (rc != 1) break;
+      if (waited > 60000) { err.set("code range %d does not take memory descriptors", r); rc = -1; break; }
+      usleep(1000);
+    }
+  }
+  close(fd);
+  return rc;
+}
+
+int export_ptr(gtb_esa *h, const ShardComm &c, const DevBuf *b, bool present, PeerPtr *out)
 {
   ErrBuf &err = h->err;
   memset(out, 0, sizeof *out);
-  out->ptr = (u64) (uintptr_t) p;
+  if (!present || !b || !b->p) return 0;
+  out->ptr = (u64) (uintptr_t) b->p;
   out->device = h->device;
-  out->valid = p != nullptr;
-  if (c.ipc && p) {
-    cudaIpcMemHandle_t mh;
-    GTB_CUDA(cudaIpcGetMemHandle(&mh, const_cast<void *>(p)));
-    static_assert(sizeof mh == sizeof out->ipc, "cudaIpcMemHandle_t is 64 bytes");
-    memcpy(out->ipc, &mh, sizeof mh);
+  out->valid = 1;
+  out->slot = slot_of(h, b);
+  out->alloc_id = b->alloc_id; out->size = b->cap;
+  if (c.ipc) {
+    if (!b->vmm || out->slot < 0) { err.set("internal: exported buffer %d is not shareable", out->slot); return -1; }
+    if (h->sent_id[out->slot] != b->alloc_id) {          // a new allocation: the peers need its descriptor
+      GTB_TRY(send_fd_everywhere(h, c, out->slot, *b));
+      h->sent_id[out->slot] = b->alloc_id;
+    }
   }
   return 0;
 }
@@ -92,18 +143,57 @@ int resolve_ptr(gtb_esa *h, const ShardComm &c, const PeerPtr &p, int peer, void
     *out = (void *) (uintptr_t) p.ptr;
     return 0;
   }
-  // another process: map its allocation once, keep the mapping for the following runs
-  const std::string key(reinterpret_cast<const char *>(p.ipc), sizeof p.ipc);
-  auto it = h->ipc_maps.find(key);
-  if (it == h->ipc_maps.end()) {
-    cudaIpcMemHandle_t mh;
-    memcpy(&mh, p.ipc, sizeof mh);
-    void *q = nullptr;
-    GTB_CUDA(cudaIpcOpenMemHandle(&q, mh, cudaIpcMemLazyEnablePeerAccess));
-    if (getenv("GTB200_SHARD_TRACE")) fprintf(stderr, "[gtb shard %d/%d] mapped a buffer of range %d (CUDA IPC), %zu mappings now\n", c.me, c.world, peer, h->ipc_maps.size() + 1);
-    it = h->ipc_maps.emplace(key, q).first;
+  // another process: its allocation is mapped once and kept for the following runs
+  const std::pair<int, int> key(peer, p.slot);
+  auto it = h->imports.find(key);
+  if (it != h->imports.end() && it->second.alloc_id == p.alloc_id) { *out = it->second.ptr; return 0; }
+  if (it != h->imports.end()) { vmm_free(it->second.ptr, it->second.mh, it->second.size); h->imports.erase(it); }
+  int fd = -1;
+  for (int tries = 0; fd < 0; tries++) {
+    for (size_t i = 0; i < h->pending_fds.size(); i++) {
+      const FdMsg &m = h->pending_fds[i].msg;
+      if (m.from == peer && m.slot == p.slot) {
+        if (m.alloc_id == p.alloc_id) fd = h->pending_fds[i].fd; else close(h->pending_fds[i].fd);   // (stale: reallocated since)
+        h->pending_fds.erase(h->pending_fds.begin() + (long) i);
+        i--;
+        if (fd >= 0) break;
+      }
+    }
+    if (fd >= 0) break;
+    if (tries > 4096) { err.set("the descriptor of buffer %d of code range %d never arrived", p.slot, peer); return -1; }
+    const size_t before = h->pending_fds.size();
+    drain_fds(h, true);                   // blocks (with the socket's timeout) for the next descriptor
+    if (h->pending_fds.size() == before) { err.set("timed out waiting for the descriptor of buffer %d of code range %d", p.slot, peer); return -1; }
   }
-  *out = it->second;
+  gtb_esa::PeerImport imp;
+  imp.alloc_id = p.alloc_id; imp.size = (size_t) p.size; imp.ptr = nullptr; imp.mh = 0;
+  const int rc = vmm_import(h->device, fd, imp.size, &imp.ptr, &imp.mh, err);
+  close(fd);
+  GTB_TRY(rc);
+  if (getenv("GTB200_SHARD_TRACE")) fprintf(stderr, "[gtb shard %d/%d] mapped buffer %d of range %d (%zu MiB)\n", c.me, c.world, p.slot, peer, imp.size >> 20);
+  h->imports[key] = imp;
+  *out = imp.ptr;
+  return 0;
+}
+
+// a job of separate processes: the shareable buffers move to the virtual-memory allocator, the
+// descriptor socket of this rank is bound (before the first sync point: everybody can send after it)
+int enter_ipc_mode(gtb_esa *h, const ShardComm &c)
+{
+  ErrBuf &err = h->err;
+  for (int i = 0; i < SHARE_SLOTS; i++) share_slot(h, i)->share_dev = h->device;
+  const char *k = getenv("GTB200_IPC_KEY");
+  if (!k) k = getenv("MASTER_PORT");
+  if (!k) k = "job";
+  char name[96];
+  snprintf(name, sizeof name, "%.40s-w%d", k, c.world);
+  if (h->ipc_sock >= 0 && h->ipc_key != name) { close(h->ipc_sock); h->ipc_sock = -1; }
+  if (h->ipc_sock < 0) {
+    h->ipc_key = name;
+    h->ipc_sock = fd_sock_open(name, c.me, err);
+    if (h->ipc_sock < 0) return -1;
+    for (int i = 0; i < 8; i++) h->sent_id[i] = 0;
+  }
   return 0;
 }
 
@@ -236,7 +326,7 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
           GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * (width + 1), err));
           GTB_TRY(h->vbuf[i].ensure(sizeof(u32) * (width + tailcnt + 1), err));
         }
-        GTB_TRY(export_ptr(h, c, h->vbuf[1].p, &cm.recv));
+        GTB_TRY(export_ptr(h, c, &h->vbuf[1], true, &cm.recv));
       }
       PhaseTimer t(h, &h->ext_ms_keygen);
       GTB_TRY(rs_owner_counts(h->rw, st, src, hi - lo, first_keys, np, cm.counts, err));
@@ -300,11 +390,11 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
       GTB_TRY(build_ranks<DNA>(h));
       view.has_map = 1; view.N = h->N; view.sa_offset = h->sa_offset;
       view.own_last = (h->lb_own && !h->counted) ? h->maxcode : ~0ull;
-      GTB_TRY(export_ptr(h, c, h->kbuf[h->res].p, &view.keys));
-      GTB_TRY(export_ptr(h, c, h->vbuf[h->res].p, &view.sa));
-      GTB_TRY(export_ptr(h, c, h->rankwords.p, &view.rw));
-      GTB_TRY(export_ptr(h, c, h->M0 > 0 ? h->trank.p : nullptr, &view.trank));
-      GTB_TRY(export_ptr(h, c, h->leftborder.p, &view.lb));
+      GTB_TRY(export_ptr(h, c, &h->kbuf[h->res], true, &view.keys));
+      GTB_TRY(export_ptr(h, c, &h->vbuf[h->res], true, &view.sa));
+      GTB_TRY(export_ptr(h, c, &h->rankwords, true, &view.rw));
+      GTB_TRY(export_ptr(h, c, &h->trank, h->M0 > 0, &view.trank));
+      GTB_TRY(export_ptr(h, c, &h->leftborder, true, &view.lb));
       GTB_CUDA(cudaStreamSynchronize(st));           // the map is complete before anybody reads it
       return 0;
     });
@@ -402,6 +492,7 @@ int run_sharded(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
   if (pl == 0) { err.set("a sharded run needs prefixlength >= 1"); rc = -1; }
   if (rc == 0) rc = check_run_args(h, pl, flags | GTB_WANT_BCK);
   if (rc == 0 && cudaSetDevice(h->device) != cudaSuccess) { err.set("cudaSetDevice(%d) failed", h->device); rc = -1; }
+  if (rc == 0 && c.ipc) rc = enter_ipc_mode(h, c);
   h->ext_ms_keygen = 0; h->ext_ms_radix = 0; h->ext_pairs = 0; h->ext_launches = 0;
   GTB_TRY(sync_barrier(h, c, rc));
   return h->dna ? sharded_body<true>(h, c, pl, flags | GTB_WANT_BCK) : sharded_body<false>(h, c, pl, flags | GTB_WANT_BCK);
@@ -514,7 +605,7 @@ int group_merge_bck(gtb_group *g)
     for (int t = 0; t < 3; t++) {
       if (cnt[t] == 0) continue;
       PeerPtr pp; memset(&pp, 0, sizeof pp);
-      pp.ptr = (u64) (uintptr_t) src[t]->p; pp.device = o->device; pp.valid = 1;
+      pp.ptr = (u64) (uintptr_t) src[t]->p; pp.device = o->device; pp.valid = src[t]->p != nullptr;
       void *p = nullptr;
       if (resolve_ptr(root, c, pp, (int) i, &p) != 0) { snprintf(err.msg, sizeof err.msg, "%s", root->err.msg); return -1; }
       k_add_u32<<<grid_for(cnt[t], 256), 256, 0, root->st>>>(dst[t]->as<u32>(), static_cast<const u32 *>(p), cnt[t]);
