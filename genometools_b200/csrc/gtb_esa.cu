@@ -127,8 +127,11 @@ struct gtb_esa {
   int cur = 0, bits_lo = 1, bits_hi = 1;
   bool isa_built = false, in_progress = false;
   KeyFmt fmt = byte_fmt();  // key format of this run (DNA: chosen from the text length)
-  int opt_key_symbols = 0;  // test knobs (environment GTB200_KEY_SYMBOLS = 17|21|25|29,
-  int opt_text_rounds = -1; // GTB200_TEXT_ROUNDS = 0..8): override the automatic choices
+  int opt_key_symbols = 0;  // test knobs (environment GTB200_KEY_SYMBOLS = 16..29,
+  int opt_text_rounds = -1; // GTB200_TEXT_ROUNDS = 0..8,
+  int opt_tail_last = -1;   // GTB200_TAIL_LAST = 0|1): override the automatic choices
+  u64 nspecialranges = 0;   // maximal special runs of the 2-bit input
+  DevBuf nearbits, tailkeys[2], tailpos[2];   // the keys with a tail field, sorted apart (stage_begin)
   unsigned text_left = 0;   // text-driven rounds still allowed before ranks are built
   float ms_count_ext = 0;   // device time of gtb_esa_count_partial/_finish since the last run
   float ms_part_ext = 0;    // ... and of gtb_esa_slice_partition (its pass counts as a radix pass)
@@ -222,6 +225,7 @@ TextSrc<DNA> make_src(gtb_esa *h, u64 klo, u64 khi)
   s.klo = klo; s.khi = khi;
   s.pos0 = 0;
   s.f = h->fmt;
+  s.skip_near = false;
   return s;
 }
 
@@ -326,6 +330,36 @@ int count_codes(gtb_esa *h, unsigned pl, bool all, u64 first = 0, u64 end = ~0ul
   return 0;
 }
 
+// Key format of a run.  DNA: when only few suffixes meet a special within a key length (genomes: N
+// runs and sequence ends are rare; reads are the opposite) the key length is a multiple of four
+// symbols -- 16 / 20 / 24 / 28, the smallest with an expected share of chance ties n / 4^m below 1 % --
+// so that the lowest radix digit holds nothing but the tail field: the first-level sort then runs
+// over the symbol digits only and the keys with a tail enter it as a second, pre-sorted source
+// (stage_begin, radix_sort): c4 sorts with 5 passes instead of 6.  Otherwise 17 / 21 / 25 / 29
+// symbols (dna_fmt_for).  Every function that makes keys of a run takes its format from here.
+bool tails_rare(const gtb_esa *h) { return h->dna && (h->nspecialranges + 1) * 2048 <= h->n; }
+
+KeyFmt choose_fmt(const gtb_esa *h, unsigned pl)
+{
+  const int k = h->opt_key_symbols;
+  if (!h->dna) {
+    if ((k == 8 || k == 10 || k == 12) && k >= (int) pl) return make_fmt(k, 5, 4);
+    return byte_fmt_for(h->n, h->K, pl);
+  }
+  if (k >= (int) pl && k >= 1 && k <= 29) return make_fmt(k, 2, k > 15 ? (k == 29 ? 6 : 5) : 4);
+  if (h->opt_tail_last != 0 && (tails_rare(h) || h->opt_tail_last == 1)) {
+    const int cand[4] = {16, 20, 24, 28};
+    for (int i = 0; i < 4; i++) {
+      const int m = cand[i];
+      if ((unsigned) m < pl) continue;
+      if ((double) h->n / (double) (1ull << (2 * m)) <= 0.01 || m == 28) return make_fmt(m, 2, 5);
+    }
+  }
+  return dna_fmt_for(h->n, pl);
+}
+// the digit below the symbols holds only the tail field (and the pass over it can be replaced)
+bool fmt_tail_digit_alone(const KeyFmt &f) { return f.b == 2 && f.tb <= 8 && (f.sh + f.tb) % 8 == 0 && f.sh + f.tb < 64; }
+
 template <bool DNA> int compact_ties(gtb_esa *h);
 template <bool DNA> int build_ranks(gtb_esa *h);
 template <bool DNA> int round_local(gtb_esa *h);
@@ -342,11 +376,7 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
   h->flags = flags;
   h->isa_built = false;
   h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0; h->text_left = 0;
-  h->fmt = DNA ? dna_fmt_for(h->n, h->pl) : byte_fmt_for(h->n, h->K, h->pl);
-  if (!DNA && (h->opt_key_symbols == 8 || h->opt_key_symbols == 10 || h->opt_key_symbols == 12) && h->opt_key_symbols >= (int) h->pl)
-    h->fmt = make_fmt(h->opt_key_symbols, 5, 4);
-  if (DNA && h->opt_key_symbols >= (int) h->pl && h->opt_key_symbols >= 1 && h->opt_key_symbols <= 29)
-    h->fmt = make_fmt(h->opt_key_symbols, 2, h->opt_key_symbols > 15 ? (h->opt_key_symbols == 29 ? 6 : 5) : 4);
+  h->fmt = choose_fmt(h, h->pl);
   const KeyFmt f = h->fmt;
   h->depth[0] = (u64) f.m;
 
@@ -405,11 +435,56 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
   u64 *kb[2] = {h->kbuf[0].as<u64>(), h->kbuf[1].as<u64>()};
   u32 *vb[2] = {h->vbuf[0].as<u32>(), h->vbuf[1].as<u32>()};
   PassPlan plan; plan.npass = 0; plan.padded = true;
-  plan_add_bits(plan, f.lowbit() & ~7, 64);
   u64 N = 0;
   h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0; h->rw.ms_hist = 0; h->rw.ms_radix = 0;
-  if (ext) GTB_TRY(radix_sort(h->rw, st, *ext, extcount, kb, vb, plan, &h->res, &N, err));
-  else GTB_TRY(radix_sort(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err));
+  // The pass over the tail digit is dropped when that digit holds nothing else and tails are rare:
+  // the keys with a tail leave the text scan, are sorted by their tail (one tiny pass) and follow
+  // the full keys as a second source of the first symbol pass -- the result is the one of the sort
+  // with the tail digit (equal symbols: full keys first, then by tail, then text order).
+  const bool tail_last = DNA && !ext && h->n > 0 && fmt_tail_digit_alone(f) && h->opt_tail_last != 0 &&
+                         (tails_rare(h) || h->opt_tail_last == 1);
+  if (tail_last) {
+    const u64 nw = (h->n + 31) >> 5;
+    u64 nt = 0;
+    GTB_TRY(h->nearbits.ensure(sizeof(u32) * (nw + 2), err));
+    k_near_bits<<<grid_for(nw, 256), 256, 0, st>>>(h->spmask.as<u32>(), nw, (unsigned) f.m, h->nearbits.as<u32>());
+    GTB_LAUNCH_CHECK();
+    u32 *tileoff = nullptr;
+    GTB_TRY(device_scan_u32(h, h->nearbits.as<u32>(), nullptr, nw, 1, &tileoff, &nt));
+    S.kernel_launches++;
+    TailSrc tsrc{nullptr, nullptr, klo, khi};
+    if (nt > 0) {
+      for (int i = 0; i < 2; i++) {
+        GTB_TRY(h->tailkeys[i].ensure(sizeof(u64) * nt, err));
+        GTB_TRY(h->tailpos[i].ensure(sizeof(u32) * nt, err));
+      }
+      // their positions ascending, their keys, then stably by the tail field
+      k_emit_special_tail<<<(unsigned) div_up(nw, SC_TILE), SC_NT, 0, st>>>(h->nearbits.as<u32>(), nw, h->n, tileoff,
+          h->tailpos[1].as<u32>(), nullptr, 0, reinterpret_cast<unsigned long long *>(h->misc.as<u64>() + 24) /* unused */);
+      GTB_LAUNCH_CHECK();
+      k_keys_from_positions<DNA><<<grid_for(nt, 256), 256, 0, st>>>(make_src<DNA>(h, 0, ~0ull), h->tailpos[1].as<u32>(), nt,
+                                                                   h->tailkeys[1].as<u64>());
+      GTB_LAUNCH_CHECK();
+      S.kernel_launches += 2;
+      PassPlan tp; tp.npass = 0; tp.padded = false;
+      plan_add_bits(tp, f.sh, f.sh + f.tb);
+      PairSrc ps{h->tailkeys[1].as<u64>(), h->tailpos[1].as<u32>()};
+      u64 *tk[2] = {h->tailkeys[0].as<u64>(), h->tailkeys[1].as<u64>()};
+      u32 *tv[2] = {h->tailpos[0].as<u32>(), h->tailpos[1].as<u32>()};
+      int tres = 0; u64 tout = 0;
+      GTB_TRY(radix_sort(h->rw, st, ps, nt, tk, tv, tp, &tres, &tout, err));
+      if (tout != nt) { err.set("internal: the tail keys lost elements"); return -1; }
+      tsrc.keys = tk[tres]; tsrc.vals = tv[tres];
+    }
+    src.skip_near = true;
+    plan_add_bits(plan, f.sh + f.tb, 64);
+    GTB_TRY((radix_sort<TextSrc<DNA>, TailSrc>(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err, nt > 0 ? &tsrc : nullptr, nt)));
+    src.skip_near = false;
+  } else {
+    plan_add_bits(plan, f.lowbit() & ~7, 64);
+    if (ext) GTB_TRY(radix_sort(h->rw, st, *ext, extcount, kb, vb, plan, &h->res, &N, err));
+    else GTB_TRY(radix_sort(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err));
+  }
   if (ext && N != Ncap) { err.set("exchanged pairs: %llu received, the code range holds %llu suffixes",
                                   (unsigned long long) N, (unsigned long long) Ncap); return -1; }
   if (N > Ncap) { err.set("internal: sorted %llu suffixes, expected at most %llu",
@@ -948,6 +1023,7 @@ gtb_esa *gtb_esa_new(int device, char *errbuf, size_t errlen)
   h->device = device;
   if (const char *e = getenv("GTB200_KEY_SYMBOLS")) h->opt_key_symbols = atoi(e);
   if (const char *e = getenv("GTB200_TEXT_ROUNDS")) h->opt_text_rounds = atoi(e) > 8 ? 8 : atoi(e);
+  if (const char *e = getenv("GTB200_TAIL_LAST")) h->opt_tail_last = atoi(e) ? 1 : 0;
   memset(&h->stats, 0, sizeof h->stats);
   if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h; return fail("cudaStreamCreate", e);
@@ -969,7 +1045,8 @@ void gtb_esa_delete(gtb_esa *h)
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
                    &h->uidx[0], &h->uidx[1], &h->ugrp[0], &h->ugrp[1], &h->upos[0], &h->upos[1],
                    &h->dkeys, &h->kd[0], &h->kd[1], &h->vd[0], &h->vd[1], &h->ulcp, &h->llvflags, &h->llv,
-                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts, &h->rankwords, &h->peertab};
+                   &h->ranks, &h->owner, &h->sendidx, &h->rcounts, &h->rankwords, &h->peertab,
+                   &h->nearbits, &h->tailkeys[0], &h->tailkeys[1], &h->tailpos[0], &h->tailpos[1]};
   for (DevBuf *b : all) b->release();
   for (auto &m : h->imports) vmm_free(m.second.ptr, m.second.mh, m.second.size);
   h->imports.clear();
@@ -1005,6 +1082,7 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
   if (nwords < (n + 31) / 32) { err.set("twobitencoding too short: %llu words for %llu bases", (unsigned long long) nwords, (unsigned long long) n); return -1; }
   PhaseTimer t(h, &h->stats.ms_upload);
   h->dna = true; h->K = 4; h->n = n; h->counted = false; h->ran = false; h->have_sep = false;
+  h->nspecialranges = nranges;
   const u64 need = (n >> 5) + 4;
   GTB_TRY(h->words.ensure(sizeof(u64) * need, err));
   const u64 ncopy = nwords < need ? nwords : need;
@@ -1085,6 +1163,7 @@ int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src)
   if (!src->have_input) { h->err.set("gtb_esa_share_input: source has no input"); return -1; }
   if (h->device != src->device) { h->err.set("gtb_esa_share_input: handles live on different devices"); return -1; }
   h->dna = src->dna; h->K = src->K; h->n = src->n; h->S = src->S; h->nmaskwords = src->nmaskwords;
+  h->nspecialranges = src->nspecialranges;
   h->readmode = src->readmode;
   h->words.borrow(src->words); h->bytes.borrow(src->bytes); h->spmask.borrow(src->spmask);
   h->sepbits.borrow(src->sepbits); h->have_sep = src->have_sep;
@@ -1134,7 +1213,7 @@ int gtb_esa_slice_partition(gtb_esa *h, unsigned prefixlength, uint64_t first_po
   GTB_CUDA(cudaSetDevice(h->device));
   if (end_pos > h->n) end_pos = h->n;
   if (first_pos > end_pos) { err.set("gtb_esa_slice_partition: empty or reversed slice"); return -1; }
-  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  h->fmt = choose_fmt(h, prefixlength);
   cudaEvent_t e0, e1;
   GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
   GTB_CUDA(cudaEventRecord(e0, h->st));
@@ -1179,7 +1258,7 @@ int gtb_esa_sort_begin_positions(gtb_esa *h, unsigned prefixlength, unsigned fla
   // the keys are regenerated once into the second key buffer: the first pass reads them
   // there and writes the first buffer
   for (int i = 0; i < 2; i++) GTB_TRY(h->kbuf[i].ensure(sizeof(u64) * (count + 1), err));
-  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  h->fmt = choose_fmt(h, prefixlength);
   PairSrc ext{h->kbuf[1].as<u64>(), dev_positions};
   return timed_stage(h, [&]() -> int {
     if (count > 0) {
@@ -1273,7 +1352,7 @@ int gtb_esa_count(gtb_esa *h, unsigned prefixlength)
   GTB_CUDA(cudaSetDevice(h->device));
   if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
   if (h->pl != prefixlength) h->counted = false;
-  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  h->fmt = choose_fmt(h, prefixlength);
   GTB_TRY(count_codes(h, prefixlength, true));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;
@@ -1287,7 +1366,7 @@ int gtb_esa_count_partial(gtb_esa *h, unsigned prefixlength, uint64_t first_pos,
   GTB_CUDA(cudaSetDevice(h->device));
   if (prefixlength == 0 || prefixlength > (h->dna ? 15u : 7u)) { err.set("bad prefixlength %u", prefixlength); return -1; }
   h->counted = false;
-  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  h->fmt = choose_fmt(h, prefixlength);
   cudaEvent_t e0, e1;
   GTB_CUDA(cudaEventCreate(&e0)); GTB_CUDA(cudaEventCreate(&e1));
   GTB_CUDA(cudaEventRecord(e0, h->st));
@@ -1339,7 +1418,7 @@ int gtb_esa_coarse_partial(gtb_esa *h, unsigned prefixlength, uint64_t first_pos
   h->counted = false; h->lb_own = false;
   h->pl = prefixlength;
   h->ncodes = ipow_u64(h->K, prefixlength);
-  h->fmt = h->dna ? dna_fmt_for(h->n, prefixlength) : byte_fmt_for(h->n, h->K, prefixlength);
+  h->fmt = choose_fmt(h, prefixlength);
   h->plc = coarse_pl(h, prefixlength);
   h->ncoarse = (u32) ipow_u64(h->K, h->plc);
   GTB_TRY(h->coarse.ensure(sizeof(u32) * (h->ncoarse + 1), err));

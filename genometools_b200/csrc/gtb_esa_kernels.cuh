@@ -91,6 +91,8 @@ struct TextSrc {
   u64 klo, khi;          // inclusive key range of this shard
   u64 pos0;              // item i of the source is text position pos0 + i
   KeyFmt f;
+  bool skip_near;        // positions that meet a special within their m symbols are no items (they are
+                         // sorted from a list of their own, k_near_bits / TailSrc)
 
   // filled key of position pos in format g (any m <= 29 for DNA, m*b + tb <= 64)
   __device__ __forceinline__ bool make_key_fmt(u64 pos, u64 &key, const KeyFmt &g) const
@@ -116,6 +118,7 @@ struct TextSrc {
   __device__ __forceinline__ bool make_key(u64 pos, u64 &key) const
   {
     if (!make_key_fmt(pos, key, f)) return false;
+    if (skip_near && (key & f.tailmask()) != 0) return false;
     return key >= klo && key <= khi;
   }
   __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
@@ -181,7 +184,7 @@ struct TextSrc {
       u64 key = ((u64) khi32 << 32) | klo32;
       const u32 win = __funnelshift_r(mlo, mhi, i) & mmask;     // specials among positions i .. i+m-1
       if (win != 0u) {
-        if (win & 1u) key = ~0ull;                      // a special position is no item
+        if ((win & 1u) || skip_near) key = ~0ull;       // a special position is no item
         else {
           const unsigned u = (unsigned) __ffs(win) - 1u;        // regular symbols before the special
           key |= (1ull << (64u - B * u)) - (1ull << (64u - B * m));   // filler over symbols u .. m-1
@@ -219,7 +222,7 @@ k_hist_text_dna(TextSrc<true> src, u64 n, PassPlan plan, unsigned long long *__r
         u64 sym = hi >> (64 - 2 * m);
         if (u < m) sym |= (1ull << (2u * (m - u))) - 1ull;
         const u64 key = (sym << (64 - 2 * m)) | ((u64) (m - u) << f.sh);
-        if (key >= src.klo && key <= src.khi) {
+        if (key >= src.klo && key <= src.khi && !(src.skip_near && u < m)) {
 #pragma unroll
           for (int p = 0; p < RS_MAXPASS; p++)
             if (p < plan.npass)
@@ -365,6 +368,35 @@ struct RankMap {
     }
     return (u32) (sa_offset + lo);
   }
+};
+
+// ---- the keys that carry a tail, sorted apart (radix_sort with a second source) ---------------
+// bit i of word w: position 32w + i is regular and meets a special (or the end of the text) within
+// its next m symbols -- its filled key has a non-zero tail field
+__global__ void k_near_bits(const u32 *__restrict__ spmask, u64 nwords, unsigned m, u32 *__restrict__ near)
+{
+  for (u64 w = blockIdx.x * (u64) blockDim.x + threadIdx.x; w < nwords; w += (u64) gridDim.x * blockDim.x) {
+    const u64 sp = (u64) spmask[w] | ((u64) spmask[w + 1] << 32);
+    u64 sm = sp >> 1;                         // special among positions +1 .. +(m-1): OR of m-1 shifts
+    unsigned have = 1;
+    while (have < m - 1) {
+      const unsigned step = have < m - 1 - have ? have : m - 1 - have;
+      sm |= sm >> step;
+      have += step;
+    }
+    near[w] = (u32) (~sp & sm);
+  }
+}
+
+struct TailSrc {                 // (key, position) pairs in memory, only those inside the key range
+  static constexpr bool ALWAYS_VALID = false;
+  static constexpr bool BLOCKED_GEN = false;
+  const u64 *keys;
+  const u32 *vals;
+  u64 klo, khi;
+  __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
+  { k = keys[idx]; return k >= klo && k <= khi; }
+  __device__ __forceinline__ u32 load_val(u64 idx) const { return vals[idx]; }
 };
 
 // ---- special mask ------------------------------------------------------------------

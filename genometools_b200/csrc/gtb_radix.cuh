@@ -476,7 +476,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u64 N,
                    unsigned bsel, unsigned dmask, const u64 *__restrict__ gbase,
                    u64 *status, u32 epoch, u32 *ticket, u32 ticket_base,
-                   const u64 *__restrict__ owner_bounds, int nowners, const u64 *__restrict__ binbase)
+                   const u64 *__restrict__ owner_bounds, int nowners, const u64 *__restrict__ binbase,
+                   u32 tile_offset)
 {
   constexpr int TILE = Cfg::TILE;
   extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -490,8 +491,10 @@ rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u6
     for (int i = threadIdx.x; i < (int) (Cfg::HIST / 4); i += Cfg::NT) s_wh[i] = 0;
   }
   __syncthreads();
+  // a pass may be fed by two launches (a second source appended to the first, radix_sort): the tile
+  // number continues (look-back across both), the items are counted from the launch's own source
   const u64 tile = s_ticket;
-  const u64 base = tile * (u64) TILE;
+  const u64 base = (tile - tile_offset) * (u64) TILE;
   const u32 count = (N - base) < (u64) TILE ? (u32) (N - base) : (u32) TILE;
   if constexpr (Src::ALWAYS_VALID) {
     if (count == (u32) TILE) {
@@ -508,6 +511,7 @@ struct RadixWork {
   u64  status_tiles = 0;
   u32 *ticket = nullptr;
   u32  ticket_base = 0;
+  u32  pending_tiles = 0;             // tiles of the first launch of a pass whose second launch is still to come
   u32  epoch = 0;
   unsigned long long *ghist = nullptr;   // [8][256] device
   u64 *gbase = nullptr;                  // [8][256] device
@@ -566,7 +570,7 @@ static inline int radix_work_reserve(RadixWork &w, u64 nitems, ErrBuf &err)
 template <class Src, class Cfg, int MODE>
 static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, u64 tiles,
                           u64 *okeys, u32 *ovals, unsigned bsel, unsigned dmask, int passidx,
-                          ErrBuf &err, bool peer_bins = false)
+                          ErrBuf &err, bool peer_bins = false, u32 tile_offset = 0)
 {
   // (the attribute is per device: one bit per device and instantiation)
   static std::atomic<unsigned long long> attr_set{0};
@@ -582,21 +586,23 @@ static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
   rs_onesweep_kernel<Src, Cfg, MODE><<<(unsigned) tiles, Cfg::NT, Cfg::SMEM, st>>>(
       src, okeys, ovals, nsrc, bsel, dmask, w.gbase + passidx * RS_BINS,
       w.status, w.epoch, w.ticket, w.ticket_base, w.bounds, MODE == 3 ? w.nbounds : 0,
-      peer_bins ? w.binbase : nullptr);
+      peer_bins ? w.binbase : nullptr, tile_offset);
   GTB_LAUNCH_CHECK();
   return 0;
 }
 
+// tiles_before > 0: this launch continues the pass a preceding launch (same pass, another source)
+// began: same epoch, the tile numbers go on
 template <class Src, class Cfg>
 static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
                           u64 *okeys, u32 *ovals, int shift, int bits, bool padded, int passidx,
-                          ErrBuf &err)
+                          ErrBuf &err, u64 tiles_before = 0, bool more_follows = false)
 {
   static_assert(Cfg::TILE >= RS_MIN_TILE, "status array sizing");
   const u64 tiles = div_up(nsrc, Cfg::TILE);
   if (tiles == 0) return 0;
-  if (tiles > w.status_tiles) { err.set("radix: status array too small"); return -1; }
-  if (++w.epoch >= 0xffffu) {           // epoch space exhausted: start over
+  if (tiles_before + tiles > w.status_tiles) { err.set("radix: status array too small"); return -1; }
+  if (tiles_before == 0 && ++w.epoch >= 0xffffu) {           // epoch space exhausted: start over
     GTB_CUDA(cudaMemsetAsync(w.status, 0, sizeof(u64) * RS_BINS * w.status_tiles, st));
     w.epoch = 1;
   }
@@ -605,13 +611,16 @@ static int rs_launch_pass(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
   const unsigned dmask = (1u << bits) - 1u;
   if (shift % 8 == 0 && (bits == 8 || padded)) {
     const unsigned bsel = 0x4440u + (unsigned) (shift % 32) / 8u;
-    if (shift < 32) GTB_TRY((rs_launch_mode<Src, Cfg, 0>(w, st, src, nsrc, tiles, okeys, ovals, bsel, dmask, passidx, err)));
-    else GTB_TRY((rs_launch_mode<Src, Cfg, 1>(w, st, src, nsrc, tiles, okeys, ovals, bsel, dmask, passidx, err)));
+    if (shift < 32) GTB_TRY((rs_launch_mode<Src, Cfg, 0>(w, st, src, nsrc, tiles, okeys, ovals, bsel, dmask, passidx, err, false, (u32) tiles_before)));
+    else GTB_TRY((rs_launch_mode<Src, Cfg, 1>(w, st, src, nsrc, tiles, okeys, ovals, bsel, dmask, passidx, err, false, (u32) tiles_before)));
   } else {
-    GTB_TRY((rs_launch_mode<Src, Cfg, 2>(w, st, src, nsrc, tiles, okeys, ovals, (unsigned) shift, dmask, passidx, err)));
+    GTB_TRY((rs_launch_mode<Src, Cfg, 2>(w, st, src, nsrc, tiles, okeys, ovals, (unsigned) shift, dmask, passidx, err, false, (u32) tiles_before)));
   }
-  w.ticket_base += (u32) tiles;
-  w.passes++; w.launches++;
+  // (the ticket counter runs on through both launches of a pass; its base moves when the pass is complete)
+  w.pending_tiles = more_follows ? (u32) (tiles_before + tiles) : 0u;
+  if (!more_follows) w.ticket_base += (u32) (tiles_before + tiles);
+  if (tiles_before == 0) w.passes++;
+  w.launches++;
   return 0;
 }
 
@@ -763,23 +772,38 @@ static int rs_partition_by_owner(RadixWork &w, cudaStream_t st, const Src &src, 
 // kbuf[*res]/vbuf[*res], *nout = number of valid pairs.  Passes whose digit is the
 // same for every key are skipped.  Synchronises the stream once (histogram
 // read-back).
-template <class Src, class Cfg = RsDefault>
+//
+// extra (optional): a second source whose items count as FOLLOWING all items of `src` in input order
+// (the first pass is fed by two launches).  This is how the first-level suffix sort drops the pass over
+// the tail field of its keys: the few keys that carry a tail are taken out of the text scan, sorted by
+// their tail and appended -- a stable LSD sort of "full keys in text order, then tail keys in
+// (tail, text) order" by the symbol digits alone ends exactly where the sort with the tail digit ends.
+template <class Src, class Extra = PairSrc, class Cfg = RsDefault>
 static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
                       u64 *kbuf[2], u32 *vbuf[2], const PassPlan &plan,
-                      int *res, u64 *nout, ErrBuf &err)
+                      int *res, u64 *nout, ErrBuf &err, const Extra *extra = nullptr, u64 nextra = 0)
 {
   *res = 0; *nout = 0;
-  if (nsrc == 0) return 0;
+  if (!extra) nextra = 0;
+  if (nsrc == 0 && nextra == 0) return 0;
   if (plan.npass < 1 || plan.npass > RS_MAXPASS) { err.set("radix: bad pass plan"); return -1; }
-  GTB_TRY(radix_work_reserve(w, nsrc, err));
+  GTB_TRY(radix_work_reserve(w, nsrc + nextra + 2 * RS_MIN_TILE, err));
   GTB_CUDA(cudaEventRecord(w.ev[0], st));
   GTB_CUDA(cudaMemsetAsync(w.ghist, 0, sizeof(unsigned long long) * RS_MAXPASS * RS_BINS, st));
   {
-    RsHistLauncher<Src>::launch(src, nsrc, plan, w.ghist, st);
-    GTB_LAUNCH_CHECK();
+    if (nsrc > 0) {
+      RsHistLauncher<Src>::launch(src, nsrc, plan, w.ghist, st);
+      GTB_LAUNCH_CHECK();
+      w.launches++;
+    }
+    if (nextra > 0) {
+      RsHistLauncher<Extra>::launch(*extra, nextra, plan, w.ghist, st);
+      GTB_LAUNCH_CHECK();
+      w.launches++;
+    }
     rs_scan_kernel<<<plan.npass, RS_BINS, 0, st>>>(w.ghist, w.gbase);
     GTB_LAUNCH_CHECK();
-    w.launches += 2;
+    w.launches++;
   }
   GTB_CUDA(cudaMemcpyAsync(w.h_hist, w.ghist, sizeof(unsigned long long) * plan.npass * RS_BINS,
                            cudaMemcpyDeviceToHost, st));
@@ -806,7 +830,12 @@ static int radix_sort(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc,
   for (int p = 0; p < plan.npass; p++) {
     if (skip[p]) continue;
     if (cur < 0) {
-      GTB_TRY((rs_launch_pass<Src, Cfg>(w, st, src, nsrc, kbuf[0], vbuf[0], plan.shift[p], plan.bits[p], plan.padded, p, err)));
+      const u64 tiles_a = div_up(nsrc, Cfg::TILE);
+      if (nsrc > 0)
+        GTB_TRY((rs_launch_pass<Src, Cfg>(w, st, src, nsrc, kbuf[0], vbuf[0], plan.shift[p], plan.bits[p], plan.padded, p, err, 0, nextra > 0)));
+      if (nextra > 0)
+        GTB_TRY((rs_launch_pass<Extra, Cfg>(w, st, *extra, nextra, kbuf[0], vbuf[0], plan.shift[p], plan.bits[p], plan.padded, p, err,
+                                            tiles_a, false)));
       cur = 0;
     } else {
       PairSrc ps{kbuf[cur], vbuf[cur]};

@@ -316,7 +316,7 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
     const u64 width = active ? out4[4 * me + 3] : 0;
     CountsMsg cm; memset(&cm, 0, sizeof cm);
     TextSrc<DNA> src = make_src<DNA>(h, 0, ~0ull);
-    h->fmt = DNA ? dna_fmt_for(n, pl) : byte_fmt_for(n, h->K, pl);
+    h->fmt = choose_fmt(h, pl);
     src.f = h->fmt; src.pos0 = lo;
     h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0;
     rc = timed_stage(h, [&]() -> int {

@@ -193,6 +193,7 @@ class EsaResult:
     distpfxidx: np.ndarray = None
     longest: int = None
     device_hashes: dict = None       # checksums of the tables in HBM (gtb_group_hash_results)
+    job_stats: dict = None           # a sharded job: the numbers of the whole job
     numoflargelcpvalues: int = 0
     maxbranchdepth: int = 0
     lcptabsum: float = 0.0
@@ -451,7 +452,7 @@ def build_esa_group(enc: EncodedSequence, prefixlength, devices, want_suf=True, 
         res = EsaResult(n, enc.numofchars, prefixlength, readmode=READMODES.index(readmode))
         st = GtbStats()
         ck(lib.gtb_group_get_stats(g, C.byref(st)))
-        res.stats.append(st.as_dict())
+        res.job_stats = st.as_dict()          # sums / maxima over the ranges (gtb_group_get_stats)
         for i in range(lib.gtb_group_size(g)):
             sti = GtbStats()
             lib.gtb_esa_get_stats(lib.gtb_group_range(g, i), C.byref(sti))

@@ -104,9 +104,13 @@ def test_cuda_edge_cases(sym):
     check_against_oracle(s, 4, 1, res, str(sym[:8]))
 
 
+# -parts runs either as a gtb_group (ranges read each other's memory: the multi-GPU product path) or with
+# the request/answer rank exchange of genometools_b200/multirange.py (the single-GPU twin of the NCCL protocol)
+@pytest.mark.parametrize("protocol", ["group", "exchange"])
 @pytest.mark.parametrize("parts", [2, 3, 7])
-def test_parts_do_not_change_the_output(parts):
+def test_parts_do_not_change_the_output(monkeypatch, parts, protocol):
     # sfx-partssuf.c: the output is independent of -parts (reference test :64-68)
+    monkeypatch.setenv("GTB200_PARTS_PROTOCOL", protocol)
     sym = synth.random_dna(200_000, 77, p_n=0.001)
     enc = encode_symbols(sym, 4)
     one = build_esa(enc, 6)
@@ -122,9 +126,11 @@ def test_parts_do_not_change_the_output(parts):
 
 @pytest.mark.parametrize("name,parts", [("repeats", 2), ("repeats", 5), ("lowcomplex", 3), ("reads_dup", 4),
                                         ("protein_dup", 3)])
-def test_parts_with_ties_across_ranges(name, parts):
+@pytest.mark.parametrize("protocol", ["group", "exchange"])
+def test_parts_with_ties_across_ranges(monkeypatch, name, parts, protocol):
     """ties whose doubling partner lives in another code range: the rank exchange between
     ranges (the multi-GPU protocol, here with all ranges on one device)"""
+    monkeypatch.setenv("GTB200_PARTS_PROTOCOL", protocol)
     if name == "repeats":
         sym, K, pl = synth.repeats_dna(200_000, 19, unit=5000, copies=12, exact_len=9000, exact_copies=4), 4, 5
     elif name == "lowcomplex":
@@ -225,6 +231,30 @@ def test_cuda_key_lengths_and_refinement_paths(monkeypatch, m, text_rounds):
     for name, sym, pl in cases:
         res = build_esa(encode_symbols(sym, 4), pl)
         check_against_oracle(sym, 4, pl, res, f"{name} m={m} text_rounds={text_rounds}")
+
+
+# the first-level sort without the pass over the tail digit (key lengths that are multiples of four
+# symbols: the keys with a tail are sorted apart and appended as a second source of the first pass),
+# forced on inputs FULL of specials, and the same formats with the tail pass -- all the oracle's bytes
+@pytest.mark.parametrize("m,tail_last,text_rounds", [(16, 1, 0), (16, 1, 2), (20, 1, 0), (24, 1, 1), (28, 1, 0),
+                                                     (20, 0, 0), (16, 0, 1), (12, 1, 0), (8, 1, 1)])
+def test_cuda_tail_keys_sorted_apart(monkeypatch, m, tail_last, text_rounds):
+    monkeypatch.setenv("GTB200_KEY_SYMBOLS", str(m))
+    monkeypatch.setenv("GTB200_TAIL_LAST", str(tail_last))
+    monkeypatch.setenv("GTB200_TEXT_ROUNDS", str(text_rounds))
+    cases = [
+        ("repeats", synth.repeats_dna(60_000, 5, unit=1500, copies=6, exact_len=900, exact_copies=3, nruns=5), 5),
+        ("reads", synth.reads(500, 60, 7, p_n=0.01), 4),
+        ("reads_dup", np.concatenate([synth.reads(200, 40, 2, 0.0), [255], synth.reads(200, 40, 2, 0.0)]).astype(np.uint8), 3),
+        ("polyT_N", np.concatenate([np.full(3000, 3, np.uint8), synth.random_dna(2000, 3, p_n=0.02),
+                                    np.full(2500, 3, np.uint8), [254], np.full(700, 3, np.uint8)]).astype(np.uint8), 3),
+        ("starts_near_special", np.array([1, 2, 254, 0, 3, 3, 3, 255, 3, 3, 1], dtype=np.uint8), 1),
+        ("no_specials", synth.random_dna(30_000, 8), 6),
+    ]
+    for name, sym, pl in cases:
+        for parts in (1, 3):
+            res = build_esa(encode_symbols(sym, 4), pl, parts=parts)
+            check_against_oracle(sym, 4, pl, res, f"{name} m={m} tail_last={tail_last} parts={parts}")
 
 
 @pytest.mark.parametrize("m,text_rounds", [(8, 0), (8, 2), (10, 1), (12, 2)])
