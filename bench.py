@@ -137,6 +137,27 @@ def time_reference(w, workdir, runs=1):
     return times
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def time_reference_sa_only(workdir, is_dna, jobs):
+    """`gt -j N suffixerator -suf -bck -pl` -- the reference's multi-threaded
+    sorter (src/match/sfx-bentsedg.c:1986-2063) computes the suffix table only (no lcp with -j N)"""
+    gtref = os.path.join(ROOT, "oracle", "_ref", "gtref")
+    fa = os.path.join(workdir, "sample.fa")
+    t0 = time.perf_counter()
+    subprocess.check_call([gtref, "-j", str(jobs), "suffixerator", "-dna" if is_dna else "-protein", "-suf", "-bck",
+                           "-pl", "-indexname", os.path.join(workdir, "refj"), "-db", fa], stdout=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
 def time_oracle_port(w):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import esa_oracle as eo
@@ -176,26 +197,37 @@ def time_dropin_cli(w, workdir, device):
 def cpu_baseline(args, wl_name, device=None):
     w = reference_sample(wl_name, args.cpu_sample)
     tmp = tempfile.mkdtemp(prefix="gtb_ref_")
-    cli = None
+    cli, sa_only = None, None
     try:
         times = time_reference(w, tmp)
         kind = "reference"
         if times is None:
             times = time_oracle_port(w)
             kind = "port"
-        elif device is not None:
+        else:
+            jobs = os.cpu_count() or 1
             try:
-                cli = time_dropin_cli(w, tmp, device)
-            except Exception as ex:      # reported, never fatal
-                cli = {"error": str(ex)}
+                tj = time_reference_sa_only(tmp, w.is_dna, jobs)
+                sa_only = {"value": (w.totallength + 1) / tj / 1e6, "unit": "Msuffixes/s (suffix table only)",
+                           "threads": jobs, "seconds": tj,
+                           "command": f"gtref -j {jobs} suffixerator -suf -bck -pl (no -lcp: the reference's threaded "
+                                      "sorter writes no lcp values)"}
+            except Exception as ex:
+                sa_only = {"error": str(ex)}
+            if device is not None:
+                try:
+                    cli = time_dropin_cli(w, tmp, device)
+                except Exception as ex:      # reported, never fatal
+                    cli = {"error": str(ex)}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     t = min(times)
     return {"value": (w.totallength + 1) / t / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
-            "seconds": t,
+            "seconds": t, "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
+            "sa_only_all_cores": sa_only,
             "sample": f"{w.name} generator at n={w.totallength} ({w.description}); "
                       + ("oracle/_ref/gtref suffixerator -suf -lcp -bck -pl, 1 thread (lcp is wrong with -j N)"
-                         if kind == "reference" else "oracle/esa_oracle.c restatement")}, cli
+                         if kind == "reference" else "oracle/esa_oracle.c restatement")}, cli, w
 
 
 def run_reference_arm(args, rank, world):
@@ -227,11 +259,77 @@ def run_reference_arm(args, rank, world):
             "config": {"workload": wl, "sample_totallength": w.totallength, "description": w.description,
                        "command": "suffixerator -suf -lcp -bck -pl (1 thread: the reference computes no lcp "
                                   "values with -j N)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
-                             "sample": f"{w.name} generator at n={w.totallength}, every step"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "cpu_model": cpu_model(),
+                             "host_cores": os.cpu_count(),
+                             "sample": f"{w.name} generator at n={w.totallength}, every step (a bounded sample of the "
+                                       "workload; the B200 arm reports `same_input` on exactly this sample)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def same_input_run(lib, device, w, cpu, steps=5):
+    """value and e2e of the B200 path on the bounded sample the reference arm sorts: a ratio on ONE input"""
+    import torch
+    from genometools_b200._lib import GtbStats, ptr
+    from genometools_b200.suffixerator import recommendedprefixlength
+    n = w.totallength
+    pl = recommendedprefixlength(w.numofchars, n)
+    buf = C.create_string_buffer(512)
+    h = lib.gtb_esa_new(device, buf, 512)
+    if not h:
+        return {"error": buf.value.decode()}
+    try:
+        def ck(rc):
+            if rc != 0:
+                raise RuntimeError(lib.gtb_esa_error(h).decode())
+
+        def upload():
+            if w.is_dna:
+                ck(lib.gtb_esa_set_input_2bit(h, ptr(w.words), w.words.shape[0], n,
+                                              ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
+            else:
+                ck(lib.gtb_esa_set_input_bytes(h, ptr(w.symbols), n, w.numofchars))
+        upload()
+        stream = torch.cuda.ExternalStream(lib.gtb_esa_stream(h), device=torch.device("cuda", device))
+        for _ in range(2):
+            ck(lib.gtb_esa_run(h, pl, 7))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            ck(lib.gtb_esa_run(h, pl, 7))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dev_s = e0.elapsed_time(e1) / 1e3 / steps
+        e = n + 1
+        suf = torch.empty(e, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        lcp = torch.empty(e, dtype=torch.uint8, pin_memory=True).numpy()
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a), C.byref(b), C.byref(c))
+        lb = np.empty(a.value + 1, dtype=np.uint32); csc = np.empty(max(b.value, 1), dtype=np.uint32)
+        dist = np.empty(max(c.value, 1), dtype=np.uint32)
+        times = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            upload()
+            ck(lib.gtb_esa_run(h, pl, 7))
+            k = int(lib.gtb_esa_num_llv(h))
+            llv = np.empty(2 * max(k, 1), dtype=np.uint64)
+            ck(lib.gtb_esa_copy_results(h, ptr(suf), ptr(lcp), ptr(llv) if k else None, ptr(lb), ptr(csc),
+                                        ptr(dist) if c.value else None))
+            times.append(time.perf_counter() - t0)
+        e2e_s = min(times[1:])
+        ref = cpu["value"] if cpu and cpu.get("value") else None
+        out = {"input": f"{w.name} generator at n={n}: the cpu_baseline sample, identical on both sides",
+               "b200_value": (n + 1) / dev_s / 1e6, "b200_e2e": (n + 1) / e2e_s / 1e6, "reference_value": ref,
+               "unit": UNIT, "b200_ms_per_step": dev_s * 1e3, "b200_e2e_ms": e2e_s * 1e3}
+        if ref:
+            out["ratio_value"] = out["b200_value"] / ref
+            out["ratio_e2e"] = out["b200_e2e"] / ref
+        return out
+    finally:
+        lib.gtb_esa_delete(h)
 
 
 # ------------------------------------------------------------------ the B200 arm
@@ -534,10 +632,13 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
-    cpu, cli = None, None
+    cpu, cli, same_input = None, None, None
     if not args.no_cpu_baseline and world == 1:
         try:
-            cpu, cli = cpu_baseline(args, args.workload, local_rank)
+            cpu, cli, wsample = cpu_baseline(args, args.workload, local_rank)
+            # the same input on both sides: the B200 path on exactly the sample the reference just sorted
+            # (device time with the sequence resident, and end to end through host buffers)
+            same_input = same_input_run(lib, local_rank, wsample, cpu)
         except Exception as ex:      # the baseline is reported, never fatal
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(ex)}
     line = {
@@ -555,7 +656,7 @@ def main():
                                        "NCCL all-to-all request/answer protocol") + ")"
                    if world > 1 else "single range", "scale": args.scale},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu, "cli": cli,
+        "roofline": roofline, "cpu_baseline": cpu, "same_input": same_input, "cli": cli,
         "wall_ms_per_step": wall_ms_max / args.steps,
         "breakdown_ms_last_step": {k: last[k] for k in ("ms_count", "ms_hist", "ms_radix", "ms_analyze",
                                                          "ms_doubling", "ms_lcp", "ms_tail")},

@@ -13,6 +13,7 @@
 //   K7 special tail
 #include <stdarg.h>
 #include <stdlib.h>
+#include <chrono>
 #include <map>
 #include <new>
 #include <string>
@@ -1560,11 +1561,17 @@ int gtb_esa_copy_suftab_u32(gtb_esa *h, uint32_t *dst, uint64_t first, uint64_t 
 }
 
 // the wide half of gtb_esa_copy_suftab_u64: chunks from the back of the dealer are widened on the
-// device (into the dead key buffers) and copied as uint64 straight into the caller's pinned buffer
+// device (into the dead key buffers) and copied as uint64 straight into the caller's pinned buffer.
+// grace_ms > 0: first give the narrow path that long; if it has dealt itself at least min_front chunks
+// by then it is faster than this path could be and keeps the whole table
 static int suftab_wide_chunks(gtb_esa *h, cudaStream_t st2, uint64_t *dst, uint64_t first, uint64_t count,
-                              u64 per, ChunkDealer *dealer, ErrBuf &err)
+                              u64 per, ChunkDealer *dealer, ErrBuf &err, int grace_ms, u64 min_front)
 {
   GTB_CUDA(cudaSetDevice(h->device));
+  if (grace_ms > 0) {
+    std::this_thread::sleep_for(std::chrono::milliseconds(grace_ms));
+    if (dealer->front_taken() >= min_front) return 0;
+  }
   u64 *stage[2];
   cudaEvent_t done[2];
   for (int i = 0; i < 2; i++) {
@@ -1595,20 +1602,25 @@ int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t 
   GTB_TRY(check_range(h, first, count));
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
-  // The .suf entries are uint64, the table in HBM uint32.  Two ways to the host: "narrow" (default)
-  // -- 4 bytes per entry cross PCIe into small pinned staging buffers (they stay in the host's last
-  // level cache) and host threads widen them into the destination; "wide" -- widened on the device,
-  // 8 bytes per entry by DMA straight into a pinned destination (bound by PCIe).
-  // GTB200_SUF_COPY = wide selects the second, = both deals the chunks from both ends to both paths
-  // (measured on the pool's 16-core hosts: narrow 334 ms, both 392 ms, wide 463 ms for c4's 24.8 GB).
+  // The .suf entries are uint64, the table in HBM uint32.  Two ways to the host: "narrow" -- 4 bytes
+  // per entry cross PCIe into small pinned staging buffers (they stay in the host's last level cache)
+  // and host threads widen them into the destination: bound by the host's cores (measured: 334-400 ms
+  // for c4's 24.8 GB with 14 threads; 1025 ms on a host whose cores stream slowly; 8 ranks sharing one
+  // host starve each other); "wide" -- widened on the device, 8 bytes per entry by DMA straight into
+  // a pinned destination: bound by PCIe (463 ms for c4 on one GPU, but it scales with the GPUs).
+  // Default (GTB200_SUF_COPY unset or "auto"): the narrow path starts; after a few milliseconds the
+  // wide path looks at how far it got -- slower than PCIe would be, and the wide path takes chunks from
+  // the other end of the table until the two meet.  GTB200_SUF_COPY = narrow | wide | both force a way.
   const char *mode = getenv("GTB200_SUF_COPY");
   const bool pinned = host_pointer_is_pinned(dst);
-  const bool want_wide = pinned && mode && (strcmp(mode, "wide") == 0 || strcmp(mode, "both") == 0);
-  const bool want_narrow = !(pinned && mode && strcmp(mode, "wide") == 0);
+  const bool m_wide = mode && strcmp(mode, "wide") == 0, m_both = mode && strcmp(mode, "both") == 0;
+  const bool m_narrow = mode && strcmp(mode, "narrow") == 0;
   GTB_TRY(h->hstage.ensure(err));
   const u64 per = h->hstage.chunk / sizeof(u32);
   const u64 nchunks = div_up(count, per);
-  if (!want_wide || nchunks < 4) {
+  const bool want_wide = pinned && !m_narrow && nchunks >= (m_wide || m_both ? 4u : 128u);
+  const bool want_narrow = !(pinned && m_wide);
+  if (!want_wide) {
     GTB_TRY(staged_d2h(h->hstage, h->st, h->vbuf[h->res].as<u32>() + first, dst, count, sizeof(u32), true, err));
     GTB_CUDA(cudaStreamSynchronize(h->st));
     return 0;
@@ -1619,7 +1631,10 @@ int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t 
   ChunkDealer dealer(nchunks);
   ErrBuf err2;
   int rc2 = 0;
-  std::thread wide([&] { rc2 = suftab_wide_chunks(h, h->st2, dst, first, count, per, &dealer, err2); });
+  // auto: 12 ms of grace; PCIe moves about 6.6 G entries/s the wide way -- the narrow path must beat 85 % of it
+  const int grace_ms = (m_wide || m_both) ? 0 : 12;
+  const u64 min_front = (u64) (0.85 * 6.6e9 * 0.012 / (double) per);
+  std::thread wide([&] { rc2 = suftab_wide_chunks(h, h->st2, dst, first, count, per, &dealer, err2, grace_ms, min_front); });
   int rc = 0;
   if (want_narrow)
     rc = staged_d2h(h->hstage, h->st, h->vbuf[h->res].as<u32>() + first, dst, count, sizeof(u32), true, err, &dealer);

@@ -11,7 +11,6 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
-#include <emmintrin.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -75,25 +74,12 @@ struct ChunkDealer {
   explicit ChunkDealer(u64 nchunks) : hi(nchunks) {}
   bool take_front(u64 *k) { std::lock_guard<std::mutex> g(mu); if (lo >= hi) return false; *k = lo++; return true; }
   bool take_back(u64 *k) { std::lock_guard<std::mutex> g(mu); if (lo >= hi) return false; *k = --hi; return true; }
+  u64 front_taken() { std::lock_guard<std::mutex> g(mu); return lo; }
 };
 
-// dst[i] = src[i] for i < n, streaming (the destination is written once and not read here)
-static inline void widen_u32_u64_host(const u32 *src, u64 *dst, u64 n)
-{
-  u64 i = 0;
-  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15u)) { dst[i] = src[i]; i++; }
-  const __m128i z = _mm_setzero_si128();
-  for (; i + 8 <= n; i += 8) {
-    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
-    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 4));
-    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_unpacklo_epi32(a, z));
-    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 2), _mm_unpackhi_epi32(a, z));
-    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_unpacklo_epi32(b, z));
-    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 6), _mm_unpackhi_epi32(b, z));
-  }
-  for (; i < n; i++) dst[i] = src[i];
-  _mm_sfence();
-}
+// dst[i] = src[i] for i < n with non-temporal stores, widest vector unit of the host (gtb_widen.cpp)
+extern "C" void gtb_widen_u32_u64(const uint32_t *src, uint64_t *dst, uint64_t n, int which);
+static inline void widen_u32_u64_host(const u32 *src, u64 *dst, u64 n) { gtb_widen_u32_u64(src, dst, n, 0); }
 
 // Copy `count` elements of `elem` bytes from device memory to host memory through the pinned
 // staging buffers; widen = true turns uint32 elements into uint64 on the way.  All device work

@@ -28,7 +28,8 @@ def test_strong_lookback_library_matches_reference(tmp_path):
     so = str(tmp_path / "libgtb200_strong.so")
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared",
                            "-Xcompiler", "-fPIC", "-DGTB_RS_STRONG", "-o", so,
-                           os.path.join(ROOT, "genometools_b200", "csrc", "gtb_esa.cu")])
+                           os.path.join(ROOT, "genometools_b200", "csrc", "gtb_esa.cu"),
+                           os.path.join(ROOT, "genometools_b200", "csrc", "gtb_widen.cpp")])
     lib = C.CDLL(so)
     lib.gtb_esa_new.restype = C.c_void_p
     lib.gtb_esa_error.restype = C.c_char_p
