@@ -227,6 +227,9 @@ TextSrc<DNA> make_src(gtb_esa *h, u64 klo, u64 khi)
   s.pos0 = 0;
   s.f = h->fmt;
   s.skip_near = false;
+  s.ranges = h->nspecialranges > 0 ? h->ranges.as<u64>() : nullptr;
+  s.nranges = h->nspecialranges;
+  s.hist4 = false;
   return s;
 }
 
@@ -478,9 +481,10 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
       tsrc.keys = tk[tres]; tsrc.vals = tv[tres];
     }
     src.skip_near = true;
+    src.hist4 = h->dna && (h->nspecialranges == 0 || h->ranges.p != nullptr) && getenv("GTB200_NO_HIST4") == nullptr;
     plan_add_bits(plan, f.sh + f.tb, 64);
     GTB_TRY((radix_sort<TextSrc<DNA>, TailSrc>(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err, nt > 0 ? &tsrc : nullptr, nt)));
-    src.skip_near = false;
+    src.skip_near = false; src.hist4 = false;
   } else {
     plan_add_bits(plan, f.lowbit() & ~7, 64);
     if (ext) GTB_TRY(radix_sort(h->rw, st, *ext, extcount, kb, vb, plan, &h->res, &N, err));
@@ -752,10 +756,16 @@ int round_local(gtb_esa *h)
     GTB_TRY(round_sort_apply<DNA>(h, g.tailmask() >> 32, g.m * g.b + g.tb, true));
   } else {
     GTB_TRY(build_ranks<DNA>(h));
+    GTB_TRY(h->sendidx.ensure(sizeof(u32) * h->M, err));       // queue of the partners that need a search
+    unsigned int *qcount = reinterpret_cast<unsigned int *>(h->misc.as<u64>() + 20);
+    GTB_CUDA(cudaMemsetAsync(qcount, 0, sizeof(unsigned int), h->st));
     k_build_dkeys<DNA><<<grid_for(h->M, 256), 256, 0, h->st>>>(make_rankmap<DNA>(h), h->upos[h->cur].as<u32>(),
-        h->ugrp[h->cur].as<u32>(), h->M, hlen, h->dkeys.as<u64>());
+        h->ugrp[h->cur].as<u32>(), h->M, hlen, h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount);
     GTB_LAUNCH_CHECK();
-    h->stats.kernel_launches++;
+    k_build_dkeys_search<DNA><<<grid_for(h->M, 256, 148u * 8u), 256, 0, h->st>>>(make_rankmap<DNA>(h), h->upos[h->cur].as<u32>(),
+        h->ugrp[h->cur].as<u32>(), hlen, h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount);
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches += 2;
     h->depth[h->round + 1] = 2 * hlen;
     GTB_TRY(round_sort_apply<DNA>(h, 0ull, h->bits_lo, false));
   }
@@ -1167,6 +1177,7 @@ int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src)
   h->nspecialranges = src->nspecialranges;
   h->readmode = src->readmode;
   h->words.borrow(src->words); h->bytes.borrow(src->bytes); h->spmask.borrow(src->spmask);
+  h->ranges.borrow(src->ranges);
   h->sepbits.borrow(src->sepbits); h->have_sep = src->have_sep;
   h->counted = false; h->ran = false; h->have_input = true;
   return 0;

@@ -93,6 +93,9 @@ struct TextSrc {
   KeyFmt f;
   bool skip_near;        // positions that meet a special within their m symbols are no items (they are
                          // sorted from a list of their own, k_near_bits / TailSrc)
+  const u64 *ranges;     // the special runs [start, end) ascending (device), for the 4-mer histogram; may be
+  u64 nranges;           // null when there are none
+  bool hist4;            // the digit histograms may be derived from one table of 4-mers (k_hist_4mer)
 
   // filled key of position pos in format g (any m <= 29 for DNA, m*b + tb <= 64)
   __device__ __forceinline__ bool make_key_fmt(u64 pos, u64 &key, const KeyFmt &g) const
@@ -290,11 +293,82 @@ struct RsHistLauncher<TextSrc<false>> {
   }
 };
 
+// ---- all digit histograms of the full keys from ONE table of 4-mers ----------------------------
+// With keys of m = 4k symbols and the tail keys sorted apart (skip_near), digit j of the key of a full
+// position i (no special in [i, i + m)) is the plain 4-mer at i + 4j.  So every digit histogram is the
+// 4-mer table T of the text minus the windows that no full position reaches: for a run [a, b) of regular
+// symbols the full positions are [a, b - m], digit j reads the windows [a + 4j, b - m + 4j] -- the first
+// 4j and the last m - 4 - 4j windows of the run drop out (all of them if the run is shorter than m).
+// One shared-memory atomic per position instead of one per position and digit (5 on c4: 11.1 -> about
+// 3 ms), and no key is built.  ghist row p holds the digit at bit plan.shift[p].
+__global__ void __launch_bounds__(256)
+k_hist_4mer(const u64 *__restrict__ words, const u32 *__restrict__ spmask, u64 n, int npass,
+            unsigned long long *__restrict__ ghist)
+{
+  __shared__ u32 s_h[RS_BINS];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const u64 nchunks = (n + 31) >> 5;
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < nchunks; c += (u64) gridDim.x * blockDim.x) {
+    u64 hi = words[c], lo = words[c + 1];                     // bases 32c .. 32c + 63
+    const u64 mw = (u64) spmask[c] | ((u64) spmask[c + 1] << 32);
+    u64 bad = mw | (mw >> 1) | (mw >> 2) | (mw >> 3);         // a special among the 4 symbols of the window
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+      if (!(bad & 1ull)) atomicAdd(&s_h[(u32) (hi >> 56)], 1u);
+      hi = (hi << 2) | (lo >> 62);
+      lo <<= 2;
+      bad >>= 1;
+    }
+  }
+  __syncthreads();
+  const u32 v = s_h[threadIdx.x];
+  if (v) for (int p = 0; p < npass; p++) atomicAdd(&ghist[p * RS_BINS + threadIdx.x], (unsigned long long) v);
+}
+
+// the windows a digit does not read: one thread per (run of regular symbols, digit)
+__global__ void k_hist_4mer_fix(const u64 *__restrict__ words, const u64 *__restrict__ ranges, u64 nranges, u64 n,
+                                unsigned m, PassPlan plan, unsigned long long *__restrict__ ghist)
+{
+  const u64 total = (nranges + 1) * (u64) plan.npass;
+  for (u64 t = blockIdx.x * (u64) blockDim.x + threadIdx.x; t < total; t += (u64) gridDim.x * blockDim.x) {
+    const u64 k = t / (u64) plan.npass;
+    const int p = (int) (t % (u64) plan.npass);
+    const unsigned j = (unsigned) (64 - plan.shift[p]) / 8u - 1u;     // digit j from the top: symbols 4j .. 4j+3
+    const u64 a = k == 0 ? 0 : ranges[2 * (k - 1) + 1], b = k == nranges ? n : ranges[2 * k];
+    if (b < a + 4) continue;                                   // no window of 4 regular symbols
+    const u64 last = b - 4;                                    // windows a .. last
+    unsigned long long *row = ghist + p * RS_BINS;
+    if (b - a < m) {
+      for (u64 q = a; q <= last; q++) atomicAdd(&row[(u32) (dna_window(words, q) >> 56)], ~0ull);
+    } else {
+      for (u64 q = a; q < a + 4 * j; q++) atomicAdd(&row[(u32) (dna_window(words, q) >> 56)], ~0ull);
+      for (u64 q = b - m + 4 * j + 1; q <= last; q++) atomicAdd(&row[(u32) (dna_window(words, q) >> 56)], ~0ull);
+    }
+  }
+}
+
 template <>
 struct RsHistLauncher<TextSrc<true>> {
   static void launch(const TextSrc<true> &src, u64 nsrc, const PassPlan &plan, unsigned long long *ghist,
                      cudaStream_t st)
   {
+    bool bytes_from_top = src.hist4 && src.skip_near && src.pos0 == 0 && src.klo == 0 && src.khi == ~0ull &&
+                          src.f.m % 4 == 0 && (src.nranges == 0 || src.ranges != nullptr);
+    for (int p = 0; p < plan.npass && bytes_from_top; p++)
+      bytes_from_top = plan.bits[p] == 8 && plan.shift[p] % 8 == 0 && plan.shift[p] >= 64 - 2 * src.f.m;
+    if (bytes_from_top) {                // every digit is a 4-mer of the key's symbols
+      const u64 chunks = (nsrc + 31) >> 5;
+      u64 g = div_up(chunks, 256);
+      if (g > 148ull * 8) g = 148ull * 8;
+      if (g < 1) g = 1;
+      k_hist_4mer<<<(unsigned) g, 256, 0, st>>>(src.words, src.spmask, nsrc, plan.npass, ghist);
+      const u64 fix = (src.nranges + 1) * (u64) plan.npass;
+      u64 g2 = div_up(fix, 128);
+      if (g2 > 148ull * 16) g2 = 148ull * 16;
+      k_hist_4mer_fix<<<(unsigned) g2, 128, 0, st>>>(src.words, src.ranges, src.nranges, nsrc, (unsigned) src.f.m, plan, ghist);
+      return;
+    }
     if (src.pos0 == 0) {                 // the whole text: rolling keys
       const u64 chunks = (nsrc + 31) >> 5;
       u64 g = div_up(chunks, 256);
@@ -345,13 +419,25 @@ struct RankMap {
     const uint4 w = __ldg(rw + (p >> 5));
     trank[w.w + (u32) __popc(w.z & ((1u << (p & 31u)) - 1u))] = r;
   }
-  __device__ u32 get(u64 q) const
+  // the part of a query that is one or two loads: end of text, special, tied.  false: q is an untied
+  // regular suffix -- its rank is its place among the sorted keys (search)
+  __device__ __forceinline__ bool get_fast(u64 q, u32 &r) const
   {
-    if (q >= n) return (u32) n;
+    if (q >= n) { r = (u32) n; return true; }
     const uint4 w = __ldg(rw + (q >> 5));
     const u32 bit = 1u << (q & 31u), below = bit - 1u;
-    if (w.x & bit) return (u32) (nonspecials + w.y + (u32) __popc(w.x & below));
-    if (w.z & bit) return trank[w.w + (u32) __popc(w.z & below)];
+    if (w.x & bit) { r = (u32) (nonspecials + w.y + (u32) __popc(w.x & below)); return true; }
+    if (w.z & bit) { r = trank[w.w + (u32) __popc(w.z & below)]; return true; }
+    return false;
+  }
+  __device__ u32 get(u64 q) const
+  {
+    u32 r;
+    if (get_fast(q, r)) return r;
+    return search(q);
+  }
+  __device__ u32 search(u64 q) const
+  {
     u64 kq;
     src.make_key_fmt(q, kq, src.f);
     u64 lo = 0, hi = N;
@@ -1031,12 +1117,47 @@ k_compact_keys(const u8 *__restrict__ hbits, const u8 *__restrict__ ubits, const
 
 // ---- prefix doubling ---------------------------------------------------------------------
 // key = (group head index, rank of the suffix h positions further)
+// Two kernels: the first answers what takes one or two loads (the partner is special or tied itself:
+// nearly all partners inside a repeat) and queues the rest; the second runs the binary searches of
+// the queued elements with every lane of a warp searching.  (One kernel doing both left 31 lanes of
+// nearly every warp waiting for the few that search: 22 % of the round-0 partners of c4 are untied.)
+__device__ __forceinline__ void queue_append(bool need, u32 c, u32 *__restrict__ queue, unsigned int *qcount)
+{
+  const unsigned m = __ballot_sync(FULL_MASK, need);
+  if (m == 0) return;
+  unsigned base = 0;
+  const unsigned lane = lane_id();
+  if (lane == (unsigned) __ffs(m) - 1u) base = atomicAdd(qcount, (unsigned) __popc(m));
+  base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+  if (need) queue[base + (unsigned) __popc(m & lanemask_lt())] = c;
+}
+
 template <bool DNA>
 __global__ void k_build_dkeys(RankMap<DNA> rm, const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
-                              u64 M, u64 h, u64 *__restrict__ dkeys)
+                              u64 M, u64 h, u64 *__restrict__ dkeys, u32 *__restrict__ queue, unsigned int *qcount)
 {
-  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x)
-    dkeys[c] = ((u64) ugrp[c] << 32) | (u64) rm.get((u64) upos[c] + h);
+  const u64 stride = (u64) gridDim.x * blockDim.x;
+  for (u64 c0 = blockIdx.x * (u64) blockDim.x; c0 < M; c0 += stride) {      // (whole warps stay in the loop)
+    const u64 c = c0 + threadIdx.x;
+    bool need = false;
+    if (c < M) {
+      u32 r;
+      if (rm.get_fast((u64) upos[c] + h, r)) dkeys[c] = ((u64) ugrp[c] << 32) | (u64) r;
+      else need = true;
+    }
+    queue_append(need, (u32) c, queue, qcount);
+  }
+}
+template <bool DNA>
+__global__ void k_build_dkeys_search(RankMap<DNA> rm, const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
+                                     u64 h, u64 *__restrict__ dkeys, const u32 *__restrict__ queue,
+                                     const unsigned int *__restrict__ qcount)
+{
+  const u64 nq = *qcount;
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < nq; i += (u64) gridDim.x * blockDim.x) {
+    const u32 c = queue[i];
+    dkeys[c] = ((u64) ugrp[c] << 32) | (u64) rm.search((u64) upos[c] + h);
+  }
 }
 
 // bitmap of the tied positions

@@ -58,47 +58,90 @@ struct PeerTableDev {
 // key = (group head, rank of the suffix h further); the rank of a position another range owns is
 // read from the owner's rank map in ITS memory.  Special positions are ranked from this range's own
 // rank words (the special bits are the same in every range).
+// which range owns the suffix with filled key kq
+__device__ __forceinline__ int owner_of_key(const u64 *s_first, int nr, u64 kq)
+{
+  int lo = 0, hi = nr - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_first[mid] <= kq) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// Two kernels, as k_build_dkeys: the first answers the partners that are special or tied (one load
+// from the own rank words, for a foreign partner two loads from the owner's memory), the second
+// searches the queued, untied partners in the owner's sorted keys with all lanes of a warp searching.
 template <bool DNA>
 __global__ void k_build_dkeys_peer(RankMap<DNA> rm, const PeerTableDev *__restrict__ pt,
                                    const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
-                                   u64 M, u64 h, u64 *__restrict__ dkeys)
+                                   u64 M, u64 h, u64 *__restrict__ dkeys, u32 *__restrict__ queue, unsigned int *qcount)
 {
   __shared__ u64 s_first[MAX_RANGES];
   const int nr = pt->n, mine = pt->mine;
   for (int i = threadIdx.x; i < nr; i += blockDim.x) s_first[i] = pt->first_key[i];
   __syncthreads();
-  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M; c += (u64) gridDim.x * blockDim.x) {
-    const u64 q = (u64) upos[c] + h;
-    u32 r;
-    if (q >= rm.n) r = (u32) rm.n;
-    else {
-      const uint4 w = __ldg(rm.rw + (q >> 5));
-      const u32 bit = 1u << (q & 31u), below = bit - 1u;
-      if (w.x & bit) r = (u32) (rm.nonspecials + w.y + (u32) __popc(w.x & below));
+  const u64 stride = (u64) gridDim.x * blockDim.x;
+  for (u64 c0 = blockIdx.x * (u64) blockDim.x; c0 < M; c0 += stride) {      // (whole warps stay in the loop)
+    const u64 c = c0 + threadIdx.x;
+    bool need = false;
+    if (c < M) {
+      const u64 q = (u64) upos[c] + h;
+      u32 r = 0;
+      bool have = true;
+      if (q >= rm.n) r = (u32) rm.n;
       else {
-        u64 kq;
-        rm.src.make_key_fmt(q, kq, rm.src.f);
-        int lo = 0, hi = nr - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_first[mid] <= kq) lo = mid; else hi = mid - 1; }
-        if (lo == mine) r = rm.get(q);
+        const uint4 w = __ldg(rm.rw + (q >> 5));
+        const u32 bit = 1u << (q & 31u), below = bit - 1u;
+        if (w.x & bit) r = (u32) (rm.nonspecials + w.y + (u32) __popc(w.x & below));
         else {
-          const PeerMapDev &m = pt->m[lo];
-          const uint4 wo = m.rw[q >> 5];
-          if (wo.z & bit) r = m.trank[wo.w + (u32) __popc(wo.z & below)];
-          else {
-            const u64 code = key_code<DNA>(kq, rm.pl, rm.K, rm.src.f);
-            u64 a = (u64) m.lb[code] - m.sa_offset;
-            u64 b = code == m.own_last ? m.N : (u64) m.lb[code + 1] - m.sa_offset;
-            while (a < b) {
-              const u64 mid = (a + b) >> 1;
-              const u64 km = m.keys[mid];
-              const bool less = km < kq || (km == kq && (u64) m.sa[mid] < q);
-              if (less) a = mid + 1; else b = mid;
-            }
-            r = (u32) (m.sa_offset + a);
+          u64 kq;
+          rm.src.make_key_fmt(q, kq, rm.src.f);
+          const int o = owner_of_key(s_first, nr, kq);
+          if (o == mine) {
+            if (w.z & bit) r = rm.trank[w.w + (u32) __popc(w.z & below)]; else have = false;
+          } else {
+            const PeerMapDev &m = pt->m[o];
+            const uint4 wo = m.rw[q >> 5];
+            if (wo.z & bit) r = m.trank[wo.w + (u32) __popc(wo.z & below)]; else have = false;
           }
         }
       }
+      if (have) dkeys[c] = ((u64) ugrp[c] << 32) | (u64) r;
+      need = !have;
+    }
+    queue_append(need, (u32) c, queue, qcount);
+  }
+}
+
+template <bool DNA>
+__global__ void k_build_dkeys_peer_search(RankMap<DNA> rm, const PeerTableDev *__restrict__ pt,
+                                          const u32 *__restrict__ upos, const u32 *__restrict__ ugrp, u64 h,
+                                          u64 *__restrict__ dkeys, const u32 *__restrict__ queue,
+                                          const unsigned int *__restrict__ qcount)
+{
+  __shared__ u64 s_first[MAX_RANGES];
+  const int nr = pt->n, mine = pt->mine;
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) s_first[i] = pt->first_key[i];
+  __syncthreads();
+  const u64 nq = *qcount;
+  for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < nq; i += (u64) gridDim.x * blockDim.x) {
+    const u32 c = queue[i];
+    const u64 q = (u64) upos[c] + h;
+    u64 kq;
+    rm.src.make_key_fmt(q, kq, rm.src.f);
+    const int o = owner_of_key(s_first, nr, kq);
+    u32 r;
+    if (o == mine) r = rm.search(q);
+    else {
+      const PeerMapDev &m = pt->m[o];
+      const u64 code = key_code<DNA>(kq, rm.pl, rm.K, rm.src.f);
+      u64 a = (u64) m.lb[code] - m.sa_offset;
+      u64 b = code == m.own_last ? m.N : (u64) m.lb[code + 1] - m.sa_offset;
+      while (a < b) {
+        const u64 mid = (a + b) >> 1;
+        const u64 km = m.keys[mid];
+        const bool less = km < kq || (km == kq && (u64) m.sa[mid] < q);
+        if (less) a = mid + 1; else b = mid;
+      }
+      r = (u32) (m.sa_offset + a);
     }
     dkeys[c] = ((u64) ugrp[c] << 32) | (u64) r;
   }

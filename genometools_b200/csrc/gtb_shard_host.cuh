@@ -433,10 +433,18 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
       if (rc == 0 && active && h->M > 0) rc = timed_stage(h, [&]() -> int {
         if (h->round >= 62) { err.set("internal: prefix doubling did not converge"); return -1; }
         PhaseTimer t(h, &h->stats.ms_doubling);
+        GTB_TRY(h->sendidx.ensure(sizeof(u32) * h->M, err));   // queue of the partners that need a search
+        unsigned int *qcount = reinterpret_cast<unsigned int *>(h->misc.as<u64>() + 20);
+        GTB_CUDA(cudaMemsetAsync(qcount, 0, sizeof(unsigned int), st));
         k_build_dkeys_peer<DNA><<<grid_for(h->M, 256), 256, 0, st>>>(make_rankmap<DNA>(h), h->peertab.as<PeerTableDev>(),
-            h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(), h->M, h->depth[h->round], h->dkeys.as<u64>());
+            h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(), h->M, h->depth[h->round], h->dkeys.as<u64>(),
+            h->sendidx.as<u32>(), qcount);
         GTB_LAUNCH_CHECK();
-        h->stats.kernel_launches++;
+        k_build_dkeys_peer_search<DNA><<<grid_for(h->M, 256, 148u * 8u), 256, 0, st>>>(make_rankmap<DNA>(h),
+            h->peertab.as<PeerTableDev>(), h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(), h->depth[h->round],
+            h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount);
+        GTB_LAUNCH_CHECK();
+        h->stats.kernel_launches += 2;
         GTB_CUDA(cudaStreamSynchronize(st));
         t.stop();
         return 0;
