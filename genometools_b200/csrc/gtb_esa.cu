@@ -148,6 +148,10 @@ struct gtb_esa {
   std::map<std::pair<int, int>, PeerImport> imports;      // (rank, slot) -> mapping on this GPU
   struct PendingFd { FdMsg msg; int fd; };
   std::vector<PendingFd> pending_fds;                      // descriptors received before they were asked for
+  std::thread ipc_thread;                                  // receives descriptors whenever they arrive: a sender
+  std::mutex ipc_mu;                                       // never waits for this range to reach a receive call
+  std::condition_variable ipc_cv;
+  std::atomic<bool> ipc_stop{false};
   int ipc_sock = -1;
   std::string ipc_key;
   u64 sent_id[8] = {0, 0, 0, 0, 0, 0, 0, 0};              // allocation of each shareable buffer the peers hold
@@ -1061,6 +1065,7 @@ void gtb_esa_delete(gtb_esa *h)
   for (DevBuf *b : all) b->release();
   for (auto &m : h->imports) vmm_free(m.second.ptr, m.second.mh, m.second.size);
   h->imports.clear();
+  stop_ipc_receiver(h);
   for (auto &f : h->pending_fds) close(f.fd);
   h->pending_fds.clear();
   if (h->ipc_sock >= 0) close(h->ipc_sock);

@@ -68,15 +68,26 @@ int slot_of(gtb_esa *h, const DevBuf *b)
   return -1;
 }
 
-// descriptors that arrived: keep them until the mapping is asked for
-void drain_fds(gtb_esa *h, bool block_once)
+// descriptors are received by a thread of their own and kept until the mapping is asked for
+void ipc_receiver(gtb_esa *h)
 {
-  for (bool first = true;; first = false) {
-    if (!(block_once && first) && !fd_sock_readable(h->ipc_sock)) return;
+  while (!h->ipc_stop.load()) {
+    struct pollfd p; p.fd = h->ipc_sock; p.events = POLLIN; p.revents = 0;
+    const int r = poll(&p, 1, 100);
+    if (r <= 0 || !(p.revents & POLLIN)) continue;
     gtb_esa::PendingFd pf;
     ErrBuf e2;
-    if (fd_recv(h->ipc_sock, &pf.msg, &pf.fd, e2) != 0) return;
-    h->pending_fds.push_back(pf);
+    if (fd_recv(h->ipc_sock, &pf.msg, &pf.fd, e2) != 0) continue;
+    { std::lock_guard<std::mutex> lk(h->ipc_mu); h->pending_fds.push_back(pf); }
+    h->ipc_cv.notify_all();
+  }
+}
+void stop_ipc_receiver(gtb_esa *h)
+{
+  if (h->ipc_thread.joinable()) {
+    h->ipc_stop.store(true);
+    h->ipc_thread.join();
+    h->ipc_stop.store(false);
   }
 }
 
@@ -90,11 +101,10 @@ int send_fd_everywhere(gtb_esa *h, const ShardComm &c, int slot, const DevBuf &b
   for (int r = 0; r < c.world && rc == 0; r++) {
     if (r == c.me) continue;
     for (int waited = 0;; waited++) {
-      drain_fds(h, false);                // (everybody sends before anybody asks: keep the queues short)
       rc = fd_send(h->ipc_sock, h->ipc_key.c_str(), r, m, fd, err);
       if (rc != 1) break;
-      if (waited > 60000) { err.set("code range %d does not take memory descriptors", r); rc = -1; break; }
-      usleep(1000);
+      if (waited > 120000) { err.set("code range %d does not take memory descriptors", r); rc = -1; break; }
+      usleep(500);                         // (its receiver thread empties the queue)
     }
   }
   close(fd);
@@ -149,21 +159,25 @@ int resolve_ptr(gtb_esa *h, const ShardComm &c, const PeerPtr &p, int peer, void
   if (it != h->imports.end() && it->second.alloc_id == p.alloc_id) { *out = it->second.ptr; return 0; }
   if (it != h->imports.end()) { vmm_free(it->second.ptr, it->second.mh, it->second.size); h->imports.erase(it); }
   int fd = -1;
-  for (int tries = 0; fd < 0; tries++) {
-    for (size_t i = 0; i < h->pending_fds.size(); i++) {
-      const FdMsg &m = h->pending_fds[i].msg;
-      if (m.from == peer && m.slot == p.slot) {
-        if (m.alloc_id == p.alloc_id) fd = h->pending_fds[i].fd; else close(h->pending_fds[i].fd);   // (stale: reallocated since)
-        h->pending_fds.erase(h->pending_fds.begin() + (long) i);
-        i--;
-        if (fd >= 0) break;
+  {
+    std::unique_lock<std::mutex> lk(h->ipc_mu);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(120);
+    for (;;) {
+      for (size_t i = 0; i < h->pending_fds.size(); i++) {
+        const FdMsg &m = h->pending_fds[i].msg;
+        if (m.from == peer && m.slot == p.slot) {
+          if (m.alloc_id == p.alloc_id) fd = h->pending_fds[i].fd; else close(h->pending_fds[i].fd);   // (stale: reallocated since)
+          h->pending_fds.erase(h->pending_fds.begin() + (long) i);
+          i--;
+          if (fd >= 0) break;
+        }
+      }
+      if (fd >= 0) break;
+      if (h->ipc_cv.wait_until(lk, deadline) == std::cv_status::timeout) {
+        err.set("timed out waiting for the descriptor of buffer %d of code range %d", p.slot, peer);
+        return -1;
       }
     }
-    if (fd >= 0) break;
-    if (tries > 4096) { err.set("the descriptor of buffer %d of code range %d never arrived", p.slot, peer); return -1; }
-    const size_t before = h->pending_fds.size();
-    drain_fds(h, true);                   // blocks (with the socket's timeout) for the next descriptor
-    if (h->pending_fds.size() == before) { err.set("timed out waiting for the descriptor of buffer %d of code range %d", p.slot, peer); return -1; }
   }
   gtb_esa::PeerImport imp;
   imp.alloc_id = p.alloc_id; imp.size = (size_t) p.size; imp.ptr = nullptr; imp.mh = 0;
@@ -187,12 +201,14 @@ int enter_ipc_mode(gtb_esa *h, const ShardComm &c)
   if (!k) k = "job";
   char name[96];
   snprintf(name, sizeof name, "%.40s-w%d", k, c.world);
-  if (h->ipc_sock >= 0 && h->ipc_key != name) { close(h->ipc_sock); h->ipc_sock = -1; }
+  if (h->ipc_sock >= 0 && h->ipc_key != name) { stop_ipc_receiver(h); close(h->ipc_sock); h->ipc_sock = -1; }
   if (h->ipc_sock < 0) {
     h->ipc_key = name;
+    stop_ipc_receiver(h);
     h->ipc_sock = fd_sock_open(name, c.me, err);
     if (h->ipc_sock < 0) return -1;
     for (int i = 0; i < 8; i++) h->sent_id[i] = 0;
+    h->ipc_thread = std::thread(ipc_receiver, h);
   }
   return 0;
 }
