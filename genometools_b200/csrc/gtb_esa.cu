@@ -220,6 +220,30 @@ int device_scan_u32(gtb_esa *h, const u32 *in, u32 *out, u64 count, int popc_mod
   return 0;
 }
 
+// exclusive sum of a[] and exclusive running maximum of b[] over the tiles, in place; total -> misc[0]
+int scan_tiles_sum_max(gtb_esa *h, u32 *a, u32 *b, u64 ntiles)
+{
+  ErrBuf &err = h->err;
+  GTB_TRY(h->misc.ensure(256, err));
+  if (ntiles <= 4ull * STM_BLOCK) {
+    k_scan_tiles_sum_max<<<1, 1024, 0, h->st>>>(a, b, ntiles, h->misc.as<u64>());
+    GTB_LAUNCH_CHECK();
+    h->stats.kernel_launches++;
+    return 0;
+  }
+  const u64 nblk = div_up(ntiles, STM_BLOCK);
+  GTB_TRY(h->scantmp.ensure(sizeof(u32) * 2 * nblk + 64, err));
+  u32 *bs = h->scantmp.as<u32>(), *bm = bs + nblk;
+  k_scan_tiles_blocks<<<(unsigned) nblk, 1024, 0, h->st>>>(a, b, ntiles, bs, bm, 0);
+  GTB_LAUNCH_CHECK();
+  k_scan_tiles_sum_max<<<1, 1024, 0, h->st>>>(bs, bm, nblk, h->misc.as<u64>());
+  GTB_LAUNCH_CHECK();
+  k_scan_tiles_blocks<<<(unsigned) nblk, 1024, 0, h->st>>>(a, b, ntiles, bs, bm, 1);
+  GTB_LAUNCH_CHECK();
+  h->stats.kernel_launches += 3;
+  return 0;
+}
+
 template <bool DNA>
 TextSrc<DNA> make_src(gtb_esa *h, u64 klo, u64 khi)
 {
@@ -375,8 +399,11 @@ template <bool DNA> int round_local(gtb_esa *h);
 // ---- stage 1: bucket table, first-level sort, analysis, special tail, compaction of ties ----
 // ext != null: the (key, position) pairs of this range already lie in device memory in text
 // order (they were generated slice-wise on several GPUs and exchanged): no text scan here
+// ext_tail: the pairs of `ext` whose keys carry a tail, sorted by that field (text order inside): the
+// first-level sort then skips them in `ext` and runs over the symbol digits only
 template <bool DNA>
-int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 extcount = 0)
+int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 extcount = 0,
+                const TailSrc *ext_tail = nullptr, u64 ntail = 0)
 {
   ErrBuf &err = h->err;
   gtb_stats &S = h->stats;
@@ -489,6 +516,10 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
     plan_add_bits(plan, f.sh + f.tb, 64);
     GTB_TRY((radix_sort<TextSrc<DNA>, TailSrc>(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err, nt > 0 ? &tsrc : nullptr, nt)));
     src.skip_near = false; src.hist4 = false;
+  } else if (ext && ext_tail) {
+    plan_add_bits(plan, f.sh + f.tb, 64);
+    PairSrcNoTail nt{ext->keys, ext->vals, f.tailmask()};
+    GTB_TRY((radix_sort<PairSrcNoTail, TailSrc>(h->rw, st, nt, extcount, kb, vb, plan, &h->res, &N, err, ntail > 0 ? ext_tail : nullptr, ntail)));
   } else {
     plan_add_bits(plan, f.lowbit() & ~7, 64);
     if (ext) GTB_TRY(radix_sort(h->rw, st, *ext, extcount, kb, vb, plan, &h->res, &N, err));
@@ -533,12 +564,10 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
             h->tile_a.as<u32>(), h->tile_b.as<u32>(), dstats, 0, 0ull, nullptr, 0, nullptr, nullptr, nullptr,
             h->hbits.as<u8>(), h->ubits.as<u8>(), 0, 0, 0);
       GTB_LAUNCH_CHECK();
-      k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles,
-                                               h->misc.as<u64>());
-      GTB_LAUNCH_CHECK();
+      GTB_TRY(scan_tiles_sum_max(h, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles));
       k_find_longest<DNA><<<1, 1, 0, st>>>(src, keys, N, h->sa_offset, dstats);
       GTB_LAUNCH_CHECK();
-      S.kernel_launches += 3;
+      S.kernel_launches += 2;
       GTB_CUDA(cudaMemcpyAsync(&M0, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
       GTB_CUDA(cudaStreamSynchronize(st));
     }
@@ -607,8 +636,8 @@ int compact_ties(gtb_esa *h)
 {
   ErrBuf &err = h->err;
   if (h->N > 0) {
-    k_compact_keys<<<(unsigned) h->atiles, AN_NT, 0, h->st>>>(h->hbits.as<u8>(), h->ubits.as<u8>(),
-        h->vbuf[h->res].as<u32>(), h->N, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->uidx[0].as<u32>(),
+    k_compact_keys<<<grid_for(h->atiles, 1, 148u * 8u), AN_NT, 0, h->st>>>(h->hbits.as<u8>(), h->ubits.as<u8>(),
+        h->vbuf[h->res].as<u32>(), h->N, h->tile_a.as<u32>(), h->tile_b.as<u32>(), h->atiles, h->M0, h->uidx[0].as<u32>(),
         h->upos[0].as<u32>(), h->ugrp[0].as<u32>());
     GTB_LAUNCH_CHECK();
     h->stats.kernel_launches++;
@@ -719,8 +748,7 @@ int round_sort_apply(gtb_esa *h, u64 tm, int keybits, bool text_round)
   GTB_TRY(h->tile_d.ensure(sizeof(u32) * (dt + 1), err));
   k_analyze_dkeys<<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], M, tm, h->tile_c.as<u32>(), h->tile_d.as<u32>());
   GTB_LAUNCH_CHECK();
-  k_scan_tiles_sum_max<<<1, 1024, 0, st>>>(h->tile_c.as<u32>(), h->tile_d.as<u32>(), dt, h->misc.as<u64>());
-  GTB_LAUNCH_CHECK();
+  GTB_TRY(scan_tiles_sum_max(h, h->tile_c.as<u32>(), h->tile_d.as<u32>(), dt));
   k_apply_dkeys<DNA><<<(unsigned) dt, AN_NT, 0, st>>>(kk[r2], vv[r2], h->uidx[cur].as<u32>(), M, tm,
       h->tile_c.as<u32>(), h->tile_d.as<u32>(), h->vbuf[h->res].as<u32>(),
       make_rankmap<DNA>(h), h->isa_built ? 1 : 0,
@@ -728,7 +756,7 @@ int round_sort_apply(gtb_esa *h, u64 tm, int keybits, bool text_round)
       h->uidx[cur ^ 1].as<u32>(), h->upos[cur ^ 1].as<u32>(), h->ugrp[cur ^ 1].as<u32>(),
       h->dstats.as<DevStats>());
   GTB_LAUNCH_CHECK();
-  S.kernel_launches += 3;
+  S.kernel_launches += 2;
   u64 Mnext = 0;
   GTB_CUDA(cudaMemcpyAsync(&Mnext, h->misc.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
   GTB_CUDA(cudaStreamSynchronize(st));

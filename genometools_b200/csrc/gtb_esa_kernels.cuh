@@ -1082,36 +1082,86 @@ k_scan_tiles_sum_max(u32 *tile_unres, u32 *tile_lasthead, u64 ntiles, u64 *total
   if (threadIdx.x == 0 && total_out) *total_out = grand;
 }
 
+// the same over many tiles (one tile per 2048 suffixes: 1.5 M tiles on c4 take a single block 2 ms):
+// blocks of 8192 tiles.  mode 0: the sum and the maximum of every block; then the single-block kernel
+// above scans those (exclusive sum / exclusive running maximum per block); mode 1: every block scans
+// its own tiles in place, carried in by its block's values.
+constexpr int STM_BLOCK = 1024 * 8;
+__global__ void __launch_bounds__(1024)
+k_scan_tiles_blocks(u32 *tile_unres, u32 *tile_lasthead, u64 ntiles, u32 *blk_sum, u32 *blk_max, int mode)
+{
+  constexpr int PT = 8;
+  __shared__ u32 scratch[1024 / 32 + 1];
+  __shared__ u32 s_wlast[32];
+  const u64 i0 = (u64) blockIdx.x * STM_BLOCK + (u64) threadIdx.x * PT;
+  u32 v[PT], h[PT], tsum = 0, tmax = 0;
+#pragma unroll
+  for (int q = 0; q < PT; q++) {
+    v[q] = i0 + q < ntiles ? tile_unres[i0 + q] : 0u;
+    h[q] = i0 + q < ntiles ? tile_lasthead[i0 + q] : 0u;
+    tsum += v[q];
+    tmax = h[q] > tmax ? h[q] : tmax;
+  }
+  u32 total;
+  u32 ex = block_exclusive_sum<1024, u32>(tsum, scratch, &total);
+  const u32 incl = block_inclusive_max<1024, u32>(tmax, scratch);
+  if (mode == 0) {
+    if (threadIdx.x == 1023) { blk_sum[blockIdx.x] = total; blk_max[blockIdx.x] = incl; }
+    return;
+  }
+  u32 prev = __shfl_up_sync(FULL_MASK, incl, 1);
+  if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (lane_id() == 0) prev = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
+  const u32 cs = blk_sum[blockIdx.x], cm = blk_max[blockIdx.x];
+  ex += cs;
+  prev = prev > cm ? prev : cm;
+#pragma unroll
+  for (int q = 0; q < PT; q++) {
+    if (i0 + q < ntiles) { tile_unres[i0 + q] = ex; tile_lasthead[i0 + q] = prev; }
+    ex += v[q];
+    prev = h[q] > prev ? h[q] : prev;
+  }
+}
+
 // pass 2: compact the unresolved elements (SA index, position, group head) from the flag
 // bytes of pass 1 -- the keys are not read again
 __global__ void __launch_bounds__(AN_NT)
 k_compact_keys(const u8 *__restrict__ hbits, const u8 *__restrict__ ubits, const u32 *__restrict__ pos, u64 N,
-               const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore,
+               const u32 *__restrict__ tile_off, const u32 *__restrict__ tile_headbefore, u64 ntiles, u64 M0,
                u32 *__restrict__ uidx, u32 *__restrict__ upos, u32 *__restrict__ ugrp)
 {
   __shared__ u32 scratch[AN_NT / 32 + 1];
-  const u64 base = (u64) blockIdx.x * AN_TILE + (u64) threadIdx.x * AN_IPT;
-  const u32 hb8 = base < N ? hbits[base >> 3] : 0u, ub8 = base < N ? ubits[base >> 3] : 0u;
-  const u32 unres = (u32) __popc(ub8);
-  const u32 lasthead = hb8 ? (u32) base + (31u - (u32) __clz(hb8)) + 1u : 0u;
-  u32 total;
-  u32 off = block_exclusive_sum<AN_NT, u32>(unres, scratch, &total) + tile_off[blockIdx.x];
-  if (total == 0) return;                         // (uniform) nothing tied in this tile
-  // head index carried into this thread = max over previous threads / tiles
-  u32 incl = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
-  u32 carry = __shfl_up_sync(FULL_MASK, incl, 1);
   __shared__ u32 s_wlast[AN_NT / 32];
-  if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  if (lane_id() == 0) carry = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
-  const u32 hb = tile_headbefore[blockIdx.x];
-  carry = carry > hb ? carry : hb;          // "+1" encoded index of the current group head
-  if (!ub8) return;
+  // a block walks over tiles; most hold nothing tied and cost two loads (one block per tile was bound
+  // by block scheduling: 1.5 M blocks on c4)
+  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const u32 toff = tile_off[tile];
+    const u64 tend = tile + 1 < ntiles ? (u64) tile_off[tile + 1] : M0;
+    if (tend == (u64) toff) continue;               // (uniform) nothing tied in this tile
+    const u64 base = tile * AN_TILE + (u64) threadIdx.x * AN_IPT;
+    const u32 hb8 = base < N ? hbits[base >> 3] : 0u, ub8 = base < N ? ubits[base >> 3] : 0u;
+    const u32 unres = (u32) __popc(ub8);
+    const u32 lasthead = hb8 ? (u32) base + (31u - (u32) __clz(hb8)) + 1u : 0u;
+    u32 total;
+    u32 off = block_exclusive_sum<AN_NT, u32>(unres, scratch, &total) + toff;
+    // head index carried into this thread = max over previous threads / tiles
+    u32 incl = block_inclusive_max<AN_NT, u32>(lasthead, scratch);
+    u32 carry = __shfl_up_sync(FULL_MASK, incl, 1);
+    if (lane_id() == 31) s_wlast[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (lane_id() == 0) carry = threadIdx.x ? s_wlast[(threadIdx.x >> 5) - 1] : 0u;
+    const u32 hb = tile_headbefore[tile];
+    carry = carry > hb ? carry : hb;          // "+1" encoded index of the current group head
+    if (ub8) {
 #pragma unroll
-  for (int i = 0; i < AN_IPT; i++) {
-    const u64 j = base + i;
-    if ((hb8 >> i) & 1u) carry = (u32) j + 1u;
-    if ((ub8 >> i) & 1u) { uidx[off] = (u32) j; upos[off] = pos[j]; ugrp[off] = carry - 1u; off++; }
+      for (int i = 0; i < AN_IPT; i++) {
+        const u64 j = base + i;
+        if ((hb8 >> i) & 1u) carry = (u32) j + 1u;
+        if ((ub8 >> i) & 1u) { uidx[off] = (u32) j; upos[off] = pos[j]; ugrp[off] = carry - 1u; off++; }
+      }
+    }
+    __syncthreads();                           // (s_wlast is reused by the next tile)
   }
 }
 
@@ -1611,15 +1661,45 @@ __global__ void k_split_ranges(const u32 *__restrict__ lb, u64 ncodes, unsigned 
   *nout = keep;
 }
 
-// keys of a list of (valid, non-special) text positions
+// keys of a list of (valid, non-special) text positions; tailbits (optional): bit i of word w = the key
+// of element 32w + i carries a tail field
 template <bool DNA>
 __global__ void k_keys_from_positions(TextSrc<DNA> src, const u32 *__restrict__ pos, u64 count,
-                                      u64 *__restrict__ keys)
+                                      u64 *__restrict__ keys, u32 *__restrict__ tailbits = nullptr)
+{
+  const u64 tm = src.f.tailmask();
+  for (u64 i0 = blockIdx.x * (u64) blockDim.x; i0 < count; i0 += (u64) gridDim.x * blockDim.x) {   // (whole warps)
+    const u64 i = i0 + threadIdx.x;
+    u64 k = 0;
+    if (i < count) {
+      src.make_key_fmt(pos[i], k, src.f);
+      keys[i] = k;
+    }
+    if (tailbits) {
+      const unsigned b = __ballot_sync(FULL_MASK, i < count && (k & tm) != 0);
+      if (lane_id() == 0 && i < count) tailbits[i >> 5] = b;
+    }
+  }
+}
+
+// pairs already in memory without the keys that carry a tail (those are sorted apart, TailSrc)
+struct PairSrcNoTail {
+  static constexpr bool ALWAYS_VALID = false;
+  static constexpr bool BLOCKED_GEN = false;
+  const u64 *keys;
+  const u32 *vals;
+  u64 tailmask;
+  __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
+  { k = keys[idx]; return (k & tailmask) == 0; }
+  __device__ __forceinline__ u32 load_val(u64 idx) const { return vals[idx]; }
+};
+
+__global__ void k_gather_pairs(const u32 *__restrict__ idx, u64 count, const u64 *__restrict__ keys,
+                               const u32 *__restrict__ vals, u64 *__restrict__ okeys, u32 *__restrict__ ovals)
 {
   for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x) {
-    u64 k = 0;
-    src.make_key_fmt(pos[i], k, src.f);
-    keys[i] = k;
+    const u32 j = idx[i];
+    okeys[i] = keys[j]; ovals[i] = vals[j];
   }
 }
 

@@ -28,6 +28,7 @@
 // gt_radixsort_inplace_GtUwordPair (/root/reference/src/core/radix_sort.h:107).
 #pragma once
 #include <atomic>
+#include <type_traits>
 #include "gtb_common.cuh"
 
 namespace gtb {
@@ -42,9 +43,12 @@ constexpr int RS_MAXPASS = 8;
 // (Measured on B200 with tools/rs_bench.cu: match.any.sync is slower than the ballot
 // loop for 8-bit digits, shared-memory atomics cost 2 cycles per active lane on the
 // LSU and lose against load + leader store -- neither is kept.)
-template <int NT_, int IPT_, int MINB_, bool VAL_EARLY_, int LB_ = 4>
+template <int NT_, int IPT_, int MINB_, bool VAL_EARLY_, int LB_ = 4, int PF_ = 0>
 struct RsCfg {
   static constexpr int NT = NT_, IPT = IPT_, MINB = MINB_, TILE = NT_ * IPT_, WARPS = NT_ / 32, LB = LB_;
+  // PF > 0: a CTA asks L2 for the pairs of the tile PF tickets ahead (one 128-byte line per thread) --
+  // the tile some CTA will load about one tile time later
+  static constexpr int PF = PF_;
   static constexpr bool VAL_EARLY = VAL_EARLY_;
   static_assert(NT_ >= RS_BINS && NT_ % 32 == 0, "one thread per bin needed");
   static_assert(IPT_ * 32 < 4096, "warp-local ranks are kept in 12 bits");
@@ -93,12 +97,16 @@ constexpr u64 RS_INVALID_KEY = ~0ull;
 struct PairSrc {                 // pairs already in memory
   static constexpr bool ALWAYS_VALID = true;
   static constexpr bool BLOCKED_GEN = false;
+  static constexpr bool IN_MEMORY = true;
   const u64 *keys;
   const u32 *vals;
   __device__ __forceinline__ bool load_key(u64 idx, u64 &k) const
   { k = keys[idx]; return true; }
   __device__ __forceinline__ u32 load_val(u64 idx) const { return vals[idx]; }
 };
+
+template <class S, class = void> struct rs_src_in_memory { static constexpr bool value = false; };
+template <class S> struct rs_src_in_memory<S, typename std::enable_if<S::IN_MEMORY>::type> { static constexpr bool value = true; };
 
 // ---- histogram of all digits in one read ---------------------------------------
 constexpr int RH_NT = 256, RH_IPT = 16, RH_TILE = RH_NT * RH_IPT;
@@ -495,6 +503,15 @@ rs_onesweep_kernel(Src src, u64 *__restrict__ okeys, u32 *__restrict__ ovals, u6
   // number continues (look-back across both), the items are counted from the launch's own source
   const u64 tile = s_ticket;
   const u64 base = (tile - tile_offset) * (u64) TILE;
+  if constexpr (Cfg::PF > 0 && rs_src_in_memory<Src>::value) {
+    const u64 pbase = base + (u64) Cfg::PF * TILE;
+    if (pbase + TILE <= N) {
+      const char *pk = reinterpret_cast<const char *>(src.keys + pbase) + 128u * threadIdx.x;
+      if (128u * threadIdx.x < sizeof(u64) * TILE) asm volatile("prefetch.global.L2 [%0];" :: "l"(pk));
+      const char *pv = reinterpret_cast<const char *>(src.vals + pbase) + 128u * threadIdx.x;
+      if (128u * threadIdx.x < sizeof(u32) * TILE) asm volatile("prefetch.global.L2 [%0];" :: "l"(pv));
+    }
+  }
   const u32 count = (N - base) < (u64) TILE ? (u32) (N - base) : (u32) TILE;
   if constexpr (Src::ALWAYS_VALID) {
     if (count == (u32) TILE) {

@@ -381,15 +381,55 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
     rc = 0;
     if (active) {
       rc = timed_stage(h, [&]() -> int {
+        // (as in the single-range sort: when tails are rare the keys that carry one are sorted apart and
+        //  the first-level sort runs over the symbol digits only)
+        const bool tail_last = DNA && received > 0 && fmt_tail_digit_alone(h->fmt) && h->opt_tail_last != 0 &&
+                               (tails_rare(h) || h->opt_tail_last == 1);
+        const u64 nw = (received + 31) >> 5;
+        if (tail_last) GTB_TRY(h->nearbits.ensure(sizeof(u32) * (nw + 2), err));
         if (received > 0) {
           PhaseTimer t(h, &h->ext_ms_keygen);
-          k_keys_from_positions<DNA><<<grid_for(received, 256), 256, 0, st>>>(make_src<DNA>(h, 0, ~0ull), h->vbuf[1].as<u32>(), received, h->kbuf[1].as<u64>());
+          k_keys_from_positions<DNA><<<grid_for(received, 256), 256, 0, st>>>(make_src<DNA>(h, 0, ~0ull), h->vbuf[1].as<u32>(), received,
+              h->kbuf[1].as<u64>(), tail_last ? h->nearbits.as<u32>() : nullptr);
           GTB_LAUNCH_CHECK();
           h->stats.kernel_launches++;
           t.stop();
         }
         PairSrc ext{h->kbuf[1].as<u64>(), h->vbuf[1].as<u32>()};
-        return stage_begin<DNA>(h, flags, &ext, received);
+        if (!tail_last) return stage_begin<DNA>(h, flags, &ext, received);
+        u64 nt = 0;
+        u32 *tileoff = nullptr;
+        GTB_TRY(device_scan_u32(h, h->nearbits.as<u32>(), nullptr, nw, 1, &tileoff, &nt));
+        u64 klo, khi;
+        code_range_to_keys(h, &klo, &khi);
+        TailSrc tsrc{nullptr, nullptr, klo, khi};
+        if (nt > 0) {
+          GTB_TRY(h->misc.ensure(256, err));
+          GTB_TRY(h->sendidx.ensure(sizeof(u32) * nt, err));
+          for (int i = 0; i < 2; i++) {
+            GTB_TRY(h->tailkeys[i].ensure(sizeof(u64) * nt, err));
+            GTB_TRY(h->tailpos[i].ensure(sizeof(u32) * nt, err));
+          }
+          // list indices of the tail keys ascending (= text order), their pairs, then stably by the tail
+          k_emit_special_tail<<<(unsigned) div_up(nw, SC_TILE), SC_NT, 0, st>>>(h->nearbits.as<u32>(), nw, received, tileoff,
+              h->sendidx.as<u32>(), nullptr, 0, reinterpret_cast<unsigned long long *>(h->misc.as<u64>() + 24));
+          GTB_LAUNCH_CHECK();
+          k_gather_pairs<<<grid_for(nt, 256), 256, 0, st>>>(h->sendidx.as<u32>(), nt, ext.keys, ext.vals,
+                                                            h->tailkeys[1].as<u64>(), h->tailpos[1].as<u32>());
+          GTB_LAUNCH_CHECK();
+          h->stats.kernel_launches += 2;
+          PassPlan tp; tp.npass = 0; tp.padded = false;
+          plan_add_bits(tp, h->fmt.sh, h->fmt.sh + h->fmt.tb);
+          PairSrc ps{h->tailkeys[1].as<u64>(), h->tailpos[1].as<u32>()};
+          u64 *tk[2] = {h->tailkeys[0].as<u64>(), h->tailkeys[1].as<u64>()};
+          u32 *tv[2] = {h->tailpos[0].as<u32>(), h->tailpos[1].as<u32>()};
+          int tres = 0; u64 tout = 0;
+          h->rw.passes = 0; h->rw.pairs_moved = 0; h->rw.launches = 0;
+          GTB_TRY(radix_sort(h->rw, st, ps, nt, tk, tv, tp, &tres, &tout, err));
+          if (tout != nt) { err.set("internal: the tail keys lost elements"); return -1; }
+          tsrc.keys = tk[tres]; tsrc.vals = tv[tres];
+        }
+        return stage_begin<DNA>(h, flags, &ext, received, &tsrc, nt);
       });
     } else finish_empty(h, flags);
   }

@@ -160,3 +160,24 @@ def test_group_repeated_runs_on_one_group():
                 assert h4[i] == mixhash(np.frombuffer(im[ext], dtype=dt)), (seed, n, ext)
     finally:
         lib.gtb_group_delete(g)
+
+
+@pytest.mark.parametrize("m,scan", [(16, "slice"), (20, "slice"), (24, "filter"), (20, "filter")])
+def test_group_tail_keys_sorted_apart(monkeypatch, m, scan):
+    """the first-level sort without the tail pass inside a sharded job -- the position-sharded scan (the
+    owner splits the tail keys off the pairs it received) and the filtered scan of the whole text --
+    forced on inputs full of specials"""
+    monkeypatch.setenv("GTB200_KEY_SYMBOLS", str(m))
+    monkeypatch.setenv("GTB200_TAIL_LAST", "1")
+    monkeypatch.setenv("GTB200_SHARD_SCAN", scan)
+    cases = [("reads", synth.reads(700, 60, 7, p_n=0.01), 4),
+             ("repeats", synth.repeats_dna(90_000, 5, unit=2500, copies=7, exact_len=1200, exact_copies=3, nruns=6), 5),
+             ("polyT_N", np.concatenate([np.full(3000, 3, np.uint8), synth.random_dna(2000, 3, p_n=0.02),
+                                         np.full(2500, 3, np.uint8), [254], np.full(700, 3, np.uint8)]).astype(np.uint8), 3)]
+    for name, sym, pl in cases:
+        o = eo.esa(sym, 4, pl)
+        im = eo.file_images(o)
+        for nranges in (2, 3, 5):
+            got = images(build_esa(encode_symbols(sym, 4), pl, devices=[0] * nranges))
+            for ext in ("bck", "suf", "lcp", "llv"):
+                assert got[ext] == im[ext], (name, m, scan, nranges, ext)

@@ -73,7 +73,7 @@ static Result run_cfg(const char *name, const std::vector<u64> &hk, int reps, bo
   for (int r = 0; r < reps + 1; r++) {
     rw.ms_radix = 0; rw.passes = 0;
     PairSrc ps{kin, vin};
-    if (radix_sort<PairSrc, Cfg>(rw, st, ps, N, kb, vb, plan, &res, &nout, err)) {
+    if (radix_sort<PairSrc, PairSrc, Cfg>(rw, st, ps, N, kb, vb, plan, &res, &nout, err)) {
       printf("%s: %s\n", name, err.msg); R.ok = false; break;
     }
     if (r > 0 && rw.passes) best = std::min(best, (double) rw.ms_radix / rw.passes);
@@ -139,6 +139,10 @@ int main(int argc, char **argv)
       RUN(256, 16, 3, false, 4);
       RUN(256, 16, 4, false, 4);
       RUN(384, 16, 2, false, 4);
+      RUN(384, 16, 2, false, 4, 296);    // + L2 prefetch of the tile one wave of CTAs ahead
+      RUN(384, 16, 2, false, 4, 148);
+      RUN(384, 16, 2, false, 4, 592);
+      RUN(384, 16, 2, false, 6, 296);
       RUN(512, 12, 2, false, 4);
       RUN(512, 16, 2, false, 4);
       RUN(512, 16, 2, false, 2);
