@@ -10,6 +10,12 @@
 #include <stdlib.h>
 
 int gt_suffixerator(int argc, const char **argv, GtError *err);
+#ifdef B200_REFERENCE_TOOLS
+/* the binary that carries gt_sfxiterator_b200.o: the reference's OWN tools, unchanged, on top of the
+   B200 Sfxiterator -- `packedindex mkindex` (src/tools/gt_packedindex.c:33-36) and, as a cross-check of
+   the iterator, the reference's suffixerator driver (src/match/sfx-run.c:719) */
+#include "match/sfx-run.h"
+#endif
 
 int main(int argc, char **argv)
 {
@@ -23,15 +29,26 @@ int main(int argc, char **argv)
     argv[2] = argv[0];
     argv += 2; argc -= 2;
   }
+#ifdef B200_REFERENCE_TOOLS
+  if (argc < 2 || (strcmp(argv[1], "suffixerator") != 0 && strcmp(argv[1], "packedindex_mkindex") != 0)) {
+    fprintf(stderr, "usage: %s [-j N] suffixerator|packedindex_mkindex [options]\n", argv[0]);
+    return 2;
+  }
+#else
   if (argc < 2 || strcmp(argv[1], "suffixerator") != 0) {
     fprintf(stderr, "usage: %s [-j N] suffixerator [options]\n", argv[0]);
     return 2;
   }
+#endif
   gt_lib_init();
   gt_jobs = jobs;
   err = gt_error_new();
   gt_error_set_progname(err, argv[0]);
+#ifdef B200_REFERENCE_TOOLS
+  rval = gt_parseargsandcallsuffixerator(strcmp(argv[1], "suffixerator") == 0, argc - 1, (const char **) argv + 1, err);
+#else
   rval = gt_suffixerator(argc - 1, (const char **) argv + 1, err);
+#endif
   if (gt_error_is_set(err))
     fprintf(stderr, "%s: error: %s\n", argv[0], gt_error_get(err));
   gt_error_delete(err);

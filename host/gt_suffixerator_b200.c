@@ -53,6 +53,7 @@
 #include "match/sfx-outprj.h"
 #include "match/sfx-strategy.h"
 #include "gtb200.h"
+#include "b200_encseq.h"
 
 static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
 {
@@ -96,16 +97,6 @@ typedef struct {
   char msg[512];
 } B200Init;
 
-/* GPUs of this run: GTB200_GPUS, else `gt -j N` (gt_jobs), never more than the box has */
-static int b200_gpu_count(void)
-{
-  const char *e = getenv("GTB200_GPUS");
-  int want = e != NULL ? atoi(e) : (int) gt_jobs, have = gtb_device_count();
-  if (want < 1) want = 1;
-  if (have >= 1 && want > have) want = have;
-  return want;
-}
-
 static void *b200_init_thread(void *p)
 {
   B200Init *init = p;
@@ -125,15 +116,6 @@ static int b200_write(const char *indexname, const char *suffix, const void *dat
   if (pad_to > 0 && (size * nmemb) % pad_to != 0)
     gt_xfwrite(zeros, 1, pad_to - (size * nmemb) % pad_to, fp);
   gt_fa_xfclose(fp);
-  return 0;
-}
-
-static int b200_append_table(FILE *fp, const uint32_t *tab, uint64_t n)
-{
-  static const char zeros[8] = {0};
-  if (n > 0) gt_xfwrite(tab, sizeof *tab, (size_t) n, fp);
-  if ((n * sizeof *tab) % 8 != 0)               /* gt_mapspec_write pads to 8 bytes,   */
-    gt_xfwrite(zeros, 1, 8 - (n * sizeof *tab) % 8, fp);  /* src/core/mapspec.c:350-365 */
   return 0;
 }
 
@@ -263,46 +245,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       if (g == NULL) { snprintf(msg, sizeof msg, "%s", init.msg); rc = -1; }
       /* GtReadmode values are the library's: fwd 0, rev 1, cpl 2, rcl 3 (src/core/readmode.h) */
       if (rc == 0) rc = gtb_group_set_readmode(g, (unsigned) readmode);
-      if (rc == 0 && gt_encseq_has_twobitencoding(encseq)) {
-        /* the 2-bit words and the special ranges as the reference's own sorter reads them */
-        const GtTwobitencoding *tbe = gt_encseq_twobitencoding_export(encseq);
-        GtUword nranges = 0, fill = 0;
-        gtb_range *ranges = NULL;
-        if (gt_encseq_has_specialranges(encseq)) {
-          GtSpecialrangeiterator *sri = gt_specialrangeiterator_new(encseq, true);
-          GtRange range;
-          GtUword alloc = gt_encseq_realspecialranges(encseq) + 16;
-          ranges = gt_malloc(sizeof *ranges * alloc);
-          while (gt_specialrangeiterator_next(sri, &range)) {
-            /* the iterator may split one run into several pieces: merge them */
-            if (fill > 0 && ranges[fill-1].end == (uint64_t) range.start) {
-              ranges[fill-1].end = range.end;
-            } else {
-              if (fill == alloc) { alloc *= 2; ranges = gt_realloc(ranges, sizeof *ranges * alloc); }
-              ranges[fill].start = range.start; ranges[fill].end = range.end; fill++;
-            }
-          }
-          gt_specialrangeiterator_delete(sri);
-          nranges = fill;
-        }
-        rc = gtb_group_set_input_2bit(g, (const uint64_t *) tbe, gt_unitsoftwobitencoding(n), n,
-                                      ranges, nranges);
-        gt_free(ranges);
-        if (rc == 0 && want_bwt) {
-          /* which special positions are separators: one before every sequence but the first */
-          const GtUword nseq = gt_encseq_num_of_sequences(encseq);
-          uint64_t *sep = gt_malloc(sizeof *sep * (nseq + 1));
-          GtUword i;
-          for (i = 1; i < nseq; i++) sep[i-1] = (uint64_t) gt_encseq_seqstartpos(encseq, i) - 1;
-          rc = gtb_group_set_separators(g, sep, nseq - 1);
-          gt_free(sep);
-        }
-      } else if (rc == 0) {
-        GtUchar *symbols = gt_malloc(n + 1);
-        if (n > 0) gt_encseq_extract_encoded(encseq, symbols, 0, n - 1);
-        rc = gtb_group_set_input_bytes(g, symbols, n, numofchars);
-        gt_free(symbols);
-      }
+      if (rc == 0) rc = b200_group_set_encseq(g, encseq, want_bwt);
       t_uploaded = b200_now();
       if (rc == 0)
         rc = gtb_group_run(g, prefixlength, (want_suf ? GTB_WANT_SUF : 0u) | (want_lcp ? GTB_WANT_LCP : 0u) |

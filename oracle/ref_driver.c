@@ -90,6 +90,9 @@ int main(int argc, char **argv)
   else if (strcmp(argv[1], "suffixerator") == 0)
     rval = gt_parseargsandcallsuffixerator(true, argc - 1,
                                            (const char**) argv + 1, err);
+  else if (strcmp(argv[1], "packedindex_mkindex") == 0)   /* gt packedindex mkindex, src/tools/gt_packedindex.c:33-36 */
+    rval = gt_parseargsandcallsuffixerator(false, argc - 1,
+                                           (const char**) argv + 1, err);
 #ifdef GTREF_WITH_SFXMAP
   else if (strcmp(argv[1], "sfxmap") == 0) {
     GtTool *tool = gt_sfxmap();
