@@ -28,6 +28,7 @@ class GtbStats(C.Structure):
         ("ms_total", C.c_float), ("ms_upload", C.c_float), ("ms_count", C.c_float),
         ("ms_hist", C.c_float), ("ms_radix", C.c_float), ("ms_analyze", C.c_float),
         ("ms_doubling", C.c_float), ("ms_lcp", C.c_float), ("ms_tail", C.c_float),
+        ("ms_radix_first", C.c_float), ("radix_passes_first", C.c_uint32), ("radix_pairs_first", C.c_uint64),
     ]
 
     def as_dict(self):

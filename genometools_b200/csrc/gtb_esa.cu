@@ -92,6 +92,8 @@ struct gtb_esa {
   cudaStream_t st3 = nullptr;   // lcp bytes beside the suffix table (gtb_esa_copy_tables)
   // input
   bool have_input = false, dna = true;
+  int borrowers = 0;             // handles that use this handle's sequence in HBM (gtb_esa_share_input)
+  gtb_esa *lender = nullptr;     // ... and the handle this one borrows from
   u64 n = 0, S = 0;
   unsigned K = 4;
   DevBuf words, bytes, spmask, ranges, sepbits, seppos;
@@ -476,6 +478,7 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
   // the keys with a tail leave the text scan, are sorted by their tail (one tiny pass) and follow
   // the full keys as a second source of the first symbol pass -- the result is the one of the sort
   // with the tail digit (equal symbols: full keys first, then by tail, then text order).
+  float first_ms0 = 0; u32 first_p0 = 0; u64 first_m0 = 0;     // (the tiny sort of the tail keys is not "first level")
   const bool tail_last = DNA && !ext && h->n > 0 && fmt_tail_digit_alone(f) && h->opt_tail_last != 0 &&
                          (tails_rare(h) || h->opt_tail_last == 1);
   if (tail_last) {
@@ -511,6 +514,7 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
       if (tout != nt) { err.set("internal: the tail keys lost elements"); return -1; }
       tsrc.keys = tk[tres]; tsrc.vals = tv[tres];
     }
+    first_ms0 = h->rw.ms_radix; first_p0 = h->rw.passes; first_m0 = h->rw.pairs_moved;
     src.skip_near = true;
     src.hist4 = h->dna && (h->nspecialranges == 0 || h->ranges.p != nullptr) && getenv("GTB200_NO_HIST4") == nullptr;
     plan_add_bits(plan, f.sh + f.tb, 64);
@@ -531,6 +535,10 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
                           (unsigned long long) N, (unsigned long long) Ncap); return -1; }
   h->N = N;
   h->entries = N + tailcnt;
+  // the first-level sort alone (plus the partition pass of a sharded scan that fed it)
+  S.ms_radix_first = h->rw.ms_radix - first_ms0 + h->ext_ms_radix;
+  S.radix_passes_first = h->rw.passes - first_p0 + (h->ext_pairs ? 1u : 0u);
+  S.radix_pairs_first = h->rw.pairs_moved - first_m0 + h->ext_pairs;
   u64 *keys = kb[h->res];
   u32 *sa = vb[h->res];
   u8 *lcp8 = h->lcp8.as<u8>();
@@ -979,6 +987,16 @@ static int check_run_args(gtb_esa *h, unsigned prefixlength, unsigned flags)
   return 0;
 }
 
+// no C++ exception crosses the C-ABI: an entry point that allocates host memory or starts threads runs
+// its body through this
+template <class F>
+static int no_throw(ErrBuf &err, F body)
+{
+  try { return body(); }
+  catch (const std::exception &e) { err.set("libgtb200: %s", e.what()); return -1; }
+  catch (...) { err.set("libgtb200: unexpected exception"); return -1; }
+}
+
 // wraps one stage: device time of the stage is added to ms_total
 template <typename F>
 static int timed_stage(gtb_esa *h, F body)
@@ -1016,6 +1034,25 @@ static int hash_table(gtb_esa *h, const T *v, u64 count, u64 index_base, u64 *ac
   GTB_CUDA(cudaMemcpyAsync(&r, d, sizeof r, cudaMemcpyDeviceToHost, h->st));
   GTB_CUDA(cudaStreamSynchronize(h->st));
   *acc += (u64) r;
+  return 0;
+}
+
+// a handle that borrowed its input gives it back (before it takes another input or goes away)
+static void return_borrowed_input(gtb_esa *h)
+{
+  if (h->lender) {
+    h->lender->borrowers--;
+    h->lender = nullptr;
+    h->words.release(); h->bytes.release(); h->spmask.release(); h->sepbits.release(); h->ranges.release();
+    h->have_input = false;
+  }
+}
+static int refuse_while_lent(gtb_esa *h, const char *what)
+{
+  if (h->borrowers > 0) {
+    h->err.set("%s: %d other handle(s) still use this handle's sequence in HBM (gtb_esa_share_input); delete them or give them another input first", what, h->borrowers);
+    return -1;
+  }
   return 0;
 }
 
@@ -1083,6 +1120,13 @@ void gtb_esa_delete(gtb_esa *h)
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
+  return_borrowed_input(h);
+  if (h->borrowers > 0) {
+    // other handles still read this sequence: it is left in HBM (and the handle with it) rather than
+    // freed under them
+    fprintf(stderr, "libgtb200: gtb_esa_delete of a handle whose sequence %d other handle(s) still use -- kept\n", h->borrowers);
+    return;
+  }
   DevBuf *all[] = {&h->words, &h->bytes, &h->spmask, &h->ranges, &h->sepbits, &h->seppos, &h->leftborder, &h->csc, &h->dist,
                    &h->distoff, &h->kbuf[0], &h->kbuf[1], &h->vbuf[0], &h->vbuf[1], &h->lcp8, &h->coarse, &h->hbits, &h->ubits, &h->tbits, &h->tpre, &h->trank, &h->spre,
                    &h->tile_a, &h->tile_b, &h->tile_c, &h->tile_d, &h->scantmp, &h->dstats, &h->misc, &h->uidx0, &h->ugrp0,
@@ -1111,7 +1155,10 @@ int gtb_esa_set_readmode(gtb_esa *h, unsigned readmode)
 {
   if (!h) return -1;
   if (readmode > 3) { h->err.set("unknown readmode, must be fwd or rev or cpl or rcl"); return -1; }
-  if (readmode != h->readmode) { h->have_input = false; h->counted = false; h->ran = false; }
+  if (readmode != h->readmode) {
+    if (h->lender) return_borrowed_input(h);
+    h->have_input = false; h->counted = false; h->ran = false;
+  }
   h->readmode = readmode;
   return 0;
 }
@@ -1122,6 +1169,8 @@ int gtb_esa_set_input_2bit(gtb_esa *h, const uint64_t *twobitenc, uint64_t nword
   if (!h) return -1;
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
+  GTB_TRY(refuse_while_lent(h, "gtb_esa_set_input_2bit"));
+  return_borrowed_input(h);
   if (n + 1 >= 0xffffffffull) { err.set("totallength %llu needs 64-bit suffix tables: not supported by this build (u32 positions)", (unsigned long long) n); return -1; }
   if (nwords < (n + 31) / 32) { err.set("twobitencoding too short: %llu words for %llu bases", (unsigned long long) nwords, (unsigned long long) n); return -1; }
   PhaseTimer t(h, &h->stats.ms_upload);
@@ -1176,6 +1225,8 @@ int gtb_esa_set_input_bytes(gtb_esa *h, const uint8_t *symbols, uint64_t n, unsi
   if (!h) return -1;
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
+  GTB_TRY(refuse_while_lent(h, "gtb_esa_set_input_bytes"));
+  return_borrowed_input(h);
   if (n + 1 >= 0xffffffffull) { err.set("totallength %llu needs 64-bit suffix tables: not supported by this build", (unsigned long long) n); return -1; }
   if (K < 1 || K > 31) { err.set("numofchars %u not supported by the byte path (1..31)", K); return -1; }
   if ((h->readmode & 2u) && K != 4) {     // sfx-run.c:541-549
@@ -1206,6 +1257,11 @@ int gtb_esa_share_input(gtb_esa *h, const gtb_esa *src)
   if (!h || !src) return -1;
   if (!src->have_input) { h->err.set("gtb_esa_share_input: source has no input"); return -1; }
   if (h->device != src->device) { h->err.set("gtb_esa_share_input: handles live on different devices"); return -1; }
+  if (h == src || src->lender) { h->err.set("gtb_esa_share_input: the source must own its sequence"); return -1; }
+  GTB_TRY(refuse_while_lent(h, "gtb_esa_share_input"));
+  return_borrowed_input(h);
+  const_cast<gtb_esa *>(src)->borrowers++;
+  h->lender = const_cast<gtb_esa *>(src);
   h->dna = src->dna; h->K = src->K; h->n = src->n; h->S = src->S; h->nmaskwords = src->nmaskwords;
   h->nspecialranges = src->nspecialranges;
   h->readmode = src->readmode;
@@ -1230,6 +1286,8 @@ int gtb_esa_set_code_range(gtb_esa *h, uint64_t mincode, uint64_t maxcode, uint6
 
 int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(h ? h->err : no_handle_err, [&]() -> int {
   if (!h) return -1;
   GTB_TRY(check_run_args(h, prefixlength, flags));
   int rc = timed_stage(h, [&]() -> int {
@@ -1239,6 +1297,7 @@ int gtb_esa_run(gtb_esa *h, unsigned prefixlength, unsigned flags)
   });
   h->ran = rc == 0;
   return rc;
+  });
 }
 
 int gtb_esa_sort_begin(gtb_esa *h, unsigned prefixlength, unsigned flags)
@@ -1643,6 +1702,8 @@ static int suftab_wide_chunks(gtb_esa *h, cudaStream_t st2, uint64_t *dst, uint6
 
 int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t count)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(h ? h->err : no_handle_err, [&]() -> int {
   GTB_TRY(check_range(h, first, count));
   ErrBuf &err = h->err;
   GTB_CUDA(cudaSetDevice(h->device));
@@ -1687,6 +1748,7 @@ int gtb_esa_copy_suftab_u64(gtb_esa *h, uint64_t *dst, uint64_t first, uint64_t 
   GTB_TRY(rc);
   GTB_CUDA(cudaStreamSynchronize(h->st));
   return 0;
+  });
 }
 
 int gtb_esa_copy_lcptab(gtb_esa *h, uint8_t *dst, uint64_t first, uint64_t count)
@@ -1729,6 +1791,8 @@ int gtb_esa_copy_tables(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t 
 int gtb_esa_copy_results(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
                          uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(h ? h->err : no_handle_err, [&]() -> int {
   if (!h) return -1;
   ErrBuf &err = h->err;
   if (!h->ran) { err.set("no results: gtb_esa_run has not succeeded"); return -1; }
@@ -1763,6 +1827,7 @@ int gtb_esa_copy_results(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t
     GTB_TRY(gtb_esa_copy_bcktab(h, later_lb ? leftborder : nullptr, later_csc ? countspecialcodes : nullptr,
                                 later_dist ? distpfxidx : nullptr));
   return 0;
+  });
 }
 
 int gtb_esa_set_separators(gtb_esa *h, const uint64_t *positions, uint64_t count)
@@ -1890,6 +1955,8 @@ int gtb_esa_hash_bcktab(gtb_esa *h, uint64_t *out)
 int gtb_esa_run_sharded(gtb_esa *h, unsigned prefixlength, unsigned flags, int rank, int world,
                         gtb_allgather_fn allgather, void *ctx, int separate_processes)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(h ? h->err : no_handle_err, [&]() -> int {
   if (!h) return -1;
   if (!allgather) { h->err.set("gtb_esa_run_sharded needs an all-gather function"); return -1; }
   if (!h->have_input) { h->err.set("no input set"); return -1; }
@@ -1897,6 +1964,7 @@ int gtb_esa_run_sharded(gtb_esa *h, unsigned prefixlength, unsigned flags, int r
   c.me = rank; c.world = world; c.ag = allgather; c.ctx = ctx; c.ipc = separate_processes != 0;
   h->ran = false;
   return run_sharded(h, c, prefixlength, flags);
+  });
 }
 
 uint64_t gtb_esa_llv_before(const gtb_esa *h) { return h && h->ran ? h->llv_before : 0; }
@@ -1943,14 +2011,20 @@ int gtb_group_set_readmode(gtb_group *g, unsigned readmode)
 int gtb_group_set_input_2bit(gtb_group *g, const uint64_t *twobitenc, uint64_t nwords, uint64_t n,
                              const gtb_range *specials, uint64_t nranges)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(g ? g->err : no_handle_err, [&]() -> int {
   if (!g) return -1;
   return group_set_input(g, [&](gtb_esa *h) { return gtb_esa_set_input_2bit(h, twobitenc, nwords, n, specials, nranges); });
+  });
 }
 
 int gtb_group_set_input_bytes(gtb_group *g, const uint8_t *symbols, uint64_t n, unsigned K)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(g ? g->err : no_handle_err, [&]() -> int {
   if (!g) return -1;
   return group_set_input(g, [&](gtb_esa *h) { return gtb_esa_set_input_bytes(h, symbols, n, K); });
+  });
 }
 
 int gtb_group_set_separators(gtb_group *g, const uint64_t *positions, uint64_t count)
@@ -1969,6 +2043,8 @@ int gtb_group_set_separators(gtb_group *g, const uint64_t *positions, uint64_t c
 
 int gtb_group_run(gtb_group *g, unsigned prefixlength, unsigned flags)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(g ? g->err : no_handle_err, [&]() -> int {
   if (!g) return -1;
   g->ran = false; g->bck_merged = false;
   g->pl = prefixlength; g->flags = flags;
@@ -1994,6 +2070,8 @@ int gtb_group_run(gtb_group *g, unsigned prefixlength, unsigned flags)
     S.unresolved_after_first_sort += t.unresolved_after_first_sort;
     if (t.doubling_rounds > S.doubling_rounds) S.doubling_rounds = t.doubling_rounds;
     S.radix_passes += t.radix_passes; S.radix_pairs_moved += t.radix_pairs_moved;
+    S.radix_passes_first += t.radix_passes_first; S.radix_pairs_first += t.radix_pairs_first;
+    if (t.ms_radix_first > S.ms_radix_first) S.ms_radix_first = t.ms_radix_first;
     S.kernel_launches += t.kernel_launches;
     float *dst[] = {&S.ms_total, &S.ms_upload, &S.ms_count, &S.ms_hist, &S.ms_radix, &S.ms_analyze, &S.ms_doubling, &S.ms_lcp, &S.ms_tail};
     const float src[] = {t.ms_total, t.ms_upload, t.ms_count, t.ms_hist, t.ms_radix, t.ms_analyze, t.ms_doubling, t.ms_lcp, t.ms_tail};
@@ -2001,6 +2079,7 @@ int gtb_group_run(gtb_group *g, unsigned prefixlength, unsigned flags)
   }
   g->ran = true;
   return 0;
+  });
 }
 
 int gtb_group_get_stats(const gtb_group *g, gtb_stats *st)
@@ -2028,6 +2107,8 @@ uint64_t gtb_group_num_llv(const gtb_group *g)
 int gtb_group_copy_results(gtb_group *g, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
                            uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(g ? g->err : no_handle_err, [&]() -> int {
   if (!g) return -1;
   if (!g->ran) { g->err.set("no results: gtb_group_run has not succeeded"); return -1; }
   if (g->hs.size() == 1)
@@ -2045,20 +2126,26 @@ int gtb_group_copy_results(gtb_group *g, uint64_t *suftab, uint8_t *lcptab, uint
     }
   }
   return 0;
+  });
 }
 
 int gtb_group_copy_bwttab(gtb_group *g, uint8_t *dst)
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(g ? g->err : no_handle_err, [&]() -> int {
   if (!g || !dst) return -1;
   if (!g->ran) { g->err.set("no results: gtb_group_run has not succeeded"); return -1; }
   return group_parallel(g, [&](int i) -> int {
     gtb_esa *h = g->hs[(size_t) i];
     return h->entries ? gtb_esa_copy_bwttab(h, dst + (g->hs.size() == 1 ? 0 : h->sa_offset), 0, h->entries) : 0;
   });
+  });
 }
 
 int gtb_group_hash_results(gtb_group *g, uint64_t out4[4])
 {
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(g ? g->err : no_handle_err, [&]() -> int {
   if (!g || !out4) return -1;
   if (!g->ran) { g->err.set("no results: gtb_group_run has not succeeded"); return -1; }
   out4[0] = out4[1] = out4[2] = out4[3] = 0;
@@ -2070,6 +2157,7 @@ int gtb_group_hash_results(gtb_group *g, uint64_t out4[4])
   GTB_TRY(group_merge_bck(g));
   if (gtb_esa_hash_bcktab(g->hs[0], &out4[3]) != 0) { snprintf(g->err.msg, sizeof g->err.msg, "%s", g->hs[0]->err.msg); return -1; }
   return 0;
+  });
 }
 
 void *gtb_esa_stream(const gtb_esa *h) { return h ? (void *) h->st : nullptr; }

@@ -128,9 +128,18 @@ static int staged_d2h(HostStage &hs, cudaStream_t st, const void *dsrc, void *hd
     }
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < T; t++) pool.emplace_back(work, t);
-
   int rc = 0;
+  try {
+    pool.reserve((size_t) T);
+    for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+  } catch (const std::exception &e) {          // no thread to be had: nothing was copied yet
+    { std::lock_guard<std::mutex> lk(mu); failed = true; }
+    cv.notify_all();
+    for (auto &th : pool) th.join();
+    err.set("could not start the host threads of the result copy: %s", e.what());
+    return -1;
+  }
+
   auto fail = [&](cudaError_t e, const char *what) {
     err.set("%s failed: %s", what, cudaGetErrorString(e));
     { std::lock_guard<std::mutex> lk(mu); failed = true; }

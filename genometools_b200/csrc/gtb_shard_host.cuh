@@ -617,7 +617,24 @@ int group_parallel(gtb_group *g, F body)
   const int n = (int) g->hs.size();
   std::vector<int> rcs((size_t) n, 0);
   std::vector<std::thread> th;
-  for (int i = 1; i < n; i++) th.emplace_back([&, i] { rcs[(size_t) i] = body(i); });
+  th.reserve((size_t) n);
+  // every range needs its thread (the ranges wait for each other): if the threads cannot all be had,
+  // none is started
+  std::mutex gate_mu; std::condition_variable gate_cv; int gate = 0;     // 0 wait, 1 go, -1 give up
+  try {
+    for (int i = 1; i < n; i++) th.emplace_back([&, i] {
+      { std::unique_lock<std::mutex> lk(gate_mu); gate_cv.wait(lk, [&] { return gate != 0; }); if (gate < 0) return; }
+      rcs[(size_t) i] = body(i);
+    });
+  } catch (const std::exception &e) {
+    { std::lock_guard<std::mutex> lk(gate_mu); gate = -1; }
+    gate_cv.notify_all();
+    for (auto &t : th) t.join();
+    g->err.set("could not start one thread per code range: %s", e.what());
+    return -1;
+  }
+  { std::lock_guard<std::mutex> lk(gate_mu); gate = 1; }
+  gate_cv.notify_all();
   rcs[0] = body(0);
   for (auto &t : th) t.join();
   for (int i = 0; i < n; i++)
@@ -638,6 +655,7 @@ int group_set_input(gtb_group *g, F upload)
     owner[(size_t) i] = i;
     for (int j = 0; j < i; j++) if (g->hs[(size_t) j]->device == g->hs[(size_t) i]->device) { owner[(size_t) i] = j; break; }
   }
+  for (int i = 0; i < n; i++) if (owner[(size_t) i] != i) return_borrowed_input(g->hs[(size_t) i]);   // (the owners take a new input)
   GTB_TRY(group_parallel(g, [&](int i) -> int { return owner[(size_t) i] == i ? upload(g->hs[(size_t) i]) : 0; }));
   for (int i = 0; i < n; i++)
     if (owner[(size_t) i] != i && gtb_esa_share_input(g->hs[(size_t) i], g->hs[(size_t) owner[(size_t) i]]) != 0) {

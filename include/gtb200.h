@@ -75,6 +75,11 @@ typedef struct {
      stream) */
   float ms_total, ms_upload, ms_count, ms_hist, ms_radix, ms_analyze,
         ms_doubling, ms_lcp, ms_tail;
+  /* the first-level sort alone (the passes over all suffixes of the handle: the dominant kernel at
+     its dominant size; ms_radix / radix_passes also count the small passes of the refinement rounds) */
+  float    ms_radix_first;
+  uint32_t radix_passes_first;
+  uint64_t radix_pairs_first;    /* sum over those passes of elements moved */
 } gtb_stats;
 
 /* flags for gtb_esa_run (mirror the -suf -lcp -bck switches, index_options.c) */

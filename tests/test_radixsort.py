@@ -71,3 +71,23 @@ def test_cuda_sort_sizes(kind, n):
         a[::3, 0] = a[1, 0]                                  # ties: stability / second key matter
         a[::7] = a[2]
     assert np.array_equal(gpu_sort(kind, a), oracle_sort(kind, a))
+
+
+RADIX_BIN = os.path.join(ROOT, "host", "_build", "gtref_b200_radixsort")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RADIX_BIN), reason="host/_build/gtref_b200_radixsort not built")
+@pytest.mark.parametrize("name", list(CASES))
+def test_reference_entry_points_on_the_gpu(tmp_path, name):
+    """host/gt_radix_sort_b200.c linked in front of src/core/radix_sort.o: gt_radixsort_inplace_ulong /
+    _GtUwordPair / _Gtuint64keyPair called by the reference's test driver, sorted by libgtb200"""
+    import subprocess
+    kind, n, seed, distinct = CASES[name]
+    a = make_input(kind, n, seed, distinct)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.ascontiguousarray(a).tofile(fin)
+    subprocess.check_call([RADIX_BIN, "radixsort", kind, fin, fout], stdout=subprocess.DEVNULL)
+    b = np.fromfile(fout, dtype=np.uint64).reshape(a.shape)
+    assert np.array_equal(b, oracle_sort(kind, a))
+    assert md5(b[:, 0] if b.ndim > 1 else b) == str(Z[name + "/md5_keys"])

@@ -65,9 +65,13 @@ def full(path, out, title, command, traffic=None, pairs=None):
             if w in hdr:
                 i = hdr.index(w)
                 fh.write(f"| {w} | {units[i]} | " + " | ".join(r[i] for r in data) + " |\n")
-        fh.write("\nKernel: `" + data[0][hdr.index("Kernel Name")][:160] + "`\n")
+        fh.write("\nKernels: " + "; ".join("`" + r[hdr.index("Kernel Name")][:90] + "`" for r in data) + "\n")
         if traffic and pairs:
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            # (launches far shorter than the longest are another instantiation on a tiny input: not averaged)
+            it = hdr.index("gpu__time_duration.sum")
+            tmax = max(float(r[it].replace(",", "")) for r in data)
+            data = [r for r in data if float(r[it].replace(",", "")) >= 0.1 * tmax]
 
             def gb(r, i):
                 v = float(r[i].replace(",", ""))
