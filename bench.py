@@ -523,6 +523,10 @@ def main():
         llv_pinned = torch.empty((max(int(lib.gtb_esa_num_llv(h)) * 2, 1024), 2), dtype=torch.int64,
                                  pin_memory=True).numpy().view(np.uint64)
         d2h = 0
+        # gtb_esa_run_to_host (the suffix table leaves for the host while the ties are refined) is correct
+        # (tests/test_gpu_configs.py) but does not pay on the bench hosts: 532 ms against 522 ms for c4 --
+        # measured, profiles/README.md -- so the timed path is run + gtb_esa_copy_results
+        overlap_copy = os.environ.get("GTB_BENCH_OVERLAP", "0") == "1"
         parts_s = [0.0, 0.0, 0.0]                   # H2D, kernels, D2H of the timed steps
         d2h_parts = [0.0]                           # gtb_esa_copy_results (incl. the warm-up step)
 
@@ -535,6 +539,18 @@ def main():
             else:
                 ck(lib.gtb_esa_set_input_bytes(h, ptr(ps), n, w.numofchars))
             tb = time.perf_counter()
+            if world == 1 and overlap_copy:
+                # one call: the suffix table crosses PCIe while the ties are refined (gtb_esa_run_to_host)
+                nl = C.c_uint64()
+                ck(lib.gtb_esa_run_to_host(h, pl, flags, ptr(suf), ptr(lcp), ptr(llv_pinned), llv_pinned.shape[0],
+                                           C.byref(nl), ptr(lbh), ptr(csch), ptr(disth) if c.value else None))
+                ck(lib.gtb_esa_get_stats(h, C.byref(st)))
+                bck_state["summed"] = False
+                e, k = lib.gtb_esa_num_entries(h), int(nl.value)
+                d2h = 8 * e + e + 16 * k + 4 * (a.value + 1 + b.value + c.value)
+                td = time.perf_counter()
+                d2h_parts[0] += td - tb
+                return tb - ta, 0.0, td - tb
             step()
             tc = time.perf_counter()
             e = lib.gtb_esa_num_entries(h)
@@ -575,9 +591,14 @@ def main():
         e2e = {"value": (n + 1) * args.e2e_steps / te.item() / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": w.input_bytes() * world, "d2h_bytes_per_step": int(tb_.item()),
                "steps": args.e2e_steps, "ms_per_step": te.item() / args.e2e_steps * 1e3,
-               "breakdown_ms": {"h2d": parts_s[0] / args.e2e_steps * 1e3, "kernels": parts_s[1] / args.e2e_steps * 1e3,
-                                "d2h": parts_s[2] / args.e2e_steps * 1e3,
-                                "d2h_all_tables_one_call": d2h_parts[0] / (args.e2e_steps + 1) * 1e3},
+               "breakdown_ms": ({"h2d": parts_s[0] / args.e2e_steps * 1e3,
+                                 "run_to_host (kernels and copies overlapped)": parts_s[2] / args.e2e_steps * 1e3}
+                                if (world == 1 and overlap_copy) else
+                                {"h2d": parts_s[0] / args.e2e_steps * 1e3, "kernels": parts_s[1] / args.e2e_steps * 1e3,
+                                 "d2h": parts_s[2] / args.e2e_steps * 1e3,
+                                 "d2h_all_tables_one_call": d2h_parts[0] / (args.e2e_steps + 1) * 1e3}),
+               "api": "gtb_esa_set_input_* + gtb_esa_run_to_host" if (world == 1 and overlap_copy) else
+                      "gtb_esa_set_input_* + run + gtb_esa_copy_results",
                "note": "pinned host buffers; results delivered as the files hold them (uint64 suftab, "
                        "uint8 lcptab, llv pairs, uint32 bucket tables); one untimed warm-up step"}
 

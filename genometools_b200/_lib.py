@@ -82,6 +82,7 @@ SYMBOLS = {
     "gtb_esa_copy_lcptab": (C.c_int, [_P, _P, _U64, _U64]),
     "gtb_esa_copy_tables": (C.c_int, [_P, _P, _P, _U64, _U64]),
     "gtb_esa_copy_results": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "gtb_esa_run_to_host": (C.c_int, [_P, C.c_uint, C.c_uint, _P, _P, _P, _U64, C.POINTER(_U64), _P, _P, _P]),
     "gtb_esa_copy_llv": (C.c_int, [_P, _P]),
     "gtb_esa_copy_bcktab": (C.c_int, [_P, _P, _P, _P]),
     "gtb_bck_sizes": (None, [C.c_uint, C.c_uint, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),

@@ -160,6 +160,18 @@ struct gtb_esa {
   u64 llv_before = 0;       // .llv pairs of the preceding ranges of the job
   int shard_np = 1;         // code ranges the last sharded run cut
   HostStage hstage;         // pinned staging + host threads of the result copies
+  // gtb_esa_run_to_host: the suffix table leaves for the host while the refinement still runs
+  struct EarlyCopy {
+    uint64_t *dst = nullptr;        // where entries [0, N) go (set before the run; null: no early copy)
+    bool started = false;
+    std::thread th;
+    ChunkDealer *dealer = nullptr;
+    ErrBuf err;
+    int rc = 0;
+    u64 per = 0, count = 0;
+  } ec;
+  void *patch_host = nullptr;       // pinned: (index : 32 | position : 32) of the entries copied too early
+  size_t patch_cap = 0;
   gtb_stats stats;
 };
 
@@ -542,6 +554,28 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
   u64 *keys = kb[h->res];
   u32 *sa = vb[h->res];
   u8 *lcp8 = h->lcp8.as<u8>();
+  // The first-level order is final for all but the tied suffixes (1.5 % of c4): when the caller wants the
+  // table on the host (gtb_esa_run_to_host) it starts to cross PCIe NOW, on a stream of its own, while the
+  // analysis, the refinement rounds and the lcp kernels run; the chunks that left before the refinement
+  // was over are patched afterwards.
+  if (h->ec.dst && !h->ec.started && N > 0) {
+    GTB_TRY(h->hstage.ensure(err));
+    if (!h->st2) GTB_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    h->ec.per = h->hstage.chunk / sizeof(u32);
+    h->ec.count = N;
+    if (div_up(N, h->ec.per) >= 64) {
+      h->ec.dealer = new ChunkDealer(div_up(N, h->ec.per));
+      h->ec.rc = 0;
+      h->ec.started = true;
+      gtb_esa *hh = h;
+      const u32 *src_sa = sa;
+      h->ec.th = std::thread([hh, src_sa] {
+        cudaSetDevice(hh->device);
+        hh->ec.rc = staged_d2h(hh->hstage, hh->st2, src_sa, hh->ec.dst, hh->ec.count, sizeof(u32), true, hh->ec.err, hh->ec.dealer);
+        if (hh->ec.rc == 0 && cudaStreamSynchronize(hh->st2) != cudaSuccess) { hh->ec.err.set("early copy of the suffix table failed"); hh->ec.rc = -1; }
+      });
+    }
+  }
   GTB_CUDA(cudaMemsetAsync(lcp8, 0, h->entries + 16, st));
   h->first_key = h->last_key = 0;
   if (N > 0) {
@@ -1137,6 +1171,9 @@ void gtb_esa_delete(gtb_esa *h)
   for (DevBuf *b : all) b->release();
   for (auto &m : h->imports) vmm_free(m.second.ptr, m.second.mh, m.second.size);
   h->imports.clear();
+  if (h->ec.started && h->ec.th.joinable()) h->ec.th.join();
+  delete h->ec.dealer;
+  if (h->patch_host) cudaFreeHost(h->patch_host);
   stop_ipc_receiver(h);
   for (auto &f : h->pending_fds) close(f.fd);
   h->pending_fds.clear();
@@ -1827,6 +1864,99 @@ int gtb_esa_copy_results(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t
     GTB_TRY(gtb_esa_copy_bcktab(h, later_lb ? leftborder : nullptr, later_csc ? countspecialcodes : nullptr,
                                 later_dist ? distpfxidx : nullptr));
   return 0;
+  });
+}
+
+// the early copy of gtb_esa_run_to_host is over (or never began): join, free
+static int finish_early_copy(gtb_esa *h)
+{
+  int rc = 0;
+  if (h->ec.started) {
+    if (h->ec.th.joinable()) h->ec.th.join();
+    rc = h->ec.rc;
+    if (rc != 0) h->err = h->ec.err;
+    delete h->ec.dealer;
+    h->ec.dealer = nullptr;
+    h->ec.started = false;
+  }
+  h->ec.dst = nullptr;
+  return rc;
+}
+
+// gtb_esa_run + gtb_esa_copy_results in one call, overlapped: what suffixeratorwithoutput() (sfx-run.c:212-317)
+// does with the iterator -- sort, then write every table -- with the suffix table already on its way to the
+// host while the ties are refined.  Host buffers as gtb_esa_copy_results; llv must hold 2 * llv_capacity uint64.
+int gtb_esa_run_to_host(gtb_esa *h, unsigned prefixlength, unsigned flags, uint64_t *suftab, uint8_t *lcptab,
+                        uint64_t *llv, uint64_t llv_capacity, uint64_t *nllv, uint32_t *leftborder,
+                        uint32_t *countspecialcodes, uint32_t *distpfxidx)
+{
+  if (!h) return -1;
+  static thread_local ErrBuf no_handle_err;
+  return no_throw(h->err, [&]() -> int {
+    ErrBuf &err = h->err;
+    const char *off = getenv("GTB200_NO_EARLY_COPY");
+    h->ec.dst = (suftab && (flags & GTB_WANT_SUF) && !off) ? suftab : nullptr;
+    int rc = gtb_esa_run(h, prefixlength, flags);
+    const bool early = h->ec.started;
+    if (rc != 0) { finish_early_copy(h); return -1; }
+    GTB_CUDA(cudaSetDevice(h->device));
+    if (nllv) *nllv = h->nllv;
+    if (llv && h->nllv > llv_capacity) {
+      finish_early_copy(h);
+      err.set("llv buffer too small: %llu entries needed", (unsigned long long) h->nllv);
+      return -1;
+    }
+    if (!early) {
+      h->ec.dst = nullptr;
+      return gtb_esa_copy_results(h, suftab, lcptab, h->nllv ? llv : nullptr, leftborder, countspecialcodes, distpfxidx);
+    }
+    // every chunk that has not been handed out yet will read the final table; the others are patched
+    const u64 N = h->N, per = h->ec.per;
+    u64 limit = h->ec.dealer->front_taken() * per;
+    if (limit > N) limit = N;
+    unsigned int npatch = 0;
+    if (h->M0 > 0 && limit > 0) {
+      GTB_TRY(h->dkeys.ensure(sizeof(u64) * h->M0, err));
+      unsigned int *dcount = reinterpret_cast<unsigned int *>(h->misc.as<u64>() + 22);
+      GTB_CUDA(cudaMemsetAsync(dcount, 0, sizeof(unsigned int), h->st));
+      k_patch_gather<<<grid_for(h->M0, 256), 256, 0, h->st>>>(h->uidx0.as<u32>(), h->M0, h->vbuf[h->res].as<u32>(), limit,
+                                                             h->dkeys.as<u64>(), dcount);
+      if (cudaGetLastError() != cudaSuccess) { finish_early_copy(h); err.set("k_patch_gather failed to launch"); return -1; }
+      GTB_CUDA(cudaMemcpyAsync(&npatch, dcount, sizeof npatch, cudaMemcpyDeviceToHost, h->st));
+      GTB_CUDA(cudaStreamSynchronize(h->st));
+      if (npatch > 0) {
+        if (h->patch_cap < sizeof(u64) * (size_t) npatch) {
+          if (h->patch_host) cudaFreeHost(h->patch_host);
+          h->patch_host = nullptr; h->patch_cap = 0;
+          const size_t want = sizeof(u64) * (size_t) npatch + (sizeof(u64) * (size_t) npatch >> 3) + 4096;
+          if (cudaHostAlloc(&h->patch_host, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError(); finish_early_copy(h); err.set("no pinned memory for %u patches", npatch); return -1;
+          }
+          h->patch_cap = want;
+        }
+        GTB_CUDA(cudaMemcpyAsync(h->patch_host, h->dkeys.p, sizeof(u64) * (size_t) npatch, cudaMemcpyDeviceToHost, h->st));
+      }
+    }
+    rc = finish_early_copy(h);                       // the table [0, N) is on the host
+    if (rc != 0) return -1;
+    GTB_CUDA(cudaStreamSynchronize(h->st));          // ... and so are the patches
+    if (npatch > 0) {
+      const u64 *pt = static_cast<const u64 *>(h->patch_host);
+      int T = h->hstage.nthreads > 0 ? h->hstage.nthreads : 1;
+      if (npatch < 65536u) T = 1;
+      std::vector<std::thread> pool;
+      auto work = [&](int t) {
+        const u64 lo = (u64) npatch * (u64) t / (u64) T, hi = (u64) npatch * (u64) (t + 1) / (u64) T;
+        for (u64 i = lo; i < hi; i++) suftab[pt[i] >> 32] = pt[i] & 0xffffffffull;
+      };
+      pool.reserve((size_t) T);
+      for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+      work(0);
+      for (auto &th : pool) th.join();
+    }
+    // the special tail and the other tables
+    if (h->entries > N) GTB_TRY(gtb_esa_copy_suftab_u64(h, suftab + N, N, h->entries - N));
+    return gtb_esa_copy_results(h, nullptr, lcptab, h->nllv ? llv : nullptr, leftborder, countspecialcodes, distpfxidx);
   });
 }
 

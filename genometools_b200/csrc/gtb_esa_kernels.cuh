@@ -1752,6 +1752,21 @@ __global__ void k_gather_records(const u64 *__restrict__ rec, unsigned width, co
   }
 }
 
+// the tied entries with a suffix-array index below `limit` as (index : 32 | position : 32): the part of the
+// table that left for the host before the refinement had finished (gtb_esa_run_to_host).  uidx0 ascends,
+// so they are a prefix of the list; *count = its length
+__global__ void k_patch_gather(const u32 *__restrict__ uidx0, u64 M0, const u32 *__restrict__ sa, u64 limit,
+                               u64 *__restrict__ out, unsigned int *count)
+{
+  for (u64 c = blockIdx.x * (u64) blockDim.x + threadIdx.x; c < M0; c += (u64) gridDim.x * blockDim.x) {
+    const u32 j = uidx0[c];
+    if ((u64) j < limit) {
+      out[c] = ((u64) j << 32) | (u64) sa[j];
+      if (c + 1 == M0 || (u64) uidx0[c + 1] >= limit) *count = (unsigned int) (c + 1);
+    }
+  }
+}
+
 __global__ void k_widen_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 count)
 {
   for (u64 i = blockIdx.x * (u64) blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)

@@ -262,6 +262,16 @@ int gtb_esa_copy_tables(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t 
    second stream while the suffix table is copied and widened.  Any pointer may be NULL. */
 int gtb_esa_copy_results(gtb_esa *h, uint64_t *suftab, uint8_t *lcptab, uint64_t *llv,
                          uint32_t *leftborder, uint32_t *countspecialcodes, uint32_t *distpfxidx);
+/* gtb_esa_run and gtb_esa_copy_results in ONE call with the copy overlapped: the first-level order is
+   final for all but the tied suffixes (1.5 % of a human-sized genome), so the suffix table starts to cross
+   PCIe right after the first-level sort, on a stream of its own, while the analysis, the refinement rounds
+   and the lcp kernels still run; the entries that left too early are patched on the host afterwards
+   (their (index, position) pairs follow in one small copy).  What suffixeratorwithoutput() (sfx-run.c:212-317)
+   does with the iterator, as one overlapped operation.  llv holds 2*llv_capacity uint64 (*nllv = pairs
+   written; error if more are needed); any output pointer may be NULL. */
+int gtb_esa_run_to_host(gtb_esa *h, unsigned prefixlength, unsigned flags, uint64_t *suftab, uint8_t *lcptab,
+                        uint64_t *llv, uint64_t llv_capacity, uint64_t *nllv, uint32_t *leftborder,
+                        uint32_t *countspecialcodes, uint32_t *distpfxidx);
 /* -bwt (bwttab2file, src/match/sfx-run.c:173-210): one encoded symbol per suffix-table
    entry, the symbol before the suffix (0..numofchars-1, 254 wildcard, 255 separator;
    UNDEFBWTCHAR = 254 for the suffix that starts at 0, chardef.h:65).  The 2-bit input does

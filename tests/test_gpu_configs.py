@@ -52,7 +52,9 @@ def bck_image(lb, csc, dist):
     return pad(lb) + pad(csc) + pad(dist)
 
 
-def run_config(key, want_md5):
+def run_config(key, want_md5, overlapped=False):
+    """overlapped: gtb_esa_run_to_host -- the suffix table crosses PCIe while the ties are refined, the
+    entries that left too early are patched -- instead of gtb_esa_run + gtb_esa_copy_results"""
     g = GOLDEN[key]
     w = sy.make_workload(g["workload"], g["scale"])
     n = w.totallength
@@ -76,7 +78,22 @@ def run_config(key, want_md5):
                                           ptr(w.ranges) if w.ranges.shape[0] else None, w.ranges.shape[0]))
         else:
             ck(lib.gtb_esa_set_input_bytes(h, ptr(w.symbols), n, w.numofchars))
-        ck(lib.gtb_esa_run(h, pl, GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK))
+        host = None
+        if overlapped:
+            e = n + 1
+            a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            lib.gtb_bck_sizes(w.numofchars, pl, C.byref(a), C.byref(b), C.byref(c))
+            kmax = g["files"]["llv"]["bytes"] // 16 + 8
+            host = {"suf": np.empty(e, dtype=np.uint64), "lcp": np.empty(e, dtype=np.uint8),
+                    "llv": np.empty(2 * kmax, dtype=np.uint64), "lb": np.empty(a.value + 1, dtype=np.uint32),
+                    "csc": np.empty(b.value, dtype=np.uint32), "dist": np.empty(c.value, dtype=np.uint32)}
+            nllv = C.c_uint64()
+            ck(lib.gtb_esa_run_to_host(h, pl, GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK, ptr(host["suf"]), ptr(host["lcp"]),
+                                       ptr(host["llv"]), kmax, C.byref(nllv), ptr(host["lb"]),
+                                       ptr(host["csc"]) if b.value else None, ptr(host["dist"]) if c.value else None))
+            host["k"] = int(nllv.value)
+        else:
+            ck(lib.gtb_esa_run(h, pl, GTB_WANT_SUF | GTB_WANT_LCP | GTB_WANT_BCK))
         st = GtbStats()
         ck(lib.gtb_esa_get_stats(h, C.byref(st)))
         # the tables in HBM against the reference's files
@@ -98,7 +115,14 @@ def run_config(key, want_md5):
         assert st.maxbranchdepth == int(prj["maxbranchdepth"])
         assert "%.2f" % (st.lcptabsum / (n + 1)) == prj["averagelcp"]
         assert st.specialcharacters == int(prj["specialcharacters"])
-        if want_md5:
+        if host is not None:
+            k = host["k"]
+            assert md5(host["suf"]) == files["suf"]["md5"], ".suf (overlapped copy)"
+            assert md5(host["lcp"]) == files["lcp"]["md5"], ".lcp (overlapped copy)"
+            assert 16 * k == files["llv"]["bytes"] and md5(host["llv"][:2 * k]) == files["llv"]["md5"], ".llv"
+            img = bck_image(host["lb"], host["csc"], host["dist"])
+            assert hashlib.md5(img).hexdigest() == files["bck"]["md5"], ".bck"
+        elif want_md5:
             e = n + 1
             k = int(lib.gtb_esa_num_llv(h))
             suf = np.empty(e, dtype=np.uint64)
@@ -137,6 +161,23 @@ def test_c5_full_size_byte_identical():
 @need("c3")
 def test_c3_full_size_byte_identical():
     run_config("c3", True)
+
+
+@need("c3")
+def test_c3_full_size_overlapped_copy_byte_identical():
+    run_config("c3", True, overlapped=True)
+
+
+@need("c5")
+def test_c5_full_size_overlapped_copy_byte_identical():
+    run_config("c5", True, overlapped=True)
+
+
+@need("c4@0.002")
+def test_overlapped_copy_patches_small_chunks(monkeypatch):
+    """64 KB staging chunks: the early copy runs on a 6.2 Mbp sample full of ties, every chunk is patched"""
+    monkeypatch.setenv("GTB200_STAGE_KB", "64")
+    run_config("c4@0.002", True, overlapped=True)
 
 
 @need("c4")
