@@ -133,6 +133,8 @@ struct gtb_esa {
   int opt_key_symbols = 0;  // test knobs (environment GTB200_KEY_SYMBOLS = 16..29,
   int opt_text_rounds = -1; // GTB200_TEXT_ROUNDS = 0..8,
   int opt_tail_last = -1;   // GTB200_TAIL_LAST = 0|1): override the automatic choices
+  int opt_pairs_by_text = 1; // GTB200_PAIRS_BY_TEXT = r: tie groups of two are compared by text in the first r doubling rounds
+  unsigned isa_round = 0;   // doubling rounds of this run so far (the first one compares pairs by text)
   u64 nspecialranges = 0;   // maximal special runs of the 2-bit input
   DevBuf nearbits, tailkeys[2], tailpos[2];   // the keys with a tail field, sorted apart (stage_begin)
   unsigned text_left = 0;   // text-driven rounds still allowed before ranks are built
@@ -424,7 +426,7 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
   cudaStream_t st = h->st;
   h->flags = flags;
   h->isa_built = false;
-  h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0; h->text_left = 0;
+  h->M0 = h->M = 0; h->cur = 0; h->round = 0; h->nllv = 0; h->text_left = 0; h->isa_round = 0;
   h->fmt = choose_fmt(h, h->pl);
   const KeyFmt f = h->fmt;
   h->depth[0] = (u64) f.m;
@@ -834,8 +836,10 @@ int round_local(gtb_esa *h)
     unsigned int *qcount = reinterpret_cast<unsigned int *>(h->misc.as<u64>() + 20);
     GTB_CUDA(cudaMemsetAsync(qcount, 0, sizeof(unsigned int), h->st));
     k_build_dkeys<DNA><<<grid_for(h->M, 256), 256, 0, h->st>>>(make_rankmap<DNA>(h), h->upos[h->cur].as<u32>(),
-        h->ugrp[h->cur].as<u32>(), h->M, hlen, h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount);
+        h->ugrp[h->cur].as<u32>(), h->M, hlen, h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount,
+        (h->isa_round < (unsigned) h->opt_pairs_by_text) ? 1 : 0);
     GTB_LAUNCH_CHECK();
+    h->isa_round++;
     k_build_dkeys_search<DNA><<<grid_for(h->M, 256, 148u * 8u), 256, 0, h->st>>>(make_rankmap<DNA>(h), h->upos[h->cur].as<u32>(),
         h->ugrp[h->cur].as<u32>(), hlen, h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount);
     GTB_LAUNCH_CHECK();
@@ -1138,6 +1142,7 @@ gtb_esa *gtb_esa_new(int device, char *errbuf, size_t errlen)
   if (const char *e = getenv("GTB200_KEY_SYMBOLS")) h->opt_key_symbols = atoi(e);
   if (const char *e = getenv("GTB200_TEXT_ROUNDS")) h->opt_text_rounds = atoi(e) > 8 ? 8 : atoi(e);
   if (const char *e = getenv("GTB200_TAIL_LAST")) h->opt_tail_last = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("GTB200_PAIRS_BY_TEXT")) h->opt_pairs_by_text = atoi(e) < 0 ? 0 : atoi(e);
   memset(&h->stats, 0, sizeof h->stats);
   if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h; return fail("cudaStreamCreate", e);

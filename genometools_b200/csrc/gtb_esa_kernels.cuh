@@ -1182,9 +1182,47 @@ __device__ __forceinline__ void queue_append(bool need, u32 c, u32 *__restrict__
   if (need) queue[base + (unsigned) __popc(m & lanemask_lt())] = c;
 }
 
+// Tie groups of exactly TWO suffixes (chance ties of random sequence: 8.7 M of the 45.7 M ties of c4, and the
+// ones whose partner h further is an untied suffix that would have to be SEARCHED) are decided by comparing
+// the text of the two suffixes from depth h on, rule R: symbols first; the suffix that meets a special first
+// is the larger one; two specials at the same depth by position.  The round then sees two different keys
+// (0 for the smaller, 1 for the larger), i.e. a resolved pair.  Undecided after PAIR_WINDOWS windows of 32
+// bases (a real repeat): the rank lookup as for every other group.
+constexpr int PAIR_WINDOWS = 4;
+__device__ __forceinline__ int dna_pair_less(const u64 *__restrict__ words, const u32 *__restrict__ spmask,
+                                             u64 pa, u64 pb, u64 off)
+{
+  for (int it = 0; it < PAIR_WINDOWS; it++, off += 32) {
+    const u32 wa = mask_window(spmask, pa + off), wb = mask_window(spmask, pb + off);
+    const unsigned la = wa ? (unsigned) __ffs(wa) - 1u : 32u, lb = wb ? (unsigned) __ffs(wb) - 1u : 32u;
+    const unsigned lim = la < lb ? la : lb;
+    const u64 xa = dna_window(words, pa + off), xb = dna_window(words, pb + off);
+    const u64 x = xa ^ xb;
+    const unsigned common = x ? (unsigned) (__clzll((long long) x) >> 1) : 32u;
+    if (common < lim) return xa < xb ? 1 : 0;              // (the first differing base decides: MSB-first words)
+    if (lim < 32u) {
+      if (la != lb) return la > lb ? 1 : 0;                // b meets a special first: a is the smaller one
+      return pa < pb ? 1 : 0;                              // both meet a special here: by position
+    }
+  }
+  return -1;
+}
+// is element c one of a group of exactly two?  *partner = the other one
+__device__ __forceinline__ bool tie_pair_partner(const u32 *__restrict__ ugrp, u64 M, u64 c, u64 *partner)
+{
+  const u32 g = ugrp[c];
+  const bool prev_same = c > 0 && ugrp[c - 1] == g, next_same = c + 1 < M && ugrp[c + 1] == g;
+  if (prev_same == next_same) return false;                // alone (cannot be) or inside a longer run
+  if (next_same) { if (c + 2 < M && ugrp[c + 2] == g) return false; *partner = c + 1; return true; }
+  if (c >= 2 && ugrp[c - 2] == g) return false;
+  *partner = c - 1;
+  return true;
+}
+
 template <bool DNA>
 __global__ void k_build_dkeys(RankMap<DNA> rm, const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
-                              u64 M, u64 h, u64 *__restrict__ dkeys, u32 *__restrict__ queue, unsigned int *qcount)
+                              u64 M, u64 h, u64 *__restrict__ dkeys, u32 *__restrict__ queue, unsigned int *qcount,
+                              int pairs_by_text)
 {
   const u64 stride = (u64) gridDim.x * blockDim.x;
   for (u64 c0 = blockIdx.x * (u64) blockDim.x; c0 < M; c0 += stride) {      // (whole warps stay in the loop)
@@ -1192,7 +1230,12 @@ __global__ void k_build_dkeys(RankMap<DNA> rm, const u32 *__restrict__ upos, con
     bool need = false;
     if (c < M) {
       u32 r;
-      if (rm.get_fast((u64) upos[c] + h, r)) dkeys[c] = ((u64) ugrp[c] << 32) | (u64) r;
+      u64 partner;
+      int less = -1;
+      if (DNA && pairs_by_text && tie_pair_partner(ugrp, M, c, &partner))
+        less = dna_pair_less(rm.src.words, rm.src.spmask, (u64) upos[c], (u64) upos[partner], h);
+      if (less >= 0) dkeys[c] = ((u64) ugrp[c] << 32) | (u64) (less ? 0u : 1u);
+      else if (rm.get_fast((u64) upos[c] + h, r)) dkeys[c] = ((u64) ugrp[c] << 32) | (u64) r;
       else need = true;
     }
     queue_append(need, (u32) c, queue, qcount);

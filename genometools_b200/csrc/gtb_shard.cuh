@@ -72,7 +72,8 @@ __device__ __forceinline__ int owner_of_key(const u64 *s_first, int nr, u64 kq)
 template <bool DNA>
 __global__ void k_build_dkeys_peer(RankMap<DNA> rm, const PeerTableDev *__restrict__ pt,
                                    const u32 *__restrict__ upos, const u32 *__restrict__ ugrp,
-                                   u64 M, u64 h, u64 *__restrict__ dkeys, u32 *__restrict__ queue, unsigned int *qcount)
+                                   u64 M, u64 h, u64 *__restrict__ dkeys, u32 *__restrict__ queue, unsigned int *qcount,
+                                   int pairs_by_text)
 {
   __shared__ u64 s_first[MAX_RANGES];
   const int nr = pt->n, mine = pt->mine;
@@ -86,7 +87,12 @@ __global__ void k_build_dkeys_peer(RankMap<DNA> rm, const PeerTableDev *__restri
       const u64 q = (u64) upos[c] + h;
       u32 r = 0;
       bool have = true;
-      if (q >= rm.n) r = (u32) rm.n;
+      u64 partner;
+      int less = -1;
+      if (DNA && pairs_by_text && tie_pair_partner(ugrp, M, c, &partner))      // (a tie group lies inside one range)
+        less = dna_pair_less(rm.src.words, rm.src.spmask, (u64) upos[c], (u64) upos[partner], h);
+      if (less >= 0) r = less ? 0u : 1u;
+      else if (q >= rm.n) r = (u32) rm.n;
       else {
         const uint4 w = __ldg(rm.rw + (q >> 5));
         const u32 bit = 1u << (q & 31u), below = bit - 1u;

@@ -494,8 +494,9 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
         GTB_CUDA(cudaMemsetAsync(qcount, 0, sizeof(unsigned int), st));
         k_build_dkeys_peer<DNA><<<grid_for(h->M, 256), 256, 0, st>>>(make_rankmap<DNA>(h), h->peertab.as<PeerTableDev>(),
             h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(), h->M, h->depth[h->round], h->dkeys.as<u64>(),
-            h->sendidx.as<u32>(), qcount);
+            h->sendidx.as<u32>(), qcount, (h->isa_round < (unsigned) h->opt_pairs_by_text) ? 1 : 0);
         GTB_LAUNCH_CHECK();
+        h->isa_round++;
         k_build_dkeys_peer_search<DNA><<<grid_for(h->M, 256, 148u * 8u), 256, 0, st>>>(make_rankmap<DNA>(h),
             h->peertab.as<PeerTableDev>(), h->upos[h->cur].as<u32>(), h->ugrp[h->cur].as<u32>(), h->depth[h->round],
             h->dkeys.as<u64>(), h->sendidx.as<u32>(), qcount);
