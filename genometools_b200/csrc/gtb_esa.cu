@@ -385,28 +385,59 @@ int count_codes(gtb_esa *h, unsigned pl, bool all, u64 first = 0, u64 end = ~0ul
 // over the symbol digits only and the keys with a tail enter it as a second, pre-sorted source
 // (stage_begin, radix_sort): c4 sorts with 5 passes instead of 6.  Otherwise 17 / 21 / 25 / 29
 // symbols (dna_fmt_for).  Every function that makes keys of a run takes its format from here.
-bool tails_rare(const gtb_esa *h) { return h->dna && (h->nspecialranges + 1) * 2048 <= h->n; }
+// Is dropping the pass over the tail digit worth it?  It replaces one pass over all N pairs by the
+// separate treatment of the keys with a tail: at most (special runs + 1) * (m - 1) of them (byte path: every
+// special counts as a run).  Yes when those are at most a sixth of the suffixes.
+bool tails_few(const gtb_esa *h, int m)
+{
+  if (h->opt_tail_last == 0) return false;
+  if (h->opt_tail_last == 1) return true;
+  const u64 runs = h->dna ? h->nspecialranges : h->S;
+  const u64 regular = h->n - h->S;
+  return (runs + 1) * (u64) (m - 1) <= regular / 6;
+}
+// ... and the digit histograms from one table of 4-mers (k_hist_4mer) when the corrections at the run ends
+// (m - 4 windows per run and digit) are few against the text
+bool hist4_pays(const gtb_esa *h, int m) { return h->dna && (h->nspecialranges + 1) * (u64) m * 8 <= h->n / 16; }
 
 KeyFmt choose_fmt(const gtb_esa *h, unsigned pl)
 {
   const int k = h->opt_key_symbols;
   if (!h->dna) {
-    if ((k == 8 || k == 10 || k == 12) && k >= (int) pl) return make_fmt(k, 5, 4);
+    // byte path, 5 bits per symbol.  Tail-last formats: the boundary between the tail field and the symbols
+    // lies on a byte (m = 8: 40 symbol bits; m = 9: 45 symbol bits + 3 zero bits), so the symbols take 5 / 6
+    // passes and the tail digit none; otherwise m = 8 / 10 / 12 with the tail directly below the symbols
+    const bool forced = (k == 8 || k == 9 || k == 10 || k == 12) && k >= (int) pl;
+    if (forced && !(k <= 9 && tails_few(h, k))) { if (k != 9) return make_fmt(k, 5, 4); }
+    const int cand[2] = {8, 9};
+    for (int i = 0; i < 2; i++) {
+      const int m = forced ? k : cand[i];
+      if (m > 9 || (unsigned) m < pl || !tails_few(h, m)) { if (forced) break; continue; }
+      double km = 1.0;
+      for (int j = 0; j < m; j++) km *= (double) (h->K < 2 ? 2 : h->K);
+      if (forced || (double) h->n / km <= 0.001) {
+        const int boundary = (64 - 5 * m) & ~7;
+        return KeyFmt{m, 5, 4, boundary - 4};
+      }
+    }
     return byte_fmt_for(h->n, h->K, pl);
   }
   if (k >= (int) pl && k >= 1 && k <= 29) return make_fmt(k, 2, k > 15 ? (k == 29 ? 6 : 5) : 4);
-  if (h->opt_tail_last != 0 && (tails_rare(h) || h->opt_tail_last == 1)) {
+  {
     const int cand[4] = {16, 20, 24, 28};
     for (int i = 0; i < 4; i++) {
       const int m = cand[i];
       if ((unsigned) m < pl) continue;
-      if ((double) h->n / (double) (1ull << (2 * m)) <= 0.01 || m == 28) return make_fmt(m, 2, 5);
+      if ((double) h->n / (double) (1ull << (2 * m)) <= 0.01 || m == 28) {
+        if (tails_few(h, m)) return make_fmt(m, 2, 5);
+        break;
+      }
     }
   }
   return dna_fmt_for(h->n, pl);
 }
 // the digit below the symbols holds only the tail field (and the pass over it can be replaced)
-bool fmt_tail_digit_alone(const KeyFmt &f) { return f.b == 2 && f.tb <= 8 && (f.sh + f.tb) % 8 == 0 && f.sh + f.tb < 64; }
+bool fmt_tail_digit_alone(const KeyFmt &f) { return f.tb <= 8 && (f.sh + f.tb) % 8 == 0 && f.sh + f.tb <= 64 - f.m * f.b && f.sh + f.tb < 64; }
 
 template <bool DNA> int compact_ties(gtb_esa *h);
 template <bool DNA> int build_ranks(gtb_esa *h);
@@ -493,8 +524,7 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
   // the full keys as a second source of the first symbol pass -- the result is the one of the sort
   // with the tail digit (equal symbols: full keys first, then by tail, then text order).
   float first_ms0 = 0; u32 first_p0 = 0; u64 first_m0 = 0;     // (the tiny sort of the tail keys is not "first level")
-  const bool tail_last = DNA && !ext && h->n > 0 && fmt_tail_digit_alone(f) && h->opt_tail_last != 0 &&
-                         (tails_rare(h) || h->opt_tail_last == 1);
+  const bool tail_last = !ext && h->n > 0 && fmt_tail_digit_alone(f) && tails_few(h, f.m);
   if (tail_last) {
     const u64 nw = (h->n + 31) >> 5;
     u64 nt = 0;
@@ -530,7 +560,7 @@ int stage_begin(gtb_esa *h, unsigned flags, const PairSrc *ext = nullptr, u64 ex
     }
     first_ms0 = h->rw.ms_radix; first_p0 = h->rw.passes; first_m0 = h->rw.pairs_moved;
     src.skip_near = true;
-    src.hist4 = h->dna && (h->nspecialranges == 0 || h->ranges.p != nullptr) && getenv("GTB200_NO_HIST4") == nullptr;
+    src.hist4 = hist4_pays(h, f.m) && (h->nspecialranges == 0 || h->ranges.p != nullptr) && getenv("GTB200_NO_HIST4") == nullptr;
     plan_add_bits(plan, f.sh + f.tb, 64);
     GTB_TRY((radix_sort<TextSrc<DNA>, TailSrc>(h->rw, st, src, h->n, kb, vb, plan, &h->res, &N, err, nt > 0 ? &tsrc : nullptr, nt)));
     src.skip_near = false; src.hist4 = false;

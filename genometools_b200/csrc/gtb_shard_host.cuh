@@ -383,8 +383,7 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
       rc = timed_stage(h, [&]() -> int {
         // (as in the single-range sort: when tails are rare the keys that carry one are sorted apart and
         //  the first-level sort runs over the symbol digits only)
-        const bool tail_last = DNA && received > 0 && fmt_tail_digit_alone(h->fmt) && h->opt_tail_last != 0 &&
-                               (tails_rare(h) || h->opt_tail_last == 1);
+        const bool tail_last = received > 0 && fmt_tail_digit_alone(h->fmt) && tails_few(h, h->fmt.m);
         const u64 nw = (received + 31) >> 5;
         if (tail_last) GTB_TRY(h->nearbits.ensure(sizeof(u32) * (nw + 2), err));
         if (received > 0) {

@@ -268,6 +268,21 @@ def test_cuda_protein_key_lengths(monkeypatch, m, text_rounds):
         check_against_oracle(sym, 20, pl, res, f"protein m={m} text_rounds={text_rounds} pl={pl}")
 
 
+@pytest.mark.parametrize("m,tail_last,text_rounds", [(8, 1, 0), (9, 1, 0), (9, 1, 2), (8, 0, 1), (9, 0, 0)])
+def test_cuda_protein_tail_keys_sorted_apart(monkeypatch, m, tail_last, text_rounds):
+    """byte path: key lengths whose tail field ends on a byte boundary (m = 8; m = 9 with three zero bits
+    between the symbols and the tail), the tail keys sorted apart -- and the same lengths with the tail pass"""
+    monkeypatch.setenv("GTB200_KEY_SYMBOLS", str(m))
+    monkeypatch.setenv("GTB200_TAIL_LAST", str(tail_last))
+    monkeypatch.setenv("GTB200_TEXT_ROUNDS", str(text_rounds))
+    sym = synth.protein(9000, 23, reclen=70, p_x=0.004)
+    sym[1200:1700] = sym[4000:4500]            # a 500-residue repeat: lcp >= 255 -> .llv
+    for pl in (1, 2):
+        for parts in (1, 3):
+            res = build_esa(encode_symbols(sym, 20), pl, parts=parts)
+            check_against_oracle(sym, 20, pl, res, f"protein m={m} tail_last={tail_last} pl={pl} parts={parts}")
+
+
 def test_cuda_partial_counts_and_range_split():
     """count allreduce building blocks: the raw counts of two halves of the text add up to the
     bucket table of the whole, and the device-side range split equals the host mirror of
