@@ -159,18 +159,9 @@ def test_c5_full_size_byte_identical():
 
 
 @need("c3")
-def test_c3_full_size_byte_identical():
-    run_config("c3", True)
-
-
-@need("c3")
-def test_c3_full_size_overlapped_copy_byte_identical():
+def test_c3_full_size_byte_identical_overlapped_copy():
+    """c3 through gtb_esa_run_to_host (c2 and c5 above: gtb_esa_run + gtb_esa_copy_results)"""
     run_config("c3", True, overlapped=True)
-
-
-@need("c5")
-def test_c5_full_size_overlapped_copy_byte_identical():
-    run_config("c5", True, overlapped=True)
 
 
 @need("c4@0.002")
