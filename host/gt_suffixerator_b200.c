@@ -151,9 +151,6 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     gt_logger_log(logger, "B200: %d GPU(s), %d bucket-code range(s) (gt -j %u, -parts %u)", init.ndevices,
                   init.nranges, gt_jobs, gt_index_options_numofparts_value(so.idxopts));
     init_ever = true;
-    /* all kernels are loaded with the context (on the init thread, beside the encoder) instead of one by
-       one at their first launch inside the sort: 0.1 s of a 64 Mbp run */
-    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     init_started = pthread_create(&init_tid, NULL, b200_init_thread, &init) == 0;
     if (!init_started) b200_init_thread(&init);
   }
