@@ -266,14 +266,19 @@ struct TiedMsg { u64 M; };
 struct SeamMsg { int nonempty, pad; u64 first_key, last_key, nllv; };
 
 // this range took no part of the codes (fewer parts than ranges): an empty, finished run
-void finish_empty(gtb_esa *h, unsigned flags)
+int finish_empty(gtb_esa *h, unsigned flags)
 {
   h->flags = flags;
+  // its bucket tables are part of the job's sum: all zero
+  h->counted = false; h->lb_own = false;
+  GTB_TRY(count_codes(h, h->pl, false));
+  h->lb_own = true;
   h->N = 0; h->entries = 0; h->nllv = 0; h->M0 = h->M = 0; h->sa_offset = 0;
   h->first_key = h->last_key = 0;
   h->stats.totallength = h->n; h->stats.specialcharacters = h->S; h->stats.nonspecials = 0;
   h->stats.longest = ~0ull; h->stats.prefixlength = h->pl; h->stats.numofchars = h->K;
   h->in_progress = false;
+  return 0;
 }
 
 template <bool DNA>
@@ -326,7 +331,7 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
   if (!slice_mode) {
     rc = 0;
     if (active) rc = timed_stage(h, [&]() -> int { return stage_begin<DNA>(h, flags); });
-    else finish_empty(h, flags);
+    else rc = finish_empty(h, flags);
   } else {
     // 2a. the owner's receive buffer (its second value buffer), sizes of the slice's groups
     const u64 width = active ? out4[4 * me + 3] : 0;
@@ -430,7 +435,7 @@ int sharded_body(gtb_esa *h, ShardComm &c, unsigned pl, unsigned flags)
         }
         return stage_begin<DNA>(h, flags, &ext, received, &tsrc, nt);
       });
-    } else finish_empty(h, flags);
+    } else rc = finish_empty(h, flags);
   }
 
   // ---- 3. refinement of the ties in lock step; ranks of foreign positions are read from the
