@@ -15,10 +15,13 @@ buffers, one untimed warm-up step, per-phase breakdown).  At N = 1 the line also
 `cpu_baseline` (the unmodified reference, one host core, bounded sample of the same generator)
 and `cli` (the drop-in binary host/_build/gt_b200 on the same FASTA sample, index files compared
 byte for byte with the reference's).
-With N > 1 ranks (torchrun) the bucket codes are sharded: count allreduce (NCCL), from 4
-ranks on key generation sharded by text position with an all-to-all of the positions to the
-owning code range, the rank's own range sorted, rank exchange (all-to-all) in the doubling
-rounds.
+With N > 1 ranks (torchrun) the bucket codes are sharded, one range per rank, and every rank calls
+the same C entry the drop-in's `gt -j N` runs with threads (gtb_esa_run_sharded): the count gather and
+a few small sync blocks travel as NCCL all-gathers, the positions of the position-sharded text scan
+(3 ranks and more) and the rank lookups of the doubling rounds go through peer memory inside the
+kernels.  GTB_BENCH_PROTOCOL=exchange keeps round 1's NCCL all-to-all request/answer protocol.
+`checks.identical_to_reference`: order-dependent checksums of all four tables in HBM, summed over the
+ranks, against the checksums of the files the unmodified reference wrote for the workload at this size.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -407,7 +410,8 @@ def main():
     def step():
         if world > 1 and protocol == "sharded":
             # the C entry the drop-in's `gt -j N` runs with threads, here one process per GPU: NCCL carries
-            # the count gather and the small sync blocks, peer memory (CUDA IPC) everything heavy
+            # the count gather and the small sync blocks, peer memory (mapped through the CUDA virtual-memory API)
+            # everything heavy
             run_sharded(lib, h, pl, flags, dist, dev, gather)
         elif world > 1:
             parts = coarse_allreduce_and_split(lib, h, pl, n, dist, dev)
@@ -687,7 +691,7 @@ def main():
                    "dtype_note": "u32 positions in HBM (n + 1 < 2^32), widened to the file's uint64 on copy-out",
                    "l2": "inputs_exceed_l2 (no flush needed)", "sharding": f"{world} bucket-code ranges, one per GPU "
                    f"({protocol}: " + ("gtb_esa_run_sharded -- NCCL all-gathers of small host blocks, positions and "
-                                       "rank lookups through peer memory (CUDA IPC)" if protocol == "sharded" else
+                                       "rank lookups through peer memory (cuMemCreate allocations mapped by the peers)" if protocol == "sharded" else
                                        "NCCL all-to-all request/answer protocol") + ")"
                    if world > 1 else "single range", "scale": args.scale},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

@@ -714,7 +714,7 @@ rs_owner_hist_kernel(Src src, u64 N, unsigned long long *__restrict__ ghist,
 //                     are written one after the other to okeys/ovals (okeys may be null: values
 //                     only).  binbase_host[r] != 0: the values of range r are stored, in source
 //                     order, from that device address on -- a buffer of the OWNER, mapped into this
-//                     GPU's address space (peer access / CUDA IPC): the exchange of the partitioned
+//                     GPU's address space (peer access, or a mapping of the owner's allocation): the exchange of the partitioned
 //                     positions is fused into the pass, the stores travel over NVLink.
 template <class Src>
 static int rs_owner_counts(RadixWork &w, cudaStream_t st, const Src &src, u64 nsrc, const u64 *bounds,

@@ -12,7 +12,7 @@ struct ShardComm {
   int me = 0, world = 1;
   gtb_allgather_fn ag = nullptr;
   void *ctx = nullptr;
-  bool ipc = false;               // the other ranges live in other processes (CUDA IPC mappings)
+  bool ipc = false;               // the other ranges live in other processes (their buffers are mapped, gtb_vmm.cuh)
 };
 
 struct SyncHead { int rc; char msg[124]; };

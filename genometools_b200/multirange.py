@@ -422,7 +422,7 @@ class DistAllgather:
 
 def run_sharded(lib, handle, prefixlength, flags, dist, device, gather=None):
     """rank r of the process group runs code range r of the job: gtb_esa_run_sharded with a NCCL
-    all-gather, buffers of the other ranks mapped with CUDA IPC.  The same C entry the drop-in's
+    all-gather, the buffers of the other ranks mapped through the CUDA virtual-memory API (csrc/gtb_vmm.cuh).  The same C entry the drop-in's
     gtb_group drives with threads."""
     gather = gather or DistAllgather(dist, device)
     rc = lib.gtb_esa_run_sharded(handle, prefixlength, flags, dist.get_rank(), dist.get_world_size(),

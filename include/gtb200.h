@@ -312,8 +312,8 @@ int gtb_esa_hash_bcktab(gtb_esa *h, uint64_t *out);
    replicated encseq") ------------------------------------------------------------------------
    Every code range -- one handle on one GPU -- executes gtb_esa_run_sharded with its rank: as a
    thread of one process (gtb_group below: what the C host does for `gt -j N`, src/gtr.c:181) or as a
-   process of its own (bench.py under torchrun, separate_processes = 1: buffers are mapped with CUDA
-   IPC).  The ranges meet at a handful of all-gathers of small host structs, the one collective the
+   process of its own (bench.py under torchrun, separate_processes = 1: the buffers peers touch are
+   virtual-memory-API allocations passed as file descriptors and mapped with 2 MB pages, csrc/gtb_vmm.cuh).  The ranges meet at a handful of all-gathers of small host structs, the one collective the
    caller provides (in-process: a shared buffer; across processes: NCCL).  The heavy exchanges go
    through peer memory inside the kernels: the partition pass of the position-sharded text scan
    stores every position straight into the owning range's HBM over NVLink, and a doubling round
