@@ -35,11 +35,43 @@ class GtbStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class GtbFastaRequest(C.Structure):
+    _fields_ = [
+        ("filenames", C.POINTER(C.c_char_p)), ("numoffiles", C.c_uint64), ("indexname", C.c_char_p),
+        ("symbolmap", C.POINTER(C.c_uint8)), ("decode", C.c_char_p), ("numofchars", C.c_uint),
+        ("out_des", C.c_int), ("out_sds", C.c_int), ("out_ssp", C.c_int), ("out_md5", C.c_int),
+        ("clip_desc", C.c_int), ("threads", C.c_int),
+    ]
+
+
+class GtbFastaSummary(C.Structure):
+    _fields_ = [
+        ("totallength", C.c_uint64), ("numofsequences", C.c_uint64), ("numoffiles", C.c_uint64),
+        ("specialcharacters", C.c_uint64), ("specialranges", C.c_uint64), ("realspecialranges", C.c_uint64),
+        ("wildcards", C.c_uint64), ("wildcardranges", C.c_uint64), ("realwildcardranges", C.c_uint64),
+        ("sat", C.c_uint64), ("satsep", C.c_uint64), ("characterdistribution", C.c_uint64 * 4),
+        ("input_bytes", C.c_uint64), ("satname", C.c_char * 16), ("threads", C.c_uint),
+        ("seconds_count", C.c_double), ("seconds_emit", C.c_double), ("seconds_lists", C.c_double),
+        ("seconds_pack", C.c_double), ("seconds_md5", C.c_double), ("seconds_write", C.c_double),
+        ("seconds_total", C.c_double),
+    ]
+
+    def as_dict(self):
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if k == "characterdistribution" else (v.decode() if isinstance(v, bytes) else v)
+        return d
+
+
+GTB_FASTA_OK, GTB_FASTA_UNSUPPORTED, GTB_FASTA_ERROR = 0, 1, -1
+
 # every symbol include/gtb200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _U64 = C.c_uint64
 SYMBOLS = {
     "gtb_abi_version": (C.c_int, []),
+    "gtb_fasta_encode": (C.c_int, [C.POINTER(GtbFastaRequest), C.POINTER(GtbFastaSummary), C.c_char_p, C.c_size_t]),
     "gtb_device_count": (C.c_int, []),
     "gtb_esa_new": (_P, [C.c_int, C.c_char_p, C.c_size_t]),
     "gtb_esa_delete": (None, [_P]),

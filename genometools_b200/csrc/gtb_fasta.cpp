@@ -1,0 +1,871 @@
+// gtb_fasta.cpp -- FASTA files -> the index files of a GtEncseq (.esq .ssp .des .sds .md5) for the
+// DNA alphabet, on all host cores; the step in front of the sorter.
+//
+// The reference does this with two passes of one thread that fetch every character through a virtual
+// call (gt_encseq_new_from_files, /root/reference/src/core/encseq.c:7503-7714: first pass
+// gt_inputfiles2sequencekeyvalues :5421-5673 with encseq_charproc.gen, second pass
+// files2encodedsequence :4529-4647 with the fill function of the chosen representation; the reader is
+// gt_sequence_buffer_fasta_advance, src/core/sequence_buffer_fasta.c:41-165): 1.5-1.9 s for 64 Mbp,
+// most of the wall time of the drop-in binary once the sort takes 50 ms.  Here the files are mapped,
+// cut into chunks at line ends (after a newline the reader is never inside a description), and every
+// pass is a parallel loop over chunks or over blocks of the symbol array:
+//
+//   count    symbols + separators per chunk, descriptions located, characters checked
+//   emit     one code per symbol into a byte array (0..3, 254 wildcard, 255 separator), separator
+//            positions, wildcard runs, distribution of the original characters
+//   pack     32 symbols per 64-bit word (GtTwobitencoding), special positions filled the way the
+//            chosen representation fills them
+//   md5      one sequence per task
+//
+// and the tables of the representation (wildcard ranges in pages, separator positions in pages) are
+// built from the run lists.  The files are written field by field in the order of the reference's
+// map specifications, every field padded to 8 bytes (gt_mapspec_write, src/core/mapspec.c:366-466).
+//
+// What is not covered returns GTB_FASTA_UNSUPPORTED with the reason, BEFORE anything is written, and
+// the caller runs the reference's encoder instead (which then also words the error messages): other
+// alphabets, compressed or non-regular files, files that do not begin with '>', characters outside the
+// alphabet, empty sequences, a description that ends with the file or holds a NUL, 2^32-2 symbols or
+// more.  Byte identity with the reference's files is tested in tests/test_fasta_encseq.py.
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cerrno>
+#include <chrono>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/gtb200.h"
+
+namespace {
+
+constexpr uint8_t CODE_WILDCARD = 254, CODE_SEPARATOR = 255, CODE_UNDEF = 253;   // src/core/chardef.h:34-46
+// GtEncseqAccessType, src/core/encseq_access_type.h:24-34
+enum Sat : uint64_t { SAT_DIRECT = 0, SAT_BYTECOMPRESS, SAT_EQUALLENGTH, SAT_BITACCESS, SAT_UCHAR, SAT_USHORT,
+                      SAT_UINT32, SAT_UNDEFINED };
+constexpr uint64_t ENCSEQ_VERSION = 3;                                           // src/core/encseq.h:40
+
+struct Unsupported { std::string why; };
+struct IoError { std::string why; };
+
+std::string format(const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  return buf;
+}
+
+double now()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- md5 (RFC 1321), one object per sequence
+struct Md5 {
+  uint32_t a = 0x67452301u, b = 0xefcdab89u, c = 0x98badcfeu, d = 0x10325476u;
+  uint64_t total = 0;
+  uint8_t tail[64];
+  unsigned ntail = 0;
+
+  static uint32_t rol(uint32_t x, int s) { return (x << s) | (x >> (32 - s)); }
+
+  void block(const uint8_t *p)
+  {
+    static const uint32_t K[64] = {
+      0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
+      0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
+      0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
+      0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
+      0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+      0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
+      0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
+      0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+    static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22,
+                              5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
+                              4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                              6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+    uint32_t w[16];
+    memcpy(w, p, 64);                                  // little-endian host
+    uint32_t A = a, B = b, C = c, D = d;
+    for (int i = 0; i < 64; i++) {
+      uint32_t f;
+      int g;
+      if (i < 16)      { f = (B & C) | (~B & D); g = i; }
+      else if (i < 32) { f = (D & B) | (~D & C); g = (5 * i + 1) & 15; }
+      else if (i < 48) { f = B ^ C ^ D;          g = (3 * i + 5) & 15; }
+      else             { f = C ^ (B | ~D);       g = (7 * i) & 15; }
+      const uint32_t t = D;
+      D = C;
+      C = B;
+      B = B + rol(A + f + K[i] + w[g], S[i]);
+      A = t;
+    }
+    a += A; b += B; c += C; d += D;
+  }
+
+  void update(const uint8_t *p, size_t n)
+  {
+    total += n;
+    if (ntail) {
+      const size_t take = std::min<size_t>(64 - ntail, n);
+      memcpy(tail + ntail, p, take);
+      ntail += (unsigned) take; p += take; n -= take;
+      if (ntail < 64) return;
+      block(tail);
+      ntail = 0;
+    }
+    for (; n >= 64; p += 64, n -= 64) block(p);
+    if (n) { memcpy(tail, p, n); ntail = (unsigned) n; }
+  }
+
+  void hex(char out[33])
+  {
+    const uint64_t bits = total * 8;
+    const uint8_t one = 0x80, zero[64] = {0};
+    update(&one, 1);
+    update(zero, (ntail <= 56) ? 56 - ntail : 120 - ntail);
+    uint8_t len[8];
+    memcpy(len, &bits, 8);
+    update(len, 8);
+    const uint32_t v[4] = {a, b, c, d};
+    const uint8_t *raw = reinterpret_cast<const uint8_t *>(v);
+    for (int i = 0; i < 16; i++) snprintf(out + 2 * i, 3, "%02x", raw[i]);
+    out[32] = '\0';
+  }
+};
+
+// ---------------------------------------------------------------- inputs
+struct Input {
+  std::string name;
+  const uint8_t *p = nullptr;
+  size_t len = 0;
+};
+
+struct Mapped {
+  std::vector<Input> files;
+  ~Mapped()
+  {
+    for (auto &f : files)
+      if (f.p != nullptr && f.len > 0) munmap(const_cast<uint8_t *>(f.p), f.len);
+  }
+};
+
+bool has_suffix(const std::string &s, const char *suf)
+{
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+void map_inputs(const gtb_fasta_request *rq, Mapped &m)
+{
+  if (rq->numoffiles == 0) throw Unsupported{"no sequence files"};
+  m.files.resize(rq->numoffiles);
+  for (uint64_t i = 0; i < rq->numoffiles; i++) {
+    Input &f = m.files[i];
+    f.name = rq->filenames[i];
+    // gt_file_mode_determine, src/core/file.c: the suffix selects the decompressor
+    if (has_suffix(f.name, ".gz") || has_suffix(f.name, ".bz2"))
+      throw Unsupported{format("file \"%s\" is compressed", f.name.c_str())};
+    const int fd = open(f.name.c_str(), O_RDONLY);
+    if (fd < 0) throw Unsupported{format("cannot open file \"%s\": %s", f.name.c_str(), strerror(errno))};
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+      close(fd);
+      throw Unsupported{format("\"%s\" is not a regular file", f.name.c_str())};
+    }
+    f.len = (size_t) st.st_size;
+    if (f.len == 0) { close(fd); throw Unsupported{format("file \"%s\" is empty", f.name.c_str())}; }
+    void *p = mmap(nullptr, f.len, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { f.len = 0; throw IoError{format("cannot map file \"%s\": %s", f.name.c_str(), strerror(errno))}; }
+    madvise(p, f.len, MADV_SEQUENTIAL);
+    f.p = static_cast<const uint8_t *>(p);
+    // gt_sequence_buffer_new_guess_type looks at the first file only (src/core/sequence_buffer.c:63-103);
+    // a later file that begins with sequence characters would continue the last sequence of the file before
+    if (f.p[0] != '>') throw Unsupported{format("file \"%s\" does not begin with '>'", f.name.c_str())};
+  }
+}
+
+// ---------------------------------------------------------------- chunks
+struct Header { size_t desc_begin, desc_end; uint64_t sep_pos; };   // description = [desc_begin, desc_end), '\n' at desc_end
+struct Run { uint64_t start, len; };
+
+struct Chunk {
+  unsigned file = 0;
+  size_t begin = 0, end = 0;
+  uint64_t emitted = 0;          // symbols + one per header (a separator; the first header overall emits none)
+  uint64_t nheaders = 0;
+  uint64_t out = 0;              // position of the first symbol this chunk emits
+  std::vector<Header> headers;
+  std::vector<Run> wild;         // maximal within the chunk
+  uint64_t orig[256];
+  std::string bad;               // why the input is not covered
+};
+
+// classes as bit flags: a stretch of text is scanned without branches, the flags of its characters OR-ed
+enum Cls : uint8_t { C_SYMBOL = 0, C_SPACE = 1, C_HEADER = 2, C_ILLEGAL = 4 };
+constexpr uint16_t E_SYMBOL = 0x100, E_WILD = 0x200;            // Tables::emit: code | flags
+
+struct Tables {
+  uint8_t cls[256];
+  uint8_t code[256];
+  uint16_t emit[256];
+};
+
+Tables make_tables(const uint8_t *symbolmap)
+{
+  Tables t;
+  for (int c = 0; c < 256; c++) {
+    t.code[c] = symbolmap[c];
+    if (isspace(c)) t.cls[c] = C_SPACE;                 // sequence_buffer_fasta.c:124
+    else if (c == '>') t.cls[c] = C_HEADER;             // :126
+    else if (symbolmap[c] == CODE_UNDEF || symbolmap[c] == CODE_SEPARATOR || c >= 128 || c == 0)
+      t.cls[c] = C_ILLEGAL;                             // process_char, sequence_buffer_inline.h:34-43
+    else t.cls[c] = C_SYMBOL;
+    t.emit[c] = symbolmap[c];
+    if (t.cls[c] == C_SYMBOL) t.emit[c] |= E_SYMBOL | (symbolmap[c] == CODE_WILDCARD ? E_WILD : 0);
+  }
+  return t;
+}
+
+std::vector<Chunk> make_chunks(const std::vector<Input> &files, size_t target)
+{
+  std::vector<Chunk> chunks;
+  for (unsigned fi = 0; fi < files.size(); fi++) {
+    const Input &f = files[fi];
+    size_t b = 0;
+    while (b < f.len) {
+      size_t e = b + target;
+      if (e >= f.len) e = f.len;
+      else {
+        const void *nl = memchr(f.p + e - 1, '\n', f.len - (e - 1));   // a chunk ends behind a newline
+        e = nl ? (size_t) (static_cast<const uint8_t *>(nl) - f.p) + 1 : f.len;
+      }
+      Chunk c;
+      c.file = fi; c.begin = b; c.end = e;
+      chunks.push_back(std::move(c));
+      b = e;
+    }
+  }
+  return chunks;
+}
+
+// first pass over a chunk: how much it emits, where its descriptions are, which characters occur.
+// Line by line: the text up to the next newline is scanned without branches; only a line that holds a
+// '>' or a character outside the alphabet is looked at again, character by character.
+void count_chunk(const Input &f, const Tables &t, Chunk &c)
+{
+  const uint8_t *p = f.p;
+  size_t i = c.begin;
+  uint64_t nsym = 0;
+  uint64_t hist[4][256];
+  memset(hist, 0, sizeof hist);
+  while (i < c.end) {
+    const void *nl = memchr(p + i, '\n', c.end - i);
+    const size_t e = nl ? (size_t) (static_cast<const uint8_t *>(nl) - p) : c.end;
+    unsigned flags = 0;
+    uint64_t cnt = 0;
+    size_t j = i;
+    for (; j + 4 <= e; j += 4) {
+      const uint8_t c0 = p[j], c1 = p[j + 1], c2 = p[j + 2], c3 = p[j + 3];
+      const unsigned k0 = t.cls[c0], k1 = t.cls[c1], k2 = t.cls[c2], k3 = t.cls[c3];
+      flags |= k0 | k1 | k2 | k3;
+      cnt += (k0 == 0) + (k1 == 0) + (k2 == 0) + (k3 == 0);
+      hist[0][c0]++; hist[1][c1]++; hist[2][c2]++; hist[3][c3]++;
+    }
+    for (; j < e; j++) {
+      const unsigned k = t.cls[p[j]];
+      flags |= k;
+      cnt += (k == 0);
+      hist[0][p[j]]++;
+    }
+    if (!(flags & (C_HEADER | C_ILLEGAL))) { nsym += cnt; i = e + 1; continue; }
+    // the line again, up to its '>' (the description then ends with the line) or its illegal character
+    for (j = i; j < e; j++) {
+      const unsigned k = t.cls[p[j]];
+      if (k == C_SYMBOL) nsym++;
+      else if (k == C_HEADER) break;
+      else if (k == C_ILLEGAL) {
+        c.bad = format("illegal character '%c' in file \"%s\"", p[j], f.name.c_str());
+        return;
+      }
+    }
+    for (size_t q = j; q < e; q++) hist[0][p[q]]--;              // the description is not sequence text
+    if (nl == nullptr) { c.bad = format("file \"%s\" ends inside a description", f.name.c_str()); return; }
+    if (memchr(p + j + 1, '\0', e - (j + 1)) != nullptr) {
+      c.bad = format("a description of file \"%s\" holds a NUL character", f.name.c_str());
+      return;
+    }
+    c.headers.push_back(Header{j + 1, e, 0});
+    i = e + 1;
+  }
+  for (int k = 0; k < 256; k++) c.orig[k] = hist[0][k] + hist[1][k] + hist[2][k] + hist[3][k];
+  c.nheaders = c.headers.size();
+  c.emitted = nsym + c.nheaders;
+}
+
+// second pass: the codes, the separator positions, the wildcard runs
+void emit_chunk(const Input &f, const Tables &t, Chunk &c, uint8_t *codes, bool first_header_overall_here)
+{
+  const uint8_t *p = f.p;
+  size_t i = c.begin, h = 0;
+  uint64_t o = c.out, wstart = 0, wlen = 0;
+  auto close_run = [&]() { if (wlen) { c.wild.push_back(Run{wstart, wlen}); wlen = 0; } };
+  auto runs_of = [&](uint64_t from, uint64_t to) {              // wildcard runs among the codes just written
+    for (uint64_t q = from; q < to; q++) {
+      if (codes[q] == CODE_WILDCARD) { if (!wlen) wstart = q; wlen++; }
+      else close_run();
+    }
+  };
+  while (i < c.end) {
+    const void *nl = memchr(p + i, '\n', c.end - i);
+    const size_t e = nl ? (size_t) (static_cast<const uint8_t *>(nl) - p) : c.end;
+    size_t stop = e;                                            // the text of this line ends here
+    const bool header_next = h < c.headers.size() && c.headers[h].desc_end == e;
+    if (header_next) stop = c.headers[h].desc_begin - 1;        // at its '>'
+    const uint64_t o0 = o;
+    unsigned any = 0;
+    for (size_t j = i; j < stop; j++) {
+      const uint16_t v = t.emit[p[j]];
+      if (v & E_SYMBOL) codes[o++] = (uint8_t) v;               // (nothing is stored for the rest: the next
+      any |= v;                                                 //  position may belong to the next chunk)
+    }
+    if (any & E_WILD) runs_of(o0, o);
+    else if (o > o0) close_run();
+    if (header_next) {
+      Header &hd = c.headers[h];
+      if (first_header_overall_here && h == 0) hd.sep_pos = UINT64_MAX;
+      else { close_run(); hd.sep_pos = o; codes[o++] = CODE_SEPARATOR; }
+      h++;
+    }
+    i = e + 1;
+  }
+  close_run();
+}
+
+template <class F> void parallel_for(unsigned nthreads, size_t ntasks, F &&fn)
+{
+  if (ntasks == 0) return;
+  std::atomic<size_t> next{0};
+  auto worker = [&]() { for (size_t i; (i = next.fetch_add(1)) < ntasks;) fn(i); };
+  const unsigned nt = (unsigned) std::min<size_t>(nthreads, ntasks);
+  std::vector<std::thread> th;
+  for (unsigned k = 1; k < nt; k++) {
+    try { th.emplace_back(worker); } catch (...) { break; }      // fewer threads, same work
+  }
+  worker();
+  for (auto &x : th) x.join();
+}
+
+// ---------------------------------------------------------------- the representation
+// GtSpecialcharinfo, src/core/chardef.h:90-115
+struct SpecialCharInfo {
+  uint64_t specialcharacters, specialranges, realspecialranges, lengthofspecialprefix, lengthofspecialsuffix,
+      wildcards, wildcardranges, realwildcardranges, lengthofwildcardprefix, lengthofwildcardsuffix,
+      lengthoflongestnonspecial, exceptioncharacters, exceptionranges, realexceptionranges;
+};
+static_assert(sizeof(SpecialCharInfo) == 112, "14 GtUword");
+
+const uint64_t MAXRANGE[3] = {0xffu, 0xffffu, 0xffffffffu};    // initSWtable, encseq.c:1738-1767
+const unsigned WIDTH[3] = {1, 2, 4};
+
+uint64_t units_of_twobit(uint64_t n)                            // gt_unitsoftwobitencoding, src/core/intbits.h:194-205
+{
+  return n < 32 ? 2 : 2 + (n - 1) / 32;
+}
+
+uint64_t ints_for_bits(uint64_t nbits)                          // GT_NUMOFINTSFORBITS, intbits.h:98-101
+{
+  return (nbits >> 6) == 0 ? 1 : 1 + ((nbits - 1) >> 6);
+}
+
+// SIZEOFSWTABLE, encseq.c:923-950
+uint64_t size_of_swtable(int kind, bool withrangelength, uint64_t n, uint64_t items)
+{
+  if (items == 0) return 0;
+  return (withrangelength ? 2 : 1) * (uint64_t) WIDTH[kind] * items + 8 * (n / MAXRANGE[kind] + 1);
+}
+
+// how many table entries the runs need when an entry covers at most maxrange+1 positions
+// (currentspecialrangevalue, encseq.c:5061-5074)
+void ranges_tab(const std::vector<Run> &runs, uint64_t tab[3])
+{
+  tab[0] = tab[1] = 0;
+  tab[2] = runs.size();
+  for (const Run &r : runs)
+    for (int k = 0; k < 2; k++) {
+      const uint64_t page = MAXRANGE[k] + 1;
+      tab[k] += r.len <= page ? 1 : (r.len + page - 1) / page;
+    }
+}
+
+struct Writer {
+  FILE *fp = nullptr;
+  std::string path;
+  uint64_t off = 0;
+  Writer(const std::string &indexname, const char *suffix) : path(indexname + suffix)
+  {
+    fp = fopen(path.c_str(), "wb");
+    if (fp == nullptr) throw IoError{format("cannot open file \"%s\" for writing: %s", path.c_str(), strerror(errno))};
+    setvbuf(fp, nullptr, _IOFBF, 1 << 20);
+  }
+  ~Writer() { if (fp) fclose(fp); }
+  void raw(const void *p, size_t bytes)
+  {
+    if (bytes && fwrite(p, 1, bytes, fp) != bytes) throw IoError{format("cannot write to \"%s\": %s", path.c_str(), strerror(errno))};
+    off += bytes;
+  }
+  // one entry of a map specification: nothing for zero units, else the units and the padding to 8 bytes
+  void field(const void *p, size_t unit, uint64_t units)
+  {
+    static const uint8_t zeros[8] = {0};
+    if (units == 0) return;
+    raw(p, unit * units);
+    if (off % 8) raw(zeros, 8 - off % 8);
+  }
+  void word(uint64_t v) { field(&v, 8, 1); }
+  void finish()
+  {
+    FILE *f = fp;
+    fp = nullptr;
+    if (fclose(f) != 0) throw IoError{format("cannot close \"%s\": %s", path.c_str(), strerror(errno))};
+  }
+};
+
+// positions / (lengths) / endidxinpage of a table with pages of maxrange+1 positions
+// (fillSWtable, src/core/accspecialrange.gen:29-262; ssptaboutinfo_*, encseq.c:1841-1910):
+// an entry holds its start modulo the page size, a run longer than a page's worth continues in a new
+// entry, endidxinpage[p] = entries that start at or before the last position of page p
+template <class T> struct SwTable {
+  std::vector<T> positions, lengths;
+  std::vector<uint64_t> endidx;
+};
+
+template <class T>
+SwTable<T> build_swtable(const std::vector<Run> &runs, int kind, uint64_t n, uint64_t items, bool withlengths)
+{
+  SwTable<T> t;
+  const uint64_t page = MAXRANGE[kind] + 1, npages = n / MAXRANGE[kind] + 1;
+  t.positions.reserve(items);
+  if (withlengths) t.lengths.reserve(items);
+  t.endidx.assign(npages, 0);
+  for (const Run &r : runs) {
+    uint64_t s = r.start, left = r.len;
+    while (left) {
+      const uint64_t take = withlengths ? std::min(left, page) : 1;
+      t.positions.push_back((T) (s & MAXRANGE[kind]));
+      if (withlengths) t.lengths.push_back((T) (take - 1));
+      t.endidx[s / page]++;
+      s += take;
+      left -= take;
+    }
+  }
+  for (uint64_t p = 1; p < npages; p++) t.endidx[p] += t.endidx[p - 1];
+  if (t.positions.size() != items) throw IoError{"internal: table entries do not add up"};
+  return t;
+}
+
+template <class T> void write_swtable(Writer &w, const SwTable<T> &t, bool withlengths)
+{
+  // addswtabletomapspectable, encseq.c:829-897
+  if (t.positions.empty()) return;
+  w.field(t.positions.data(), sizeof(T), t.positions.size());
+  if (withlengths) w.field(t.lengths.data(), sizeof(T), t.lengths.size());
+  w.field(t.endidx.data(), 8, t.endidx.size());
+}
+
+void write_table_of_kind(Writer &w, const std::vector<Run> &runs, int kind, uint64_t n, uint64_t items, bool withlengths)
+{
+  if (items == 0) return;
+  if (kind == 0) write_swtable(w, build_swtable<uint8_t>(runs, 0, n, items, withlengths), withlengths);
+  else if (kind == 1) write_swtable(w, build_swtable<uint16_t>(runs, 1, n, items, withlengths), withlengths);
+  else write_swtable(w, build_swtable<uint32_t>(runs, 2, n, items, withlengths), withlengths);
+}
+
+const char *sat_name(uint64_t sat)                              // src/core/encseq_access_type.c:28-37
+{
+  static const char *names[] = {"direct", "bytecompress", "eqlen", "bit", "uchar", "ushort", "uint32", "undefined"};
+  return names[sat <= SAT_UNDEFINED ? sat : SAT_UNDEFINED];
+}
+
+int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
+{
+  const double t0 = now();
+  if (rq->numofchars != 4) throw Unsupported{"the alphabet is not the DNA alphabet"};
+  unsigned nthreads = rq->threads > 0 ? (unsigned) rq->threads : std::thread::hardware_concurrency();
+  if (nthreads == 0) nthreads = 1;
+  if (rq->threads <= 0 && nthreads > 32) nthreads = 32;
+  const Tables tables = make_tables(rq->symbolmap);
+  const std::string indexname = rq->indexname;
+
+  Mapped mapped;
+  map_inputs(rq, mapped);
+  const std::vector<Input> &files = mapped.files;
+  size_t total_bytes = 0;
+  for (const Input &f : files) total_bytes += f.len;
+  size_t target = std::max<size_t>(size_t(1) << 16, std::min<size_t>(size_t(8) << 20, total_bytes / (8 * (size_t) nthreads) + 1));
+  if (const char *e = getenv("GTB200_FASTA_CHUNK"))              // tests: chunk borders everywhere
+    if (atol(e) > 0) target = (size_t) atol(e);
+  std::vector<Chunk> chunks = make_chunks(files, target);
+
+  // ---- count
+  parallel_for(nthreads, chunks.size(), [&](size_t i) { count_chunk(files[chunks[i].file], tables, chunks[i]); });
+  for (const Chunk &c : chunks)
+    if (!c.bad.empty()) throw Unsupported{c.bad};
+  uint64_t emitted = 0, numofsequences = 0;
+  for (Chunk &c : chunks) {
+    c.out = emitted == 0 ? 0 : emitted - 1;     // the first header overall (file 0, offset 0) emits no separator
+    emitted += c.emitted;
+    numofsequences += c.nheaders;
+  }
+  const uint64_t n = emitted - 1;
+  if (n == 0) throw Unsupported{"no symbols"};
+  if (n + 1 >= 0xffffffffull) throw Unsupported{"2^32-2 symbols or more"};
+  const double t_count = now();
+
+  // ---- emit
+  uint8_t *codes = static_cast<uint8_t *>(malloc(n + 64));
+  if (codes == nullptr) throw IoError{"out of memory (symbol array)"};
+  struct Free { void *p; ~Free() { free(p); } } free_codes{codes};
+  parallel_for(nthreads, chunks.size(), [&](size_t i) { emit_chunk(files[chunks[i].file], tables, chunks[i], codes, i == 0); });
+  const double t_emit = now();
+
+  // ---- the lists: separator positions, descriptions, wildcard runs (joined over chunk borders), special runs
+  std::vector<uint64_t> seppos;
+  seppos.reserve(numofsequences);
+  std::vector<Run> wild;
+  uint64_t orig[256] = {0};
+  std::vector<uint64_t> file_symbols(files.size(), 0), file_headers(files.size(), 0);
+  for (const Chunk &c : chunks) {
+    for (const Header &h : c.headers)
+      if (h.sep_pos != UINT64_MAX) seppos.push_back(h.sep_pos);
+    for (const Run &r : c.wild) {
+      if (!wild.empty() && wild.back().start + wild.back().len == r.start) wild.back().len += r.len;
+      else wild.push_back(r);
+    }
+    for (int k = 0; k < 256; k++) orig[k] += c.orig[k];
+    file_symbols[c.file] += c.emitted - c.nheaders;
+    file_headers[c.file] += c.nheaders;
+  }
+  // sequence lengths; an empty sequence is an error of the reference ("contains an empty sequence",
+  // encseq_charproc.gen) or, as the last one, a case not worth a second implementation
+  uint64_t minseqlen = UINT64_MAX, maxseqlen = 0, first_len = 0;
+  bool all_equal = true;
+  {
+    uint64_t start = 0;
+    for (uint64_t s = 0; s <= seppos.size(); s++) {
+      const uint64_t end = s < seppos.size() ? seppos[s] : n;
+      const uint64_t len = end - start;
+      if (len == 0) throw Unsupported{"an empty sequence"};
+      if (s == 0) first_len = len;
+      else if (len != first_len) all_equal = false;
+      minseqlen = std::min(minseqlen, len);
+      maxseqlen = std::max(maxseqlen, len);
+      start = end + 1;
+    }
+  }
+  // special runs = wildcard runs and separators, neighbours joined
+  std::vector<Run> special;
+  special.reserve(wild.size() + seppos.size());
+  {
+    size_t a = 0, b = 0;
+    while (a < wild.size() || b < seppos.size()) {
+      Run r;
+      if (b >= seppos.size() || (a < wild.size() && wild[a].start < seppos[b])) r = wild[a++];
+      else r = Run{seppos[b++], 1};
+      if (!special.empty() && special.back().start + special.back().len == r.start) special.back().len += r.len;
+      else special.push_back(r);
+    }
+  }
+  SpecialCharInfo sci;
+  memset(&sci, 0, sizeof sci);
+  for (const Run &r : wild) sci.wildcards += r.len;
+  sci.specialcharacters = sci.wildcards + seppos.size();
+  sci.realspecialranges = special.size();
+  sci.realwildcardranges = wild.size();
+  if (!special.empty() && special.front().start == 0) sci.lengthofspecialprefix = special.front().len;
+  if (!special.empty() && special.back().start + special.back().len == n) sci.lengthofspecialsuffix = special.back().len;
+  if (!wild.empty() && wild.front().start == 0) sci.lengthofwildcardprefix = wild.front().len;
+  if (!wild.empty() && wild.back().start + wild.back().len == n) sci.lengthofwildcardsuffix = wild.back().len;
+  {
+    uint64_t prev_end = 0;
+    for (const Run &r : special) {
+      sci.lengthoflongestnonspecial = std::max(sci.lengthoflongestnonspecial, r.start - prev_end);
+      prev_end = r.start + r.len;
+    }
+    sci.lengthoflongestnonspecial = std::max(sci.lengthoflongestnonspecial, n - prev_end);
+  }
+  // equallength: every sequence as long as the first and nothing special but the separators
+  // (gt_inputfiles2sequencekeyvalues, encseq.c:5574-5587,5640-5655)
+  const bool equallength = all_equal && sci.wildcards == 0;
+
+  // character distribution; the distinct original characters per code (determine_original_subdist,
+  // encseq.c:5270-5359: printable characters 1..127)
+  uint64_t chardist[4] = {0, 0, 0, 0};
+  uint64_t numofallchars = 0, perclass[256] = {0};
+  for (int c = 1; c < 128; c++) {
+    if (orig[c] == 0 || tables.cls[c] != C_SYMBOL) continue;    // (the histogram also saw the white space)
+    const uint8_t code = tables.code[c];
+    if (code < 4) chardist[code] += orig[c];
+    perclass[code]++;
+    numofallchars++;
+  }
+  uint64_t maxsub = 0;
+  for (int k = 0; k < 4; k++) maxsub = std::max(maxsub, perclass[k]);
+  maxsub = std::max(maxsub, perclass[CODE_WILDCARD]);
+  unsigned lpc = 0;                                             // determineleastprobablecharacter, encseq.c:4468-4485
+  for (unsigned k = 1; k < 4; k++)
+    if (chardist[k] < chardist[lpc]) lpc = k;
+
+  // ---- which representation (doupdatesumranges, encseq.c:5215-5256; determinesmallestrep,
+  //      src/core/encseq_access_type.c:96-129): sizes differ only in what follows the header
+  uint64_t specialtab[3], wildtab[3];
+  ranges_tab(special, specialtab);
+  ranges_tab(wild, wildtab);
+  const uint64_t twobit_bytes = units_of_twobit(n) * 8;
+  {
+    uint64_t smallest = 0;
+    for (int k = 0; k < 3; k++) {
+      const uint64_t size = twobit_bytes + size_of_swtable(k, true, n, wildtab[k]);
+      if (k == 0 || size < smallest) {
+        smallest = size;
+        sci.specialranges = specialtab[k];
+        sci.wildcardranges = wildtab[k];
+      }
+    }
+  }
+  uint64_t sat = SAT_BITACCESS, table_items = wildtab[0];
+  int table_kind = -1;
+  if (equallength) sat = SAT_EQUALLENGTH;
+  else {
+    uint64_t cmin = twobit_bytes + ((wildtab[0] > 0 || numofsequences > 1) ? 8 * ints_for_bits(n + 64) : 0);
+    for (int k = 0; k < 3; k++) {
+      const uint64_t size = twobit_bytes + size_of_swtable(k, true, n, wildtab[k]);
+      if (size < cmin) { cmin = size; sat = SAT_UCHAR + (uint64_t) k; table_kind = k; table_items = wildtab[k]; }
+    }
+  }
+  // the separator table (determineoptimalsssptablerep, encseq.c:1714-1736; files2encodedsequence :4609-4619)
+  int sep_kind = -1;
+  if (numofsequences > 1 && sat != SAT_EQUALLENGTH && (rq->out_ssp || table_kind >= 0)) {
+    uint64_t smallest = size_of_swtable(0, false, n, numofsequences - 1);
+    sep_kind = 0;
+    for (int k = 1; k < 3; k++) {
+      const uint64_t size = size_of_swtable(k, false, n, numofsequences - 1);
+      if (size < smallest) { smallest = size; sep_kind = k; }
+    }
+  }
+  const double t_lists = now();
+
+  // ---- pack (fillSWtable / fillViaequallength / fillViabitaccess: a special position holds the least
+  //      probable character, with bit access 0 for a wildcard and 1 for a separator)
+  const uint64_t units = units_of_twobit(n), full = n / 32;
+  std::vector<uint64_t> words(units, 0);
+  uint8_t fill[256];
+  for (int c = 0; c < 256; c++) fill[c] = (uint8_t) (c < 4 ? c : lpc);
+  if (sat == SAT_BITACCESS) { fill[CODE_WILDCARD] = 0; fill[CODE_SEPARATOR] = 1; }
+  {
+    const uint64_t block = 1 << 15;                              // words per task
+    parallel_for(nthreads, (size_t) ((full + block - 1) / block), [&](size_t task) {
+      const uint64_t w0 = task * block, w1 = std::min(full, w0 + block);
+      for (uint64_t w = w0; w < w1; w++) {
+        const uint8_t *c = codes + 32 * w;
+        uint64_t v = 0;
+        for (int j = 0; j < 32; j++) v = (v << 2) | fill[c[j]];
+        words[w] = v;
+      }
+    });
+    if (n % 32) {
+      uint64_t v = 0;
+      for (uint64_t j = 32 * full; j < n; j++) v = (v << 2) | fill[codes[j]];
+      words[full] = v << (2 * (32 - n % 32));
+    }
+  }
+  const double t_pack = now();
+
+  // ---- md5 of every sequence: upper case of the decoded symbols (encseq_charproc.gen)
+  std::vector<char> md5tab;
+  if (rq->out_md5) {
+    md5tab.assign(33 * numofsequences, '\0');
+    uint8_t up[256];
+    for (int c = 0; c < 256; c++) up[c] = (uint8_t) toupper((unsigned char) rq->decode[c]);
+    parallel_for(nthreads, (size_t) numofsequences, [&](size_t s) {
+      const uint64_t start = s == 0 ? 0 : seppos[s - 1] + 1, end = s < seppos.size() ? seppos[s] : n;
+      Md5 m;
+      uint8_t buf[1 << 14];
+      for (uint64_t i = start; i < end;) {
+        const size_t take = (size_t) std::min<uint64_t>(sizeof buf, end - i);
+        for (size_t j = 0; j < take; j++) buf[j] = up[codes[i + j]];
+        m.update(buf, take);
+        i += take;
+      }
+      m.hex(&md5tab[33 * s]);
+    });
+  }
+  const double t_md5 = now();
+
+  // ---- the files
+  {
+    Writer w(indexname, ".esq");                                // gt_encseq_assign_header_mapspec, encseq.c:1288-1307
+    const uint8_t is64bit = 1;
+    w.field(&is64bit, 1, 1);
+    w.word(ENCSEQ_VERSION);
+    w.word(sat);
+    w.word(n);
+    w.word(numofsequences);
+    w.word(files.size());
+    std::string names;                                          // every name with its NUL
+    for (const Input &f : files) { names += f.name; names.push_back('\0'); }
+    w.word(names.size());
+    w.field(&sci, sizeof sci, 1);
+    w.word(minseqlen);
+    w.word(maxseqlen);
+    w.word(0);                                                  // alphatype: DNA (alphabet_to_key_values, encseq.c:1080-1111)
+    w.word(0);                                                  // lengthofalphadef
+    w.field(names.data(), 1, names.size());
+    const uint8_t maxsubalphasize = (uint8_t) maxsub;
+    w.field(&maxsubalphasize, 1, 1);
+    w.word(numofallchars);
+    // GtFilelengthvalues: bytes of the file; symbols + separators it contributed, the separator in
+    // front of a later file's first sequence not counted (sequence_buffer_fasta.c:52-146)
+    std::vector<uint64_t> flv(2 * files.size());
+    for (size_t i = 0; i < files.size(); i++) {
+      flv[2 * i] = files[i].len;
+      flv[2 * i + 1] = file_symbols[i] + file_headers[i] - 1;
+    }
+    w.field(flv.data(), 16, files.size());
+    w.field(chardist, 8, 4);
+    w.field(words.data(), 8, units);                            // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
+    if (sat == SAT_BITACCESS && (wildtab[0] > 0 || numofsequences > 1)) {
+      const uint64_t nw = ints_for_bits(n + 64);
+      std::vector<uint64_t> bits(nw, 0);
+      auto setbit = [&](uint64_t i) { bits[i >> 6] |= (uint64_t(1) << 63) >> (i & 63); };
+      for (const Run &r : special)
+        for (uint64_t i = 0; i < r.len; i++) setbit(r.start + i);
+      for (uint64_t i = n; i < n + 64; i++) setbit(i);
+      w.field(bits.data(), 8, nw);
+    } else if (table_kind >= 0)
+      write_table_of_kind(w, wild, table_kind, n, table_items, true);
+    w.finish();
+  }
+  if (sep_kind >= 0) {
+    Writer w(indexname, ".ssp");
+    std::vector<Run> seps(seppos.size());
+    for (size_t i = 0; i < seppos.size(); i++) seps[i] = Run{seppos[i], 1};
+    write_table_of_kind(w, seps, sep_kind, n, numofsequences - 1, false);
+    w.finish();
+  }
+  if (rq->out_des) {
+    // descriptions without '\r', each followed by '\n'; behind the last one the length of the longest
+    // and a word of ones; .sds: where each description but the last ends (encseq_charproc.gen,
+    // encseq.c:5612-5623; gt_desc_buffer_*, src/core/desc_buffer.c)
+    Writer des(indexname, ".des");
+    std::vector<uint64_t> sds;
+    uint64_t longest = 0, seq = 0;
+    std::string d;
+    for (const Chunk &c : chunks) {
+      const uint8_t *p = files[c.file].p;
+      for (const Header &h : c.headers) {
+        d.clear();
+        bool clipped = false;
+        for (size_t i = h.desc_begin; i < h.desc_end; i++) {
+          const uint8_t ch = p[i];
+          if (ch == '\r') continue;
+          if (rq->clip_desc) {
+            if (clipped) continue;
+            if (isspace(ch)) { clipped = true; continue; }
+          }
+          d.push_back((char) ch);
+        }
+        longest = std::max<uint64_t>(longest, d.size());
+        des.raw(d.data(), d.size());
+        if (++seq < numofsequences) sds.push_back(des.off);
+        des.raw("\n", 1);
+      }
+    }
+    const uint64_t fin = ~uint64_t(0);
+    des.raw(&longest, 8);
+    des.raw(&fin, 8);
+    des.finish();
+    if (rq->out_sds) {
+      Writer w(indexname, ".sds");
+      w.raw(sds.data(), 8 * sds.size());
+      w.finish();
+    }
+  } else if (rq->out_sds) {
+    Writer w(indexname, ".sds");                                // opened by the reference, never written
+    w.finish();
+  }
+  if (rq->out_md5) {
+    Writer w(indexname, ".md5");
+    w.raw(md5tab.data(), md5tab.size());
+    w.finish();
+  }
+  const double t_write = now();
+
+  if (sum != nullptr) {
+    memset(sum, 0, sizeof *sum);
+    sum->totallength = n;
+    sum->numofsequences = numofsequences;
+    sum->numoffiles = files.size();
+    sum->specialcharacters = sci.specialcharacters;
+    sum->specialranges = sci.specialranges;
+    sum->realspecialranges = sci.realspecialranges;
+    sum->wildcards = sci.wildcards;
+    sum->wildcardranges = sci.wildcardranges;
+    sum->realwildcardranges = sci.realwildcardranges;
+    sum->sat = sat;
+    sum->satsep = sep_kind >= 0 ? SAT_UCHAR + (uint64_t) sep_kind : (uint64_t) SAT_UNDEFINED;
+    for (int k = 0; k < 4; k++) sum->characterdistribution[k] = chardist[k];
+    snprintf(sum->satname, sizeof sum->satname, "%s", sat_name(sat));
+    sum->threads = nthreads;
+    sum->input_bytes = total_bytes;
+    sum->seconds_count = t_count - t0;
+    sum->seconds_emit = t_emit - t_count;
+    sum->seconds_lists = t_lists - t_emit;
+    sum->seconds_pack = t_pack - t_lists;
+    sum->seconds_md5 = t_md5 - t_pack;
+    sum->seconds_write = t_write - t_md5;
+    sum->seconds_total = t_write - t0;
+  }
+  return GTB_FASTA_OK;
+}
+
+}  // namespace
+
+extern "C" int gtb_fasta_encode(const gtb_fasta_request *rq, gtb_fasta_summary *summary, char *msg, size_t msglen)
+{
+  auto say = [&](const std::string &s) { if (msg != nullptr && msglen > 0) snprintf(msg, msglen, "%s", s.c_str()); };
+  if (msg != nullptr && msglen > 0) msg[0] = '\0';
+  if (rq == nullptr || rq->filenames == nullptr || rq->indexname == nullptr || rq->symbolmap == nullptr ||
+      rq->decode == nullptr) {
+    say("gtb_fasta_encode: incomplete request");
+    return GTB_FASTA_ERROR;
+  }
+  try {
+    return encode(rq, summary);
+  } catch (const Unsupported &u) {
+    say(u.why);
+    return GTB_FASTA_UNSUPPORTED;
+  } catch (const IoError &e) {
+    say(e.why);
+    return GTB_FASTA_ERROR;
+  } catch (const std::exception &e) {
+    say(std::string("gtb_fasta_encode: ") + e.what());
+    return GTB_FASTA_ERROR;
+  } catch (...) {
+    say("gtb_fasta_encode: unknown error");
+    return GTB_FASTA_ERROR;
+  }
+}

@@ -8,6 +8,7 @@ gt_encseq_extract_encoded for non-2-bit alphabets).  This module produces the
 same three things from FASTA / symbol arrays so that the library can be used,
 tested and benchmarked without a GenomeTools build.
 """
+import os
 from dataclasses import dataclass, field
 import numpy as np
 
@@ -177,3 +178,47 @@ def encode_fasta(paths, alphabet="dna"):
         nseq += r
     sym = np.concatenate(parts) if len(parts) > 1 else parts[0]
     return EncodedSequence(np.ascontiguousarray(sym), numofchars, nseq)
+
+
+class FastaUnsupported(Exception):
+    """the input is outside what gtb_fasta_encode covers (nothing was written): use the reference's encoder"""
+
+
+def dna_decode_table():
+    """gt_alphabet_decode of the DNA alphabet (src/core/alphabet.c:84-92): a c g t, wildcard shown as n"""
+    t = bytearray(b"\0" * 256)
+    for i, ch in enumerate(DNA_BASES):
+        t[i] = ord(ch)
+    t[WILDCARD] = ord("n")
+    return bytes(t)
+
+
+def write_index_files(paths, indexname, des=True, sds=True, ssp=True, md5=True, clip_desc=False, threads=0):
+    """FASTA file(s) -> <indexname>.esq/.ssp/.des/.sds/.md5 as `gt encseq encode -dna` /
+    `gt suffixerator -dna -tis` write them (gtb_fasta_encode, include/gtb200.h; host code of libgtb200.so).
+    Returns the summary dict; raises FastaUnsupported when the library declines the input."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    if isinstance(paths, (str, bytes)):
+        paths = [paths]
+    names = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    symbolmap = np.ascontiguousarray(ALPHABETS["dna"][1], dtype=np.uint8)
+    rq = _lib.GtbFastaRequest()
+    rq.filenames = names
+    rq.numoffiles = len(paths)
+    rq.indexname = os.fsencode(indexname)
+    rq.symbolmap = symbolmap.ctypes.data_as(C.POINTER(C.c_uint8))
+    rq.decode = dna_decode_table()
+    rq.numofchars = 4
+    rq.out_des, rq.out_sds, rq.out_ssp, rq.out_md5 = int(des), int(sds), int(ssp), int(md5)
+    rq.clip_desc = int(clip_desc)
+    rq.threads = int(threads)
+    summary = _lib.GtbFastaSummary()
+    msg = C.create_string_buffer(1024)
+    rc = lib.gtb_fasta_encode(C.byref(rq), C.byref(summary), msg, 1024)
+    if rc == _lib.GTB_FASTA_UNSUPPORTED:
+        raise FastaUnsupported(msg.value.decode(errors="replace"))
+    if rc != _lib.GTB_FASTA_OK:
+        raise _lib.GtbError(msg.value.decode(errors="replace"))
+    return summary.as_dict()

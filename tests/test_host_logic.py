@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()                      # raises if the .so is missing
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.gtb_abi_version() == 2
+    assert lib.gtb_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device():
