@@ -83,35 +83,51 @@ struct Md5 {
 
   void block(const uint8_t *p)
   {
-    static const uint32_t K[64] = {
-      0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
-      0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
-      0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
-      0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
-      0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
-      0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
-      0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
-      0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
-    static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22,
-                              5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
-                              4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
-                              6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
     uint32_t w[16];
     memcpy(w, p, 64);                                  // little-endian host
     uint32_t A = a, B = b, C = c, D = d;
-    for (int i = 0; i < 64; i++) {
-      uint32_t f;
-      int g;
-      if (i < 16)      { f = (B & C) | (~B & D); g = i; }
-      else if (i < 32) { f = (D & B) | (~D & C); g = (5 * i + 1) & 15; }
-      else if (i < 48) { f = B ^ C ^ D;          g = (3 * i + 5) & 15; }
-      else             { f = C ^ (B | ~D);       g = (7 * i) & 15; }
-      const uint32_t t = D;
-      D = C;
-      C = B;
-      B = B + rol(A + f + K[i] + w[g], S[i]);
-      A = t;
-    }
+#define GTB_MD5_F(x, y, z) ((z) ^ ((x) & ((y) ^ (z))))
+#define GTB_MD5_G(x, y, z) ((y) ^ ((z) & ((x) ^ (y))))
+#define GTB_MD5_H(x, y, z) ((x) ^ (y) ^ (z))
+#define GTB_MD5_I(x, y, z) ((y) ^ ((x) | ~(z)))
+#define GTB_MD5_STEP(f, a_, b_, c_, d_, k, s, t) a_ = b_ + rol(a_ + f(b_, c_, d_) + w[k] + t, s)
+    GTB_MD5_STEP(GTB_MD5_F, A, B, C, D, 0, 7, 0xd76aa478u);  GTB_MD5_STEP(GTB_MD5_F, D, A, B, C, 1, 12, 0xe8c7b756u);
+    GTB_MD5_STEP(GTB_MD5_F, C, D, A, B, 2, 17, 0x242070dbu); GTB_MD5_STEP(GTB_MD5_F, B, C, D, A, 3, 22, 0xc1bdceeeu);
+    GTB_MD5_STEP(GTB_MD5_F, A, B, C, D, 4, 7, 0xf57c0fafu);  GTB_MD5_STEP(GTB_MD5_F, D, A, B, C, 5, 12, 0x4787c62au);
+    GTB_MD5_STEP(GTB_MD5_F, C, D, A, B, 6, 17, 0xa8304613u); GTB_MD5_STEP(GTB_MD5_F, B, C, D, A, 7, 22, 0xfd469501u);
+    GTB_MD5_STEP(GTB_MD5_F, A, B, C, D, 8, 7, 0x698098d8u);  GTB_MD5_STEP(GTB_MD5_F, D, A, B, C, 9, 12, 0x8b44f7afu);
+    GTB_MD5_STEP(GTB_MD5_F, C, D, A, B, 10, 17, 0xffff5bb1u); GTB_MD5_STEP(GTB_MD5_F, B, C, D, A, 11, 22, 0x895cd7beu);
+    GTB_MD5_STEP(GTB_MD5_F, A, B, C, D, 12, 7, 0x6b901122u); GTB_MD5_STEP(GTB_MD5_F, D, A, B, C, 13, 12, 0xfd987193u);
+    GTB_MD5_STEP(GTB_MD5_F, C, D, A, B, 14, 17, 0xa679438eu); GTB_MD5_STEP(GTB_MD5_F, B, C, D, A, 15, 22, 0x49b40821u);
+    GTB_MD5_STEP(GTB_MD5_G, A, B, C, D, 1, 5, 0xf61e2562u);  GTB_MD5_STEP(GTB_MD5_G, D, A, B, C, 6, 9, 0xc040b340u);
+    GTB_MD5_STEP(GTB_MD5_G, C, D, A, B, 11, 14, 0x265e5a51u); GTB_MD5_STEP(GTB_MD5_G, B, C, D, A, 0, 20, 0xe9b6c7aau);
+    GTB_MD5_STEP(GTB_MD5_G, A, B, C, D, 5, 5, 0xd62f105du);  GTB_MD5_STEP(GTB_MD5_G, D, A, B, C, 10, 9, 0x02441453u);
+    GTB_MD5_STEP(GTB_MD5_G, C, D, A, B, 15, 14, 0xd8a1e681u); GTB_MD5_STEP(GTB_MD5_G, B, C, D, A, 4, 20, 0xe7d3fbc8u);
+    GTB_MD5_STEP(GTB_MD5_G, A, B, C, D, 9, 5, 0x21e1cde6u);  GTB_MD5_STEP(GTB_MD5_G, D, A, B, C, 14, 9, 0xc33707d6u);
+    GTB_MD5_STEP(GTB_MD5_G, C, D, A, B, 3, 14, 0xf4d50d87u); GTB_MD5_STEP(GTB_MD5_G, B, C, D, A, 8, 20, 0x455a14edu);
+    GTB_MD5_STEP(GTB_MD5_G, A, B, C, D, 13, 5, 0xa9e3e905u); GTB_MD5_STEP(GTB_MD5_G, D, A, B, C, 2, 9, 0xfcefa3f8u);
+    GTB_MD5_STEP(GTB_MD5_G, C, D, A, B, 7, 14, 0x676f02d9u); GTB_MD5_STEP(GTB_MD5_G, B, C, D, A, 12, 20, 0x8d2a4c8au);
+    GTB_MD5_STEP(GTB_MD5_H, A, B, C, D, 5, 4, 0xfffa3942u);  GTB_MD5_STEP(GTB_MD5_H, D, A, B, C, 8, 11, 0x8771f681u);
+    GTB_MD5_STEP(GTB_MD5_H, C, D, A, B, 11, 16, 0x6d9d6122u); GTB_MD5_STEP(GTB_MD5_H, B, C, D, A, 14, 23, 0xfde5380cu);
+    GTB_MD5_STEP(GTB_MD5_H, A, B, C, D, 1, 4, 0xa4beea44u);  GTB_MD5_STEP(GTB_MD5_H, D, A, B, C, 4, 11, 0x4bdecfa9u);
+    GTB_MD5_STEP(GTB_MD5_H, C, D, A, B, 7, 16, 0xf6bb4b60u); GTB_MD5_STEP(GTB_MD5_H, B, C, D, A, 10, 23, 0xbebfbc70u);
+    GTB_MD5_STEP(GTB_MD5_H, A, B, C, D, 13, 4, 0x289b7ec6u); GTB_MD5_STEP(GTB_MD5_H, D, A, B, C, 0, 11, 0xeaa127fau);
+    GTB_MD5_STEP(GTB_MD5_H, C, D, A, B, 3, 16, 0xd4ef3085u); GTB_MD5_STEP(GTB_MD5_H, B, C, D, A, 6, 23, 0x04881d05u);
+    GTB_MD5_STEP(GTB_MD5_H, A, B, C, D, 9, 4, 0xd9d4d039u);  GTB_MD5_STEP(GTB_MD5_H, D, A, B, C, 12, 11, 0xe6db99e5u);
+    GTB_MD5_STEP(GTB_MD5_H, C, D, A, B, 15, 16, 0x1fa27cf8u); GTB_MD5_STEP(GTB_MD5_H, B, C, D, A, 2, 23, 0xc4ac5665u);
+    GTB_MD5_STEP(GTB_MD5_I, A, B, C, D, 0, 6, 0xf4292244u);  GTB_MD5_STEP(GTB_MD5_I, D, A, B, C, 7, 10, 0x432aff97u);
+    GTB_MD5_STEP(GTB_MD5_I, C, D, A, B, 14, 15, 0xab9423a7u); GTB_MD5_STEP(GTB_MD5_I, B, C, D, A, 5, 21, 0xfc93a039u);
+    GTB_MD5_STEP(GTB_MD5_I, A, B, C, D, 12, 6, 0x655b59c3u); GTB_MD5_STEP(GTB_MD5_I, D, A, B, C, 3, 10, 0x8f0ccc92u);
+    GTB_MD5_STEP(GTB_MD5_I, C, D, A, B, 10, 15, 0xffeff47du); GTB_MD5_STEP(GTB_MD5_I, B, C, D, A, 1, 21, 0x85845dd1u);
+    GTB_MD5_STEP(GTB_MD5_I, A, B, C, D, 8, 6, 0x6fa87e4fu);  GTB_MD5_STEP(GTB_MD5_I, D, A, B, C, 15, 10, 0xfe2ce6e0u);
+    GTB_MD5_STEP(GTB_MD5_I, C, D, A, B, 6, 15, 0xa3014314u); GTB_MD5_STEP(GTB_MD5_I, B, C, D, A, 13, 21, 0x4e0811a1u);
+    GTB_MD5_STEP(GTB_MD5_I, A, B, C, D, 4, 6, 0xf7537e82u);  GTB_MD5_STEP(GTB_MD5_I, D, A, B, C, 11, 10, 0xbd3af235u);
+    GTB_MD5_STEP(GTB_MD5_I, C, D, A, B, 2, 15, 0x2ad7d2bbu); GTB_MD5_STEP(GTB_MD5_I, B, C, D, A, 9, 21, 0xeb86d391u);
+#undef GTB_MD5_STEP
+#undef GTB_MD5_F
+#undef GTB_MD5_G
+#undef GTB_MD5_H
+#undef GTB_MD5_I
     a += A; b += B; c += C; d += D;
   }
 
@@ -668,6 +684,36 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   }
   const double t_lists = now();
 
+  // ---- md5 of every sequence: upper case of the decoded symbols (encseq_charproc.gen).  One sequence per
+  //      task; it starts now, on threads of its own beside the packing and the writing of the other files
+  //      (a genome of one sequence is one task, as long as everything else together)
+  std::vector<char> md5tab;
+  std::thread md5_thread;
+  double md5_seconds = 0;
+  struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_md5{md5_thread};
+  if (rq->out_md5) {
+    md5tab.assign(33 * numofsequences, '\0');
+    auto all_md5 = [&]() {
+      const double t = now();
+      uint8_t up[256];
+      for (int c = 0; c < 256; c++) up[c] = (uint8_t) toupper((unsigned char) rq->decode[c]);
+      parallel_for(nthreads, (size_t) numofsequences, [&](size_t s) {
+        const uint64_t start = s == 0 ? 0 : seppos[s - 1] + 1, end = s < seppos.size() ? seppos[s] : n;
+        Md5 m;
+        uint8_t buf[1 << 14];
+        for (uint64_t i = start; i < end;) {
+          const size_t take = (size_t) std::min<uint64_t>(sizeof buf, end - i);
+          for (size_t j = 0; j < take; j++) buf[j] = up[codes[i + j]];
+          m.update(buf, take);
+          i += take;
+        }
+        m.hex(&md5tab[33 * s]);
+      });
+      md5_seconds = now() - t;
+    };
+    try { md5_thread = std::thread(all_md5); } catch (...) { all_md5(); }
+  }
+
   // ---- pack (fillSWtable / fillViaequallength / fillViabitaccess: a special position holds the least
   //      probable character, with bit access 0 for a wildcard and 1 for a separator)
   const uint64_t units = units_of_twobit(n), full = n / 32;
@@ -682,7 +728,21 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
       for (uint64_t w = w0; w < w1; w++) {
         const uint8_t *c = codes + 32 * w;
         uint64_t v = 0;
-        for (int j = 0; j < 32; j++) v = (v << 2) | fill[c[j]];
+        for (int q = 0; q < 4; q++) {                            // 8 codes at a time
+          uint64_t x;
+          memcpy(&x, c + 8 * q, 8);
+          if (x & 0xfcfcfcfcfcfcfcfcull) {                       // a special among them
+            uint64_t y = 0;
+            for (int j = 0; j < 8; j++) y = (y << 2) | fill[c[8 * q + j]];
+            v = (v << 16) | y;
+            continue;
+          }
+          x = __builtin_bswap64(x);                              // first code in the top byte
+          x = (x | (x >> 6)) & 0x000f000f000f000full;
+          x = (x | (x >> 12)) & 0x000000ff000000ffull;
+          x = (x | (x >> 24)) & 0xffffull;
+          v = (v << 16) | x;
+        }
         words[w] = v;
       }
     });
@@ -693,27 +753,6 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     }
   }
   const double t_pack = now();
-
-  // ---- md5 of every sequence: upper case of the decoded symbols (encseq_charproc.gen)
-  std::vector<char> md5tab;
-  if (rq->out_md5) {
-    md5tab.assign(33 * numofsequences, '\0');
-    uint8_t up[256];
-    for (int c = 0; c < 256; c++) up[c] = (uint8_t) toupper((unsigned char) rq->decode[c]);
-    parallel_for(nthreads, (size_t) numofsequences, [&](size_t s) {
-      const uint64_t start = s == 0 ? 0 : seppos[s - 1] + 1, end = s < seppos.size() ? seppos[s] : n;
-      Md5 m;
-      uint8_t buf[1 << 14];
-      for (uint64_t i = start; i < end;) {
-        const size_t take = (size_t) std::min<uint64_t>(sizeof buf, end - i);
-        for (size_t j = 0; j < take; j++) buf[j] = up[codes[i + j]];
-        m.update(buf, take);
-        i += take;
-      }
-      m.hex(&md5tab[33 * s]);
-    });
-  }
-  const double t_md5 = now();
 
   // ---- the files
   {
@@ -808,6 +847,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     w.finish();
   }
   if (rq->out_md5) {
+    if (md5_thread.joinable()) md5_thread.join();
     Writer w(indexname, ".md5");
     w.raw(md5tab.data(), md5tab.size());
     w.finish();
@@ -835,8 +875,8 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     sum->seconds_emit = t_emit - t_count;
     sum->seconds_lists = t_lists - t_emit;
     sum->seconds_pack = t_pack - t_lists;
-    sum->seconds_md5 = t_md5 - t_pack;
-    sum->seconds_write = t_write - t_md5;
+    sum->seconds_md5 = md5_seconds;                   /* beside pack + write */
+    sum->seconds_write = t_write - t_pack;
     sum->seconds_total = t_write - t0;
   }
   return GTB_FASTA_OK;

@@ -8,7 +8,9 @@
 
     * option parsing / -help:  gt_suffixeratoroptions        (src/match/sfx-opt.c:225)
     * FASTA -> GtEncseq:       gt_encseq_encoder_encode, gt_encseq_loader_load
-                               (as src/match/sfx-run.c:496-531 does)
+                               (as src/match/sfx-run.c:496-531 does); for DNA in plain FASTA files
+                               the index files are written by gtb_fasta_encode instead (all host
+                               cores, byte-identical files) and only LOADED by the reference
     * prefix length policy:    gt_recommendedprefixlength, gt_whatisthemaximalprefixlength,
                                gt_checkprefixlength          (src/match/sfx-apfxlen.c)
     * project file:            gt_outprjfile                 (src/match/sfx-outprj.c:84)
@@ -37,6 +39,7 @@
 #include <string.h>
 #include <sys/time.h>
 #include "core/alphabet.h"
+#include "core/chardef.h"
 #include "core/encseq.h"
 #include "core/error_api.h"
 #include "core/fa.h"
@@ -106,6 +109,68 @@ static void *b200_init_thread(void *p)
   return NULL;
 }
 
+/* FASTA -> .esq/.ssp/.des/.sds/.md5 with gtb_fasta_encode (all host cores; include/gtb200.h) where
+   it covers the request: DNA (given with -dna or guessed by the reference from the first file),
+   no -plain / -lossless / -sat / -smap.  Returns 0 when the files are written, 1 when the reference's
+   encoder has to run (also for every input the library declines: gt_encseq_encoder_encode then words
+   the error messages), -1 on an I/O error.  GTB200_ENCODER=reference switches it off. */
+static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *err)
+{
+  GtEncseqOptions *o = so->encopts;
+  const char *which = getenv("GTB200_ENCODER");
+  GtAlphabet *alpha = NULL;
+  gtb_fasta_request rq;
+  gtb_fasta_summary sum;
+  const char **names;
+  char decode[256], msg[1024];
+  GtUword i, nfiles = gt_str_array_size(so->db);
+  int rc;
+
+  if (which != NULL && strcmp(which, "reference") == 0) return 1;
+  if (nfiles == 0 || gt_encseq_options_plain_value(o) || gt_encseq_options_plain_value(so->loadopts) ||
+      gt_encseq_options_protein_value(o) || gt_encseq_options_lossless_value(o) ||
+      gt_str_length(gt_encseq_options_sat_value(o)) > 0 || gt_str_length(gt_encseq_options_smap_value(o)) > 0)
+    return 1;
+  if (gt_encseq_options_dna_value(o)) alpha = gt_alphabet_new_dna();
+  else {                                 /* gt_encseq_new_from_files, src/core/encseq.c:7560-7569 */
+    alpha = gt_alphabet_new_from_sequence(so->db, err);
+    if (alpha == NULL) { gt_error_unset(err); return 1; }
+  }
+  if (!gt_alphabet_is_dna(alpha)) { gt_alphabet_delete(alpha); return 1; }
+  memset(decode, 0, sizeof decode);
+  for (i = 0; i < (GtUword) gt_alphabet_num_of_chars(alpha); i++) decode[i] = gt_alphabet_decode(alpha, (GtUchar) i);
+  decode[WILDCARD] = gt_alphabet_decode(alpha, (GtUchar) WILDCARD);
+  names = gt_malloc(sizeof *names * nfiles);
+  for (i = 0; i < nfiles; i++) names[i] = gt_str_array_get(so->db, i);
+  memset(&rq, 0, sizeof rq);
+  rq.filenames = names;
+  rq.numoffiles = nfiles;
+  rq.indexname = gt_str_get(so->indexname);
+  rq.symbolmap = gt_alphabet_symbolmap(alpha);
+  rq.decode = decode;
+  rq.numofchars = gt_alphabet_num_of_chars(alpha);
+  rq.out_des = gt_encseq_options_des_value(o);
+  rq.out_sds = gt_encseq_options_sds_value(o);
+  rq.out_ssp = gt_encseq_options_ssp_value(o);
+  rq.out_md5 = gt_encseq_options_md5_value(o);
+  rq.clip_desc = gt_encseq_options_clip_desc_value(o);
+  rq.threads = 0;
+  rc = gtb_fasta_encode(&rq, &sum, msg, sizeof msg);
+  gt_free(names);
+  gt_alphabet_delete(alpha);
+  if (rc == GTB_FASTA_UNSUPPORTED) {
+    gt_logger_log(logger, "B200 encoder does not cover this input (%s): the reference's encoder runs", msg);
+    return 1;
+  }
+  if (rc != GTB_FASTA_OK) { gt_error_set(err, "libgtb200: %s", msg); return -1; }
+  gt_logger_log(logger, "B200 encoder: %llu symbols in %llu sequence(s), representation %s, %u threads, %.3f s "
+                        "(count %.3f, emit %.3f, pack %.3f, md5 %.3f beside pack and write %.3f)",
+                (unsigned long long) sum.totallength, (unsigned long long) sum.numofsequences, sum.satname,
+                sum.threads, sum.seconds_total, sum.seconds_count, sum.seconds_emit, sum.seconds_pack,
+                sum.seconds_md5, sum.seconds_write);
+  return 0;
+}
+
 static int b200_write(const char *indexname, const char *suffix, const void *data,
                       size_t size, size_t nmemb, size_t pad_to, GtError *err)
 {
@@ -126,7 +191,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   GtLogger *logger = NULL;
   B200Init init;
   pthread_t init_tid;
-  bool init_started = false, init_ever = false;
+  bool init_started = false, init_ever = false, encoded = false;
   int retval, had_err = 0;
   double t_start = b200_now(), t_encoded = 0, t_uploaded = 0, t_sorted = 0, t_copied = 0;
 
@@ -155,7 +220,12 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     if (!init_started) b200_init_thread(&init);
   }
 
-  if (!had_err) {                        /* encode + load, exactly the reference's calls */
+  if (!had_err) {
+    int fast = b200_fast_encode(&so, logger, err);
+    if (fast < 0) had_err = -1;
+    else encoded = (fast == 0);
+  }
+  if (!had_err) {                        /* encode (unless done above) + load, exactly the reference's calls */
     GtEncseqEncoder *ee = gt_encseq_encoder_new_from_options(so.encopts, err);
     if (ee == NULL) had_err = -1;
     /* '-plain' implies no description support (src/match/sfx-run.c:498-502) */
@@ -163,7 +233,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       gt_encseq_encoder_do_not_create_des_tab(ee);
       gt_encseq_encoder_do_not_create_sds_tab(ee);
     }
-    if (!had_err) {
+    if (!had_err && !encoded) {
       gt_encseq_encoder_set_logger(ee, logger);
       if (gt_encseq_encoder_encode(ee, so.db, gt_str_get(so.indexname), err) != 0)
         had_err = -1;

@@ -1,0 +1,167 @@
+"""CPU: the FASTA -> encseq encoder of libgtb200.so (gtb_fasta_encode, host code)
+against the unmodified reference.
+
+tests/golden/fasta_index_md5.json holds the md5 of every index file `gtref suffixerator -dna -tis
+[-des/-sds/-ssp/-md5 yes|no] [-clipdesc]` wrote for the inputs of tests/golden/fasta_cases.py
+(make_golden_fasta.py; the reference's encoder is gt_encseq_new_from_files,
+/root/reference/src/core/encseq.c:7503-7714).  The library must write the same bytes: .esq (header,
+2-bit words, wildcard range table or special bits), .ssp, .des, .sds, .md5 -- with one chunk per file
+and with chunk borders every 50 bytes (the parallel decomposition must not show).  Where the reference
+binary is present (this container) the drop-in binary is run beside it on inputs both accept and
+inputs the library declines.
+"""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import fasta_cases
+from conftest import ROOT
+from genometools_b200.encseq import FastaUnsupported, write_index_files
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "fasta_index_md5.json")))
+CASES = fasta_cases.all_cases()
+GTREF = os.path.join(ROOT, "oracle", "_ref", "gtref")
+GT_B200 = os.path.join(ROOT, "host", "_build", "gt_b200")
+SUFFIXES = ("esq", "ssp", "des", "sds", "md5")
+
+
+def write_inputs(files, d):
+    names = []
+    for i, raw in enumerate(files):
+        names.append("f%d.fa" % i)          # relative: the .esq header stores the names as given
+        (d / names[-1]).write_bytes(raw)
+    return names
+
+
+def check_case(name, tmp_path, monkeypatch, chunk=None, threads=0):
+    files, opts = CASES[name]
+    g = GOLDEN[name]
+    assert [hashlib.md5(f).hexdigest() for f in files] == g["input_md5"], "generator drifted from the golden inputs"
+    monkeypatch.chdir(tmp_path)
+    if chunk:
+        monkeypatch.setenv("GTB200_FASTA_CHUNK", str(chunk))
+    names = write_inputs(files, tmp_path)
+    s = write_index_files(names, "our", threads=threads, **opts)
+    for suf in SUFFIXES:
+        p = tmp_path / ("our." + suf)
+        assert p.exists() == (suf in g["files"]), f"{name}: .{suf} written: {p.exists()}, reference: {suf in g['files']}"
+        if p.exists():
+            data = p.read_bytes()
+            assert len(data) == g["files"][suf]["bytes"], f"{name}: .{suf} length"
+            assert hashlib.md5(data).hexdigest() == g["files"][suf]["md5"], f"{name}: .{suf} differs from the reference's"
+    prj = dict(line.split("=", 1) for line in g["prj"].strip().split("\n"))
+    for key in ("totallength", "specialcharacters", "specialranges", "realspecialranges", "wildcards",
+                "wildcardranges", "realwildcardranges"):
+        assert s[key] == int(prj[key]), key
+    assert s["numofsequences"] == int(prj["numofdbsequences"])
+    return s
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_index_files_identical_to_reference(name, tmp_path, monkeypatch):
+    check_case(name, tmp_path, monkeypatch)
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith(("small_0", "odd_"))])
+def test_chunk_borders_do_not_show(name, tmp_path, monkeypatch):
+    check_case(name, tmp_path, monkeypatch, chunk=50, threads=3)
+
+
+def test_every_representation_is_reached(tmp_path, monkeypatch):
+    seen = set()
+    for i, name in enumerate(("uint32_single", "ushort_multi", "equal_length_reads", "small_004", "small_000")):
+        d = tmp_path / str(i)
+        d.mkdir()
+        seen.add(check_case(name, d, monkeypatch)["satname"])
+    for name in sorted(CASES):
+        if len(seen) == 5:
+            break
+        if name.startswith("small_"):
+            d = tmp_path / name
+            d.mkdir()
+            seen.add(check_case(name, d, monkeypatch)["satname"])
+    assert seen == {"eqlen", "bit", "uchar", "ushort", "uint32"}, seen
+
+
+DECLINED = {
+    "illegal_character": [b">a\nACGT\nACXT\n"],
+    "empty_sequence": [b">a\nACGT\n>b\n>c\nAC\n"],
+    "empty_last_sequence": [b">a\nACGT\n>b\n"],
+    "description_cut_off": [b">a\nACGT\n>b"],
+    "no_header": [b"ACGT\n"],
+    "second_file_without_header": [b">a\nACGT\n", b"ACGT\n"],
+    "nul_in_description": [b">a\0b\nACGT\n"],
+    "empty_file": [b""],
+}
+
+
+@pytest.mark.parametrize("name", sorted(DECLINED))
+def test_declined_inputs_write_nothing(name, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    names = write_inputs(DECLINED[name], tmp_path)
+    with pytest.raises(FastaUnsupported):
+        write_index_files(names, "our")
+    assert sorted(os.listdir(tmp_path)) == sorted(names)
+
+
+def test_compressed_and_missing_files_are_declined(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "a.fa.gz").write_bytes(b">a\nACGT\n")
+    with pytest.raises(FastaUnsupported):
+        write_index_files(["a.fa.gz"], "our")
+    with pytest.raises(FastaUnsupported):
+        write_index_files(["missing.fa"], "our")
+
+
+def run_tool(exe, args, cwd):
+    return subprocess.run([exe, "suffixerator"] + args, cwd=cwd, capture_output=True, text=True)
+
+
+needs_binaries = pytest.mark.skipif(not (os.path.exists(GTREF) and os.path.exists(GT_B200)),
+                                    reason="oracle/_ref/gtref and host/_build/gt_b200 are built where /root/reference is")
+
+
+@needs_binaries
+@pytest.mark.parametrize("name,extra", [
+    ("three_files", ["-dna"]), ("three_files", []), ("many_sequences", ["-dna", "-clipdesc"]),
+    ("odd_header_in_midline", ["-dna", "-md5", "no"]), ("small_004", ["-dna", "-des", "no", "-sds", "no"]),
+    ("ushort_multi", ["-dna", "-sat", "uint32"]), ("small_001", ["-dna", "-lossless"]),
+])
+def test_dropin_binary_without_sort(name, extra, tmp_path):
+    """`gt_b200 suffixerator -tis` (no table requested: no GPU involved) beside `gtref`: same files, the
+    .prj included; -sat and -lossless go through the reference's encoder inside the drop-in"""
+    files, _ = CASES[name]
+    out = {}
+    for who, exe in (("ref", GTREF), ("our", GT_B200)):
+        d = tmp_path / who
+        d.mkdir()
+        names = write_inputs(files, d)
+        r = run_tool(exe, ["-tis", "-v", "-indexname", "i", "-db"] + names + extra, d)
+        assert r.returncode == 0, r.stderr
+        out[who] = ({f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.startswith("i.")}, r.stdout)
+    assert sorted(out["ref"][0]) == sorted(out["our"][0])
+    for f in out["ref"][0]:
+        assert out["ref"][0][f] == out["our"][0][f], f
+    fast = "B200 encoder:" in out["our"][1]
+    assert fast == ("-sat" not in extra and "-lossless" not in extra)
+
+
+@needs_binaries
+@pytest.mark.parametrize("name", sorted(DECLINED))
+def test_dropin_binary_on_declined_inputs(name, tmp_path):
+    """what the library declines the reference's encoder handles inside the drop-in: same exit code, same
+    message, same files left behind"""
+    res = {}
+    for who, exe in (("ref", GTREF), ("our", GT_B200)):
+        d = tmp_path / who
+        d.mkdir()
+        names = write_inputs(DECLINED[name], d)
+        r = run_tool(exe, ["-dna", "-tis", "-indexname", "i", "-db"] + names, d)
+        msg = r.stderr.split(": error: ", 1)[-1]
+        res[who] = (r.returncode, msg, {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.startswith("i.")})
+    assert res["ref"][0] == res["our"][0]
+    assert res["ref"][1] == res["our"][1]
+    assert res["ref"][2] == res["our"][2]
