@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import GtbError, GtbStats, ptr, GTB_WANT_SUF, GTB_WANT_LCP, GTB_WANT_BCK, GTB_REUSE_COUNTS
-from .encseq import EncodedSequence, encode_fasta
+from .encseq import EncodedSequence, FastaUnsupported, encode_fasta, write_index_files
 from .sharding import suftab_parts
 
 GT_RECOMMENDED_MULTIPLIER_DEFAULT = 0.25       # sfx-apfxlen.h:23
@@ -101,6 +101,11 @@ class SuffixeratorOptions:
     dir: str = "fwd"
     device: int = 0
     verbose: bool = False
+    tis: bool = False         # -tis: write <indexname>.esq (+ .ssp .des .sds .md5 unless switched off)
+    des: bool = True
+    sds: bool = True
+    ssp: bool = True
+    md5: bool = True
 
     UNSUPPORTED = ("-mirrored", "-dc", "-spmopt", "-sortmaxdepth", "-suftabuint",
                    "-compressedoutput", "-genomediff", "-lcpdist", "-memlimit", "-algbds",
@@ -113,7 +118,7 @@ class SuffixeratorOptions:
         i = 0
         flags = {"-dna": "dna", "-protein": "protein", "-suf": "suf", "-lcp": "lcp", "-bck": "bck",
                  "-bwt": "bwt", "-v": "verbose"}
-        ignorable_yes = ("-tis", "-des", "-sds", "-ssp", "-md5")   # written by the encoder, not this path
+        tables = ("-tis", "-des", "-sds", "-ssp", "-md5")   # the encoder's files (gtb_fasta_encode, DNA only)
         while i < len(argv):
             a = argv[i]
             if a in flags:
@@ -151,9 +156,12 @@ class SuffixeratorOptions:
                 o.dir = argv[i]
             elif a == "-device":
                 i += 1; o.device = int(argv[i])
-            elif a in ignorable_yes:
+            elif a in tables:
+                value = True
                 if i + 1 < len(argv) and argv[i + 1] in ("yes", "no"):
                     i += 1
+                    value = argv[i] == "yes"
+                setattr(o, a[1:], value)
             elif a in cls.UNSUPPORTED:
                 raise GtbError(f"option \"{a}\" is not supported by the B200 suffixerator path "
                                "(no silent fallback); use the CPU `gt suffixerator` for it")
@@ -521,6 +529,13 @@ def suffixerator_main(argv, out=sys.stdout):
         if not o.dna and not o.protein:
             raise GtbError("one of the options -dna or -protein is required (alphabet guessing is not on this path)")
         enc = encode_fasta(o.db, alphabet)
+        if o.tis:
+            if not o.dna:
+                raise GtbError("-tis is written for DNA only on this path (gtb_fasta_encode)")
+            try:
+                write_index_files(o.db, o.indexname, des=o.des, sds=o.sds and o.des, ssp=o.ssp, md5=o.md5)
+            except FastaUnsupported as e:
+                raise GtbError(f"the index files of this input need the reference's encoder: {e}")
         pl = o.pl
         res = build_esa(enc, pl if pl else None, o.device, o.parts, o.suf, o.lcp, o.bck or pl is not None,
                         want_bwt=o.bwt, readmode=o.dir)
