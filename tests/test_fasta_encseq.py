@@ -165,3 +165,39 @@ def test_dropin_binary_on_declined_inputs(name, tmp_path):
     assert res["ref"][0] == res["our"][0]
     assert res["ref"][1] == res["our"][1]
     assert res["ref"][2] == res["our"][2]
+
+
+TESTDATA = "/root/reference/testdata"
+
+
+@needs_binaries
+@pytest.mark.skipif(not os.path.isdir(TESTDATA), reason="the reference's testdata is only in this container")
+def test_reference_testdata_through_dropin(tmp_path):
+    """every FASTA-like file of the reference's testdata (alphabet guessed, as in
+    testsuite/gt_suffixerator_include.rb) through `suffixerator -tis` of both binaries: same exit code, same
+    message, same files -- whether the library encodes it (DNA) or declines it (protein, malformed input)"""
+    import glob
+    files = []
+    for f in sorted(glob.glob(os.path.join(TESTDATA, "*"))):
+        if os.path.isfile(f) and 0 < os.path.getsize(f) < 5_000_000:
+            with open(f, "rb") as fh:
+                if fh.read(1) == b">":
+                    files.append(f)
+    assert len(files) > 100
+    fast = 0
+    for f in files:
+        res = {}
+        for who, exe in (("ref", GTREF), ("our", GT_B200)):
+            d = tmp_path / who
+            if d.exists():
+                for x in os.listdir(d):
+                    os.unlink(d / x)
+            else:
+                d.mkdir()
+            r = run_tool(exe, ["-tis", "-v", "-indexname", str(d / "i"), "-db", f], tmp_path)
+            res[who] = (r.returncode, r.stderr.split(": error: ", 1)[-1],
+                        {x: hashlib.md5((d / x).read_bytes()).hexdigest() for x in sorted(os.listdir(d))})
+            if who == "our" and "B200 encoder:" in r.stdout:
+                fast += 1
+        assert res["ref"] == res["our"], f
+    assert fast > 100          # most of them are DNA
