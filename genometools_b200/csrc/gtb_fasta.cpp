@@ -15,7 +15,7 @@
 //            positions, wildcard runs, distribution of the original characters
 //   pack     32 symbols per 64-bit word (GtTwobitencoding), special positions filled the way the
 //            chosen representation fills them
-//   md5      one sequence per task
+//   md5      one sequence per task, read from the text, on threads of its own from the end of `count` on
 //
 // and the tables of the representation (wildcard ranges in pages, separator positions in pages) are
 // built from the run lists.  The files are written field by field in the order of the reference's
@@ -385,6 +385,34 @@ template <class F> void parallel_for(unsigned nthreads, size_t ntasks, F &&fn)
   for (auto &x : th) x.join();
 }
 
+// the two big arrays (one byte per symbol, the packed words): anonymous mappings that ask for huge pages --
+// with 4 KB pages the first touch of 64 MB is 16 000 page faults, taken by all threads at once on one
+// address-space lock (and on the lock the thread that creates the CUDA context holds most of the time)
+struct BigBuffer {
+  void *p = nullptr;
+  size_t bytes = 0;
+  bool mapped = false;
+  explicit BigBuffer(size_t want)
+  {
+    const size_t huge = size_t(2) << 20;
+    bytes = (want + huge - 1) / huge * huge;
+    void *q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (q != MAP_FAILED) {
+      p = q;
+      mapped = true;
+#ifdef MADV_HUGEPAGE
+      madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+    } else {
+      p = calloc(want, 1);
+      if (p == nullptr) throw IoError{"out of memory"};
+    }
+  }
+  ~BigBuffer() { if (mapped) munmap(p, bytes); else free(p); }
+  BigBuffer(const BigBuffer &) = delete;
+  BigBuffer &operator=(const BigBuffer &) = delete;
+};
+
 // ---------------------------------------------------------------- the representation
 // GtSpecialcharinfo, src/core/chardef.h:90-115
 struct SpecialCharInfo {
@@ -551,10 +579,53 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   if (n + 1 >= 0xffffffffull) throw Unsupported{"2^32-2 symbols or more"};
   const double t_count = now();
 
+  // ---- md5 of every sequence: upper case of the decoded symbols (encseq_charproc.gen).  One sequence per task,
+  //      read from the text itself (the descriptions found above bound it), so that it can start now, on threads
+  //      of its own beside everything that follows: a genome of one sequence is ONE task and takes as long as
+  //      all other passes together
+  struct Span { unsigned file; size_t begin, end; };
+  std::vector<Span> spans;
+  std::vector<char> md5tab;
+  std::thread md5_thread;
+  double md5_seconds = 0;
+  struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_md5{md5_thread};
+  if (rq->out_md5) {
+    spans.reserve(numofsequences);
+    for (const Chunk &c : chunks)
+      for (const Header &h : c.headers) {
+        if (!spans.empty() && spans.back().file == c.file) spans.back().end = h.desc_begin - 1;   // at its '>'
+        spans.push_back(Span{c.file, h.desc_end + 1, files[c.file].len});
+      }
+    md5tab.assign(33 * numofsequences, '\0');
+    auto all_md5 = [&]() {
+      const double t = now();
+      uint8_t up[256];                                          // 0: not a symbol (white space)
+      for (int c = 0; c < 256; c++)
+        up[c] = tables.cls[c] == C_SYMBOL ? (uint8_t) toupper((unsigned char) rq->decode[tables.code[c]]) : 0;
+      parallel_for(nthreads, spans.size(), [&](size_t s) {
+        const uint8_t *p = files[spans[s].file].p;
+        Md5 m;
+        uint8_t buf[(1 << 14) + 8];
+        for (size_t i = spans[s].begin; i < spans[s].end;) {
+          const size_t stop = std::min(spans[s].end, i + (size_t(1) << 14));
+          size_t k = 0;
+          for (; i < stop; i++) {
+            const uint8_t u = up[p[i]];
+            buf[k] = u;
+            k += (u != 0);
+          }
+          m.update(buf, k);
+        }
+        m.hex(&md5tab[33 * s]);
+      });
+      md5_seconds = now() - t;
+    };
+    try { md5_thread = std::thread(all_md5); } catch (...) { all_md5(); }
+  }
+
   // ---- emit
-  uint8_t *codes = static_cast<uint8_t *>(malloc(n + 64));
-  if (codes == nullptr) throw IoError{"out of memory (symbol array)"};
-  struct Free { void *p; ~Free() { free(p); } } free_codes{codes};
+  BigBuffer codes_buffer(n + 64);
+  uint8_t *codes = static_cast<uint8_t *>(codes_buffer.p);
   parallel_for(nthreads, chunks.size(), [&](size_t i) { emit_chunk(files[chunks[i].file], tables, chunks[i], codes, i == 0); });
   const double t_emit = now();
 
@@ -684,40 +755,11 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   }
   const double t_lists = now();
 
-  // ---- md5 of every sequence: upper case of the decoded symbols (encseq_charproc.gen).  One sequence per
-  //      task; it starts now, on threads of its own beside the packing and the writing of the other files
-  //      (a genome of one sequence is one task, as long as everything else together)
-  std::vector<char> md5tab;
-  std::thread md5_thread;
-  double md5_seconds = 0;
-  struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_md5{md5_thread};
-  if (rq->out_md5) {
-    md5tab.assign(33 * numofsequences, '\0');
-    auto all_md5 = [&]() {
-      const double t = now();
-      uint8_t up[256];
-      for (int c = 0; c < 256; c++) up[c] = (uint8_t) toupper((unsigned char) rq->decode[c]);
-      parallel_for(nthreads, (size_t) numofsequences, [&](size_t s) {
-        const uint64_t start = s == 0 ? 0 : seppos[s - 1] + 1, end = s < seppos.size() ? seppos[s] : n;
-        Md5 m;
-        uint8_t buf[1 << 14];
-        for (uint64_t i = start; i < end;) {
-          const size_t take = (size_t) std::min<uint64_t>(sizeof buf, end - i);
-          for (size_t j = 0; j < take; j++) buf[j] = up[codes[i + j]];
-          m.update(buf, take);
-          i += take;
-        }
-        m.hex(&md5tab[33 * s]);
-      });
-      md5_seconds = now() - t;
-    };
-    try { md5_thread = std::thread(all_md5); } catch (...) { all_md5(); }
-  }
-
   // ---- pack (fillSWtable / fillViaequallength / fillViabitaccess: a special position holds the least
   //      probable character, with bit access 0 for a wildcard and 1 for a separator)
   const uint64_t units = units_of_twobit(n), full = n / 32;
-  std::vector<uint64_t> words(units, 0);
+  BigBuffer words_buffer(units * 8);
+  uint64_t *words = static_cast<uint64_t *>(words_buffer.p);   // zeros: the words behind the last symbol stay 0
   uint8_t fill[256];
   for (int c = 0; c < 256; c++) fill[c] = (uint8_t) (c < 4 ? c : lpc);
   if (sat == SAT_BITACCESS) { fill[CODE_WILDCARD] = 0; fill[CODE_SEPARATOR] = 1; }
@@ -785,7 +827,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     }
     w.field(flv.data(), 16, files.size());
     w.field(chardist, 8, 4);
-    w.field(words.data(), 8, units);                            // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
+    w.field(words, 8, units);                            // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
     if (sat == SAT_BITACCESS && (wildtab[0] > 0 || numofsequences > 1)) {
       const uint64_t nw = ints_for_bits(n + 64);
       std::vector<uint64_t> bits(nw, 0);
@@ -875,7 +917,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     sum->seconds_emit = t_emit - t_count;
     sum->seconds_lists = t_lists - t_emit;
     sum->seconds_pack = t_pack - t_lists;
-    sum->seconds_md5 = md5_seconds;                   /* beside pack + write */
+    sum->seconds_md5 = md5_seconds;                   /* beside emit, pack and write */
     sum->seconds_write = t_write - t_pack;
     sum->seconds_total = t_write - t0;
   }

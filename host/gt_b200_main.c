@@ -8,6 +8,8 @@
 #include "core/error_api.h"
 #include "core/thread_api.h"
 #include <stdlib.h>
+#include <sys/time.h>
+#include <unistd.h>
 
 int gt_suffixerator(int argc, const char **argv, GtError *err);
 #ifdef B200_REFERENCE_TOOLS
@@ -17,11 +19,24 @@ int gt_suffixerator(int argc, const char **argv, GtError *err);
 #include "match/sfx-run.h"
 #endif
 
+/* GTB200_TRACE_WALL=1: wall-clock stamps (seconds since the epoch) at the start of main, around the tool and
+   at the end of main, so that a caller that stamps before it starts the process and after it has waited for
+   it can tell the time in front of main (loading) and behind it (the exit handlers) from the tool's own */
+static void b200_stamp(const char *what)
+{
+  struct timeval tv;
+  const char *e = getenv("GTB200_TRACE_WALL");
+  if (e == NULL || e[0] != '1') return;
+  gettimeofday(&tv, NULL);
+  fprintf(stderr, "wallstamp %s %.6f\n", what, (double) tv.tv_sec + 1e-6 * (double) tv.tv_usec);
+}
+
 int main(int argc, char **argv)
 {
   GtError *err;
   int rval;
   unsigned int jobs = 1;
+  b200_stamp("main");
   /* `gt -j N <tool>`: the global option of gt (src/gtr.c:181); here N = number of GPUs */
   if (argc >= 4 && strcmp(argv[1], "-j") == 0) {
     int j = atoi(argv[2]);
@@ -41,6 +56,7 @@ int main(int argc, char **argv)
   }
 #endif
   gt_lib_init();
+  b200_stamp("tool");
   gt_jobs = jobs;
   err = gt_error_new();
   gt_error_set_progname(err, argv[0]);
@@ -49,9 +65,17 @@ int main(int argc, char **argv)
 #else
   rval = gt_suffixerator(argc - 1, (const char **) argv + 1, err);
 #endif
+  b200_stamp("tool_done");
   if (gt_error_is_set(err))
     fprintf(stderr, "%s: error: %s\n", argv[0], gt_error_get(err));
   gt_error_delete(err);
   if (gt_lib_clean()) return 3;
+  b200_stamp("main_done");
+  /* GTB200_QUICK_EXIT=1: leave without the exit handlers (the CUDA runtime unloads its modules and
+     destroys the context there); every file of the tool is closed by now */
+  if (getenv("GTB200_QUICK_EXIT") != NULL && getenv("GTB200_QUICK_EXIT")[0] == '1') {
+    fflush(NULL);
+    _exit(rval ? 1 : 0);
+  }
   return rval ? 1 : 0;
 }

@@ -164,10 +164,10 @@ static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *
   }
   if (rc != GTB_FASTA_OK) { gt_error_set(err, "libgtb200: %s", msg); return -1; }
   gt_logger_log(logger, "B200 encoder: %llu symbols in %llu sequence(s), representation %s, %u threads, %.3f s "
-                        "(count %.3f, emit %.3f, pack %.3f, md5 %.3f beside pack and write %.3f)",
+                        "(count %.3f, emit %.3f, pack %.3f, write %.3f; md5 %.3f beside emit, pack and write)",
                 (unsigned long long) sum.totallength, (unsigned long long) sum.numofsequences, sum.satname,
                 sum.threads, sum.seconds_total, sum.seconds_count, sum.seconds_emit, sum.seconds_pack,
-                sum.seconds_md5, sum.seconds_write);
+                sum.seconds_write, sum.seconds_md5);
   return 0;
 }
 

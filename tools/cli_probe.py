@@ -10,13 +10,21 @@ tmp = tempfile.mkdtemp()
 fa = os.path.join(tmp, "s.fa"); synth.to_fasta(w.to_symbols(), fa, "dna")
 print("host cores", os.cpu_count(), "fasta bytes", os.path.getsize(fa))
 exe = os.path.join(ROOT, "host", "_build", "gt_b200")
-for label, env in (("library encoder", None), ("reference encoder", dict(os.environ, GTB200_ENCODER="reference"))):
+for label, env in (("library encoder", {}), ("library encoder, quick exit", {"GTB200_QUICK_EXIT": "1"}),
+                   ("reference encoder", {"GTB200_ENCODER": "reference"})):
     for i in range(3):
+        w0 = time.time()
         t0 = time.perf_counter()
         r = subprocess.run([exe, "suffixerator", "-dna", "-suf", "-lcp", "-bck", "-pl", "-v", "-indexname",
-                            os.path.join(tmp, "x"), "-db", fa], capture_output=True, text=True, env=env)
-        print(label, round(time.perf_counter() - t0, 3),
-              [l for l in r.stdout.split("\n") if "wall seconds" in l or "B200 encoder" in l], r.stderr[-200:])
+                            os.path.join(tmp, "x"), "-db", fa], capture_output=True, text=True,
+                           env=dict(os.environ, GTB200_TRACE_WALL="1", **env))
+        w1 = time.time()
+        st = {l.split()[1]: float(l.split()[2]) for l in r.stderr.split("\n") if l.startswith("wallstamp")}
+        where = ("before main %.3f, init %.3f, tool %.3f, cleanup %.3f, after main %.3f" %
+                 (st["main"] - w0, st["tool"] - st["main"], st["tool_done"] - st["tool"],
+                  st["main_done"] - st["tool_done"], w1 - st["main_done"])) if len(st) == 4 else str(st)
+        print(label, round(time.perf_counter() - t0, 3), where,
+              [l for l in r.stdout.split("\n") if "wall seconds" in l or "B200 encoder" in l])
 gtref = os.path.join(ROOT, "oracle", "_ref", "gtref")
 if os.path.exists(gtref):
     for i in range(2):
