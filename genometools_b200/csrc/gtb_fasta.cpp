@@ -203,10 +203,12 @@ void map_inputs(const gtb_fasta_request *rq, Mapped &m)
     }
     f.len = (size_t) st.st_size;
     if (f.len == 0) { close(fd); throw Unsupported{format("file \"%s\" is empty", f.name.c_str())}; }
-    void *p = mmap(nullptr, f.len, PROT_READ, MAP_PRIVATE, fd, 0);
+    const char *how = getenv("GTB200_FASTA_MAP");               // experiments: populate | seq | (plain)
+    const bool populate = how != nullptr && strcmp(how, "populate") == 0;
+    void *p = mmap(nullptr, f.len, PROT_READ, MAP_PRIVATE | (populate ? MAP_POPULATE : 0), fd, 0);
     close(fd);
     if (p == MAP_FAILED) { f.len = 0; throw IoError{format("cannot map file \"%s\": %s", f.name.c_str(), strerror(errno))}; }
-    madvise(p, f.len, MADV_SEQUENTIAL);
+    if (how != nullptr && strcmp(how, "seq") == 0) madvise(p, f.len, MADV_SEQUENTIAL);
     f.p = static_cast<const uint8_t *>(p);
     // gt_sequence_buffer_new_guess_type looks at the first file only (src/core/sequence_buffer.c:63-103);
     // a later file that begins with sequence characters would continue the last sequence of the file before

@@ -37,7 +37,11 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/time.h>
+#include <sys/types.h>
+#include <unistd.h>
+#include <stdio.h>
 #include "core/alphabet.h"
 #include "core/chardef.h"
 #include "core/encseq.h"
@@ -171,15 +175,91 @@ static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *
   return 0;
 }
 
+/* the big result tables: anonymous mappings that ask for huge pages (the first touch of 512 MB in 4 KB pages
+   is 131 000 page faults under the copy threads of the library) */
+static void *b200_big_alloc(size_t bytes)
+{
+  const size_t huge = (size_t) 2 << 20;
+  size_t size = (bytes + huge - 1) / huge * huge;
+  void *p = mmap(NULL, size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) {
+    fprintf(stderr, "cannot map %lu bytes of memory\n", (unsigned long) size);
+    exit(EXIT_FAILURE);                      /* what gt_malloc does when memory runs out */
+  }
+#ifdef MADV_HUGEPAGE
+  (void) madvise(p, size, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+
+static void b200_big_free(void *p, size_t bytes)
+{
+  const size_t huge = (size_t) 2 << 20;
+  if (p != NULL) (void) munmap(p, (bytes + huge - 1) / huge * huge);
+}
+
+/* one file of the index.  Large tables are written by several threads, each with pwrite on its own
+   slice: the time goes into copying into the page cache, which one thread does at 2-3 GB/s. */
+typedef struct {
+  int fd;
+  const char *data;
+  size_t begin, end;
+  int failed;
+} B200WriteSlice;
+
+static void *b200_write_slice(void *p)
+{
+  B200WriteSlice *w = p;
+  size_t off = w->begin;
+  while (off < w->end) {
+    size_t chunk = w->end - off;
+    ssize_t done;
+    if (chunk > ((size_t) 64 << 20)) chunk = (size_t) 64 << 20;
+    done = pwrite(w->fd, w->data + off, chunk, (off_t) off);
+    if (done <= 0) { w->failed = 1; return NULL; }
+    off += (size_t) done;
+  }
+  return NULL;
+}
+
 static int b200_write(const char *indexname, const char *suffix, const void *data,
                       size_t size, size_t nmemb, size_t pad_to, GtError *err)
 {
   static const char zeros[8] = {0};
+  const size_t bytes = size * nmemb;
   FILE *fp = gt_fa_fopen_with_suffix(indexname, suffix, "wb", err);
   if (fp == NULL) return -1;
+  if (bytes >= ((size_t) 32 << 20) && pad_to == 0) {
+    enum { MAXT = 8 };
+    B200WriteSlice sl[MAXT];
+    pthread_t tid[MAXT];
+    int started[MAXT], i, nt = MAXT, failed = 0;
+    long cores = sysconf(_SC_NPROCESSORS_ONLN);
+    if (cores > 0 && cores < nt) nt = (int) cores;
+    for (i = 0; i < nt; i++) {
+      sl[i].fd = fileno(fp);
+      sl[i].data = data;
+      sl[i].begin = bytes / (size_t) nt * (size_t) i;
+      sl[i].end = i == nt - 1 ? bytes : bytes / (size_t) nt * (size_t) (i + 1);
+      sl[i].failed = 0;
+      started[i] = i > 0 && pthread_create(&tid[i], NULL, b200_write_slice, &sl[i]) == 0;
+    }
+    for (i = 0; i < nt; i++)
+      if (!started[i]) b200_write_slice(&sl[i]);       /* slice 0, and any slice without a thread */
+    for (i = 0; i < nt; i++) {
+      if (started[i]) pthread_join(tid[i], NULL);
+      failed |= sl[i].failed;
+    }
+    gt_fa_xfclose(fp);
+    if (failed) {
+      gt_error_set(err, "cannot write %lu bytes to file \"%s%s\"", (unsigned long) bytes, indexname, suffix);
+      return -1;
+    }
+    return 0;
+  }
   if (nmemb > 0) gt_xfwrite(data, size, nmemb, fp);
-  if (pad_to > 0 && (size * nmemb) % pad_to != 0)
-    gt_xfwrite(zeros, 1, pad_to - (size * nmemb) % pad_to, fp);
+  if (pad_to > 0 && bytes % pad_to != 0)
+    gt_xfwrite(zeros, 1, pad_to - bytes % pad_to, fp);
   gt_fa_xfclose(fp);
   return 0;
 }
@@ -328,10 +408,10 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       }
       if (rc == 0) {
         /* the result tables, sized from what the run produced */
-        if (want_suf) suftab = gt_malloc(sizeof *suftab * (n + 1));
+        if (want_suf) suftab = b200_big_alloc(sizeof *suftab * (n + 1));
         if (want_lcp) {
           nllv = gtb_group_num_llv(g);
-          lcptab = gt_malloc(sizeof *lcptab * (n + 1));
+          lcptab = b200_big_alloc(sizeof *lcptab * (n + 1));
           llv = gt_malloc(sizeof *llv * 2 * (nllv + 1));
         }
         if (want_bck) {
@@ -343,7 +423,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
         /* the gather: every range copies its shard to its offset of the one table, all tables in one call */
         rc = gtb_group_copy_results(g, suftab, lcptab, nllv > 0 ? llv : NULL, leftborder, csc, dist);
         if (rc == 0 && want_bwt) {
-          bwttab = gt_malloc(sizeof *bwttab * (n + 1));
+          bwttab = b200_big_alloc(sizeof *bwttab * (n + 1));
           rc = gtb_group_copy_bwttab(g, bwttab);
         }
         if (rc == 0) rc = gtb_group_get_stats(g, &stats);
@@ -392,7 +472,10 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
                             "%.3f, sort %.3f, copy to host %.3f, write files %.3f",
                     t_encoded - t_start, t_uploaded - t_encoded, t_sorted - t_uploaded, t_copied - t_sorted,
                     b200_now() - t_copied);
-    gt_free(suftab); gt_free(lcptab); gt_free(llv); gt_free(bwttab);
+    b200_big_free(suftab, sizeof *suftab * (n + 1));
+    b200_big_free(lcptab, sizeof *lcptab * (n + 1));
+    b200_big_free(bwttab, sizeof *bwttab * (n + 1));
+    gt_free(llv);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
   }
   if (init_started) pthread_join(init_tid, NULL);
