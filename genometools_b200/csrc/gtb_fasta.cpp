@@ -7,8 +7,8 @@
 // files2encodedsequence :4529-4647 with the fill function of the chosen representation; the reader is
 // gt_sequence_buffer_fasta_advance, src/core/sequence_buffer_fasta.c:41-165): 1.5-1.9 s for 64 Mbp,
 // most of the wall time of the drop-in binary once the sort takes 50 ms.  Here the files are mapped,
-// cut into chunks at line ends (after a newline the reader is never inside a description), and every
-// pass is a parallel loop over chunks or over blocks of the symbol array:
+// cut into chunks anywhere but inside a description (make_chunks), and every pass is a parallel loop
+// over chunks or over blocks of the symbol array:
 //
 //   count    symbols + separators per chunk, descriptions located, characters checked
 //   emit     one code per symbol into a byte array (0..3, 254 wildcard, 255 separator), separator
@@ -258,28 +258,6 @@ Tables make_tables(const uint8_t *symbolmap)
   return t;
 }
 
-std::vector<Chunk> make_chunks(const std::vector<Input> &files, size_t target)
-{
-  std::vector<Chunk> chunks;
-  for (unsigned fi = 0; fi < files.size(); fi++) {
-    const Input &f = files[fi];
-    size_t b = 0;
-    while (b < f.len) {
-      size_t e = b + target;
-      if (e >= f.len) e = f.len;
-      else {
-        const void *nl = memchr(f.p + e - 1, '\n', f.len - (e - 1));   // a chunk ends behind a newline
-        e = nl ? (size_t) (static_cast<const uint8_t *>(nl) - f.p) + 1 : f.len;
-      }
-      Chunk c;
-      c.file = fi; c.begin = b; c.end = e;
-      chunks.push_back(std::move(c));
-      b = e;
-    }
-  }
-  return chunks;
-}
-
 // first pass over a chunk: how much it emits, where its descriptions are, which characters occur.
 // Line by line: the text up to the next newline is scanned without branches; only a line that holds a
 // '>' or a character outside the alphabet is looked at again, character by character.
@@ -385,6 +363,55 @@ template <class F> void parallel_for(unsigned nthreads, size_t ntasks, F &&fn)
   }
   worker();
   for (auto &x : th) x.join();
+}
+
+// The files are cut every `target` bytes, wherever that falls -- a FASTA file may hold its sequence on one line --
+// except inside a description: a position is inside one iff a '>' stands between the last newline in front of it
+// and itself.  Per piece, in parallel: where its last newline is and whether a '>' follows it (or stands anywhere
+// in a piece without newline); then one walk over the pieces, and a cut that fell into a description moves behind
+// the newline that ends it.  Every chunk therefore begins outside a description, and a description never leaves
+// the chunk its '>' is in.
+std::vector<Chunk> make_chunks(const std::vector<Input> &files, size_t target, unsigned nthreads)
+{
+  struct Piece { unsigned file; size_t begin, end; bool has_nl, gt_after; };
+  std::vector<Piece> pieces;
+  for (unsigned fi = 0; fi < files.size(); fi++)
+    for (size_t b = 0; b < files[fi].len; b += target)
+      pieces.push_back(Piece{fi, b, std::min(files[fi].len, b + target), false, false});
+  parallel_for(nthreads, pieces.size(), [&](size_t i) {
+    Piece &pc = pieces[i];
+    const uint8_t *p = files[pc.file].p;
+    const void *nl = memrchr(p + pc.begin, '\n', pc.end - pc.begin);
+    const size_t from = nl ? (size_t) (static_cast<const uint8_t *>(nl) - p) + 1 : pc.begin;
+    pc.has_nl = nl != nullptr;
+    pc.gt_after = from < pc.end && memchr(p + from, '>', pc.end - from) != nullptr;
+  });
+  std::vector<Chunk> chunks;
+  size_t k = 0;
+  for (unsigned fi = 0; fi < files.size(); fi++) {
+    const Input &f = files[fi];
+    size_t last_cut = 0;
+    bool in_desc = false;                                        // at the begin of the piece looked at
+    for (; k < pieces.size() && pieces[k].file == fi; k++) {
+      const Piece &pc = pieces[k];
+      size_t cut = pc.begin;
+      if (cut > 0 && in_desc) {
+        const void *nl = memchr(f.p + cut, '\n', f.len - cut);
+        cut = nl ? (size_t) (static_cast<const uint8_t *>(nl) - f.p) + 1 : f.len;
+      }
+      if (cut > last_cut && cut < f.len) {
+        Chunk c;
+        c.file = fi; c.begin = last_cut; c.end = cut;
+        chunks.push_back(std::move(c));
+        last_cut = cut;
+      }
+      in_desc = pc.has_nl ? pc.gt_after : (in_desc || pc.gt_after);
+    }
+    Chunk c;
+    c.file = fi; c.begin = last_cut; c.end = f.len;
+    chunks.push_back(std::move(c));
+  }
+  return chunks;
 }
 
 // the two big arrays (one byte per symbol, the packed words): anonymous mappings that ask for huge pages --
@@ -564,7 +591,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   size_t target = std::max<size_t>(size_t(1) << 16, std::min<size_t>(size_t(8) << 20, total_bytes / (8 * (size_t) nthreads) + 1));
   if (const char *e = getenv("GTB200_FASTA_CHUNK"))              // tests: chunk borders everywhere
     if (atol(e) > 0) target = (size_t) atol(e);
-  std::vector<Chunk> chunks = make_chunks(files, target);
+  std::vector<Chunk> chunks = make_chunks(files, target, nthreads);
 
   // ---- count
   parallel_for(nthreads, chunks.size(), [&](size_t i) { count_chunk(files[chunks[i].file], tables, chunks[i]); });

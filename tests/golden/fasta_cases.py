@@ -112,6 +112,8 @@ def big_cases():
     c["page_edge_65536x2"] = ([big_file(9, 1, 65536 * 2, 1, [65537])], ALL_ON)
     c["run_of_256"] = ([big_file(10, 1, 2000, 1, [256])], ALL_ON)
     c["run_of_257"] = ([big_file(11, 1, 2000, 1, [257])], ALL_ON)
+    c["one_line_3M"] = ([big_file(13, 1, 3_000_000, 5, [1, 40, 70000], width=1 << 30)], ALL_ON)
+    c["one_line_per_sequence"] = ([big_file(14, 7, 2_000_000, 3, [1, 300], width=1 << 30)], ALL_ON)
     c["equal_length_reads"] = ([big_file(12, 1, 100, 0, [1]).replace(b"seq0", b"r") * 2000], ALL_ON)
     return c
 

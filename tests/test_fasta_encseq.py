@@ -65,9 +65,22 @@ def test_index_files_identical_to_reference(name, tmp_path, monkeypatch):
     check_case(name, tmp_path, monkeypatch)
 
 
+@pytest.mark.parametrize("chunk", [50, 7])
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith(("small_0", "odd_"))])
-def test_chunk_borders_do_not_show(name, tmp_path, monkeypatch):
-    check_case(name, tmp_path, monkeypatch, chunk=50, threads=3)
+def test_chunk_borders_do_not_show(name, chunk, tmp_path, monkeypatch):
+    """the files are cut every `chunk` bytes (anywhere but inside a description): in the middle of lines, of
+    wildcard runs, of CR LF pairs, right in front of a '>'"""
+    check_case(name, tmp_path, monkeypatch, chunk=chunk, threads=3)
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith("odd_")])
+def test_a_chunk_per_character(name, tmp_path, monkeypatch):
+    check_case(name, tmp_path, monkeypatch, chunk=1, threads=2)
+
+
+def test_sequence_on_one_line_is_cut_too(tmp_path, monkeypatch):
+    s = check_case("one_line_3M", tmp_path, monkeypatch, chunk=1 << 16, threads=4)
+    assert s["totallength"] == 3_000_000
 
 
 def test_every_representation_is_reached(tmp_path, monkeypatch):
