@@ -73,6 +73,7 @@ SYMBOLS = {
     "gtb_abi_version": (C.c_int, []),
     "gtb_fasta_encode": (C.c_int, [C.POINTER(GtbFastaRequest), C.POINTER(GtbFastaSummary), C.c_char_p, C.c_size_t]),
     "gtb_device_count": (C.c_int, []),
+    "gtb_release_devices": (C.c_int, []),
     "gtb_esa_new": (_P, [C.c_int, C.c_char_p, C.c_size_t]),
     "gtb_esa_delete": (None, [_P]),
     "gtb_esa_error": (C.c_char_p, [_P]),

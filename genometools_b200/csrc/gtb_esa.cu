@@ -1138,6 +1138,34 @@ int gtb_device_count(void)
   return n;
 }
 
+// live handles per device (gtb_esa_new / gtb_esa_delete), for gtb_release_devices
+static std::mutex g_live_mutex;
+static int g_live[64];
+static bool g_used[64];
+
+static void live_handles(int device, int delta)
+{
+  if (device < 0 || device >= 64) return;
+  std::lock_guard<std::mutex> lock(g_live_mutex);
+  g_live[device] += delta;
+  g_used[device] = true;
+}
+
+int gtb_release_devices(void)
+{
+  int released = 0;
+  for (int d = 0; d < 64; d++) {
+    {
+      std::lock_guard<std::mutex> lock(g_live_mutex);
+      if (!g_used[d] || g_live[d] > 0) continue;
+      g_used[d] = false;
+    }
+    if (cudaSetDevice(d) == cudaSuccess && cudaDeviceReset() == cudaSuccess) released++;
+    else cudaGetLastError();
+  }
+  return released;
+}
+
 void gtb_bck_sizes(unsigned K, unsigned pl, uint64_t *nall, uint64_t *nspecial, uint64_t *ndist)
 {
   u64 d = 0;
@@ -1169,17 +1197,18 @@ gtb_esa *gtb_esa_new(int device, char *errbuf, size_t errlen)
   gtb_esa *h = new (std::nothrow) gtb_esa();
   if (!h) { if (errbuf && errlen) snprintf(errbuf, errlen, "out of host memory"); return nullptr; }
   h->device = device;
+  live_handles(device, +1);
   if (const char *e = getenv("GTB200_KEY_SYMBOLS")) h->opt_key_symbols = atoi(e);
   if (const char *e = getenv("GTB200_TEXT_ROUNDS")) h->opt_text_rounds = atoi(e) > 8 ? 8 : atoi(e);
   if (const char *e = getenv("GTB200_TAIL_LAST")) h->opt_tail_last = atoi(e) ? 1 : 0;
   if (const char *e = getenv("GTB200_PAIRS_BY_TEXT")) h->opt_pairs_by_text = atoi(e) < 0 ? 0 : atoi(e);
   memset(&h->stats, 0, sizeof h->stats);
   if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) {
-    delete h; return fail("cudaStreamCreate", e);
+    live_handles(device, -1); delete h; return fail("cudaStreamCreate", e);
   }
   if (radix_work_init(h->rw, h->err) != 0) {
     if (errbuf && errlen) snprintf(errbuf, errlen, "%s", h->err.msg);
-    cudaStreamDestroy(h->st); delete h; return nullptr;
+    cudaStreamDestroy(h->st); live_handles(device, -1); delete h; return nullptr;
   }
   return h;
 }
@@ -1218,6 +1247,7 @@ void gtb_esa_delete(gtb_esa *h)
   if (h->st2) cudaStreamDestroy(h->st2);
   if (h->st3) cudaStreamDestroy(h->st3);
   cudaStreamDestroy(h->st);
+  live_handles(h->device, -1);
   delete h;
 }
 

@@ -104,6 +104,13 @@ typedef struct {
   char msg[512];
 } B200Init;
 
+static void *b200_release_thread(void *p)
+{
+  (void) p;
+  (void) gtb_release_devices();
+  return NULL;
+}
+
 static void *b200_init_thread(void *p)
 {
   B200Init *init = p;
@@ -198,30 +205,6 @@ static void b200_big_free(void *p, size_t bytes)
   if (p != NULL) (void) munmap(p, (bytes + huge - 1) / huge * huge);
 }
 
-/* one file of the index.  Large tables are written by several threads, each with pwrite on its own
-   slice: the time goes into copying into the page cache, which one thread does at 2-3 GB/s. */
-typedef struct {
-  int fd;
-  const char *data;
-  size_t begin, end;
-  int failed;
-} B200WriteSlice;
-
-static void *b200_write_slice(void *p)
-{
-  B200WriteSlice *w = p;
-  size_t off = w->begin;
-  while (off < w->end) {
-    size_t chunk = w->end - off;
-    ssize_t done;
-    if (chunk > ((size_t) 64 << 20)) chunk = (size_t) 64 << 20;
-    done = pwrite(w->fd, w->data + off, chunk, (off_t) off);
-    if (done <= 0) { w->failed = 1; return NULL; }
-    off += (size_t) done;
-  }
-  return NULL;
-}
-
 static int b200_write(const char *indexname, const char *suffix, const void *data,
                       size_t size, size_t nmemb, size_t pad_to, GtError *err)
 {
@@ -229,34 +212,6 @@ static int b200_write(const char *indexname, const char *suffix, const void *dat
   const size_t bytes = size * nmemb;
   FILE *fp = gt_fa_fopen_with_suffix(indexname, suffix, "wb", err);
   if (fp == NULL) return -1;
-  if (bytes >= ((size_t) 32 << 20) && pad_to == 0) {
-    enum { MAXT = 8 };
-    B200WriteSlice sl[MAXT];
-    pthread_t tid[MAXT];
-    int started[MAXT], i, nt = MAXT, failed = 0;
-    long cores = sysconf(_SC_NPROCESSORS_ONLN);
-    if (cores > 0 && cores < nt) nt = (int) cores;
-    for (i = 0; i < nt; i++) {
-      sl[i].fd = fileno(fp);
-      sl[i].data = data;
-      sl[i].begin = bytes / (size_t) nt * (size_t) i;
-      sl[i].end = i == nt - 1 ? bytes : bytes / (size_t) nt * (size_t) (i + 1);
-      sl[i].failed = 0;
-      started[i] = i > 0 && pthread_create(&tid[i], NULL, b200_write_slice, &sl[i]) == 0;
-    }
-    for (i = 0; i < nt; i++)
-      if (!started[i]) b200_write_slice(&sl[i]);       /* slice 0, and any slice without a thread */
-    for (i = 0; i < nt; i++) {
-      if (started[i]) pthread_join(tid[i], NULL);
-      failed |= sl[i].failed;
-    }
-    gt_fa_xfclose(fp);
-    if (failed) {
-      gt_error_set(err, "cannot write %lu bytes to file \"%s%s\"", (unsigned long) bytes, indexname, suffix);
-      return -1;
-    }
-    return 0;
-  }
   if (nmemb > 0) gt_xfwrite(data, size, nmemb, fp);
   if (pad_to > 0 && bytes % pad_to != 0)
     gt_xfwrite(zeros, 1, pad_to - bytes % pad_to, fp);
@@ -271,7 +226,8 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   GtLogger *logger = NULL;
   B200Init init;
   pthread_t init_tid;
-  bool init_started = false, init_ever = false, encoded = false;
+  bool init_started = false, init_ever = false, encoded = false, release_started = false;
+  pthread_t release_tid;
   int retval, had_err = 0;
   double t_start = b200_now(), t_encoded = 0, t_uploaded = 0, t_sorted = 0, t_copied = 0;
 
@@ -433,6 +389,10 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
     }
     t_copied = b200_now();
+    /* nothing is left on the GPUs: their contexts are destroyed beside the writing of the files
+       (gtb_release_devices, include/gtb200.h) instead of behind the end of main */
+    if (want_any && !had_err)
+      release_started = pthread_create(&release_tid, NULL, b200_release_thread, NULL) == 0;
     /* the reference's files */
     if (!had_err && want_suf)
       had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, err);
@@ -478,6 +438,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     gt_free(llv);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
   }
+  if (release_started) pthread_join(release_tid, NULL);
   if (init_started) pthread_join(init_tid, NULL);
   if (init_ever && init.group != NULL) gtb_group_delete(init.group);   /* an error came first: never used */
   gt_encseq_delete(encseq);

@@ -92,6 +92,12 @@ typedef struct {
 
 int  gtb_abi_version(void);
 int  gtb_device_count(void);
+/* Destroys the CUDA context of every device this process has used through the library and has no
+   live handle on any more (cudaDeviceReset); returns how many.  For a tool that has its tables on
+   the host and only files left to write: destroying a context takes the driver 0.3-1 s, which
+   otherwise follows the end of main -- called on a thread of its own it passes beside the writes
+   (host/gt_suffixerator_b200.c).  No counterpart in the reference. */
+int  gtb_release_devices(void);
 
 /* gt_Sfxiterator_new_withadditionalvalues (sfx-suffixer.c:1363): create the
    sorter object on CUDA device `device`. NULL on error (message in errbuf). */
