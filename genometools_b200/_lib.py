@@ -39,6 +39,7 @@ class GtbFastaRequest(C.Structure):
     _fields_ = [
         ("filenames", C.POINTER(C.c_char_p)), ("numoffiles", C.c_uint64), ("indexname", C.c_char_p),
         ("symbolmap", C.POINTER(C.c_uint8)), ("decode", C.c_char_p), ("numofchars", C.c_uint),
+        ("alphatype", C.c_uint), ("bits_per_symbol", C.c_uint),
         ("out_des", C.c_int), ("out_sds", C.c_int), ("out_ssp", C.c_int), ("out_md5", C.c_int),
         ("clip_desc", C.c_int), ("threads", C.c_int),
     ]
@@ -49,7 +50,7 @@ class GtbFastaSummary(C.Structure):
         ("totallength", C.c_uint64), ("numofsequences", C.c_uint64), ("numoffiles", C.c_uint64),
         ("specialcharacters", C.c_uint64), ("specialranges", C.c_uint64), ("realspecialranges", C.c_uint64),
         ("wildcards", C.c_uint64), ("wildcardranges", C.c_uint64), ("realwildcardranges", C.c_uint64),
-        ("sat", C.c_uint64), ("satsep", C.c_uint64), ("characterdistribution", C.c_uint64 * 4),
+        ("sat", C.c_uint64), ("satsep", C.c_uint64), ("characterdistribution", C.c_uint64 * 32),
         ("input_bytes", C.c_uint64), ("satname", C.c_char * 16), ("threads", C.c_uint),
         ("seconds_count", C.c_double), ("seconds_emit", C.c_double), ("seconds_lists", C.c_double),
         ("seconds_pack", C.c_double), ("seconds_md5", C.c_double), ("seconds_write", C.c_double),

@@ -576,7 +576,13 @@ const char *sat_name(uint64_t sat)                              // src/core/encs
 int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
 {
   const double t0 = now();
-  if (rq->numofchars != 4) throw Unsupported{"the alphabet is not the DNA alphabet"};
+  // the two alphabets the reference knows by name (alphabet_to_key_values, encseq.c:1080-1111: alphatype 0 and 1;
+  // any other is stored with its definition, which is not rebuilt here)
+  const bool dna = rq->alphatype == 0 && rq->numofchars == 4;
+  const bool protein = rq->alphatype == 1 && rq->numofchars > 4 && rq->numofchars <= 64 && rq->bits_per_symbol >= 1 &&
+                       rq->bits_per_symbol <= 8 && (1u << rq->bits_per_symbol) >= rq->numofchars + 2;
+  if (!dna && !protein) throw Unsupported{"neither the DNA nor the protein alphabet"};
+  const unsigned K = rq->numofchars;
   unsigned nthreads = rq->threads > 0 ? (unsigned) rq->threads : std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   if (rq->threads <= 0 && nthreads > 32) nthreads = 32;
@@ -729,20 +735,20 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
 
   // character distribution; the distinct original characters per code (determine_original_subdist,
   // encseq.c:5270-5359: printable characters 1..127)
-  uint64_t chardist[4] = {0, 0, 0, 0};
+  uint64_t chardist[64] = {0};
   uint64_t numofallchars = 0, perclass[256] = {0};
   for (int c = 1; c < 128; c++) {
     if (orig[c] == 0 || tables.cls[c] != C_SYMBOL) continue;    // (the histogram also saw the white space)
     const uint8_t code = tables.code[c];
-    if (code < 4) chardist[code] += orig[c];
+    if (code < K) chardist[code] += orig[c];
     perclass[code]++;
     numofallchars++;
   }
   uint64_t maxsub = 0;
-  for (int k = 0; k < 4; k++) maxsub = std::max(maxsub, perclass[k]);
+  for (unsigned k = 0; k < K; k++) maxsub = std::max(maxsub, perclass[k]);
   maxsub = std::max(maxsub, perclass[CODE_WILDCARD]);
   unsigned lpc = 0;                                             // determineleastprobablecharacter, encseq.c:4468-4485
-  for (unsigned k = 1; k < 4; k++)
+  for (unsigned k = 1; k < K; k++)
     if (chardist[k] < chardist[lpc]) lpc = k;
 
   // ---- which representation (doupdatesumranges, encseq.c:5215-5256; determinesmallestrep,
@@ -764,7 +770,8 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   }
   uint64_t sat = SAT_BITACCESS, table_items = wildtab[0];
   int table_kind = -1;
-  if (equallength) sat = SAT_EQUALLENGTH;
+  if (!dna) sat = SAT_BYTECOMPRESS;                             // gt_encseq_access_type_determine, encseq_access_type.c:152-163
+  else if (equallength) sat = SAT_EQUALLENGTH;
   else {
     uint64_t cmin = twobit_bytes + ((wildtab[0] > 0 || numofsequences > 1) ? 8 * ints_for_bits(n + 64) : 0);
     for (int k = 0; k < 3; k++) {
@@ -786,13 +793,40 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
 
   // ---- pack (fillSWtable / fillViaequallength / fillViabitaccess: a special position holds the least
   //      probable character, with bit access 0 for a wildcard and 1 for a separator)
-  const uint64_t units = units_of_twobit(n), full = n / 32;
-  BigBuffer words_buffer(units * 8);
+  const uint64_t units = dna ? units_of_twobit(n) : 0, full = n / 32;
+  // protein: a bit string, bits_per_symbol bits per symbol from the top of byte 0 on, wildcard = K, separator = K+1
+  // (fillViabytecompress, encseq.c:2324-2440; gt_bsStoreUInt32, src/core/bitpackstringop32.c)
+  const unsigned bps = rq->bits_per_symbol;
+  const uint64_t packed_bytes = dna ? 0 : (n * bps + 7) / 8;
+  BigBuffer words_buffer(dna ? units * 8 : packed_bytes + 16);
   uint64_t *words = static_cast<uint64_t *>(words_buffer.p);   // zeros: the words behind the last symbol stay 0
+  uint8_t *packed = static_cast<uint8_t *>(words_buffer.p);
   uint8_t fill[256];
   for (int c = 0; c < 256; c++) fill[c] = (uint8_t) (c < 4 ? c : lpc);
   if (sat == SAT_BITACCESS) { fill[CODE_WILDCARD] = 0; fill[CODE_SEPARATOR] = 1; }
-  {
+  if (!dna) {
+    for (int c = 0; c < 256; c++) fill[c] = (uint8_t) c;
+    fill[CODE_WILDCARD] = (uint8_t) K;
+    fill[CODE_SEPARATOR] = (uint8_t) (K + 1);
+    const uint64_t groups = n / 8, block = 1 << 16;             // 8 symbols = bps bytes
+    parallel_for(nthreads, (size_t) ((groups + block - 1) / block), [&](size_t task) {
+      const uint64_t g0 = task * block, g1 = std::min(groups, g0 + block);
+      for (uint64_t g = g0; g < g1; g++) {
+        uint64_t v = 0;
+        for (int j = 0; j < 8; j++) v = (v << bps) | fill[codes[8 * g + j]];
+        uint8_t *out = packed + g * bps;
+        for (unsigned b = 0; b < bps; b++) out[b] = (uint8_t) (v >> (8 * (bps - 1 - b)));
+      }
+    });
+    if (n % 8) {
+      uint64_t v = 0;
+      for (uint64_t j = 8 * groups; j < n; j++) v = (v << bps) | fill[codes[j]];
+      v <<= bps * (8 - n % 8);
+      uint8_t *out = packed + groups * bps;
+      const uint64_t left = packed_bytes - groups * bps;
+      for (uint64_t b = 0; b < left; b++) out[b] = (uint8_t) (v >> (8 * (bps - 1 - b)));
+    }
+  } else {
     const uint64_t block = 1 << 15;                              // words per task
     parallel_for(nthreads, (size_t) ((full + block - 1) / block), [&](size_t task) {
       const uint64_t w0 = task * block, w1 = std::min(full, w0 + block);
@@ -841,7 +875,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     w.field(&sci, sizeof sci, 1);
     w.word(minseqlen);
     w.word(maxseqlen);
-    w.word(0);                                                  // alphatype: DNA (alphabet_to_key_values, encseq.c:1080-1111)
+    w.word(rq->alphatype);                                      // 0 DNA, 1 protein (alphabet_to_key_values, encseq.c:1080-1111)
     w.word(0);                                                  // lengthofalphadef
     w.field(names.data(), 1, names.size());
     const uint8_t maxsubalphasize = (uint8_t) maxsub;
@@ -855,8 +889,9 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
       flv[2 * i + 1] = file_symbols[i] + file_headers[i] - 1;
     }
     w.field(flv.data(), 16, files.size());
-    w.field(chardist, 8, 4);
-    w.field(words, 8, units);                            // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
+    w.field(chardist, 8, K);
+    if (!dna) w.field(packed, 1, packed_bytes);                 // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
+    else w.field(words, 8, units);
     if (sat == SAT_BITACCESS && (wildtab[0] > 0 || numofsequences > 1)) {
       const uint64_t nw = ints_for_bits(n + 64);
       std::vector<uint64_t> bits(nw, 0);
@@ -938,7 +973,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     sum->realwildcardranges = sci.realwildcardranges;
     sum->sat = sat;
     sum->satsep = sep_kind >= 0 ? SAT_UCHAR + (uint64_t) sep_kind : (uint64_t) SAT_UNDEFINED;
-    for (int k = 0; k < 4; k++) sum->characterdistribution[k] = chardist[k];
+    for (unsigned k = 0; k < K && k < 32; k++) sum->characterdistribution[k] = chardist[k];
     snprintf(sum->satname, sizeof sum->satname, "%s", sat_name(sat));
     sum->threads = nthreads;
     sum->input_bytes = total_bytes;

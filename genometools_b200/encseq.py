@@ -184,18 +184,21 @@ class FastaUnsupported(Exception):
     """the input is outside what gtb_fasta_encode covers (nothing was written): use the reference's encoder"""
 
 
-def dna_decode_table():
-    """gt_alphabet_decode of the DNA alphabet (src/core/alphabet.c:84-92): a c g t, wildcard shown as n"""
+def decode_table(alphabet="dna"):
+    """gt_alphabet_decode (src/core/alphabet.c:84-92,466-548): DNA a c g t with the wildcard shown as n,
+    protein L V I ... C with the wildcard shown as X"""
     t = bytearray(b"\0" * 256)
-    for i, ch in enumerate(DNA_BASES):
+    chars, wildcard = (DNA_BASES, "n") if alphabet == "dna" else (PROTEIN_AMINOACIDS, "X")
+    for i, ch in enumerate(chars):
         t[i] = ord(ch)
-    t[WILDCARD] = ord("n")
+    t[WILDCARD] = ord(wildcard)
     return bytes(t)
 
 
-def write_index_files(paths, indexname, des=True, sds=True, ssp=True, md5=True, clip_desc=False, threads=0):
-    """FASTA file(s) -> <indexname>.esq/.ssp/.des/.sds/.md5 as `gt encseq encode -dna` /
-    `gt suffixerator -dna -tis` write them (gtb_fasta_encode, include/gtb200.h; host code of libgtb200.so).
+def write_index_files(paths, indexname, des=True, sds=True, ssp=True, md5=True, clip_desc=False, threads=0,
+                      alphabet="dna"):
+    """FASTA file(s) -> <indexname>.esq/.ssp/.des/.sds/.md5 as `gt encseq encode -dna|-protein` /
+    `gt suffixerator -dna|-protein -tis` write them (gtb_fasta_encode, include/gtb200.h; host code of libgtb200.so).
     Returns the summary dict; raises FastaUnsupported when the library declines the input."""
     import ctypes as C
     from . import _lib
@@ -203,14 +206,17 @@ def write_index_files(paths, indexname, des=True, sds=True, ssp=True, md5=True, 
     if isinstance(paths, (str, bytes)):
         paths = [paths]
     names = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
-    symbolmap = np.ascontiguousarray(ALPHABETS["dna"][1], dtype=np.uint8)
+    numofchars, symbolmap = ALPHABETS[alphabet]
+    symbolmap = np.ascontiguousarray(symbolmap, dtype=np.uint8)
     rq = _lib.GtbFastaRequest()
     rq.filenames = names
     rq.numoffiles = len(paths)
     rq.indexname = os.fsencode(indexname)
     rq.symbolmap = symbolmap.ctypes.data_as(C.POINTER(C.c_uint8))
-    rq.decode = dna_decode_table()
-    rq.numofchars = 4
+    rq.decode = decode_table(alphabet)
+    rq.numofchars = numofchars
+    rq.alphatype = 0 if alphabet == "dna" else 1
+    rq.bits_per_symbol = 3 if alphabet == "dna" else 5       # src/core/alphabet.c:476,543
     rq.out_des, rq.out_sds, rq.out_ssp, rq.out_md5 = int(des), int(sds), int(ssp), int(md5)
     rq.clip_desc = int(clip_desc)
     rq.threads = int(threads)

@@ -530,10 +530,9 @@ def suffixerator_main(argv, out=sys.stdout):
             raise GtbError("one of the options -dna or -protein is required (alphabet guessing is not on this path)")
         enc = encode_fasta(o.db, alphabet)
         if o.tis:
-            if not o.dna:
-                raise GtbError("-tis is written for DNA only on this path (gtb_fasta_encode)")
             try:
-                write_index_files(o.db, o.indexname, des=o.des, sds=o.sds and o.des, ssp=o.ssp, md5=o.md5)
+                write_index_files(o.db, o.indexname, des=o.des, sds=o.sds and o.des, ssp=o.ssp, md5=o.md5,
+                                  alphabet=alphabet)
             except FastaUnsupported as e:
                 raise GtbError(f"the index files of this input need the reference's encoder: {e}")
         pl = o.pl

@@ -121,8 +121,8 @@ static void *b200_init_thread(void *p)
 }
 
 /* FASTA -> .esq/.ssp/.des/.sds/.md5 with gtb_fasta_encode (all host cores; include/gtb200.h) where
-   it covers the request: DNA (given with -dna or guessed by the reference from the first file),
-   no -plain / -lossless / -sat / -smap.  Returns 0 when the files are written, 1 when the reference's
+   it covers the request: DNA or protein (given with -dna / -protein or guessed by the reference from the
+   first file), no -plain / -lossless / -sat / -smap.  Returns 0 when the files are written, 1 when the reference's
    encoder has to run (also for every input the library declines: gt_encseq_encoder_encode then words
    the error messages), -1 on an I/O error.  GTB200_ENCODER=reference switches it off. */
 static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *err)
@@ -139,15 +139,16 @@ static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *
 
   if (which != NULL && strcmp(which, "reference") == 0) return 1;
   if (nfiles == 0 || gt_encseq_options_plain_value(o) || gt_encseq_options_plain_value(so->loadopts) ||
-      gt_encseq_options_protein_value(o) || gt_encseq_options_lossless_value(o) ||
+      gt_encseq_options_lossless_value(o) ||
       gt_str_length(gt_encseq_options_sat_value(o)) > 0 || gt_str_length(gt_encseq_options_smap_value(o)) > 0)
     return 1;
   if (gt_encseq_options_dna_value(o)) alpha = gt_alphabet_new_dna();
+  else if (gt_encseq_options_protein_value(o)) alpha = gt_alphabet_new_protein();
   else {                                 /* gt_encseq_new_from_files, src/core/encseq.c:7560-7569 */
     alpha = gt_alphabet_new_from_sequence(so->db, err);
     if (alpha == NULL) { gt_error_unset(err); return 1; }
   }
-  if (!gt_alphabet_is_dna(alpha)) { gt_alphabet_delete(alpha); return 1; }
+  if (!gt_alphabet_is_dna(alpha) && !gt_alphabet_is_protein(alpha)) { gt_alphabet_delete(alpha); return 1; }
   memset(decode, 0, sizeof decode);
   for (i = 0; i < (GtUword) gt_alphabet_num_of_chars(alpha); i++) decode[i] = gt_alphabet_decode(alpha, (GtUchar) i);
   decode[WILDCARD] = gt_alphabet_decode(alpha, (GtUchar) WILDCARD);
@@ -160,6 +161,8 @@ static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *
   rq.symbolmap = gt_alphabet_symbolmap(alpha);
   rq.decode = decode;
   rq.numofchars = gt_alphabet_num_of_chars(alpha);
+  rq.alphatype = gt_alphabet_is_dna(alpha) ? 0u : 1u;
+  rq.bits_per_symbol = gt_alphabet_bits_per_symbol(alpha);
   rq.out_des = gt_encseq_options_des_value(o);
   rq.out_sds = gt_encseq_options_sds_value(o);
   rq.out_ssp = gt_encseq_options_ssp_value(o);

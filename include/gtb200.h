@@ -414,16 +414,16 @@ int gtb_radixsort_u64keypair(int device, uint64_t *pairs, uint64_t count, char *
 /* ---- FASTA -> GtEncseq index files -------------------------------
    gtb_fasta_encode writes <indexname>.esq and, as requested, .ssp .des .sds .md5 -- the files
    gt_encseq_encoder_encode (src/core/encseq.c:8479-8505 -> gt_encseq_new_from_files :7503-7714)
-   writes for DNA sequences in FASTA files, byte for byte -- with all host cores instead of the
+   writes for DNA or protein sequences in FASTA files, byte for byte -- with all host cores instead of the
    reference's one (genometools_b200/csrc/gtb_fasta.cpp; host code, no GPU involved: 64 MB of text
    are not worth a PCIe round trip, and the index files are written by the host anyway).  The caller
    hands over the alphabet as the reference holds it, so that the tables are not restated here:
-     symbolmap  gt_alphabet_symbolmap (src/core/alphabet.h): 256 codes, 0..3 bases, 254 wildcard,
+     symbolmap  gt_alphabet_symbolmap (src/core/alphabet.h): 256 codes, 0..numofchars-1, 254 wildcard,
                 253 undefined
-     decode     gt_alphabet_decode of the codes 0..3 and 254 (256 entries, the rest unused)
+     decode     gt_alphabet_decode of the codes 0..numofchars-1 and 254 (256 entries, the rest unused)
    Returns GTB_FASTA_OK; GTB_FASTA_UNSUPPORTED (msg says why; NOTHING was written) when the input is
    outside what this encoder covers -- the caller then runs gt_encseq_encoder_encode, which also words
-   the reference's error messages: another alphabet, .gz/.bz2 or non-regular files, a file that does not
+   the reference's error messages: an alphabet read from a file, .gz/.bz2 or non-regular files, a file that does not
    begin with '>', a character outside the alphabet, an empty sequence, a description cut off by the end
    of the file or holding a NUL, 2^32-2 symbols or more; GTB_FASTA_ERROR for I/O errors. */
 #define GTB_FASTA_OK 0
@@ -436,7 +436,10 @@ typedef struct {
   const char *indexname;
   const uint8_t *symbolmap;       /* 256 entries */
   const char *decode;             /* 256 entries */
-  unsigned numofchars;            /* gt_alphabet_num_of_chars: 4, anything else is unsupported */
+  unsigned numofchars;            /* gt_alphabet_num_of_chars: 4 (DNA) or 20 (protein) */
+  unsigned alphatype;             /* 0: the DNA alphabet, 1: the protein alphabet (gt_alphabet_is_dna / _is_protein);
+                                     alphabets read from a file are unsupported */
+  unsigned bits_per_symbol;       /* gt_alphabet_bits_per_symbol: protein 5 (unused for DNA) */
   int out_des, out_sds, out_ssp, out_md5;   /* -des -sds -ssp -md5 of the encseq options */
   int clip_desc;                  /* -clipdesc: descriptions end at their first white space */
   int threads;                    /* 0: all cores, at most 32 */
@@ -447,7 +450,7 @@ typedef struct {
   uint64_t specialcharacters, specialranges, realspecialranges;
   uint64_t wildcards, wildcardranges, realwildcardranges;
   uint64_t sat, satsep;           /* GtEncseqAccessType (src/core/encseq_access_type.h:24-34); 7 = none */
-  uint64_t characterdistribution[4];
+  uint64_t characterdistribution[32];
   uint64_t input_bytes;
   char satname[16];
   unsigned threads;

@@ -4,7 +4,8 @@ Every case is generated from its seed: make_golden_fasta.py runs the unmodified 
 (`gtref suffixerator -tis ...`) and stores the md5 of each index file in fasta_index_md5.json;
 tests/test_fasta_encseq.py generates the same bytes again and compares what the library writes.
 The cases are chosen to reach every representation the reference picks for DNA (eqlen, bit, uchar,
-ushort, uint32: src/core/encseq_access_type.c:96-129), wildcard runs longer than a table page,
+ushort, uint32: src/core/encseq_access_type.c:96-129) and the one it picks for protein (bytecompress),
+wildcard runs longer than a table page,
 totals around the page borders, several files, and the odd FASTA the reference's reader accepts
 ('>' in the middle of a line, blank lines, white space inside lines, CR LF, empty descriptions).
 """
@@ -80,6 +81,40 @@ def big_file(seed, nseq, total, nruns, runlens, width=70):
     return b"".join(parts)
 
 
+AMINO = "LVIFKREDAGSTNQYWPHMC"
+AMINO_WILD = "XUBZJO*-"
+
+
+def protein_case(seed):
+    """protein: the byte-compressed representation (5 bits per residue, fillViabytecompress, encseq.c:2324-2440)"""
+    rng = random.Random(1000 + seed)
+    files = []
+    for _ in range(rng.choice([1, 1, 2])):
+        nseq = rng.choice([1, 1, 2, 3, 7, 40])
+        base = rng.choice([1, 7, 8, 9, 33, 100, 1000, 5000])
+        equal = rng.random() < 0.2
+        out = []
+        for s in range(nseq):
+            n = base if equal else max(1, int(rng.expovariate(1 / base)))
+            q = [rng.choice(AMINO) for _ in range(n)]
+            for _ in range(rng.randint(0, 4)):
+                a = rng.randrange(n)
+                b = min(n, a + rng.choice([1, 1, 2, 30, 300]))
+                for i in range(a, b):
+                    q[i] = rng.choice(AMINO_WILD)
+            q = "".join(q)
+            width = rng.choice([60, 7, 100000])
+            eol = rng.choice(["\n", "\r\n"])
+            out.append(">p%d some protein\n" % s + eol.join(q[i:i + width] for i in range(0, n, width)) + eol)
+        files.append("".join(out).encode())
+    opts = {k: rng.random() < 0.8 for k in ("des", "sds", "ssp", "md5")}
+    if not opts["des"]:
+        opts["sds"] = False
+    opts["clip_desc"] = False
+    opts["alphabet"] = "protein"
+    return files, opts
+
+
 ALL_ON = {"des": True, "sds": True, "ssp": True, "md5": True, "clip_desc": False}
 
 ODD = {
@@ -127,4 +162,10 @@ def all_cases(nsmall=120):
     cases["odd_clip_leading_space"] = ([b">  lead\nACGT\n>x y\nAC\n"], dict(ALL_ON, clip_desc=True))
     cases["odd_second_file_continues"] = ([b">a\nACGT\n", b">b\nAC\n>c\nGGG\n"], ALL_ON)
     cases.update(big_cases())
+    for seed in range(40):
+        cases["protein_%02d" % seed] = protein_case(seed)
+    rng = np.random.default_rng(77)
+    residues = np.frombuffer(AMINO.encode(), dtype=np.uint8)[rng.integers(0, 20, 1_000_003)]
+    cases["protein_1M"] = ([b">one protein of a million residues\n" + residues.tobytes() + b"\n>second\nMKV\n"],
+                           dict(ALL_ON, alphabet="protein"))
     return cases

@@ -26,7 +26,7 @@ def reference_files(files, opts, workdir):
         names.append("f%d.fa" % i)
         with open(os.path.join(workdir, names[-1]), "wb") as fh:
             fh.write(raw)
-    cmd = [GTREF, "suffixerator", "-dna", "-tis"]
+    cmd = [GTREF, "suffixerator", "-" + opts.get("alphabet", "dna"), "-tis"]
     for k in ("des", "sds", "ssp", "md5"):
         cmd += ["-" + k, "yes" if opts[k] else "no"]
     if opts["clip_desc"]:

@@ -4,8 +4,9 @@ against the unmodified reference.
 tests/golden/fasta_index_md5.json holds the md5 of every index file `gtref suffixerator -dna -tis
 [-des/-sds/-ssp/-md5 yes|no] [-clipdesc]` wrote for the inputs of tests/golden/fasta_cases.py
 (make_golden_fasta.py; the reference's encoder is gt_encseq_new_from_files,
-/root/reference/src/core/encseq.c:7503-7714).  The library must write the same bytes: .esq (header,
-2-bit words, wildcard range table or special bits), .ssp, .des, .sds, .md5 -- with one chunk per file
+/root/reference/src/core/encseq.c:7503-7714; `-protein` for the protein cases).  The library must write the
+same bytes: .esq (header, 2-bit words, wildcard range table or special bits; 5-bit string for protein), .ssp,
+.des, .sds, .md5 -- with one chunk per file
 and with chunk borders every 50 bytes (the parallel decomposition must not show).  Where the reference
 binary is present (this container) the drop-in binary is run beside it on inputs both accept and
 inputs the library declines.
@@ -66,7 +67,7 @@ def test_index_files_identical_to_reference(name, tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize("chunk", [50, 7])
-@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith(("small_0", "odd_"))])
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith(("small_0", "odd_", "protein_0"))])
 def test_chunk_borders_do_not_show(name, chunk, tmp_path, monkeypatch):
     """the files are cut every `chunk` bytes (anywhere but inside a description): in the middle of lines, of
     wildcard runs, of CR LF pairs, right in front of a '>'"""
@@ -97,6 +98,15 @@ def test_every_representation_is_reached(tmp_path, monkeypatch):
             d.mkdir()
             seen.add(check_case(name, d, monkeypatch)["satname"])
     assert seen == {"eqlen", "bit", "uchar", "ushort", "uint32"}, seen
+
+
+def test_lower_case_protein_is_declined(tmp_path, monkeypatch):
+    """the protein alphabet maps upper case only (assignproteinsymbolmap, src/core/alphabet.c:488-506)"""
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "p.fa").write_bytes(b">p\nMKVlaag\n")
+    with pytest.raises(FastaUnsupported):
+        write_index_files(["p.fa"], "our", alphabet="protein")
+    assert sorted(os.listdir(tmp_path)) == ["p.fa"]
 
 
 DECLINED = {
@@ -142,6 +152,7 @@ needs_binaries = pytest.mark.skipif(not (os.path.exists(GTREF) and os.path.exist
     ("three_files", ["-dna"]), ("three_files", []), ("many_sequences", ["-dna", "-clipdesc"]),
     ("odd_header_in_midline", ["-dna", "-md5", "no"]), ("small_004", ["-dna", "-des", "no", "-sds", "no"]),
     ("ushort_multi", ["-dna", "-sat", "uint32"]), ("small_001", ["-dna", "-lossless"]),
+    ("protein_1M", ["-protein"]), ("protein_03", []), ("protein_05", ["-protein", "-sat", "direct"]),
 ])
 def test_dropin_binary_without_sort(name, extra, tmp_path):
     """`gt_b200 suffixerator -tis` (no table requested: no GPU involved) beside `gtref`: same files, the
