@@ -67,9 +67,8 @@ static int b200_unsupported(const Suffixeratoroptions *so, GtError *err)
   Sfxstrategy st = gt_index_options_sfxstrategy_value(so->idxopts);
   const char *what = NULL;
 
-  if (so->inputindex != NULL && gt_str_length(so->inputindex) > 0) what = "-ii";
   /* a mirrored GtEncseq reports 2n+1 symbols while gt_encseq_twobitencoding_export holds n */
-  else if (gt_encseq_options_mirrored_value(so->loadopts)) what = "-mirrored";
+  if (gt_encseq_options_mirrored_value(so->loadopts)) what = "-mirrored";
   else if (gt_index_options_outkystab_value(so->idxopts)) what = "-kys";
   else if (gt_index_options_lcpdist_value(so->idxopts)) what = "-lcpdist";
   else if (gt_index_options_maximumspace_value(so->idxopts) > 0) what = "-memlimit";
@@ -230,6 +229,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
   B200Init init;
   pthread_t init_tid;
   bool init_started = false, init_ever = false, encoded = false, release_started = false;
+  const char *load_from = NULL;
   pthread_t release_tid;
   int retval, had_err = 0;
   double t_start = b200_now(), t_encoded = 0, t_uploaded = 0, t_sorted = 0, t_copied = 0;
@@ -259,7 +259,12 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     if (!init_started) b200_init_thread(&init);
   }
 
-  if (!had_err) {
+  /* -ii: the sequences are encoded already, the index files are only loaded (src/match/sfx-run.c:454-492) */
+  if (!had_err && so.inputindex != NULL && gt_str_length(so.inputindex) > 0) {
+    encoded = true;
+    load_from = gt_str_get(so.inputindex);
+  }
+  if (!had_err && !encoded) {
     int fast = b200_fast_encode(&so, logger, err);
     if (fast < 0) had_err = -1;
     else encoded = (fast == 0);
@@ -284,7 +289,7 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       gt_encseq_loader_do_not_require_des_tab(el);
       gt_encseq_loader_do_not_require_sds_tab(el);
       gt_encseq_loader_do_not_require_ssp_tab(el);
-      encseq = gt_encseq_loader_load(el, gt_str_get(so.indexname), err);
+      encseq = gt_encseq_loader_load(el, load_from != NULL ? load_from : gt_str_get(so.indexname), err);
       gt_encseq_loader_delete(el);
       if (encseq == NULL) had_err = -1;
       else if (gt_encseq_is_mirrored(encseq)) {

@@ -213,3 +213,57 @@ def test_dropin_multi_gpu_identical_to_reference(tmp_path, ngpu):
     assert f"B200: {ngpu} GPU(s), {ngpu} bucket-code range(s)" in r.stdout
     for ext in ("suf", "lcp", "llv", "bck", "bwt", "prj"):
         assert open(f"{idx}.{ext}", "rb").read() == open(f"{ref}.{ext}", "rb").read(), ext
+
+
+@need_bins
+def test_dropin_from_an_existing_index(tmp_path):
+    """`suffixerator -ii <index>`: the sequences were encoded before (here by the drop-in itself, `-tis` only);
+    both binaries build the tables from the loaded index (src/match/sfx-run.c:454-492)"""
+    fa = str(tmp_path / "in.fa")
+    synth.to_fasta(synth.repeats_dna(200_000, 5, unit=3000, copies=6, exact_len=9000, exact_copies=3), fa, "dna")
+    enc = str(tmp_path / "enc")
+    subprocess.check_call([GT_B200, "suffixerator", "-dna", "-tis", "-indexname", enc, "-db", fa],
+                          stdout=subprocess.DEVNULL)
+    out = {}
+    for name, exe in (("b200", GT_B200), ("ref", GTREF)):
+        idx = str(tmp_path / name)
+        subprocess.check_call([exe, "suffixerator", "-ii", enc, "-suf", "-lcp", "-bck", "-pl", "-indexname", idx],
+                              stdout=subprocess.DEVNULL)
+        out[name] = {ext: open(idx + "." + ext, "rb").read() for ext in ("suf", "lcp", "llv", "bck", "prj")}
+        assert not os.path.exists(idx + ".esq")
+    for ext in out["ref"]:
+        assert out["b200"][ext] == out["ref"][ext], ext
+
+
+RELEASE_SCRIPT = r"""
+import ctypes as C, gc, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+import synth
+from genometools_b200 import _lib, encode_symbols
+from genometools_b200.suffixerator import build_esa
+lib = _lib.load()
+sym = synth.random_dna(30_000, 11, 0.01)
+first = build_esa(encode_symbols(sym, 4), prefixlength=4, device=0)
+suf = first.suf_bytes()
+buf = C.create_string_buffer(256)
+h = lib.gtb_esa_new(0, buf, 256)
+assert h
+assert lib.gtb_release_devices() == 0, "a live handle: nothing may be released"
+lib.gtb_esa_delete(h)
+del first
+gc.collect()
+assert lib.gtb_release_devices() == 1, "no handle left on device 0: its context goes"
+assert lib.gtb_release_devices() == 0, "nothing left to release"
+again = build_esa(encode_symbols(sym, 4), prefixlength=4, device=0)
+assert again.suf_bytes() == suf
+print("ok")
+"""
+
+
+def test_release_devices_between_handles():
+    """gtb_release_devices destroys the context of a device without live handles (what the drop-in does beside its
+    file writes); the next handle builds a new one and sorts as before.  In a process of its own: the reset takes
+    the context away from everything else in the process, torch included"""
+    import sys
+    r = subprocess.run([sys.executable, "-c", RELEASE_SCRIPT, ROOT], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
