@@ -1162,6 +1162,7 @@ int gtb_release_devices(void)
     }
     if (cudaSetDevice(d) == cudaSuccess && cudaDeviceReset() == cudaSuccess) released++;
     else cudaGetLastError();
+    g_context_generation[d].fetch_add(1);
   }
   return released;
 }

@@ -36,6 +36,10 @@ namespace gtb {
 constexpr int RS_BINS  = 256;
 constexpr int RS_MAXPASS = 8;
 
+// how many times the context of a device was destroyed by this library (gtb_release_devices): what is cached
+// per context -- the shared-memory attribute of a kernel -- is set again when the count has moved on
+inline std::atomic<unsigned> g_context_generation[64];
+
 // Kernel shape.  NT threads x IPT pairs per tile; MINB = CTAs per SM the register
 // allocation is bounded for; VAL_EARLY: values are loaded together with the keys
 // (IPT more live registers) instead of just before they are staged; LB: predecessor
@@ -589,16 +593,16 @@ static int rs_launch_mode(RadixWork &w, cudaStream_t st, const Src &src, u64 nsr
                           u64 *okeys, u32 *ovals, unsigned bsel, unsigned dmask, int passidx,
                           ErrBuf &err, bool peer_bins = false, u32 tile_offset = 0)
 {
-  // (the attribute is per device: one bit per device and instantiation)
-  static std::atomic<unsigned long long> attr_set{0};
+  // (the attribute is per device, instantiation and context: gtb_release_devices destroys contexts)
+  static std::atomic<unsigned> attr_set[64];
   int dev = 0;
   GTB_CUDA(cudaGetDevice(&dev));
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (!(attr_set.load(std::memory_order_relaxed) & bit)) {
+  const unsigned generation = g_context_generation[dev & 63].load(std::memory_order_relaxed) + 1;
+  if (attr_set[dev & 63].load(std::memory_order_relaxed) != generation) {
     GTB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<Src, Cfg, MODE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int) Cfg::SMEM));
-    attr_set.fetch_or(bit, std::memory_order_relaxed);
+    attr_set[dev & 63].store(generation, std::memory_order_relaxed);
   }
   rs_onesweep_kernel<Src, Cfg, MODE><<<(unsigned) tiles, Cfg::NT, Cfg::SMEM, st>>>(
       src, okeys, ovals, nsrc, bsel, dmask, w.gbase + passidx * RS_BINS,
