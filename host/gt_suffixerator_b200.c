@@ -207,50 +207,6 @@ static void b200_big_free(void *p, size_t bytes)
   if (p != NULL) (void) munmap(p, (bytes + huge - 1) / huge * huge);
 }
 
-/* A large result table that is a file of the index (.suf .lcp .bwt): the file is created at its final
-   size and mapped, the library copies the table from the GPU straight into the mapping -- the page
-   cache pages ARE the file, there is no second copy through fwrite (0.3 s for the 580 MB of a 64 Mbp
-   index).  Where a file cannot be mapped the table goes through memory and fwrite as before;
-   GTB200_OUTPUT=buffer asks for that. */
-typedef struct {
-  void *p;
-  size_t bytes;
-  FILE *fp;
-  bool mapped;
-} B200Table;
-
-static int b200_table_open(B200Table *t, const char *indexname, const char *suffix, size_t bytes, GtError *err)
-{
-  const char *how = getenv("GTB200_OUTPUT");
-  memset(t, 0, sizeof *t);
-  t->bytes = bytes;
-  t->fp = gt_fa_fopen_with_suffix(indexname, suffix, "wb+", err);
-  if (t->fp == NULL) return -1;
-  if ((how == NULL || strcmp(how, "buffer") != 0) && bytes > 0 && ftruncate(fileno(t->fp), (off_t) bytes) == 0) {
-    void *p = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fileno(t->fp), 0);
-    if (p != MAP_FAILED) {
-      t->p = p;
-      t->mapped = true;
-      return 0;
-    }
-    if (ftruncate(fileno(t->fp), 0) != 0) { /* written from the start below in any case */ }
-  }
-  t->p = b200_big_alloc(bytes);
-  return 0;
-}
-
-static void b200_table_close(B200Table *t, bool write_it)
-{
-  if (t->fp == NULL) return;
-  if (t->mapped) (void) munmap(t->p, t->bytes);
-  else {
-    if (write_it && t->bytes > 0) gt_xfwrite(t->p, 1, t->bytes, t->fp);
-    b200_big_free(t->p, t->bytes);
-  }
-  gt_fa_xfclose(t->fp);
-  memset(t, 0, sizeof *t);
-}
-
 static int b200_write(const char *indexname, const char *suffix, const void *data,
                       size_t size, size_t nmemb, size_t pad_to, GtError *err)
 {
@@ -355,14 +311,13 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     const GtReadmode readmode = gt_index_options_readmode_value(so.idxopts);
     const unsigned int numofchars = gt_encseq_alphabetnumofchars(encseq);
     unsigned int prefixlength = gt_index_options_prefixlength_value(so.idxopts);
-    uint64_t *llv = NULL, nllv = 0, nall = 0, nspec = 0, ndist = 0;
-    B200Table suftab, lcptab, bwttab;
+    uint64_t *suftab = NULL, *llv = NULL, nllv = 0, nall = 0, nspec = 0, ndist = 0;
+    uint8_t *lcptab = NULL, *bwttab = NULL;
     uint32_t *leftborder = NULL, *csc = NULL, *dist = NULL;
     gtb_stats stats;
     char msg[512];
 
     memset(&stats, 0, sizeof stats);
-    memset(&suftab, 0, sizeof suftab); memset(&lcptab, 0, sizeof lcptab); memset(&bwttab, 0, sizeof bwttab);
     /* the two -dir checks of gt_runsuffixerator, src/match/sfx-run.c:541-549,586-593 */
     if ((readmode == GT_READMODE_COMPL || readmode == GT_READMODE_REVCOMPL) &&
         !gt_alphabet_is_dna(gt_encseq_alphabet(encseq))) {
@@ -417,12 +372,10 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       }
       if (rc == 0) {
         /* the result tables, sized from what the run produced */
-        const char *idx = gt_str_get(so.indexname);
-        if (want_suf && b200_table_open(&suftab, idx, ".suf", sizeof (uint64_t) * (n + 1), err) != 0) rc = -3;
-        if (rc == 0 && want_bwt && b200_table_open(&bwttab, idx, ".bwt", n + 1, err) != 0) rc = -3;
-        if (rc == 0 && want_lcp) {
+        if (want_suf) suftab = b200_big_alloc(sizeof *suftab * (n + 1));
+        if (want_lcp) {
           nllv = gtb_group_num_llv(g);
-          if (b200_table_open(&lcptab, idx, ".lcp", n + 1, err) != 0) rc = -3;
+          lcptab = b200_big_alloc(sizeof *lcptab * (n + 1));
           llv = gt_malloc(sizeof *llv * 2 * (nllv + 1));
         }
         if (want_bck) {
@@ -432,15 +385,16 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
           dist = gt_malloc(sizeof *dist * (ndist + 1));
         }
         /* the gather: every range copies its shard to its offset of the one table, all tables in one call */
-        if (rc == 0)
-          rc = gtb_group_copy_results(g, suftab.p, lcptab.p, nllv > 0 ? llv : NULL, leftborder, csc, dist);
-        if (rc == 0 && want_bwt) rc = gtb_group_copy_bwttab(g, bwttab.p);
+        rc = gtb_group_copy_results(g, suftab, lcptab, nllv > 0 ? llv : NULL, leftborder, csc, dist);
+        if (rc == 0 && want_bwt) {
+          bwttab = b200_big_alloc(sizeof *bwttab * (n + 1));
+          rc = gtb_group_copy_bwttab(g, bwttab);
+        }
         if (rc == 0) rc = gtb_group_get_stats(g, &stats);
       }
       if (rc == -1 && g != NULL) snprintf(msg, sizeof msg, "%s", gtb_group_error(g));
       gtb_group_delete(g);
-      if (rc == -3) had_err = -1;               /* a file could not be created: err is set */
-      else if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
+      if (rc != 0) { gt_error_set(err, "libgtb200: %s", msg); had_err = -1; }
     }
     t_copied = b200_now();
     /* nothing is left on the GPUs: their contexts are destroyed beside the writing of the files
@@ -448,11 +402,15 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     if (want_any && !had_err)
       release_started = pthread_create(&release_tid, NULL, b200_release_thread, NULL) == 0;
     /* the reference's files */
-    b200_table_close(&suftab, !had_err);
-    b200_table_close(&bwttab, !had_err);
-    b200_table_close(&lcptab, !had_err);
-    if (!had_err && want_lcp)
-      had_err = b200_write(gt_str_get(so.indexname), ".llv", llv, sizeof *llv, 2 * nllv, 0, err);
+    if (!had_err && want_suf)
+      had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, err);
+    if (!had_err && want_bwt)
+      had_err = b200_write(gt_str_get(so.indexname), ".bwt", bwttab, 1, n + 1, 0, err);
+    if (!had_err && want_lcp) {
+      had_err = b200_write(gt_str_get(so.indexname), ".lcp", lcptab, 1, n + 1, 0, err);
+      if (!had_err)
+        had_err = b200_write(gt_str_get(so.indexname), ".llv", llv, sizeof *llv, 2 * nllv, 0, err);
+    }
     if (!had_err && want_bck) {
       FILE *fp = gt_fa_fopen_with_suffix(gt_str_get(so.indexname), ".bck", "wb", err);
       if (fp == NULL) had_err = -1;
@@ -482,6 +440,9 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
                             "%.3f, sort %.3f, copy to host %.3f, write files %.3f",
                     t_encoded - t_start, t_uploaded - t_encoded, t_sorted - t_uploaded, t_copied - t_sorted,
                     b200_now() - t_copied);
+    b200_big_free(suftab, sizeof *suftab * (n + 1));
+    b200_big_free(lcptab, sizeof *lcptab * (n + 1));
+    b200_big_free(bwttab, sizeof *bwttab * (n + 1));
     gt_free(llv);
     gt_free(leftborder); gt_free(csc); gt_free(dist);
   }
