@@ -36,6 +36,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -351,11 +353,24 @@ void emit_chunk(const Input &f, const Tables &t, Chunk &c, uint8_t *codes, bool 
   close_run();
 }
 
+// tasks 0..ntasks-1 dealt to nthreads threads; what a task throws (out of memory) is thrown again here,
+// after every thread has been joined
 template <class F> void parallel_for(unsigned nthreads, size_t ntasks, F &&fn)
 {
   if (ntasks == 0) return;
   std::atomic<size_t> next{0};
-  auto worker = [&]() { for (size_t i; (i = next.fetch_add(1)) < ntasks;) fn(i); };
+  std::atomic<bool> failed{false};
+  std::exception_ptr first;
+  std::mutex first_mutex;
+  auto worker = [&]() {
+    try {
+      for (size_t i; !failed.load(std::memory_order_relaxed) && (i = next.fetch_add(1)) < ntasks;) fn(i);
+    } catch (...) {
+      std::lock_guard<std::mutex> lock(first_mutex);
+      if (!first) first = std::current_exception();
+      failed.store(true);
+    }
+  };
   const unsigned nt = (unsigned) std::min<size_t>(nthreads, ntasks);
   std::vector<std::thread> th;
   for (unsigned k = 1; k < nt; k++) {
@@ -363,6 +378,7 @@ template <class F> void parallel_for(unsigned nthreads, size_t ntasks, F &&fn)
   }
   worker();
   for (auto &x : th) x.join();
+  if (first) std::rethrow_exception(first);
 }
 
 // The files are cut every `target` bytes, wherever that falls -- a FASTA file may hold its sequence on one line --
@@ -586,6 +602,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   unsigned nthreads = rq->threads > 0 ? (unsigned) rq->threads : std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   if (rq->threads <= 0 && nthreads > 32) nthreads = 32;
+  if (nthreads > 256) nthreads = 256;
   const Tables tables = make_tables(rq->symbolmap);
   const std::string indexname = rq->indexname;
 
@@ -623,6 +640,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   std::vector<char> md5tab;
   std::thread md5_thread;
   double md5_seconds = 0;
+  bool md5_failed = false;
   struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_md5{md5_thread};
   if (rq->out_md5) {
     spans.reserve(numofsequences);
@@ -633,6 +651,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
       }
     md5tab.assign(33 * numofsequences, '\0');
     auto all_md5 = [&]() {
+      try {
       const double t = now();
       uint8_t up[256];                                          // 0: not a symbol (white space)
       for (int c = 0; c < 256; c++)
@@ -654,6 +673,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
         m.hex(&md5tab[33 * s]);
       });
       md5_seconds = now() - t;
+      } catch (...) { md5_failed = true; }
     };
     try { md5_thread = std::thread(all_md5); } catch (...) { all_md5(); }
   }
@@ -954,6 +974,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   }
   if (rq->out_md5) {
     if (md5_thread.joinable()) md5_thread.join();
+    if (md5_failed) throw IoError{"out of memory (md5 of the sequences)"};
     Writer w(indexname, ".md5");
     w.raw(md5tab.data(), md5tab.size());
     w.finish();
