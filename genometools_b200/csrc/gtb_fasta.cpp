@@ -159,7 +159,8 @@ struct Md5 {
     update(len, 8);
     const uint32_t v[4] = {a, b, c, d};
     const uint8_t *raw = reinterpret_cast<const uint8_t *>(v);
-    for (int i = 0; i < 16; i++) snprintf(out + 2 * i, 3, "%02x", raw[i]);
+    static const char digits[] = "0123456789abcdef";
+    for (int i = 0; i < 16; i++) { out[2 * i] = digits[raw[i] >> 4]; out[2 * i + 1] = digits[raw[i] & 15]; }
     out[32] = '\0';
   }
 };
