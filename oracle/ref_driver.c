@@ -9,10 +9,11 @@
                                    (/root/reference/src/match/sfx-run.c:719)
     gtref sfxmap <args>         -> gt_sfxmap (brute-force ESA verifier,
                                    /root/reference/src/tools/gt_sfxmap.c)
-    gtref radixsort ulong|ulongpair|keypair <in> <out>
+    gtref radixsort ulong|ulongpair|keypair|flba<bytes> <in> <out>
                                 -> gt_radixsort_inplace_ulong / _GtUwordPair /
-                                   _Gtuint64keyPair (/root/reference/src/core/radix_sort.h:91,107,125)
-                                   on a file of raw uint64 values; prints the seconds of the call
+                                   _Gtuint64keyPair / _flba (/root/reference/src/core/radix_sort.h:91,107,125,138)
+                                   on a file of raw uint64 values (flba: records of <bytes> bytes);
+                                   prints the seconds of the call
 
   It replaces src/gt.c + the toolbox so that only the files on the
   suffixerator path have to be compiled.  No reference source is copied.
@@ -38,24 +39,27 @@ static int ref_radixsort(int argc, char **argv)
   uint64_t *buf;
   struct timeval t0, t1;
 
-  if (argc != 5) { fprintf(stderr, "usage: radixsort ulong|ulongpair|keypair <in> <out>\n"); return 1; }
+  if (argc != 5) { fprintf(stderr, "usage: radixsort ulong|ulongpair|keypair|flba<bytes> <in> <out>\n"); return 1; }
   fp = fopen(argv[3], "rb");
   if (fp == NULL) { perror(argv[3]); return 1; }
   fseek(fp, 0, SEEK_END); bytes = ftell(fp); fseek(fp, 0, SEEK_SET);
   n = (size_t) bytes / sizeof (uint64_t);
-  buf = gt_malloc(bytes > 0 ? (size_t) bytes : 8);
-  if (fread(buf, sizeof (uint64_t), n, fp) != n) { fclose(fp); return 1; }
+  buf = gt_malloc(bytes > 0 ? (size_t) bytes + 8 : 8);
+  if (fread(buf, 1, (size_t) bytes, fp) != (size_t) bytes) { fclose(fp); return 1; }
   fclose(fp);
   gettimeofday(&t0, NULL);
   if (strcmp(argv[2], "ulong") == 0) gt_radixsort_inplace_ulong((GtUword*) buf, (GtUword) n);
   else if (strcmp(argv[2], "ulongpair") == 0) gt_radixsort_inplace_GtUwordPair((GtUwordPair*) buf, (GtUword) (n / 2));
   else if (strcmp(argv[2], "keypair") == 0) gt_radixsort_inplace_Gtuint64keyPair((Gtuint64keyPair*) buf, (GtUword) (n / 2));
+  else if (strncmp(argv[2], "flba", 4) == 0 && atoi(argv[2] + 4) > 0)   /* records of that many bytes */
+    gt_radixsort_inplace_flba((uint8_t*) buf, (GtUword) ((size_t) bytes / (size_t) atoi(argv[2] + 4)),
+                              (size_t) atoi(argv[2] + 4));
   else { fprintf(stderr, "unknown kind %s\n", argv[2]); return 1; }
   gettimeofday(&t1, NULL);
   printf("%.6f\n", (double) (t1.tv_sec - t0.tv_sec) + 1e-6 * (double) (t1.tv_usec - t0.tv_usec));
   fp = fopen(argv[4], "wb");
   if (fp == NULL) { perror(argv[4]); return 1; }
-  fwrite(buf, sizeof (uint64_t), n, fp);
+  fwrite(buf, 1, (size_t) bytes, fp);
   fclose(fp);
   gt_free(buf);
   return 0;

@@ -1,6 +1,6 @@
 """Generate tests/golden/radixsort_vectors.npz: md5 sums of what the UNMODIFIED reference's
-gt_radixsort_inplace_ulong / _GtUwordPair / _Gtuint64keyPair (/root/reference/src/core/radix_sort.h:91,
-107,125; called through `oracle/_ref/gtref radixsort`, oracle/ref_driver.c) return for seeded inputs
+gt_radixsort_inplace_ulong / _GtUwordPair / _Gtuint64keyPair / _flba (/root/reference/src/core/radix_sort.h:91,
+107,125,138; called through `oracle/_ref/gtref radixsort`, oracle/ref_driver.c) return for seeded inputs
 ("next" row 4).  Needs /root/reference.
     python tests/golden/make_golden_radixsort.py
 """
@@ -21,6 +21,21 @@ CASES = {  # name: (kind, records, seed, distinct values of the key or 0 = all 6
     "pair_dups": ("ulongpair", 60_000, 6, 1000), "keypair_100k": ("keypair", 100_000, 7, 0),
     "keypair_dups": ("keypair", 80_000, 8, 50),
 }
+
+
+# gt_radixsort_inplace_flba (radix_sort.h:138): records of `unitsize` bytes in memcmp order.
+# name: (unitsize, records, seed, distinct byte values per position or 0 = all 256)
+# (one-byte records: the reference itself dies with SIGSEGV on 10 000 of them; 37 are sorted by its insertion sort)
+FLBA_CASES = {
+    "flba1_small": (1, 37, 11, 0), "flba2": (2, 50_000, 20, 0), "flba3": (3, 100_000, 12, 0), "flba5_dups": (5, 100_000, 13, 3),
+    "flba8": (8, 100_000, 14, 0), "flba9": (9, 100_000, 15, 0), "flba12_dups": (12, 80_000, 16, 2),
+    "flba16": (16, 100_000, 17, 0), "flba7_small": (7, 37, 18, 0), "flba16_one": (16, 1, 19, 0),
+}
+
+
+def make_flba(unitsize, n, seed, distinct):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, distinct if distinct else 256, size=(n, unitsize), dtype=np.uint8)
 
 
 def make_input(kind, n, seed, distinct):
@@ -47,6 +62,14 @@ def main():
             b = np.fromfile(os.path.join(tmp, "out"), dtype=np.uint64).reshape(a.shape)
             out[name + "/md5"] = hashlib.md5(b.tobytes()).hexdigest()
             out[name + "/md5_keys"] = hashlib.md5(np.ascontiguousarray(b[:, 0]).tobytes()).hexdigest()
+            print(name, out[name + "/md5"])
+        for name, (unitsize, n, seed, distinct) in FLBA_CASES.items():
+            a = make_flba(unitsize, n, seed, distinct)
+            a.tofile(os.path.join(tmp, "in"))
+            subprocess.check_output([GTREF, "radixsort", "flba%d" % unitsize, os.path.join(tmp, "in"),
+                                     os.path.join(tmp, "out")])
+            b = np.fromfile(os.path.join(tmp, "out"), dtype=np.uint8).reshape(a.shape)
+            out[name + "/md5"] = hashlib.md5(b.tobytes()).hexdigest()
             print(name, out[name + "/md5"])
     out["__cases__"] = np.array(list(CASES))
     np.savez_compressed(os.path.join(HERE, "radixsort_vectors.npz"), **out)

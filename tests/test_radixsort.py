@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from make_golden_radixsort import CASES, make_input
+from make_golden_radixsort import CASES, FLBA_CASES, make_flba, make_input
 from genometools_b200 import _lib
 
 Z = np.load(os.path.join(ROOT, "tests", "golden", "radixsort_vectors.npz"), allow_pickle=False)
@@ -91,3 +91,42 @@ def test_reference_entry_points_on_the_gpu(tmp_path, name):
     b = np.fromfile(fout, dtype=np.uint64).reshape(a.shape)
     assert np.array_equal(b, oracle_sort(kind, a))
     assert md5(b[:, 0] if b.ndim > 1 else b) == str(Z[name + "/md5_keys"])
+
+
+def flba_oracle(a):
+    return a[np.lexsort(a.T[::-1])] if a.shape[0] > 1 else a          # memcmp order
+
+
+@pytest.mark.parametrize("name", list(FLBA_CASES))
+def test_flba_oracle_matches_reference(name):
+    """gt_radixsort_inplace_flba (radix_sort.h:138): records of unitsize bytes, most significant byte first"""
+    a = make_flba(*FLBA_CASES[name])
+    assert md5(flba_oracle(a)) == str(Z[name + "/md5"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RADIX_BIN), reason="host/_build/gtref_b200_radixsort not built")
+@pytest.mark.parametrize("name", list(FLBA_CASES))
+def test_flba_entry_point_on_the_gpu(tmp_path, name):
+    """gt_radixsort_inplace_flba of host/gt_radix_sort_b200.c under the reference's test driver: the records
+    travel as big-endian 64-bit keys (up to 8 bytes) or key pairs (up to 16) through libgtb200"""
+    import subprocess
+    unitsize = FLBA_CASES[name][0]
+    a = make_flba(*FLBA_CASES[name])
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    a.tofile(fin)
+    subprocess.check_call([RADIX_BIN, "radixsort", "flba%d" % unitsize, fin, fout], stdout=subprocess.DEVNULL)
+    b = np.fromfile(fout, dtype=np.uint8).reshape(a.shape)
+    assert np.array_equal(b, flba_oracle(a))
+    assert md5(b) == str(Z[name + "/md5"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RADIX_BIN), reason="host/_build/gtref_b200_radixsort not built")
+def test_flba_longer_than_16_bytes_is_refused(tmp_path):
+    import subprocess
+    a = make_flba(17, 100, 1, 0)
+    fin = str(tmp_path / "in.bin")
+    a.tofile(fin)
+    r = subprocess.run([RADIX_BIN, "radixsort", "flba17", fin, str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode != 0 and "at most 16" in r.stderr
