@@ -18,6 +18,7 @@ import subprocess
 
 import pytest
 
+import encseq_oracle
 import fasta_cases
 from conftest import ROOT
 from genometools_b200.encseq import FastaUnsupported, write_index_files
@@ -225,3 +226,67 @@ def test_reference_testdata_through_dropin(tmp_path):
                 fast += 1
         assert res["ref"] == res["our"], f
     assert fast > 100          # most of them are DNA
+
+
+# ---- the sequential restatement (oracle/encseq_oracle.py): pinned to the reference, then used as the checker
+
+ORACLE_CASES = [n for n in sorted(CASES) if sum(len(f) for f in CASES[n][0]) < 200_000]
+
+
+@pytest.mark.parametrize("name", ORACLE_CASES)
+def test_oracle_matches_reference(name):
+    files, opts = CASES[name]
+    g = GOLDEN[name]
+    out = encseq_oracle.encode(files, ["f%d.fa" % i for i in range(len(files))], **opts)
+    assert sorted(out) == sorted(g["files"])
+    for suf, data in out.items():
+        assert hashlib.md5(data).hexdigest() == g["files"][suf]["md5"], suf
+
+
+def random_fasta(rng, alphabet):
+    letters = "ACGT" if alphabet == "dna" else fasta_cases.AMINO
+    wild = fasta_cases.WILD if alphabet == "dna" else fasta_cases.AMINO_WILD
+    out = []
+    for s in range(rng.choice([1, 2, 5, 30])):
+        n = rng.choice([1, 2, 31, 32, 33, 255, 256, 257, 700, 3000])
+        q = [rng.choice(letters) for _ in range(n)]
+        for _ in range(rng.choice([0, 0, 1, 3, 40])):
+            a = rng.randrange(n)
+            for i in range(a, min(n, a + rng.choice([1, 2, 9, 300]))):
+                q[i] = rng.choice(wild)
+        eol = rng.choice(["\n", "\r\n"])
+        width = rng.choice([1, 13, 60, 10 ** 9])
+        text = eol.join("".join(q[i:i + width]) for i in range(0, n, width))
+        if rng.random() < 0.3:
+            k = rng.randrange(len(text) + 1)
+            text = text[:k] + rng.choice([" ", "\t", eol + eol]) + text[k:]
+        out.append(">%s%s%s" % (rng.choice(["", "id%d" % s, "id %d\tx  y" % s]), eol, text) +
+                   (eol if rng.random() < 0.9 or s + 1 < 30 else ""))
+    return "".join(out).encode()
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_library_against_oracle_on_random_inputs(seed, tmp_path, monkeypatch):
+    """inputs that are in no golden file: random option sets, widths, page-border lengths; random chunk size"""
+    import random
+    rng = random.Random(5000 + seed)
+    alphabet = rng.choice(["dna", "dna", "protein"])
+    files = [random_fasta(rng, alphabet) for _ in range(rng.choice([1, 1, 2, 3]))]
+    opts = {k: rng.random() < 0.7 for k in ("des", "ssp", "md5")}
+    opts["sds"] = opts["des"] and rng.random() < 0.7
+    opts["clip_desc"] = rng.random() < 0.3
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("GTB200_FASTA_CHUNK", str(rng.choice([1, 5, 64, 1000, 1 << 20])))
+    names = write_inputs(files, tmp_path)
+    try:
+        want = encseq_oracle.encode(files, names, alphabet=alphabet, **opts)
+    except encseq_oracle.Declined:
+        with pytest.raises(FastaUnsupported):
+            write_index_files(names, "our", alphabet=alphabet, **opts)
+        return
+    write_index_files(names, "our", alphabet=alphabet, threads=rng.choice([1, 2, 5]), **opts)
+    for suf in SUFFIXES:
+        p = tmp_path / ("our." + suf)
+        assert p.exists() == (suf in want), suf
+        if p.exists():
+            assert p.read_bytes() == want[suf], suf
