@@ -228,6 +228,56 @@ def test_reference_testdata_through_dropin(tmp_path):
     assert fast > 100          # most of them are DNA
 
 
+ENCODER_BIN = os.path.join(ROOT, "host", "_build", "gtref_b200_encoder")
+
+
+@pytest.mark.skipif(not (os.path.exists(GTREF) and os.path.exists(ENCODER_BIN)),
+                    reason="oracle/_ref/gtref and host/_build/gtref_b200_encoder are built where /root/reference is")
+@pytest.mark.parametrize("name,tool,extra,fast", [
+    ("ushort_multi", "suffixerator", ["-dna", "-suf", "-lcp", "-bck", "-pl"], True),
+    ("three_files", "suffixerator", ["-tis"], True),
+    ("protein_1M", "suffixerator", ["-protein", "-tis"], True),
+    ("many_sequences", "packedindex_mkindex", ["-dna", "-tis"], True),
+    ("small_004", "suffixerator", ["-dna", "-tis", "-clipdesc", "-md5", "no"], True),
+    ("small_001", "suffixerator", ["-dna", "-tis", "-lossless"], False),
+    ("ushort_multi", "suffixerator", ["-dna", "-tis", "-sat", "uint32"], False),
+])
+def test_encoder_api_under_the_reference_tools(name, tool, extra, fast, tmp_path):
+    """host/gt_encseq_encoder_b200.c = gt_encseq_encoder_encode (src/core/encseq_api.h:347) on top of the library,
+    linked into the UNMODIFIED reference tools (its own suffixerator with the CPU sorter, packedindex mkindex): every
+    file they write is the file the all-reference binary writes; -lossless / -sat reach the reference's function"""
+    files, _ = CASES[name]
+    out = {}
+    for who, exe in (("ref", GTREF), ("our", ENCODER_BIN)):
+        d = tmp_path / who
+        d.mkdir()
+        names = write_inputs(files, d)
+        r = subprocess.run([exe, tool, "-indexname", "i", "-db"] + names + extra, cwd=d, capture_output=True, text=True,
+                           env=dict(os.environ, GTB200_TRACE_ENCODER="1"))
+        assert r.returncode == 0, r.stderr
+        out[who] = ({f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.startswith("i.")}, r.stderr)
+    assert sorted(out["ref"][0]) == sorted(out["our"][0])
+    for f in out["ref"][0]:
+        assert out["ref"][0][f] == out["our"][0][f], f
+    assert ("B200 encoder:" in out["our"][1]) == fast
+
+
+@pytest.mark.skipif(not (os.path.exists(GTREF) and os.path.exists(ENCODER_BIN)),
+                    reason="oracle/_ref/gtref and host/_build/gtref_b200_encoder are built where /root/reference is")
+@pytest.mark.parametrize("name", sorted(DECLINED))
+def test_encoder_api_on_declined_inputs(name, tmp_path):
+    res = {}
+    for who, exe in (("ref", GTREF), ("our", ENCODER_BIN)):
+        d = tmp_path / who
+        d.mkdir()
+        names = write_inputs(DECLINED[name], d)
+        r = subprocess.run([exe, "suffixerator", "-dna", "-tis", "-indexname", "i", "-db"] + names, cwd=d,
+                           capture_output=True, text=True)
+        res[who] = (r.returncode, r.stderr.split(": error: ", 1)[-1],
+                    {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.startswith("i.")})
+    assert res["ref"] == res["our"]
+
+
 # ---- the sequential restatement (oracle/encseq_oracle.py): pinned to the reference, then used as the checker
 
 ORACLE_CASES = [n for n in sorted(CASES) if sum(len(f) for f in CASES[n][0]) < 200_000]
