@@ -607,6 +607,13 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   const Tables tables = make_tables(rq->symbolmap);
   const std::string indexname = rq->indexname;
 
+  // the directory of the index must take new files: if not, the reference's encoder is the one to say so
+  {
+    const size_t slash = indexname.rfind('/');
+    const std::string dir = slash == std::string::npos ? "." : (slash == 0 ? "/" : indexname.substr(0, slash));
+    if (access(dir.c_str(), W_OK | X_OK) != 0)
+      throw Unsupported{format("cannot create files in \"%s\": %s", dir.c_str(), strerror(errno))};
+  }
   Mapped mapped;
   map_inputs(rq, mapped);
   const std::vector<Input> &files = mapped.files;

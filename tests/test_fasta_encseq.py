@@ -140,6 +140,13 @@ def test_compressed_and_missing_files_are_declined(tmp_path, monkeypatch):
         write_index_files(["missing.fa"], "our")
 
 
+def test_index_directory_that_does_not_exist_is_declined(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "a.fa").write_bytes(b">a\nACGT\n")
+    with pytest.raises(FastaUnsupported):
+        write_index_files(["a.fa"], "no/such/dir/our")
+
+
 def run_tool(exe, args, cwd):
     return subprocess.run([exe, "suffixerator"] + args, cwd=cwd, capture_output=True, text=True)
 
@@ -172,6 +179,19 @@ def test_dropin_binary_without_sort(name, extra, tmp_path):
         assert out["ref"][0][f] == out["our"][0][f], f
     fast = "B200 encoder:" in out["our"][1]
     assert fast == ("-sat" not in extra and "-lossless" not in extra)
+
+
+@needs_binaries
+def test_dropin_binary_when_the_index_cannot_be_written(tmp_path):
+    res = {}
+    for who, exe in (("ref", GTREF), ("our", GT_B200)):
+        d = tmp_path / who
+        d.mkdir()
+        names = write_inputs([b">a\nACGT\n"], d)
+        r = run_tool(exe, ["-dna", "-tis", "-indexname", "no/such/dir/i", "-db"] + names, d)
+        res[who] = (r.returncode, r.stderr.split(": error: ", 1)[-1], sorted(os.listdir(d)))
+    assert res["ref"][0] != 0
+    assert res["ref"] == res["our"]
 
 
 @needs_binaries
