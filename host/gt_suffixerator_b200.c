@@ -37,6 +37,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/time.h>
 #include <sys/types.h>
@@ -207,12 +208,67 @@ static void b200_big_free(void *p, size_t bytes)
   if (p != NULL) (void) munmap(p, (bytes + huge - 1) / huge * huge);
 }
 
+/* The sizes of .suf and .lcp are known as soon as the sequences are encoded, long before their contents:
+   while the driver builds the CUDA context and the GPU sorts, the host has nothing to do.  A thread uses that
+   time to write the two files once with zeros, so that the page cache holds their pages when the tables
+   arrive; the real write then only copies into pages that exist (most of what a buffered write costs is
+   getting the pages).  The thread is stopped and joined before the real write of a file starts; the file is
+   then opened without truncation.  GTB200_PREFILL=0 switches it off. */
+typedef struct {
+  char path[2][4096];
+  size_t bytes[2];
+  volatile int stop;
+  int done[2];                 /* the file exists and has been written up to bytes[i] (or the stop) */
+  pthread_t tid;
+  bool started;
+} B200Prefill;
+
+static void *b200_prefill_thread(void *p)
+{
+  B200Prefill *pf = p;
+  const size_t chunk = (size_t) 4 << 20;
+  char *zeros = calloc(1, chunk);
+  int i;
+  if (zeros == NULL) return NULL;
+  for (i = 0; i < 2 && !pf->stop; i++) {
+    size_t off = 0;
+    int fd;
+    if (pf->bytes[i] == 0) continue;
+    fd = open(pf->path[i], O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) continue;
+    pf->done[i] = 1;
+    while (off < pf->bytes[i] && !pf->stop) {
+      size_t want = pf->bytes[i] - off < chunk ? pf->bytes[i] - off : chunk;
+      ssize_t got = write(fd, zeros, want);
+      if (got <= 0) break;
+      off += (size_t) got;
+    }
+    close(fd);
+  }
+  free(zeros);
+  return NULL;
+}
+
+static void b200_prefill_finish(B200Prefill *pf)
+{
+  if (!pf->started) return;
+  pf->stop = 1;
+  pthread_join(pf->tid, NULL);
+  pf->started = false;
+}
+
 static int b200_write(const char *indexname, const char *suffix, const void *data,
-                      size_t size, size_t nmemb, size_t pad_to, GtError *err)
+                      size_t size, size_t nmemb, size_t pad_to, bool prefilled, GtError *err)
 {
   static const char zeros[8] = {0};
   const size_t bytes = size * nmemb;
-  FILE *fp = gt_fa_fopen_with_suffix(indexname, suffix, "wb", err);
+  FILE *fp = NULL;
+  if (prefilled) {             /* keep the pages: no truncation; the length is set below */
+    fp = gt_fa_fopen_with_suffix(indexname, suffix, "rb+", err);
+    if (fp != NULL && ftruncate(fileno(fp), (off_t) bytes) != 0) { gt_fa_xfclose(fp); fp = NULL; }
+    if (fp == NULL) gt_error_unset(err);
+  }
+  if (fp == NULL) fp = gt_fa_fopen_with_suffix(indexname, suffix, "wb", err);
   if (fp == NULL) return -1;
   if (nmemb > 0) gt_xfwrite(data, size, nmemb, fp);
   if (pad_to > 0 && bytes % pad_to != 0)
@@ -315,9 +371,11 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     uint8_t *lcptab = NULL, *bwttab = NULL;
     uint32_t *leftborder = NULL, *csc = NULL, *dist = NULL;
     gtb_stats stats;
+    B200Prefill prefill;
     char msg[512];
 
     memset(&stats, 0, sizeof stats);
+    memset(&prefill, 0, sizeof prefill);
     /* the two -dir checks of gt_runsuffixerator, src/match/sfx-run.c:541-549,586-593 */
     if ((readmode == GT_READMODE_COMPL || readmode == GT_READMODE_REVCOMPL) &&
         !gt_alphabet_is_dna(gt_encseq_alphabet(encseq))) {
@@ -346,6 +404,19 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       gt_error_set(err, "sequences of total length >= 2^32-2 are not supported by the B200 "
                         "suffixerator path");
       had_err = -1;
+    }
+    if (!had_err && want_any && (want_suf || want_lcp) &&
+        !(getenv("GTB200_PREFILL") != NULL && getenv("GTB200_PREFILL")[0] == '0')) {
+      memset(&prefill, 0, sizeof prefill);
+      if (want_suf) {
+        snprintf(prefill.path[0], sizeof prefill.path[0], "%s.suf", gt_str_get(so.indexname));
+        prefill.bytes[0] = sizeof (uint64_t) * ((size_t) n + 1);
+      }
+      if (want_lcp) {
+        snprintf(prefill.path[1], sizeof prefill.path[1], "%s.lcp", gt_str_get(so.indexname));
+        prefill.bytes[1] = (size_t) n + 1;
+      }
+      prefill.started = pthread_create(&prefill.tid, NULL, b200_prefill_thread, &prefill) == 0;
     }
     if (!had_err && want_any) {
       int rc = 0;
@@ -402,14 +473,19 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
     if (want_any && !had_err)
       release_started = pthread_create(&release_tid, NULL, b200_release_thread, NULL) == 0;
     /* the reference's files */
+    b200_prefill_finish(&prefill);
+    if (had_err) {                         /* no tables: the zero-filled files go */
+      if (prefill.done[0]) (void) unlink(prefill.path[0]);
+      if (prefill.done[1]) (void) unlink(prefill.path[1]);
+    }
     if (!had_err && want_suf)
-      had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, err);
+      had_err = b200_write(gt_str_get(so.indexname), ".suf", suftab, sizeof *suftab, n + 1, 0, prefill.done[0], err);
     if (!had_err && want_bwt)
-      had_err = b200_write(gt_str_get(so.indexname), ".bwt", bwttab, 1, n + 1, 0, err);
+      had_err = b200_write(gt_str_get(so.indexname), ".bwt", bwttab, 1, n + 1, 0, false, err);
     if (!had_err && want_lcp) {
-      had_err = b200_write(gt_str_get(so.indexname), ".lcp", lcptab, 1, n + 1, 0, err);
+      had_err = b200_write(gt_str_get(so.indexname), ".lcp", lcptab, 1, n + 1, 0, prefill.done[1], err);
       if (!had_err)
-        had_err = b200_write(gt_str_get(so.indexname), ".llv", llv, sizeof *llv, 2 * nllv, 0, err);
+        had_err = b200_write(gt_str_get(so.indexname), ".llv", llv, sizeof *llv, 2 * nllv, 0, false, err);
     }
     if (!had_err && want_bck) {
       FILE *fp = gt_fa_fopen_with_suffix(gt_str_get(so.indexname), ".bck", "wb", err);

@@ -10,8 +10,12 @@ tmp = tempfile.mkdtemp()
 fa = os.path.join(tmp, "s.fa"); synth.to_fasta(w.to_symbols(), fa, "dna")
 print("host cores", os.cpu_count(), "fasta bytes", os.path.getsize(fa))
 exe = os.path.join(ROOT, "host", "_build", "gt_b200")
-for label, env in (("library encoder", {}), ("library encoder, quick exit", {"GTB200_QUICK_EXIT": "1"}),
-                   ("reference encoder", {"GTB200_ENCODER": "reference"})):
+variants = (("library encoder", {}), ("library encoder, output files not prefilled", {"GTB200_PREFILL": "0"}),
+            ("library encoder, quick exit", {"GTB200_QUICK_EXIT": "1"}),
+            ("reference encoder", {"GTB200_ENCODER": "reference"}))
+if len(sys.argv) > 1:
+    variants = variants[:int(sys.argv[1])]
+for label, env in variants:
     for i in range(3):
         w0 = time.time()
         t0 = time.perf_counter()
