@@ -15,11 +15,18 @@
 #include "gtb200.h"
 
 /* GPUs of a run: GTB200_GPUS, else `gt -j N` (gt_jobs, src/gtr.c:181), never more than the box has */
-static inline int b200_gpu_count(void)
+/* how many GPUs the caller asked for: `gt -j N` (gt_jobs, src/gtr.c:181) or GTB200_GPUS; does not ask the
+   driver (that is the expensive first call into CUDA) */
+static inline int b200_gpus_wanted(void)
 {
   const char *e = getenv("GTB200_GPUS");
-  int want = e != NULL ? atoi(e) : (int) gt_jobs, have = gtb_device_count();
-  if (want < 1) want = 1;
+  int want = e != NULL ? atoi(e) : (int) gt_jobs;
+  return want < 1 ? 1 : want;
+}
+
+static inline int b200_gpu_count(void)
+{
+  int want = b200_gpus_wanted(), have = gtb_device_count();
   if (have >= 1 && want > have) want = have;
   return want;
 }

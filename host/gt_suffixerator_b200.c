@@ -95,12 +95,15 @@ static double b200_now(void)
   return (double) tv.tv_sec + 1e-6 * (double) tv.tv_usec;
 }
 
-/* Creating the sorter object means creating a CUDA context (a few hundred milliseconds in a fresh
-   process): it is started on a thread of its own before the FASTA files are encoded, so that it
-   costs nothing next to the reference's encoder. */
+/* The first call into the CUDA runtime initialises the driver (0.5-1.8 s in a fresh process on the bench
+   boxes), creating the sorter objects builds the contexts (0.2-0.8 s): both happen on a thread of their own
+   that is started before the FASTA files are encoded -- the main thread asks the driver nothing, not even
+   how many GPUs there are, until it has joined that thread. */
 typedef struct {
   gtb_group *group;
-  int ndevices, nranges;
+  int want_devices;              /* gt -j N / GTB200_GPUS */
+  unsigned int parts;            /* -parts */
+  int ndevices, nranges;         /* what the thread settled on */
   char msg[512];
 } B200Init;
 
@@ -114,9 +117,14 @@ static void *b200_release_thread(void *p)
 static void *b200_init_thread(void *p)
 {
   B200Init *init = p;
-  int devices[64], i, nranges = init->nranges;
-  for (i = 0; i < nranges; i++) devices[i] = i % init->ndevices;   /* range i on GPU i mod N */
-  init->group = gtb_group_new(devices, nranges, init->msg, sizeof init->msg);
+  int devices[64], i, have = gtb_device_count();
+  unsigned int parts = init->parts < 1 ? 1u : init->parts;
+  init->ndevices = init->want_devices < 1 ? 1 : init->want_devices;
+  if (have >= 1 && init->ndevices > have) init->ndevices = have;
+  if ((unsigned int) init->ndevices * parts > 64u) parts = 64u / (unsigned int) init->ndevices;
+  init->nranges = init->ndevices * (int) parts;
+  for (i = 0; i < init->nranges; i++) devices[i] = i % init->ndevices;   /* range i on GPU i mod N */
+  init->group = gtb_group_new(devices, init->nranges, init->msg, sizeof init->msg);
   return NULL;
 }
 
@@ -302,14 +310,9 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
                    gt_index_options_outbcktab_value(so.idxopts) || gt_index_options_outbwttab_value(so.idxopts))) {
     /* one code range per GPU, times -parts (at most 64 ranges; they are all resident at once: unlike
        the reference's parts loop, src/match/sfx-suffixer.c:1791-1838, -parts does not bound memory) */
-    unsigned int parts = gt_index_options_numofparts_value(so.idxopts);
     memset(&init, 0, sizeof init);
-    init.ndevices = b200_gpu_count();
-    if (parts < 1) parts = 1;
-    if ((unsigned int) init.ndevices * parts > 64u) parts = 64u / (unsigned int) init.ndevices;
-    init.nranges = init.ndevices * (int) parts;
-    gt_logger_log(logger, "B200: %d GPU(s), %d bucket-code range(s) (gt -j %u, -parts %u)", init.ndevices,
-                  init.nranges, gt_jobs, gt_index_options_numofparts_value(so.idxopts));
+    init.want_devices = b200_gpus_wanted();
+    init.parts = gt_index_options_numofparts_value(so.idxopts);
     init_ever = true;
     init_started = pthread_create(&init_tid, NULL, b200_init_thread, &init) == 0;
     if (!init_started) b200_init_thread(&init);
@@ -428,6 +431,8 @@ int gt_suffixerator(int argc, const char **argv, GtError *err)
       g = init.group;
       init.group = NULL;
       if (g == NULL) { snprintf(msg, sizeof msg, "%s", init.msg); rc = -1; }
+      else gt_logger_log(logger, "B200: %d GPU(s), %d bucket-code range(s) (gt -j %u, -parts %u)", init.ndevices,
+                         init.nranges, gt_jobs, gt_index_options_numofparts_value(so.idxopts));
       /* GtReadmode values are the library's: fwd 0, rev 1, cpl 2, rcl 3 (src/core/readmode.h) */
       if (rc == 0) rc = gtb_group_set_readmode(g, (unsigned) readmode);
       if (rc == 0) rc = b200_group_set_encseq(g, encseq, want_bwt);
