@@ -13,8 +13,9 @@ tail -- results left in HBM (`value`), or through the host-buffer C-ABI includin
 H2D copy of the packed sequence and the D2H copy of .suf/.lcp/.llv/.bck (`e2e`: pinned host
 buffers, one untimed warm-up step, per-phase breakdown).  At N = 1 the line also carries
 `cpu_baseline` (the unmodified reference, one host core, bounded sample of the same generator)
-and `cli` (the drop-in binary host/_build/gt_b200 on the same FASTA sample, index files compared
-byte for byte with the reference's).
+and `cli` (the drop-in binary host/_build/gt_b200 on the same FASTA sample -- FASTA file in, ten index
+files out, each compared byte for byte with the reference's; its stage times in `cli.log`; once more with the
+reference's FASTA encoder inside the same binary, `cli.seconds_with_reference_encoder`).
 With N > 1 ranks (torchrun) the bucket codes are sharded, one range per rank, and every rank calls
 the same C entry the drop-in's `gt -j N` runs with threads (gtb_esa_run_sharded): the count gather and
 a few small sync blocks travel as NCCL all-gathers, the positions of the position-sharded text scan
