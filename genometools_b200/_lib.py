@@ -41,7 +41,7 @@ class GtbFastaRequest(C.Structure):
         ("symbolmap", C.POINTER(C.c_uint8)), ("decode", C.c_char_p), ("numofchars", C.c_uint),
         ("alphatype", C.c_uint), ("bits_per_symbol", C.c_uint),
         ("out_des", C.c_int), ("out_sds", C.c_int), ("out_ssp", C.c_int), ("out_md5", C.c_int),
-        ("clip_desc", C.c_int), ("threads", C.c_int),
+        ("clip_desc", C.c_int), ("sat", C.c_char_p), ("threads", C.c_int),
     ]
 
 

@@ -798,7 +798,27 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
   }
   uint64_t sat = SAT_BITACCESS, table_items = wildtab[0];
   int table_kind = -1;
-  if (!dna) sat = SAT_BYTECOMPRESS;                             // gt_encseq_access_type_determine, encseq_access_type.c:152-163
+  // -sat: the representation is given (getsatforcevalue, encseq.c:797-814: a table type also decides which entry
+  // counts the header carries; gt_encseq_access_type_determine, encseq_access_type.c:164-247: what the reference
+  // refuses -- eqlen without equal lengths, bytecompress for DNA, a 2-bit type for protein -- is left to it)
+  const std::string forced = rq->sat != nullptr ? rq->sat : "";
+  if (!forced.empty()) {
+    static const char *table_names[3] = {"uchar", "ushort", "uint32"};
+    int k = -1;
+    for (int i = 0; i < 3; i++)
+      if (forced == table_names[i]) k = i;
+    if (forced == "direct") sat = SAT_DIRECT;
+    else if (!dna && forced == "bytecompress") sat = SAT_BYTECOMPRESS;
+    else if (dna && forced == "bit") sat = SAT_BITACCESS;
+    else if (dna && forced == "eqlen" && equallength) sat = SAT_EQUALLENGTH;
+    else if (dna && k >= 0) {
+      sat = SAT_UCHAR + (uint64_t) k;
+      table_kind = k;
+      table_items = wildtab[k];
+      sci.specialranges = specialtab[k];
+      sci.wildcardranges = wildtab[k];
+    } else throw Unsupported{format("-sat %s for this input", forced.c_str())};
+  } else if (!dna) sat = SAT_BYTECOMPRESS;                      // gt_encseq_access_type_determine, encseq_access_type.c:152-163
   else if (equallength) sat = SAT_EQUALLENGTH;
   else {
     uint64_t cmin = twobit_bytes + ((wildtab[0] > 0 || numofsequences > 1) ? 8 * ints_for_bits(n + 64) : 0);
@@ -821,18 +841,19 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
 
   // ---- pack (fillSWtable / fillViaequallength / fillViabitaccess: a special position holds the least
   //      probable character, with bit access 0 for a wildcard and 1 for a separator)
-  const uint64_t units = dna ? units_of_twobit(n) : 0, full = n / 32;
+  const bool twobit = dna && sat != SAT_DIRECT, bitstring = !dna && sat != SAT_DIRECT;
+  const uint64_t units = twobit ? units_of_twobit(n) : 0, full = n / 32;
   // protein: a bit string, bits_per_symbol bits per symbol from the top of byte 0 on, wildcard = K, separator = K+1
   // (fillViabytecompress, encseq.c:2324-2440; gt_bsStoreUInt32, src/core/bitpackstringop32.c)
   const unsigned bps = rq->bits_per_symbol;
-  const uint64_t packed_bytes = dna ? 0 : (n * bps + 7) / 8;
-  BigBuffer words_buffer(dna ? units * 8 : packed_bytes + 16);
+  const uint64_t packed_bytes = bitstring ? (n * bps + 7) / 8 : 0;
+  BigBuffer words_buffer(twobit ? units * 8 : packed_bytes + 16);
   uint64_t *words = static_cast<uint64_t *>(words_buffer.p);   // zeros: the words behind the last symbol stay 0
   uint8_t *packed = static_cast<uint8_t *>(words_buffer.p);
   uint8_t fill[256];
   for (int c = 0; c < 256; c++) fill[c] = (uint8_t) (c < 4 ? c : lpc);
   if (sat == SAT_BITACCESS) { fill[CODE_WILDCARD] = 0; fill[CODE_SEPARATOR] = 1; }
-  if (!dna) {
+  if (bitstring) {
     for (int c = 0; c < 256; c++) fill[c] = (uint8_t) c;
     fill[CODE_WILDCARD] = (uint8_t) K;
     fill[CODE_SEPARATOR] = (uint8_t) (K + 1);
@@ -854,7 +875,7 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
       const uint64_t left = packed_bytes - groups * bps;
       for (uint64_t b = 0; b < left; b++) out[b] = (uint8_t) (v >> (8 * (bps - 1 - b)));
     }
-  } else {
+  } else if (twobit) {
     const uint64_t block = 1 << 15;                              // words per task
     parallel_for(nthreads, (size_t) ((full + block - 1) / block), [&](size_t task) {
       const uint64_t w0 = task * block, w1 = std::min(full, w0 + block);
@@ -918,7 +939,8 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     }
     w.field(flv.data(), 16, files.size());
     w.field(chardist, 8, K);
-    if (!dna) w.field(packed, 1, packed_bytes);                 // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
+    if (sat == SAT_DIRECT) w.field(codes, 1, n);                // gt_encseq_assign_sequence_mapspec, encseq.c:1346-1402
+    else if (bitstring) w.field(packed, 1, packed_bytes);       // (direct: the codes as they are, fillViadirectaccess :2162-2270)
     else w.field(words, 8, units);
     if (sat == SAT_BITACCESS && (wildtab[0] > 0 || numofsequences > 1)) {
       const uint64_t nw = ints_for_bits(n + 64);

@@ -196,7 +196,7 @@ def decode_table(alphabet="dna"):
 
 
 def write_index_files(paths, indexname, des=True, sds=True, ssp=True, md5=True, clip_desc=False, threads=0,
-                      alphabet="dna"):
+                      alphabet="dna", sat=None):
     """FASTA file(s) -> <indexname>.esq/.ssp/.des/.sds/.md5 as `gt encseq encode -dna|-protein` /
     `gt suffixerator -dna|-protein -tis` write them (gtb_fasta_encode, include/gtb200.h; host code of libgtb200.so).
     Returns the summary dict; raises FastaUnsupported when the library declines the input."""
@@ -219,6 +219,7 @@ def write_index_files(paths, indexname, des=True, sds=True, ssp=True, md5=True, 
     rq.bits_per_symbol = 3 if alphabet == "dna" else 5       # src/core/alphabet.c:476,543
     rq.out_des, rq.out_sds, rq.out_ssp, rq.out_md5 = int(des), int(sds), int(ssp), int(md5)
     rq.clip_desc = int(clip_desc)
+    rq.sat = sat.encode() if sat else None
     rq.threads = int(threads)
     summary = _lib.GtbFastaSummary()
     msg = C.create_string_buffer(1024)

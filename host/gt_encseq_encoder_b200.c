@@ -64,7 +64,6 @@ int gt_encseq_encoder_encode(GtEncseqEncoder *ee, GtStrArray *seqfiles, const ch
   covered = !(which != NULL && strcmp(which, "reference") == 0) &&
             gt_str_array_size(seqfiles) > 0 &&
             b200_flags_are_readable(ee, f) && !f->oistab && !f->esq_no_header && !f->isplain &&
-            gt_str_length(gt_encseq_encoder_representation(ee)) == 0 &&
             strlen(gt_encseq_encoder_symbolmap_file(ee)) == 0;
   if (covered) {
     if (f->isdna) alpha = gt_alphabet_new_dna();
@@ -100,6 +99,7 @@ int gt_encseq_encoder_encode(GtEncseqEncoder *ee, GtStrArray *seqfiles, const ch
     rq.out_ssp = f->ssptab;
     rq.out_md5 = f->md5tab;
     rq.clip_desc = f->clip_desc;
+    rq.sat = gt_str_get(gt_encseq_encoder_representation(ee));
     rc = gtb_fasta_encode(&rq, &sum, msg, sizeof msg);
     gt_free(names);
     gt_alphabet_delete(alpha);

@@ -130,7 +130,7 @@ static void *b200_init_thread(void *p)
 
 /* FASTA -> .esq/.ssp/.des/.sds/.md5 with gtb_fasta_encode (all host cores; include/gtb200.h) where
    it covers the request: DNA or protein (given with -dna / -protein or guessed by the reference from the
-   first file), no -plain / -lossless / -sat / -smap.  Returns 0 when the files are written, 1 when the reference's
+   first file), no -plain / -lossless / -smap.  Returns 0 when the files are written, 1 when the reference's
    encoder has to run (also for every input the library declines: gt_encseq_encoder_encode then words
    the error messages), -1 on an I/O error.  GTB200_ENCODER=reference switches it off. */
 static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *err)
@@ -147,8 +147,7 @@ static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *
 
   if (which != NULL && strcmp(which, "reference") == 0) return 1;
   if (nfiles == 0 || gt_encseq_options_plain_value(o) || gt_encseq_options_plain_value(so->loadopts) ||
-      gt_encseq_options_lossless_value(o) ||
-      gt_str_length(gt_encseq_options_sat_value(o)) > 0 || gt_str_length(gt_encseq_options_smap_value(o)) > 0)
+      gt_encseq_options_lossless_value(o) || gt_str_length(gt_encseq_options_smap_value(o)) > 0)
     return 1;
   if (gt_encseq_options_dna_value(o)) alpha = gt_alphabet_new_dna();
   else if (gt_encseq_options_protein_value(o)) alpha = gt_alphabet_new_protein();
@@ -176,6 +175,7 @@ static int b200_fast_encode(Suffixeratoroptions *so, GtLogger *logger, GtError *
   rq.out_ssp = gt_encseq_options_ssp_value(o);
   rq.out_md5 = gt_encseq_options_md5_value(o);
   rq.clip_desc = gt_encseq_options_clip_desc_value(o);
+  rq.sat = gt_str_get(gt_encseq_options_sat_value(o));
   rq.threads = 0;
   rc = gtb_fasta_encode(&rq, &sum, msg, sizeof msg);
   gt_free(names);

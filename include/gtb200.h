@@ -424,7 +424,7 @@ int gtb_radixsort_u64keypair(int device, uint64_t *pairs, uint64_t count, char *
    Returns GTB_FASTA_OK; GTB_FASTA_UNSUPPORTED (msg says why; NOTHING was written) when the input is
    outside what this encoder covers -- the caller then runs gt_encseq_encoder_encode, which also words
    the reference's error messages: an alphabet read from a file, .gz/.bz2 or non-regular files, a file that does not
-   begin with '>', a character outside the alphabet, an empty sequence, a description cut off by the end
+   begin with '>', a -sat the reference refuses, a character outside the alphabet, an empty sequence, a description cut off by the end
    of the file or holding a NUL, 2^32-2 symbols or more; GTB_FASTA_ERROR for I/O errors. */
 #define GTB_FASTA_OK 0
 #define GTB_FASTA_UNSUPPORTED 1
@@ -442,6 +442,9 @@ typedef struct {
   unsigned bits_per_symbol;       /* gt_alphabet_bits_per_symbol: protein 5 (unused for DNA) */
   int out_des, out_sds, out_ssp, out_md5;   /* -des -sds -ssp -md5 of the encseq options */
   int clip_desc;                  /* -clipdesc: descriptions end at their first white space */
+  const char *sat;                /* -sat: NULL or "" = the smallest representation (the default), else one of
+                                     direct bytecompress eqlen bit uchar ushort uint32 (what the reference refuses
+                                     for the input is unsupported here: it then words the error) */
   int threads;                    /* 0: all cores, at most 32 */
 } gtb_fasta_request;
 

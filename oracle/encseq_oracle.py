@@ -141,10 +141,11 @@ def swtable(starts_and_lengths, sat, n, withlen):
     return out + field("Q", endidx)
 
 
-def encode(files, names, alphabet="dna", des=True, sds=True, ssp=True, md5=True, clip_desc=False):
+def encode(files, names, alphabet="dna", des=True, sds=True, ssp=True, md5=True, clip_desc=False, sat=None):
     """-> {suffix: bytes} for the files the reference writes"""
     chars, _, wildshow = DNA if alphabet == "dna" else PROTEIN
     K = len(chars)
+    forced = sat
     smap = symbolmap(alphabet)
     codes, orig, descs, flv = read_fasta(files, smap)
     n = len(codes)
@@ -223,7 +224,17 @@ def encode(files, names, alphabet="dna", des=True, sds=True, ssp=True, md5=True,
         if smallest is None or size < smallest:
             smallest = size
             sci["specialranges"], sci["wildcardranges"] = specialtab[k], wildtab[k]
-    if alphabet != "dna":
+    if forced:                                # -sat (getsatforcevalue, encseq.c:797-814; encseq_access_type.c:164-247)
+        if forced == "direct" or (alphabet != "dna" and forced == "bytecompress") or \
+                (alphabet == "dna" and (forced == "bit" or (forced == "eqlen" and equallength))):
+            sat, items = SAT[forced], wildtab[0]
+        elif alphabet == "dna" and forced in ("uchar", "ushort", "uint32"):
+            sat = SAT[forced]
+            items = wildtab[sat - 4]
+            sci["specialranges"], sci["wildcardranges"] = specialtab[sat - 4], wildtab[sat - 4]
+        else:
+            raise Declined("-sat %s is an error of the reference for this input" % forced)
+    elif alphabet != "dna":
         sat, items = SAT["bytecompress"], 0
     elif equallength:
         sat, items = SAT["eqlen"], 0
@@ -252,7 +263,9 @@ def encode(files, names, alphabet="dna", des=True, sds=True, ssp=True, md5=True,
                 start = pos
         elif start is not None:
             wild_ranges.append((start, pos - start)); start = None
-    if alphabet == "dna":
+    if sat == SAT["direct"]:
+        body = pad8(bytes(codes))
+    elif alphabet == "dna":
         words = [0] * units_twobit(n)
         for pos, cc in enumerate(codes):
             v = cc if cc < 4 else (lpc if sat != SAT["bit"] else (0 if cc == WILDCARD else 1))

@@ -164,6 +164,18 @@ def all_cases(nsmall=120):
     cases.update(big_cases())
     for seed in range(40):
         cases["protein_%02d" % seed] = protein_case(seed)
+    # -sat: every representation forced on inputs that would get another one (or the same)
+    for i, sat in enumerate(("uchar", "ushort", "uint32", "bit", "direct")):
+        for seed in (3, 17, 40 + i):
+            files, opts = small_case(seed)
+            cases["sat_%s_%03d" % (sat, seed)] = (files, dict(opts, sat=sat))
+    cases["sat_eqlen_reads"] = (cases["equal_length_reads"][0], dict(ALL_ON, sat="eqlen"))
+    cases["sat_uint32_long_runs"] = (cases["long_runs"][0], dict(ALL_ON, sat="uint32"))
+    cases["sat_uchar_long_runs"] = (cases["long_runs"][0], dict(ALL_ON, sat="uchar"))
+    for sat in ("bytecompress", "direct"):
+        for seed in (2, 9):
+            files, opts = protein_case(seed)
+            cases["sat_%s_protein_%02d" % (sat, seed)] = (files, dict(opts, sat=sat))
     rng = np.random.default_rng(77)
     residues = np.frombuffer(AMINO.encode(), dtype=np.uint8)[rng.integers(0, 20, 1_000_003)]
     cases["protein_1M"] = ([b">one protein of a million residues\n" + residues.tobytes() + b"\n>second\nMKV\n"],

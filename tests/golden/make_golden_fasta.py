@@ -31,6 +31,8 @@ def reference_files(files, opts, workdir):
         cmd += ["-" + k, "yes" if opts[k] else "no"]
     if opts["clip_desc"]:
         cmd.append("-clipdesc")
+    if opts.get("sat"):
+        cmd += ["-sat", opts["sat"]]
     cmd += ["-indexname", "ref", "-db"] + names
     r = subprocess.run(cmd, cwd=workdir, capture_output=True, text=True)
     assert r.returncode == 0, (cmd, r.stderr)

@@ -178,7 +178,7 @@ def test_dropin_binary_without_sort(name, extra, tmp_path):
     for f in out["ref"][0]:
         assert out["ref"][0][f] == out["our"][0][f], f
     fast = "B200 encoder:" in out["our"][1]
-    assert fast == ("-sat" not in extra and "-lossless" not in extra)
+    assert fast == ("-lossless" not in extra)
 
 
 @needs_binaries
@@ -260,7 +260,7 @@ ENCODER_BIN = os.path.join(ROOT, "host", "_build", "gtref_b200_encoder")
     ("many_sequences", "packedindex_mkindex", ["-dna", "-tis"], True),
     ("small_004", "suffixerator", ["-dna", "-tis", "-clipdesc", "-md5", "no"], True),
     ("small_001", "suffixerator", ["-dna", "-tis", "-lossless"], False),
-    ("ushort_multi", "suffixerator", ["-dna", "-tis", "-sat", "uint32"], False),
+    ("ushort_multi", "suffixerator", ["-dna", "-tis", "-sat", "uint32"], True),
 ])
 def test_encoder_api_under_the_reference_tools(name, tool, extra, fast, tmp_path):
     """host/gt_encseq_encoder_b200.c = gt_encseq_encoder_encode (src/core/encseq_api.h:347) on top of the library,
@@ -341,6 +341,8 @@ def test_library_against_oracle_on_random_inputs(seed, tmp_path, monkeypatch):
     import random
     rng = random.Random(5000 + seed)
     alphabet = rng.choice(["dna", "dna", "protein"])
+    sat = rng.choice([None, None] + (["uchar", "ushort", "uint32", "bit", "direct", "eqlen"] if alphabet == "dna"
+                                     else ["bytecompress", "direct", "ushort"]))
     files = [random_fasta(rng, alphabet) for _ in range(rng.choice([1, 1, 2, 3]))]
     opts = {k: rng.random() < 0.7 for k in ("des", "ssp", "md5")}
     opts["sds"] = opts["des"] and rng.random() < 0.7
@@ -349,12 +351,12 @@ def test_library_against_oracle_on_random_inputs(seed, tmp_path, monkeypatch):
     monkeypatch.setenv("GTB200_FASTA_CHUNK", str(rng.choice([1, 5, 64, 1000, 1 << 20])))
     names = write_inputs(files, tmp_path)
     try:
-        want = encseq_oracle.encode(files, names, alphabet=alphabet, **opts)
+        want = encseq_oracle.encode(files, names, alphabet=alphabet, sat=sat, **opts)
     except encseq_oracle.Declined:
         with pytest.raises(FastaUnsupported):
-            write_index_files(names, "our", alphabet=alphabet, **opts)
+            write_index_files(names, "our", alphabet=alphabet, sat=sat, **opts)
         return
-    write_index_files(names, "our", alphabet=alphabet, threads=rng.choice([1, 2, 5]), **opts)
+    write_index_files(names, "our", alphabet=alphabet, sat=sat, threads=rng.choice([1, 2, 5]), **opts)
     for suf in SUFFIXES:
         p = tmp_path / ("our." + suf)
         assert p.exists() == (suf in want), suf
