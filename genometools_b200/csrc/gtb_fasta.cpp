@@ -965,29 +965,46 @@ int encode(const gtb_fasta_request *rq, gtb_fasta_summary *sum)
     // descriptions without '\r', each followed by '\n'; behind the last one the length of the longest
     // and a word of ones; .sds: where each description but the last ends (encseq_charproc.gen,
     // encseq.c:5612-5623; gt_desc_buffer_*, src/core/desc_buffer.c)
+    // (the text of every chunk's descriptions is put together in parallel -- a read set has millions of them --
+    //  and the chunks' texts are then written one after the other)
     Writer des(indexname, ".des");
-    std::vector<uint64_t> sds;
-    uint64_t longest = 0, seq = 0;
-    std::string d;
-    for (const Chunk &c : chunks) {
+    struct DesPart { std::string text; std::vector<uint32_t> lengths; };
+    std::vector<DesPart> parts(chunks.size());
+    const bool clip = rq->clip_desc != 0;
+    parallel_for(nthreads, chunks.size(), [&](size_t k) {
+      const Chunk &c = chunks[k];
       const uint8_t *p = files[c.file].p;
+      DesPart &part = parts[k];
+      part.lengths.reserve(c.headers.size());
       for (const Header &h : c.headers) {
-        d.clear();
+        const size_t before = part.text.size();
         bool clipped = false;
         for (size_t i = h.desc_begin; i < h.desc_end; i++) {
           const uint8_t ch = p[i];
           if (ch == '\r') continue;
-          if (rq->clip_desc) {
+          if (clip) {
             if (clipped) continue;
             if (isspace(ch)) { clipped = true; continue; }
           }
-          d.push_back((char) ch);
+          part.text.push_back((char) ch);
         }
-        longest = std::max<uint64_t>(longest, d.size());
-        des.raw(d.data(), d.size());
-        if (++seq < numofsequences) sds.push_back(des.off);
-        des.raw("\n", 1);
+        part.lengths.push_back((uint32_t) (part.text.size() - before));
+        part.text.push_back('\n');
       }
+    });
+    std::vector<uint64_t> sds;
+    sds.reserve(numofsequences);
+    uint64_t longest = 0, seq = 0, base = 0;
+    for (const DesPart &part : parts) {
+      uint64_t off = base;
+      for (const uint32_t len : part.lengths) {
+        longest = std::max<uint64_t>(longest, len);
+        off += len;
+        if (++seq < numofsequences) sds.push_back(off);       // where the description ends, in front of its '\n'
+        off += 1;
+      }
+      des.raw(part.text.data(), part.text.size());
+      base += part.text.size();
     }
     const uint64_t fin = ~uint64_t(0);
     des.raw(&longest, 8);
