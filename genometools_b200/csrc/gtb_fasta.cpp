@@ -23,7 +23,8 @@
 //
 // What is not covered returns GTB_FASTA_UNSUPPORTED with the reason, BEFORE anything is written, and
 // the caller runs the reference's encoder instead (which then also words the error messages): other
-// alphabets, compressed or non-regular files, files that do not begin with '>', characters outside the
+// alphabets, bzip2-compressed or non-regular files (.gz files are inflated with zlib), files that do not begin with
+// '>', characters outside the
 // alphabet, empty sequences, a description that ends with the file or holds a NUL, 2^32-2 symbols or
 // more.  Byte identity with the reference's files is tested in tests/test_fasta_encseq.py.
 #include <algorithm>
@@ -41,6 +42,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -170,16 +172,74 @@ struct Input {
   std::string name;
   const uint8_t *p = nullptr;
   size_t len = 0;
+  bool inflated = false;         // p is a malloc'ed buffer with the text of a .gz file
 };
 
 struct Mapped {
   std::vector<Input> files;
   ~Mapped()
   {
-    for (auto &f : files)
-      if (f.p != nullptr && f.len > 0) munmap(const_cast<uint8_t *>(f.p), f.len);
+    for (auto &f : files) {
+      if (f.inflated) free(const_cast<uint8_t *>(f.p));
+      else if (f.p != nullptr && f.len > 0) munmap(const_cast<uint8_t *>(f.p), f.len);
+    }
   }
 };
+
+// zlib, found at run time (the library gains no dependency; without it .gz files are declined)
+struct Zlib {
+  void *(*open)(const char *, const char *) = nullptr;
+  int (*read)(void *, void *, unsigned) = nullptr;
+  int (*close)(void *) = nullptr;
+  int (*buffer)(void *, unsigned) = nullptr;
+  bool ok = false;
+  Zlib()
+  {
+    void *h = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (h == nullptr) return;
+    open = reinterpret_cast<void *(*)(const char *, const char *)>(dlsym(h, "gzopen"));
+    read = reinterpret_cast<int (*)(void *, void *, unsigned)>(dlsym(h, "gzread"));
+    close = reinterpret_cast<int (*)(void *)>(dlsym(h, "gzclose"));
+    buffer = reinterpret_cast<int (*)(void *, unsigned)>(dlsym(h, "gzbuffer"));
+    ok = open != nullptr && read != nullptr && close != nullptr;
+  }
+};
+
+// the text of a .gz file (gt_file_mode_determine, src/core/file.c: the suffix selects gzopen/gzread, which also pass
+// a file through that is not compressed at all); one thread -- a deflate stream has no second entry point -- but
+// everything after it is parallel again
+void inflate_input(Input &f)
+{
+  static Zlib z;
+  if (!z.ok) throw Unsupported{format("file \"%s\" is compressed and libz.so.1 is not there", f.name.c_str())};
+  struct stat st;
+  if (stat(f.name.c_str(), &st) != 0 || !S_ISREG(st.st_mode))
+    throw Unsupported{format("cannot read file \"%s\"", f.name.c_str())};
+  void *gz = z.open(f.name.c_str(), "rb");
+  if (gz == nullptr) throw Unsupported{format("cannot open file \"%s\"", f.name.c_str())};
+  if (z.buffer != nullptr) z.buffer(gz, 1u << 20);
+  size_t cap = (size_t) st.st_size * 4 + (size_t(1) << 16), len = 0;
+  uint8_t *buf = static_cast<uint8_t *>(malloc(cap));
+  for (;;) {
+    if (buf == nullptr) { z.close(gz); throw IoError{"out of memory (inflated text)"}; }
+    const size_t room = std::min<size_t>(cap - len, size_t(1) << 30);
+    const int got = z.read(gz, buf + len, (unsigned) room);
+    if (got < 0) { z.close(gz); free(buf); throw Unsupported{format("file \"%s\" cannot be inflated", f.name.c_str())}; }
+    if (got == 0) break;
+    len += (size_t) got;
+    if (len == cap) {
+      cap *= 2;
+      uint8_t *bigger = static_cast<uint8_t *>(realloc(buf, cap));
+      if (bigger == nullptr) free(buf);
+      buf = bigger;
+    }
+  }
+  z.close(gz);
+  if (len == 0) { free(buf); throw Unsupported{format("file \"%s\" is empty", f.name.c_str())}; }
+  f.p = buf;
+  f.len = len;
+  f.inflated = true;
+}
 
 bool has_suffix(const std::string &s, const char *suf)
 {
@@ -195,8 +255,12 @@ void map_inputs(const gtb_fasta_request *rq, Mapped &m)
     Input &f = m.files[i];
     f.name = rq->filenames[i];
     // gt_file_mode_determine, src/core/file.c: the suffix selects the decompressor
-    if (has_suffix(f.name, ".gz") || has_suffix(f.name, ".bz2"))
-      throw Unsupported{format("file \"%s\" is compressed", f.name.c_str())};
+    if (has_suffix(f.name, ".bz2")) throw Unsupported{format("file \"%s\" is bzip2-compressed", f.name.c_str())};
+    if (has_suffix(f.name, ".gz")) {
+      inflate_input(f);
+      if (f.p[0] != '>') throw Unsupported{format("file \"%s\" does not begin with '>'", f.name.c_str())};
+      continue;
+    }
     const int fd = open(f.name.c_str(), O_RDONLY);
     if (fd < 0) throw Unsupported{format("cannot open file \"%s\": %s", f.name.c_str(), strerror(errno))};
     struct stat st;

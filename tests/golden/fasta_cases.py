@@ -153,6 +153,18 @@ def big_cases():
     return c
 
 
+def file_names_and_bytes(files, opts):
+    """the names the files are written under and what is written: f<i>.fa, or f<i>.fa.gz with the gzip of the text"""
+    import gzip
+    out = []
+    for i, raw in enumerate(files):
+        if opts.get("gz") and opts["gz"][i]:
+            out.append(("f%d.fa.gz" % i, gzip.compress(raw, compresslevel=1, mtime=0)))
+        else:
+            out.append(("f%d.fa" % i, raw))
+    return out
+
+
 def all_cases(nsmall=120):
     cases = {}
     for seed in range(nsmall):
@@ -176,6 +188,10 @@ def all_cases(nsmall=120):
         for seed in (2, 9):
             files, opts = protein_case(seed)
             cases["sat_%s_protein_%02d" % (sat, seed)] = (files, dict(opts, sat=sat))
+    # .gz files (inflated by zlib in the reference as well as here); "gz": which of the files are compressed
+    cases["gz_small_010"] = (small_case(10)[0], dict(small_case(10)[1], gz=[True] * len(small_case(10)[0])))
+    cases["gz_mixed_three_files"] = (cases["three_files"][0], dict(ALL_ON, gz=[True, False, True]))
+    cases["gz_protein_04"] = (protein_case(4)[0], dict(protein_case(4)[1], gz=[True] * len(protein_case(4)[0])))
     rng = np.random.default_rng(77)
     residues = np.frombuffer(AMINO.encode(), dtype=np.uint8)[rng.integers(0, 20, 1_000_003)]
     cases["protein_1M"] = ([b">one protein of a million residues\n" + residues.tobytes() + b"\n>second\nMKV\n"],

@@ -22,10 +22,10 @@ SUFFIXES = ("esq", "ssp", "des", "sds", "md5")
 
 def reference_files(files, opts, workdir):
     names = []
-    for i, raw in enumerate(files):
-        names.append("f%d.fa" % i)
-        with open(os.path.join(workdir, names[-1]), "wb") as fh:
-            fh.write(raw)
+    for name, data in fasta_cases.file_names_and_bytes(files, opts):
+        names.append(name)
+        with open(os.path.join(workdir, name), "wb") as fh:
+            fh.write(data)
     cmd = [GTREF, "suffixerator", "-" + opts.get("alphabet", "dna"), "-tis"]
     for k in ("des", "sds", "ssp", "md5"):
         cmd += ["-" + k, "yes" if opts[k] else "no"]

@@ -30,11 +30,11 @@ GT_B200 = os.path.join(ROOT, "host", "_build", "gt_b200")
 SUFFIXES = ("esq", "ssp", "des", "sds", "md5")
 
 
-def write_inputs(files, d):
+def write_inputs(files, d, opts=None):
     names = []
-    for i, raw in enumerate(files):
-        names.append("f%d.fa" % i)          # relative: the .esq header stores the names as given
-        (d / names[-1]).write_bytes(raw)
+    for name, data in fasta_cases.file_names_and_bytes(files, opts or {}):
+        names.append(name)                  # relative: the .esq header stores the names as given
+        (d / name).write_bytes(data)
     return names
 
 
@@ -45,8 +45,8 @@ def check_case(name, tmp_path, monkeypatch, chunk=None, threads=0):
     monkeypatch.chdir(tmp_path)
     if chunk:
         monkeypatch.setenv("GTB200_FASTA_CHUNK", str(chunk))
-    names = write_inputs(files, tmp_path)
-    s = write_index_files(names, "our", threads=threads, **opts)
+    names = write_inputs(files, tmp_path, opts)
+    s = write_index_files(names, "our", threads=threads, **{k: v for k, v in opts.items() if k != "gz"})
     for suf in SUFFIXES:
         p = tmp_path / ("our." + suf)
         assert p.exists() == (suf in g["files"]), f"{name}: .{suf} written: {p.exists()}, reference: {suf in g['files']}"
@@ -131,11 +131,14 @@ def test_declined_inputs_write_nothing(name, tmp_path, monkeypatch):
     assert sorted(os.listdir(tmp_path)) == sorted(names)
 
 
-def test_compressed_and_missing_files_are_declined(tmp_path, monkeypatch):
+def test_bzip2_and_missing_files_are_declined(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
-    (tmp_path / "a.fa.gz").write_bytes(b">a\nACGT\n")
+    (tmp_path / "a.fa.bz2").write_bytes(b">a\nACGT\n")
     with pytest.raises(FastaUnsupported):
-        write_index_files(["a.fa.gz"], "our")
+        write_index_files(["a.fa.bz2"], "our")
+    (tmp_path / "broken.fa.gz").write_bytes(b"\x1f\x8b\x08\x00 this is not a deflate stream")
+    with pytest.raises(FastaUnsupported):
+        write_index_files(["broken.fa.gz"], "our")
     with pytest.raises(FastaUnsupported):
         write_index_files(["missing.fa"], "our")
 
@@ -161,16 +164,17 @@ needs_binaries = pytest.mark.skipif(not (os.path.exists(GTREF) and os.path.exist
     ("odd_header_in_midline", ["-dna", "-md5", "no"]), ("small_004", ["-dna", "-des", "no", "-sds", "no"]),
     ("ushort_multi", ["-dna", "-sat", "uint32"]), ("small_001", ["-dna", "-lossless"]),
     ("protein_1M", ["-protein"]), ("protein_03", []), ("protein_05", ["-protein", "-sat", "direct"]),
+    ("gz_mixed_three_files", ["-dna"]), ("gz_protein_04", []),
 ])
 def test_dropin_binary_without_sort(name, extra, tmp_path):
     """`gt_b200 suffixerator -tis` (no table requested: no GPU involved) beside `gtref`: same files, the
     .prj included; -sat and -lossless go through the reference's encoder inside the drop-in"""
-    files, _ = CASES[name]
+    files, opts = CASES[name]
     out = {}
     for who, exe in (("ref", GTREF), ("our", GT_B200)):
         d = tmp_path / who
         d.mkdir()
-        names = write_inputs(files, d)
+        names = write_inputs(files, d, opts)
         r = run_tool(exe, ["-tis", "-v", "-indexname", "i", "-db"] + names + extra, d)
         assert r.returncode == 0, r.stderr
         out[who] = ({f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.startswith("i.")}, r.stdout)
@@ -307,7 +311,8 @@ ORACLE_CASES = [n for n in sorted(CASES) if sum(len(f) for f in CASES[n][0]) < 2
 def test_oracle_matches_reference(name):
     files, opts = CASES[name]
     g = GOLDEN[name]
-    out = encseq_oracle.encode(files, ["f%d.fa" % i for i in range(len(files))], **opts)
+    names = [nm for nm, _ in fasta_cases.file_names_and_bytes(files, opts)]
+    out = encseq_oracle.encode(files, names, **{k: v for k, v in opts.items() if k != "gz"})
     assert sorted(out) == sorted(g["files"])
     for suf, data in out.items():
         assert hashlib.md5(data).hexdigest() == g["files"][suf]["md5"], suf
