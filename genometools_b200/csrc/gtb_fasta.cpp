@@ -23,8 +23,8 @@
 //
 // What is not covered returns GTB_FASTA_UNSUPPORTED with the reason, BEFORE anything is written, and
 // the caller runs the reference's encoder instead (which then also words the error messages): other
-// alphabets, bzip2-compressed or non-regular files (.gz files are inflated with zlib), files that do not begin with
-// '>', characters outside the
+// alphabets, non-regular files (.gz and .bz2 files are inflated with zlib / libbz2, by one thread), files that do not
+// begin with '>', characters outside the
 // alphabet, empty sequences, a description that ends with the file or holds a NUL, 2^32-2 symbols or
 // more.  Byte identity with the reference's files is tested in tests/test_fasta_encseq.py.
 #include <algorithm>
@@ -172,7 +172,7 @@ struct Input {
   std::string name;
   const uint8_t *p = nullptr;
   size_t len = 0;
-  bool inflated = false;         // p is a malloc'ed buffer with the text of a .gz file
+  bool inflated = false;         // p is a malloc'ed buffer with the text of a .gz / .bz2 file
 };
 
 struct Mapped {
@@ -186,45 +186,53 @@ struct Mapped {
   }
 };
 
-// zlib, found at run time (the library gains no dependency; without it .gz files are declined)
-struct Zlib {
+// zlib and libbz2, found at run time (the library gains no dependency; without them such files are declined).
+// Both through their stdio-like interface, as the reference reads them (gt_xgzread, src/core/xzlib.c:62-71;
+// gt_xbzread, src/core/xbzlib.c:70-78).
+struct Inflater {
   void *(*open)(const char *, const char *) = nullptr;
   int (*read)(void *, void *, unsigned) = nullptr;
-  int (*close)(void *) = nullptr;
+  void (*close_void)(void *) = nullptr;
+  int (*close_int)(void *) = nullptr;
   int (*buffer)(void *, unsigned) = nullptr;
   bool ok = false;
-  Zlib()
+  Inflater(const char *lib, const char *fopen_, const char *fread_, const char *fclose_, bool close_returns_int,
+           const char *fbuffer)
   {
-    void *h = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    void *h = dlopen(lib, RTLD_NOW | RTLD_LOCAL);
     if (h == nullptr) return;
-    open = reinterpret_cast<void *(*)(const char *, const char *)>(dlsym(h, "gzopen"));
-    read = reinterpret_cast<int (*)(void *, void *, unsigned)>(dlsym(h, "gzread"));
-    close = reinterpret_cast<int (*)(void *)>(dlsym(h, "gzclose"));
-    buffer = reinterpret_cast<int (*)(void *, unsigned)>(dlsym(h, "gzbuffer"));
-    ok = open != nullptr && read != nullptr && close != nullptr;
+    open = reinterpret_cast<void *(*)(const char *, const char *)>(dlsym(h, fopen_));
+    read = reinterpret_cast<int (*)(void *, void *, unsigned)>(dlsym(h, fread_));
+    if (close_returns_int) close_int = reinterpret_cast<int (*)(void *)>(dlsym(h, fclose_));
+    else close_void = reinterpret_cast<void (*)(void *)>(dlsym(h, fclose_));
+    if (fbuffer != nullptr) buffer = reinterpret_cast<int (*)(void *, unsigned)>(dlsym(h, fbuffer));
+    ok = open != nullptr && read != nullptr && (close_int != nullptr || close_void != nullptr);
   }
+  void close(void *f) const { if (close_int) close_int(f); else close_void(f); }
 };
 
-// the text of a .gz file (gt_file_mode_determine, src/core/file.c: the suffix selects gzopen/gzread, which also pass
-// a file through that is not compressed at all); one thread -- a deflate stream has no second entry point -- but
-// everything after it is parallel again
-void inflate_input(Input &f)
+// the text of a .gz / .bz2 file (gt_file_mode_determine, src/core/file.c: the suffix selects the library; gzread also
+// passes a file through that is not compressed at all); one thread -- such a stream has no second entry point --
+// but everything after it is parallel again
+void inflate_input(Input &f, bool bzip2)
 {
-  static Zlib z;
-  if (!z.ok) throw Unsupported{format("file \"%s\" is compressed and libz.so.1 is not there", f.name.c_str())};
+  static const Inflater gz("libz.so.1", "gzopen", "gzread", "gzclose", true, "gzbuffer");
+  static const Inflater bz("libbz2.so.1.0", "BZ2_bzopen", "BZ2_bzread", "BZ2_bzclose", false, nullptr);
+  const Inflater &z = bzip2 ? bz : gz;
+  if (!z.ok) throw Unsupported{format("file \"%s\" is compressed and the library to read it is not there", f.name.c_str())};
   struct stat st;
   if (stat(f.name.c_str(), &st) != 0 || !S_ISREG(st.st_mode))
     throw Unsupported{format("cannot read file \"%s\"", f.name.c_str())};
-  void *gz = z.open(f.name.c_str(), "rb");
-  if (gz == nullptr) throw Unsupported{format("cannot open file \"%s\"", f.name.c_str())};
-  if (z.buffer != nullptr) z.buffer(gz, 1u << 20);
+  void *in = z.open(f.name.c_str(), "rb");
+  if (in == nullptr) throw Unsupported{format("cannot open file \"%s\"", f.name.c_str())};
+  if (z.buffer != nullptr) z.buffer(in, 1u << 20);
   size_t cap = (size_t) st.st_size * 4 + (size_t(1) << 16), len = 0;
   uint8_t *buf = static_cast<uint8_t *>(malloc(cap));
   for (;;) {
-    if (buf == nullptr) { z.close(gz); throw IoError{"out of memory (inflated text)"}; }
+    if (buf == nullptr) { z.close(in); throw IoError{"out of memory (inflated text)"}; }
     const size_t room = std::min<size_t>(cap - len, size_t(1) << 30);
-    const int got = z.read(gz, buf + len, (unsigned) room);
-    if (got < 0) { z.close(gz); free(buf); throw Unsupported{format("file \"%s\" cannot be inflated", f.name.c_str())}; }
+    const int got = z.read(in, buf + len, (unsigned) room);
+    if (got < 0) { z.close(in); free(buf); throw Unsupported{format("file \"%s\" cannot be inflated", f.name.c_str())}; }
     if (got == 0) break;
     len += (size_t) got;
     if (len == cap) {
@@ -234,7 +242,7 @@ void inflate_input(Input &f)
       buf = bigger;
     }
   }
-  z.close(gz);
+  z.close(in);
   if (len == 0) { free(buf); throw Unsupported{format("file \"%s\" is empty", f.name.c_str())}; }
   f.p = buf;
   f.len = len;
@@ -255,9 +263,8 @@ void map_inputs(const gtb_fasta_request *rq, Mapped &m)
     Input &f = m.files[i];
     f.name = rq->filenames[i];
     // gt_file_mode_determine, src/core/file.c: the suffix selects the decompressor
-    if (has_suffix(f.name, ".bz2")) throw Unsupported{format("file \"%s\" is bzip2-compressed", f.name.c_str())};
-    if (has_suffix(f.name, ".gz")) {
-      inflate_input(f);
+    if (has_suffix(f.name, ".gz") || has_suffix(f.name, ".bz2")) {
+      inflate_input(f, has_suffix(f.name, ".bz2"));
       if (f.p[0] != '>') throw Unsupported{format("file \"%s\" does not begin with '>'", f.name.c_str())};
       continue;
     }

@@ -10,8 +10,8 @@
 
     * asks the encoder object what was requested (its public getters),
     * hands DNA / protein FASTA input to gtb_fasta_encode (all host cores, byte-identical index files),
-    * and calls the reference's own function for everything else -- other alphabets, -lossless, -plain, .bz2
-      files, inputs the library declines (it declines before it writes anything).
+    * and calls the reference's own function for everything else -- other alphabets, -lossless, -plain,
+      inputs the library declines (it declines before it writes anything).
 
   Two settings of the encoder have no getter (lossless support, header-less .esq).  They are read from the
   object itself: its ten flags are declared below in the order of src/core/encseq.c:8141-8151, and before they

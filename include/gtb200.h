@@ -423,8 +423,8 @@ int gtb_radixsort_u64keypair(int device, uint64_t *pairs, uint64_t count, char *
      decode     gt_alphabet_decode of the codes 0..numofchars-1 and 254 (256 entries, the rest unused)
    Returns GTB_FASTA_OK; GTB_FASTA_UNSUPPORTED (msg says why; NOTHING was written) when the input is
    outside what this encoder covers -- the caller then runs gt_encseq_encoder_encode, which also words
-   the reference's error messages: an alphabet read from a file, .bz2 or non-regular files (.gz files are inflated with
-   the zlib found at run time, by one thread), a file that does not
+   the reference's error messages: an alphabet read from a file, non-regular files (.gz / .bz2 files are inflated with
+   the zlib / libbz2 found at run time, by one thread), a file that does not
    begin with '>', a -sat the reference refuses, a character outside the alphabet, an empty sequence, a description cut off by the end
    of the file or holding a NUL, 2^32-2 symbols or more; GTB_FASTA_ERROR for I/O errors. */
 #define GTB_FASTA_OK 0

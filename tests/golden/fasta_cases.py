@@ -155,10 +155,13 @@ def big_cases():
 
 def file_names_and_bytes(files, opts):
     """the names the files are written under and what is written: f<i>.fa, or f<i>.fa.gz with the gzip of the text"""
+    import bz2
     import gzip
     out = []
     for i, raw in enumerate(files):
-        if opts.get("gz") and opts["gz"][i]:
+        if opts.get("gz") and opts["gz"][i] == "bz2":
+            out.append(("f%d.fa.bz2" % i, bz2.compress(raw, 1)))
+        elif opts.get("gz") and opts["gz"][i]:
             out.append(("f%d.fa.gz" % i, gzip.compress(raw, compresslevel=1, mtime=0)))
         else:
             out.append(("f%d.fa" % i, raw))
@@ -188,9 +191,11 @@ def all_cases(nsmall=120):
         for seed in (2, 9):
             files, opts = protein_case(seed)
             cases["sat_%s_protein_%02d" % (sat, seed)] = (files, dict(opts, sat=sat))
-    # .gz files (inflated by zlib in the reference as well as here); "gz": which of the files are compressed
+    # .gz / .bz2 files (inflated by zlib / libbz2 in the reference as well as here); "gz": which of the files are
+    # compressed (True: gzip, "bz2": bzip2)
     cases["gz_small_010"] = (small_case(10)[0], dict(small_case(10)[1], gz=[True] * len(small_case(10)[0])))
-    cases["gz_mixed_three_files"] = (cases["three_files"][0], dict(ALL_ON, gz=[True, False, True]))
+    cases["gz_mixed_three_files"] = (cases["three_files"][0], dict(ALL_ON, gz=[True, False, "bz2"]))
+    cases["bz2_small_011"] = (small_case(11)[0], dict(small_case(11)[1], gz=["bz2"] * len(small_case(11)[0])))
     cases["gz_protein_04"] = (protein_case(4)[0], dict(protein_case(4)[1], gz=[True] * len(protein_case(4)[0])))
     rng = np.random.default_rng(77)
     residues = np.frombuffer(AMINO.encode(), dtype=np.uint8)[rng.integers(0, 20, 1_000_003)]

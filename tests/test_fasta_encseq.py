@@ -131,9 +131,9 @@ def test_declined_inputs_write_nothing(name, tmp_path, monkeypatch):
     assert sorted(os.listdir(tmp_path)) == sorted(names)
 
 
-def test_bzip2_and_missing_files_are_declined(tmp_path, monkeypatch):
+def test_broken_and_missing_files_are_declined(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
-    (tmp_path / "a.fa.bz2").write_bytes(b">a\nACGT\n")
+    (tmp_path / "a.fa.bz2").write_bytes(b">a\nACGT\n")         # libbz2 passes nothing through that is not bzip2
     with pytest.raises(FastaUnsupported):
         write_index_files(["a.fa.bz2"], "our")
     (tmp_path / "broken.fa.gz").write_bytes(b"\x1f\x8b\x08\x00 this is not a deflate stream")
